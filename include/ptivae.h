@@ -1,0 +1,103 @@
+/* ptivae.h -- C ABI of libptivae.so: the B200 (sm_100a) kernels behind the PTI-LDM-VAE hot path.
+ *
+ * The reference (Sukikui/PTI-LDM-VAE) is pure Python: its hot path is
+ *   pti_ldm_vae.models.VAEModel            /root/reference/src/pti_ldm_vae/models/autoencoder.py:6-171
+ *     -> monai.networks.nets.AutoencoderKL /root/reference/src/pti_ldm_vae/models/autoencoder.py:67-79
+ * i.e. there is no FFI in the reference; what this library replaces are the ATen/cuDNN/cuBLAS calls
+ * MONAI 1.5.1 issues for that path.  Each entry point below names the reference operator it stands in
+ * for.  The Python binding a maintainer adds is the ctypes stub in INTEGRATION.md (mirrored by
+ * pti-ldm-vae_b200/_lib.py).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - nothing allocates, nothing synchronises; the caller owns every buffer;
+ *   - return value: 0 = launched; <0 = argument/shape error (no launch happened):
+ *        -1 bad argument, -2 unsupported shape, -3 driver entry point / tensor-map encode failure;
+ *     >0 = the cudaError_t reported by the launch;
+ *   - activations: bf16 NHWC ("bf16 [N][H][W][C]"), latents/images at the boundary: fp32 NCHW.
+ */
+#ifndef PTIVAE_H_
+#define PTIVAE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library / build identification: returns e.g. 100 for sm_100a builds, and the ABI revision. */
+int ptivae_abi_version(void);
+
+/* nn.Conv2d / nn.Linear on tensor cores (tcgen05 implicit GEMM).
+ *   replaces: monai Convolution(conv_only) 3x3 s1 p1, AEKLDownsample (F.pad(0,1,0,1)+3x3 s2),
+ *             UpSample(nearest x2)+postconv 3x3, nin_shortcut 1x1, SABlock.to_q/to_k/to_v/out_proj
+ *             (monai 1.5.1 networks/nets/autoencoderkl.py, blocks/selfattention.py; called from
+ *             autoencoder.py:114/:139/:151).
+ *   in        bf16 [N][H][W][Cin]         Cin in {32, 64k}
+ *   w_packed  bf16 [T][Cout][Cin]         from ptivae_pack_conv_weight (T = 9, 1, or 16 for mode 2)
+ *   bias      fp32 [Cout]
+ *   residual  bf16, same shape as out, added in the epilogue (may be NULL)
+ *   out       bf16 [N][Hout][Wout][Cout]  Cout in {32,64,128,256k}
+ *   gn_acc    fp32 [N][gn_groups][2] (sum, sum of squares of the bf16-rounded output), accumulated
+ *             with atomics -- must be zeroed by the caller; ignored when gn_groups == 0
+ *   mode      0: 3x3 stride 1 pad 1 (Hout=H)      1: pad right/bottom + 3x3 stride 2 (Hout=H/2, H,W even)
+ *             2: nearest x2 upsample + 3x3 pad 1 (Hout=2H)   3: 1x1 */
+int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual, void* out,
+                     float* gn_acc, int gn_groups, int N, int H, int W, int Cin, int Cout, int mode, void* stream);
+
+/* fp32 master weights [Cout][Cin][k][k] -> bf16 UMMA operand [T][Cout][Cin].
+ *   mode 0: T = k*k (k in {1,3}); mode 2: T = 16, the 4-phase x (2x2)-tap decomposition of
+ *   nearest-x2-upsample + 3x3 (weights of taps that hit the same low-res pixel are pre-summed). */
+int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, void* stream);
+
+/* nn.GroupNorm statistics: acc[n][g] += (sum, sumsq) over the bf16 NHWC tensor x [N][HW][C]. */
+int ptivae_gn_stats(const void* x, float* acc, int N, int HW, int C, int G, void* stream);
+/* acc -> scale_shift fp32 [N][C][2] with scale = gamma*rstd, shift = beta - mean*scale
+ * (biased variance, eps inside the sqrt: nn.GroupNorm(eps=norm_eps, affine=True)). */
+int ptivae_gn_finalize(const float* acc, const float* gamma, const float* beta, float* scale_shift, int N, int HW,
+                       int C, int G, float eps, void* stream);
+/* y = act(x*scale + shift): act = SiLU when silu != 0 (AEKLResBlock: F.silu(norm(x))), identity otherwise
+ * (SpatialAttentionBlock.norm). x,y bf16 [N][HW][C]. */
+int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, int N, int HW, int C, int silu, void* stream);
+
+/* Thin-end 3x3 s1 p1 convolutions on CUDA cores.
+ *   small_cin : x fp32 NCHW [N][Cin<=16][H][W], w fp32 [Cout][Cin][3][3] -> out bf16 NHWC
+ *               (encoder.blocks.0, decoder.blocks.0)
+ *   small_cout: x bf16 NHWC, optional fused GroupNorm affine scale_shift [N][Cin][2] (NO activation:
+ *               encoder.blocks.15/decoder.blocks.15 are bare GroupNorms), zero padding applied after
+ *               the norm -> out fp32 NCHW [N][Cout<=16][H][W]  (encoder.blocks.16, decoder.blocks.16) */
+int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int N, int H, int W,
+                             int Cin, int Cout, void* stream);
+int ptivae_conv3x3_small_cout(const void* x, const float* w, const float* bias, const float* scale_shift, float* out,
+                              int N, int H, int W, int Cin, int Cout, void* stream);
+/* 1x1 conv, fp32 NCHW in/out, Cin,Cout <= 16 (quant_conv_mu, quant_conv_log_sigma, post_quant_conv).
+ *   act 0: none;  act 1: exp(clamp(v,-30,20)/2)  == AutoencoderKL.encode's z_sigma. */
+int ptivae_conv1x1_small(const float* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
+                         int Cout, int act, void* stream);
+
+/* Single-head self-attention core: out = softmax(Q K^T * D^-0.5) V; q,k,v,out bf16 [B][L][D], D in {64,128,256}
+ * (monai SABlock with num_heads = 1, use_flash_attention=False semantics). */
+int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D, void* stream);
+
+/* AutoencoderKL.sampling: z = mu + sigma*eps.  eps_in != NULL: use the injected noise; else draw
+ * eps from Philox4x32-10 (key = seed, counter = (element/4, offset)) + Box-Muller.  eps_out (may be
+ * NULL) receives the noise that was used.  rng_dev (may be NULL): device array {seed, offset} that
+ * overrides the by-value pair, so a captured CUDA graph draws fresh noise on every replay
+ * (ptivae_rng_advance bumps the offset).  n = element count. */
+int ptivae_latent_sample(const float* mu, const float* sigma, const float* eps_in, float* z, float* eps_out,
+                         const unsigned long long* rng_dev, long long n, unsigned long long seed,
+                         unsigned long long offset, void* stream);
+int ptivae_rng_advance(unsigned long long* rng_dev, void* stream);
+
+/* compute_kl_loss (/root/reference/src/pti_ldm_vae/models/losses.py:4-30):
+ *   out[0] = mean_b( -0.5 * sum_{chw}(1 + t - mu^2 - exp(t)) ), t = `t` if input_is_logvar else log(t^2+1e-8).
+ *   workspace: N floats. */
+int ptivae_kl_loss(const float* mu, const float* t, float* workspace, float* out, int N, int per_img,
+                   int input_is_logvar, void* stream);
+/* nn.L1Loss()/nn.MSELoss() (train_vae.py:289-296): out[0] = mean|a-b|, out[1] = mean (a-b)^2.
+ *   n % 4 == 0, 16-byte aligned inputs; workspace: 2*1184 floats. */
+int ptivae_l1l2(const float* a, const float* b, float* workspace, float* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTIVAE_H_ */

@@ -1,0 +1,312 @@
+"""B200-native drop-in for ``monai.networks.nets.AutoencoderKL`` as constructed by the reference
+(/root/reference/src/pti_ldm_vae/models/autoencoder.py:67-79): same 11 kwargs, same methods
+(``forward/encode/decode/sampling/encode_stage_2_inputs/decode_stage_2_outputs/reconstruct``),
+same module tree and therefore the same ``state_dict`` keys / fp32 NCHW weight layout, so existing
+checkpoints load with ``strict=True``.
+
+The ``nn.Module`` tree below only HOLDS parameters (fp32 masters).  No torch operator computes
+anything on the hot path: ``_Executor`` walks the tree and launches the sm_100a kernels of
+libptivae.so (bf16 NHWC activations, fp32 accumulation, fp32 latents / outputs).
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+__all__ = ["AutoencoderKL", "B200AutoencoderKL"]
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (key names of monai 1.5.1)
+# ---------------------------------------------------------------------------------------------
+class Convolution(nn.Module):
+    """``<P>.conv.weight`` / ``<P>.conv.bias``."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=True)
+
+
+class AEKLResBlock(nn.Module):
+    def __init__(self, cin, cout, groups, eps):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps, affine=True)
+        self.conv1 = Convolution(cin, cout, 3, 1, 1)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps, affine=True)
+        self.conv2 = Convolution(cout, cout, 3, 1, 1)
+        self.nin_shortcut = Convolution(cin, cout, 1, 1, 0) if cin != cout else nn.Identity()
+
+
+class AEKLDownsample(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = Convolution(c, c, 3, 2, 0)
+
+
+class UpSample(nn.Module):
+    """nearest x2 (``upsample_non_trainable``, no params) + ``postconv``."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.upsample_non_trainable = nn.Identity()
+        self.postconv = Convolution(c, c, 3, 1, 1)
+
+
+class SABlock(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.to_q = nn.Linear(c, c)
+        self.to_k = nn.Linear(c, c)
+        self.to_v = nn.Linear(c, c)
+        self.out_proj = nn.Linear(c, c)
+
+
+class SpatialAttentionBlock(nn.Module):
+    def __init__(self, c, groups, eps):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, c, eps=eps, affine=True)
+        self.attn = SABlock(c)
+
+
+class _Blocks(nn.Module):
+    def __init__(self, blocks):
+        super().__init__()
+        self.blocks = nn.ModuleList(blocks)
+
+
+def _encoder(cin, channels, cout, nres, groups, eps, attn_levels, nonlocal_attn):
+    blocks = [Convolution(cin, channels[0], 3, 1, 1)]
+    oc = channels[0]
+    for i, ch in enumerate(channels):
+        ic, oc = oc, ch
+        for _ in range(nres[i]):
+            blocks.append(AEKLResBlock(ic, oc, groups, eps))
+            ic = oc
+            if attn_levels[i]:
+                blocks.append(SpatialAttentionBlock(ic, groups, eps))
+        if i != len(channels) - 1:
+            blocks.append(AEKLDownsample(ic))
+    if nonlocal_attn:
+        c = channels[-1]
+        blocks += [AEKLResBlock(c, c, groups, eps), SpatialAttentionBlock(c, groups, eps),
+                   AEKLResBlock(c, c, groups, eps)]
+    blocks.append(nn.GroupNorm(groups, channels[-1], eps=eps, affine=True))
+    blocks.append(Convolution(channels[-1], cout, 3, 1, 1))
+    return _Blocks(blocks)
+
+
+def _decoder(channels, cin, cout, nres, groups, eps, attn_levels, nonlocal_attn):
+    rev, rattn, rres = channels[::-1], list(attn_levels)[::-1], list(nres)[::-1]
+    blocks = [Convolution(cin, rev[0], 3, 1, 1)]
+    if nonlocal_attn:
+        c = rev[0]
+        blocks += [AEKLResBlock(c, c, groups, eps), SpatialAttentionBlock(c, groups, eps),
+                   AEKLResBlock(c, c, groups, eps)]
+    oc = rev[0]
+    for i, ch in enumerate(rev):
+        ic, oc = oc, ch
+        for _ in range(rres[i]):
+            blocks.append(AEKLResBlock(ic, oc, groups, eps))
+            ic = oc
+            if rattn[i]:
+                blocks.append(SpatialAttentionBlock(ic, groups, eps))
+        if i != len(rev) - 1:
+            blocks.append(UpSample(ic))
+    blocks.append(nn.GroupNorm(groups, ic, eps=eps, affine=True))
+    blocks.append(Convolution(ic, cout, 3, 1, 1))
+    return _Blocks(blocks)
+
+
+# ---------------------------------------------------------------------------------------------
+# executor
+# ---------------------------------------------------------------------------------------------
+class _Act:
+    """bf16 NHWC activation + (optional) GroupNorm statistics accumulated by its producer."""
+    __slots__ = ("t", "acc")
+
+    def __init__(self, t, acc=None):
+        self.t, self.acc = t, acc
+
+
+class _Executor:
+    def __init__(self, groups: int, eps: float, fused_stats: bool = True):
+        self.groups, self.eps, self.fused_stats = groups, eps, fused_stats
+        self._packed: dict = {}
+
+    # -- weights: bf16 UMMA operands cached until the fp32 master changes (optimizer step, load_state_dict, .to())
+    def packed(self, w: torch.Tensor, mode: int = 0) -> torch.Tensor:
+        key = (id(w), mode)
+        ver = (w.data_ptr(), w._version, w.device)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.pack_conv_weight(w, mode))
+            self._packed[key] = hit
+        return hit[1]
+
+    @staticmethod
+    def f32(p: torch.Tensor) -> torch.Tensor:
+        return p.detach()
+
+    def conv(self, a: _Act, conv: nn.Module, mode: int, residual=None, stats: bool = True) -> _Act:
+        w = conv.weight
+        cout = w.shape[0]
+        g = self.groups
+        want = stats and self.fused_stats and cout % g == 0 and 32 % (cout // g) == 0
+        acc = torch.zeros((a.t.shape[0], g, 2), device=a.t.device, dtype=torch.float32) if want else None
+        out = ops.conv_umma(a.t, self.packed(w, 2 if mode == 2 else 0), self.f32(conv.bias), mode,
+                            residual=residual, gn_acc=acc, gn_groups=g if want else 0)
+        return _Act(out, acc)
+
+    def scale_shift(self, a: _Act, norm: nn.GroupNorm) -> torch.Tensor:
+        acc = a.acc if a.acc is not None else ops.gn_stats(a.t, norm.num_groups)
+        n, c = a.t.shape[0], a.t.shape[-1]
+        hw = a.t.numel() // (n * c)
+        return ops.gn_finalize(acc, self.f32(norm.weight), self.f32(norm.bias), hw, norm.eps)
+
+    def resblock(self, blk: AEKLResBlock, a: _Act) -> _Act:
+        y = _Act(ops.gn_apply(a.t, self.scale_shift(a, blk.norm1), silu=True))
+        h = self.conv(y, blk.conv1.conv, 0)
+        y2 = _Act(ops.gn_apply(h.t, self.scale_shift(h, blk.norm2), silu=True))
+        if isinstance(blk.nin_shortcut, Convolution):
+            sc = self.conv(a, blk.nin_shortcut.conv, 3, stats=False).t
+        else:
+            sc = a.t
+        return self.conv(y2, blk.conv2.conv, 0, residual=sc)
+
+    def attention(self, blk: SpatialAttentionBlock, a: _Act) -> _Act:
+        xn = _Act(ops.gn_apply(a.t, self.scale_shift(a, blk.norm), silu=False))
+        q = self.conv(xn, blk.attn.to_q, 3, stats=False).t
+        k = self.conv(xn, blk.attn.to_k, 3, stats=False).t
+        v = self.conv(xn, blk.attn.to_v, 3, stats=False).t
+        n, h, w, c = q.shape
+        o = ops.attention(q.view(n, h * w, c), k.view(n, h * w, c), v.view(n, h * w, c)).view(n, h, w, c)
+        return self.conv(_Act(o), blk.attn.out_proj, 3, residual=a.t)
+
+    def run_stack(self, blocks: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:
+        """x fp32 NCHW -> fp32 NCHW through encoder.blocks / decoder.blocks."""
+        first, last_norm, last = blocks[0], blocks[-2], blocks[-1]
+        a = _Act(ops.conv3x3_small_cin(x, self.f32(first.conv.weight), self.f32(first.conv.bias)))
+        for blk in list(blocks)[1:-2]:
+            if isinstance(blk, AEKLResBlock):
+                a = self.resblock(blk, a)
+            elif isinstance(blk, SpatialAttentionBlock):
+                a = self.attention(blk, a)
+            elif isinstance(blk, AEKLDownsample):
+                a = self.conv(a, blk.conv.conv, 1)
+            elif isinstance(blk, UpSample):
+                a = self.conv(a, blk.postconv.conv, 2)
+            else:  # pragma: no cover
+                raise TypeError(f"unexpected block {type(blk)}")
+        ss = self.scale_shift(a, last_norm)
+        return ops.conv3x3_small_cout(a.t, self.f32(last.conv.weight), self.f32(last.conv.bias), ss)
+
+
+# ---------------------------------------------------------------------------------------------
+# the model
+# ---------------------------------------------------------------------------------------------
+class AutoencoderKL(nn.Module):
+    """Same constructor contract as the reference's call at autoencoder.py:67-79 (2D only)."""
+
+    def __init__(self, spatial_dims: int = 2, in_channels: int = 1, out_channels: int = 1,
+                 num_res_blocks: Sequence[int] | int = (2, 2, 2, 2), channels: Sequence[int] = (32, 64, 64, 64),
+                 attention_levels: Sequence[bool] = (False, False, True, True), latent_channels: int = 3,
+                 norm_num_groups: int = 32, norm_eps: float = 1e-6, with_encoder_nonlocal_attn: bool = True,
+                 with_decoder_nonlocal_attn: bool = True) -> None:
+        super().__init__()
+        if spatial_dims != 2:
+            raise ValueError("the B200 hot path implements spatial_dims=2 only (all reference configs are 2D)")
+        if any((c % norm_num_groups) != 0 for c in channels):
+            raise ValueError("AutoencoderKL expects all channels being multiple of norm_num_groups")
+        if len(channels) != len(attention_levels):
+            raise ValueError("AutoencoderKL expects channels being same size of attention_levels")
+        if isinstance(num_res_blocks, int):
+            num_res_blocks = (num_res_blocks,) * len(channels)
+        if len(num_res_blocks) != len(channels):
+            raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same "
+                             "length as `channels`.")
+        channels = list(channels)
+        for c in channels:
+            if c not in (32, 64, 128, 256, 512):
+                raise ValueError(f"channel width {c} has no sm_100a kernel instantiation (supported: 32,64,128,256,512)")
+        if in_channels > 16 or out_channels > 16 or latent_channels > 16:
+            raise ValueError("in/out/latent channels must be <= 16 (thin-end direct kernels)")
+        self.encoder = _encoder(in_channels, channels, latent_channels, num_res_blocks, norm_num_groups, norm_eps,
+                                attention_levels, with_encoder_nonlocal_attn)
+        self.decoder = _decoder(channels, latent_channels, out_channels, num_res_blocks, norm_num_groups, norm_eps,
+                                attention_levels, with_decoder_nonlocal_attn)
+        self.quant_conv_mu = Convolution(latent_channels, latent_channels, 1)
+        self.quant_conv_log_sigma = Convolution(latent_channels, latent_channels, 1)
+        self.post_quant_conv = Convolution(latent_channels, latent_channels, 1)
+        self.latent_channels = latent_channels
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self._exec = _Executor(norm_num_groups, norm_eps)
+        self._rng_offset = 0
+        self._rng_dev = None  # device-resident (seed, offset) when running under CUDA-graph capture
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _prep(self, x: torch.Tensor) -> torch.Tensor:
+        if isinstance(x, torch.Tensor) and type(x) is not torch.Tensor:
+            x = x.as_subclass(torch.Tensor)  # MONAI MetaTensor batches
+        if not x.is_cuda:
+            raise RuntimeError("B200 AutoencoderKL runs on CUDA only; there is no CPU fallback "
+                               "(the CPU restatement lives in oracle/ and is test-only)")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("the backward kernels (SURVEY 8a row a20) are not built yet: call under "
+                                      "torch.no_grad() / model.eval() -- forward, encode, decode are inference-only")
+        return x.detach().contiguous().float()
+
+    def set_fused_stats(self, enabled: bool) -> None:
+        """GroupNorm statistics from the producing conv's epilogue (default) vs. a separate pass."""
+        self._exec.fused_stats = bool(enabled)
+
+    # -- reference API ------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor):
+        x = self._prep(x)
+        h = self._exec.run_stack(self.encoder.blocks, x)
+        mu = ops.conv1x1_small(h, self.quant_conv_mu.conv.weight.detach(), self.quant_conv_mu.conv.bias.detach(), 0)
+        sigma = ops.conv1x1_small(h, self.quant_conv_log_sigma.conv.weight.detach(),
+                                  self.quant_conv_log_sigma.conv.bias.detach(), 1)
+        return mu, sigma
+
+    @torch.no_grad()
+    def sampling(self, z_mu: torch.Tensor, z_sigma: torch.Tensor, eps: torch.Tensor | None = None) -> torch.Tensor:
+        z_mu = z_mu.detach().contiguous().float()
+        z_sigma = z_sigma.detach().contiguous().float()
+        if eps is not None:
+            return ops.latent_sample(z_mu, z_sigma, eps=eps.detach().contiguous().float())
+        if self._rng_dev is not None:
+            z = ops.latent_sample(z_mu, z_sigma, rng_dev=self._rng_dev)
+            ops.rng_advance(self._rng_dev)
+            return z
+        self._rng_offset += 1
+        return ops.latent_sample(z_mu, z_sigma, seed=torch.initial_seed(), offset=self._rng_offset)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        z = self._prep(z)
+        zq = ops.conv1x1_small(z, self.post_quant_conv.conv.weight.detach(), self.post_quant_conv.conv.bias.detach(), 0)
+        return self._exec.run_stack(self.decoder.blocks, zq)
+
+    def forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        z_mu, z_sigma = self.encode(x)
+        z = self.sampling(z_mu, z_sigma, eps)
+        return self.decode(z), z_mu, z_sigma
+
+    def reconstruct(self, x: torch.Tensor) -> torch.Tensor:
+        return self.decode(self.encode(x)[0])
+
+    def encode_stage_2_inputs(self, x: torch.Tensor, eps: torch.Tensor | None = None) -> torch.Tensor:
+        z_mu, z_sigma = self.encode(x)
+        return self.sampling(z_mu, z_sigma, eps)
+
+    def decode_stage_2_outputs(self, z: torch.Tensor) -> torch.Tensor:
+        return self.decode(z)
+
+
+B200AutoencoderKL = AutoencoderKL

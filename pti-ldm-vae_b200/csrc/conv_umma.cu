@@ -1,0 +1,386 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA).  Replaces the cuDNN/aten::convolution calls issued by MONAI's Convolution /
+// AEKLDownsample / UpSample.postconv / nin_shortcut and the attention nn.Linear layers
+// (reference call site
+// /root/reference/src/pti_ldm_vae/models/autoencoder.py:67-79,114).
+//
+// Data layout: activations NHWC bf16, weights packed [tap][Cout][Cin] bf16 (K-major for both UMMA
+// operands), fp32 accumulate, fp32 bias, bf16 output.
+//   GEMM view:  M = 128 output pixels (a TH x TW = 8 x 16 patch of one image)
+//               N = Cout tile (32..256),  K = taps * Cin, walked tap-major in chunks of KCH channels.
+// The A tile of tap (dy,dx) is ONE TMA box load of the NHWC tensor at (y0+dy, x0+dx): the halo /
+// zero padding comes from TMA out-of-bounds zero fill, so there is no im2col buffer anywhere.
+//   mode 0: 3x3 stride 1 pad 1          mode 1: F.pad(0,1,0,1) + 3x3 stride 2 (even/odd pixel split
+//   mode 3: 1x1 (also nn.Linear)                 folded into a 5-D tensor map: no strided gather)
+//   mode 2: nearest x2 upsample + 3x3 pad 1, computed as 4 output phases of 2x2 taps on the
+//           low-res grid with pre-summed weights (4/9 of the MACs of the direct form).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> +bias (+residual) -> bf16 -> global, optional
+// per-(image, group) sum / sum-of-squares for the NEXT GroupNorm).
+#include "common.cuh"
+#include "ptivae_internal.h"
+
+namespace ptivae {
+
+constexpr int kTW = 16;  // tile width  (pixels)
+constexpr int kTH = 8;   // tile height (pixels)
+constexpr int kMaxStages = 8;
+constexpr int kMaxTaps = 9;
+
+struct ConvTap {
+  int16_t dx, dy;   // offset added to the tile origin, in tensor-map coordinates
+  int16_t pz;       // coordinate along the parity dim (stride-2 row parity), else 0
+  int16_t cmul;     // channel-dim base = cmul * Cin (stride-2 column parity), else 0
+  int32_t wtap;     // index of the [Cout][Cin] weight slab
+};
+
+struct ConvArgs {
+  int Ho, Wo;        // extent of the tile grid (low-res grid for mode 2)
+  int Hout, Wout;    // spatial extent of the output tensor
+  int Cin, Cout;
+  int os;            // output coordinate scale (2 for the up-sampling phases)
+  int ntaps;         // taps per phase
+  int tiles_x, tiles_y;
+  int nstages;
+  int gn_groups;     // >0: accumulate per-(n, group) sum/sumsq of the fp32 output into gn_acc
+  ConvTap taps[4][kMaxTaps];
+  const float* bias;
+  const __nv_bfloat16* residual;  // same shape as out, or nullptr
+  __nv_bfloat16* out;
+  float* gn_acc;                  // [N][groups][2]
+};
+
+template <int KCH, int BN>
+__global__ void __launch_bounds__(192, 2)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvArgs args) {
+  constexpr uint32_t A_BYTES = 128u * KCH * 2u;
+  constexpr uint32_t B_BYTES = uint32_t(BN) * KCH * 2u;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t kLayout = (KCH == 64) ? kLayoutSW128 : kLayoutSW64;
+  constexpr uint32_t kSBO = 8u * KCH * 2u;  // 8 rows of one swizzle atom
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const int nstages = args.nstages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int bx = blockIdx.x;
+  const int tix = bx % args.tiles_x;
+  const int tiy = (bx / args.tiles_x) % args.tiles_y;
+  const int n = bx / (args.tiles_x * args.tiles_y);
+  const int x0 = tix * kTW, y0 = tiy * kTH;
+  const int n0 = blockIdx.y * BN;
+  const int phase_id = blockIdx.z;
+  const int KC = args.Cin / KCH;
+  const int iters = args.ntaps * KC;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int t = it / KC, kc = it - t * KC;
+        const int s = it % nstages;
+        const uint32_t ph = (it / nstages) & 1;
+        const ConvTap tap = args.taps[phase_id][t];
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_5d(sa, &tmA, &full_bar[s], tap.cmul * args.Cin + kc * KCH, x0 + tap.dx, tap.pz, y0 + tap.dy, n);
+        tma_load_3d(sa + A_BYTES, &tmB, &full_bar[s], kc * KCH, n0, tap.wtap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % nstages;
+        const uint32_t ph = (it / nstages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KCH / 16; ++k) {
+          const uint64_t adesc = make_smem_desc(sa + k * 32, 16, kSBO, kLayout);
+          const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, kSBO, kLayout);
+          umma_bf16(tmem_base, adesc, bdesc, kIdesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m / kTW, tx = m % kTW;
+    const int gy = y0 + ty, gx = x0 + tx;
+    const bool valid = (gy < args.Ho) && (gx < args.Wo);
+    const int py = (args.os == 2) ? (phase_id >> 1) : 0;
+    const int px = (args.os == 2) ? (phase_id & 1) : 0;
+    const size_t pix = (static_cast<size_t>(n) * args.Hout + (gy * args.os + py)) * args.Wout + (gx * args.os + px);
+    __nv_bfloat16* optr = args.out + pix * args.Cout + n0;
+    const __nv_bfloat16* rptr = args.residual ? args.residual + pix * args.Cout + n0 : nullptr;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int cpg = args.gn_groups > 0 ? args.Cout / args.gn_groups : 0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(args.bias + n0 + c * 32 + j);
+      if (rptr != nullptr && valid) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c * 32) + j4);
+          const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[j4 * 8 + 2 * e] += bf16lo_f(w[e]);
+            v[j4 * 8 + 2 * e + 1] += bf16hi_f(w[e]);
+          }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 o;
+          o.x = pack_bf16x2(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+          o.y = pack_bf16x2(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+          o.z = pack_bf16x2(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+          o.w = pack_bf16x2(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+          *(reinterpret_cast<uint4*>(optr + c * 32) + j4) = o;
+        }
+      }
+      if (cpg > 0) {
+        // Statistics of the bf16-rounded values the consumer will actually read.
+        // Transposing butterfly over the 32 pixel lanes: each step halves the live value count,
+        // so 31 shuffles per quantity leave lane L holding the column-L total of this warp.
+        float s[32], ss[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float b = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+          s[j] = b;
+          ss[j] = b * b;
+        }
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const bool upper = (lane & step) != 0;
+#pragma unroll
+          for (int i = 0; i < step; ++i) {
+            const float send_s = upper ? s[i] : s[i + step];
+            const float keep_s = upper ? s[i + step] : s[i];
+            const float send_q = upper ? ss[i] : ss[i + step];
+            const float keep_q = upper ? ss[i + step] : ss[i];
+            s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, step);
+            ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, step);
+          }
+        }
+        float a = s[0], b2 = ss[0];  // column (c*32 + lane)
+        for (int o = 1; o < cpg && o < 32; o <<= 1) {  // fold the cpg adjacent columns of one group
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+        }
+        if ((lane % cpg) == 0) {
+          const int grp = (n0 + c * 32 + lane) / cpg;
+          atomicAdd(args.gn_acc + (static_cast<size_t>(n) * args.gn_groups + grp) * 2 + 0, a);
+          atomicAdd(args.gn_acc + (static_cast<size_t>(n) * args.gn_groups + grp) * 2 + 1, b2);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return PTIVAE_ERR_DRIVER;
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_bytes[i - 1];
+  }
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PTIVAE_OK : PTIVAE_ERR_DRIVER;
+}
+
+template <int KCH, int BN>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs& a, int N, int nphase,
+                       cudaStream_t stream) {
+  constexpr int STAGE = (128 + BN) * KCH * 2;
+  const int iters = a.ntaps * (a.Cin / KCH);
+  int stages = (100 * 1024) / STAGE;            // aim for 2 CTAs per SM
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > iters) stages = iters;
+  if (stages < 2 && iters >= 2) stages = 2;
+  if (stages < 1) stages = 1;
+  a.nstages = stages;
+  const size_t smem = size_t(stages) * STAGE + 1024 /*align*/ + (2 * kMaxStages + 1) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  dim3 grid(a.tiles_x * a.tiles_y * N, a.Cout / BN, nphase);
+  conv_umma_kernel<KCH, BN><<<grid, 192, smem, stream>>>(tmA, tmB, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace ptivae
+
+using namespace ptivae;
+
+extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual,
+                                void* out, float* gn_acc, int gn_groups, int N, int H, int W, int Cin, int Cout,
+                                int mode, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !w_packed || !bias || !out) return PTIVAE_ERR_ARG;
+  if (N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
+  if (mode < 0 || mode > 3) return PTIVAE_ERR_ARG;
+  if (!(Cin == 32 || (Cin % 64 == 0 && Cin <= 1024))) return PTIVAE_ERR_UNSUPPORTED;
+  if (!(Cout == 32 || Cout == 64 || Cout == 128 || Cout % 256 == 0)) return PTIVAE_ERR_UNSUPPORTED;
+  if (mode == 1 && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;  // even extents only (F.pad(0,1,0,1) + s2)
+  if (gn_groups > 0 && (!gn_acc || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0)) return PTIVAE_ERR_ARG;
+
+  ConvArgs a{};
+  a.Cin = Cin;
+  a.Cout = Cout;
+  a.bias = bias;
+  a.residual = static_cast<const __nv_bfloat16*>(residual);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.gn_acc = gn_acc;
+  a.gn_groups = gn_groups;
+  a.os = 1;
+  int nphase = 1, T = 9;
+  const int KCH = (Cin == 32) ? 32 : 64;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5] = {static_cast<uint32_t>(KCH), kTW, 1, kTH, 1};
+  const uint64_t C2 = uint64_t(Cin) * 2;
+  if (mode == 1) {
+    a.Ho = H / 2; a.Wo = W / 2; a.Hout = a.Ho; a.Wout = a.Wo; a.ntaps = 9;
+    dims[0] = 2 * Cin; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+    strides[0] = 2 * C2; strides[1] = uint64_t(W) * C2; strides[2] = 2 * uint64_t(W) * C2;
+    strides[3] = uint64_t(H) * W * C2;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        ConvTap& t = a.taps[0][ky * 3 + kx];
+        t.dy = ky >> 1; t.pz = ky & 1; t.dx = kx >> 1; t.cmul = kx & 1; t.wtap = ky * 3 + kx;
+      }
+  } else {
+    dims[0] = Cin; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+    strides[0] = C2; strides[1] = uint64_t(W) * C2; strides[2] = uint64_t(W) * C2; strides[3] = uint64_t(H) * W * C2;
+    a.Ho = H; a.Wo = W;
+    if (mode == 0) {
+      a.Hout = H; a.Wout = W; a.ntaps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          ConvTap& t = a.taps[0][ky * 3 + kx];
+          t.dy = ky - 1; t.dx = kx - 1; t.pz = 0; t.cmul = 0; t.wtap = ky * 3 + kx;
+        }
+    } else if (mode == 3) {
+      a.Hout = H; a.Wout = W; a.ntaps = 1; T = 1;
+      a.taps[0][0] = ConvTap{0, 0, 0, 0, 0};
+    } else {  // mode 2: 4 phases x (2x2) taps, weight slab index ((py*2+px)*2+ty)*2+tx
+      a.Hout = 2 * H; a.Wout = 2 * W; a.ntaps = 4; a.os = 2; nphase = 4; T = 16;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          for (int ty = 0; ty < 2; ++ty)
+            for (int tx = 0; tx < 2; ++tx) {
+              ConvTap& t = a.taps[py * 2 + px][ty * 2 + tx];
+              t.dy = (py == 0) ? ty - 1 : ty;
+              t.dx = (px == 0) ? tx - 1 : tx;
+              t.pz = 0; t.cmul = 0;
+              t.wtap = ((py * 2 + px) * 2 + ty) * 2 + tx;
+            }
+    }
+  }
+  a.tiles_x = (a.Wo + kTW - 1) / kTW;
+  a.tiles_y = (a.Ho + kTH - 1) / kTH;
+
+  CUtensorMap tmA, tmB;
+  int rc = encode_tmap_bf16(&tmA, in, 5, dims, strides, box, KCH * 2);
+  if (rc != PTIVAE_OK) return rc;
+  const int BN = Cout >= 256 ? 256 : Cout;
+  uint64_t wd[3] = {uint64_t(Cin), uint64_t(Cout), uint64_t(T)};
+  uint64_t ws[2] = {C2, uint64_t(Cout) * C2};
+  uint32_t wb[3] = {static_cast<uint32_t>(KCH), static_cast<uint32_t>(BN), 1};
+  rc = encode_tmap_bf16(&tmB, w_packed, 3, wd, ws, wb, KCH * 2);
+  if (rc != PTIVAE_OK) return rc;
+
+  if (KCH == 32) {
+    switch (BN) {
+      case 32: return launch_conv<32, 32>(tmA, tmB, a, N, nphase, stream);
+      case 64: return launch_conv<32, 64>(tmA, tmB, a, N, nphase, stream);
+      case 128: return launch_conv<32, 128>(tmA, tmB, a, N, nphase, stream);
+      default: return launch_conv<32, 256>(tmA, tmB, a, N, nphase, stream);
+    }
+  }
+  switch (BN) {
+    case 32: return launch_conv<64, 32>(tmA, tmB, a, N, nphase, stream);
+    case 64: return launch_conv<64, 64>(tmA, tmB, a, N, nphase, stream);
+    case 128: return launch_conv<64, 128>(tmA, tmB, a, N, nphase, stream);
+    default: return launch_conv<64, 256>(tmA, tmB, a, N, nphase, stream);
+  }
+}

@@ -1,0 +1,179 @@
+"""Thin torch-tensor wrappers over the C ABI (include/ptivae.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every op below hands raw
+device pointers to libptivae.so.  No op has a CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# --- instrumentation used by bench.py: launch counting and per-op CUDA-event timing -------------
+LAUNCHES = 0          # kernels launched through this module since import
+PROFILE = None        # set to a list to record (name, meta, start_event, end_event) per C call
+
+
+def _call(name: str, meta, kernels: int, fn, *args) -> None:
+    global LAUNCHES
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.append((name, meta, e0, e1))
+    else:
+        rc = fn(*args)
+    _lib.check(rc, f"{name}{meta if meta is not None else ''}")
+    LAUNCHES += kernels
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PtivaeError("ptivae ops need CUDA tensors (there is no CPU path)")
+
+
+def pack_conv_weight(w: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    """fp32 [Cout,Cin,k,k] (or Linear [out,in]) -> bf16 [T,Cout,Cin]."""
+    _need_cuda(w)
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    w = w.detach().contiguous().float()
+    cout, cin, k, _ = w.shape
+    t = 16 if mode == 2 else k * k
+    out = torch.empty((t, cout, cin), device=w.device, dtype=BF16)
+    _call("pack_conv_weight", None, 1, _lib.lib().ptivae_pack_conv_weight, _p(w), _p(out), cout, cin, k, mode, _stream())
+    return out
+
+
+def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode: int, residual=None,
+              gn_acc=None, gn_groups: int = 0) -> torch.Tensor:
+    """x bf16 NHWC [N,H,W,Cin] -> bf16 NHWC.  mode: 0 3x3 s1 | 1 pad+3x3 s2 | 2 up2x+3x3 | 3 1x1."""
+    _need_cuda(x, w_packed, bias)
+    n, h, w, cin = x.shape
+    cout = w_packed.shape[1]
+    ho, wo = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+    out = torch.empty((n, ho, wo, cout), device=x.device, dtype=BF16)
+    if residual is not None and residual.shape != out.shape:
+        raise _lib.PtivaeError("residual shape mismatch")
+    _call("conv_umma", (mode, n, h, w, cin, cout), 1, _lib.lib().ptivae_conv_umma, _p(x), _p(w_packed), _p(bias),
+          _p(residual), _p(out), _p(gn_acc), gn_groups if gn_acc is not None else 0, n, h, w, cin, cout, mode,
+          _stream())
+    return out
+
+
+def gn_stats(x: torch.Tensor, groups: int, acc: torch.Tensor | None = None) -> torch.Tensor:
+    _need_cuda(x)
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    if acc is None:
+        acc = torch.zeros((n, groups, 2), device=x.device, dtype=torch.float32)
+    _call("gn_stats", (n, hw, c), 1, _lib.lib().ptivae_gn_stats, _p(x), _p(acc), n, hw, c, groups, _stream())
+    return acc
+
+
+def gn_finalize(acc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, eps: float) -> torch.Tensor:
+    n, g, _ = acc.shape
+    c = gamma.numel()
+    ss = torch.empty((n, c, 2), device=acc.device, dtype=torch.float32)
+    _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(acc), _p(gamma), _p(beta), _p(ss), n, hw, c, g, float(eps),
+                                             _stream())
+    return ss
+
+
+def gn_apply(x: torch.Tensor, scale_shift: torch.Tensor, silu: bool) -> torch.Tensor:
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    y = torch.empty_like(x)
+    _call("gn_apply", (n, hw, c), 1, _lib.lib().ptivae_gn_apply, _p(x), _p(scale_shift), _p(y), n, hw, c, int(silu), _stream())
+    return y
+
+
+def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW -> bf16 NHWC."""
+    _need_cuda(x, w, b)
+    n, cin, h, wd = x.shape
+    cout = w.shape[0]
+    out = torch.empty((n, h, wd, cout), device=x.device, dtype=BF16)
+    _call("conv3x3_small_cin", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x), _p(w), _p(b), _p(out), n, h, wd, cin, cout, _stream())
+    return out
+
+
+def conv3x3_small_cout(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, scale_shift=None) -> torch.Tensor:
+    """bf16 NHWC (+ fused GroupNorm affine) -> fp32 NCHW."""
+    _need_cuda(x, w, b)
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    out = torch.empty((n, cout, h, wd), device=x.device, dtype=torch.float32)
+    _call("conv3x3_small_cout", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cout, _p(x), _p(w), _p(b), _p(scale_shift), _p(out), n, h, wd, cin,
+                                                    cout, _stream())
+    return out
+
+
+def conv1x1_small(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, act: int = 0) -> torch.Tensor:
+    _need_cuda(x, w, b)
+    n, cin = x.shape[:2]
+    hw = x.numel() // (n * cin)
+    cout = w.shape[0]
+    out = torch.empty((n, cout) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
+    _call("conv1x1_small", None, 1, _lib.lib().ptivae_conv1x1_small, _p(x), _p(w), _p(b), _p(out), n, hw, cin, cout, act, _stream())
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """bf16 [B,L,D] x3 -> bf16 [B,L,D]; single head, scale D^-0.5."""
+    _need_cuda(q, k, v)
+    b, l, d = q.shape
+    out = torch.empty_like(q)
+    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), b, l, d, _stream())
+    return out
+
+
+def latent_sample(mu, sigma, eps=None, seed: int = 0, offset: int = 0, rng_dev=None, return_eps: bool = False):
+    _need_cuda(mu, sigma)
+    z = torch.empty_like(mu)
+    eps_out = torch.empty_like(mu) if return_eps else None
+    _call("latent_sample", None, 1, _lib.lib().ptivae_latent_sample, _p(mu), _p(sigma), _p(eps), _p(z), _p(eps_out), _p(rng_dev),
+                                               mu.numel(), seed & (2**64 - 1), offset & (2**64 - 1), _stream())
+    return (z, eps_out) if return_eps else z
+
+
+def rng_advance(rng_dev: torch.Tensor) -> None:
+    _call("rng_advance", None, 1, _lib.lib().ptivae_rng_advance, _p(rng_dev), _stream())
+
+
+def kl_loss(mu: torch.Tensor, t: torch.Tensor, input_is_logvar: bool = True) -> torch.Tensor:
+    _need_cuda(mu, t)
+    mu = mu.contiguous().float()
+    t = t.contiguous().float()
+    n = mu.shape[0]
+    ws = torch.empty(n, device=mu.device, dtype=torch.float32)
+    out = torch.empty(1, device=mu.device, dtype=torch.float32)
+    _call("kl_loss", None, 2, _lib.lib().ptivae_kl_loss, _p(mu), _p(t), _p(ws), _p(out), n, mu.numel() // n, int(input_is_logvar),
+                                         _stream())
+    return out[0]
+
+
+def l1l2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """returns a 2-vector: (mean |a-b|, mean (a-b)^2)."""
+    _need_cuda(a, b)
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    if a.shape != b.shape:
+        raise _lib.PtivaeError("l1l2 shape mismatch")
+    ws = torch.empty(2 * 1184, device=a.device, dtype=torch.float32)
+    out = torch.empty(2, device=a.device, dtype=torch.float32)
+    _call("l1l2", None, 2, _lib.lib().ptivae_l1l2, _p(a), _p(b), _p(ws), _p(out), a.numel(), _stream())
+    return out

@@ -1,0 +1,96 @@
+"""Generates the committed golden fixtures (run in the build container, NOT on the GPU box):
+
+  python tests/golden/make_golden.py
+
+* ``losses_ref.npz``  -- outputs of the REFERENCE's own ``compute_kl_loss`` / ``compute_total_loss``
+  (/root/reference/src/pti_ldm_vae/models/losses.py, imported by file path: it only needs torch) on
+  seeded inputs.  This is the one piece of the hot path the reference itself can execute here; it
+  pins oracle/aekl_ref.py::kl_loss_ref / total_loss_ref.
+* ``aekl_*.npz``      -- outputs of the oracle restatement of monai 1.5.1 AutoencoderKL (MONAI is
+  not installable here -> "parity unpinned" for the network body) on seeded weights/inputs/eps, in
+  fp32 and fp64, with a few intermediate activations for bisecting.
+"""
+import importlib.util
+import pathlib
+import sys
+
+import numpy as np
+import torch
+
+HERE = pathlib.Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import aekl_ref  # noqa: E402
+
+import _pkg  # noqa: E402
+
+CFG = _pkg.load().config
+
+
+def ref_losses():
+    p = pathlib.Path("/root/reference/src/pti_ldm_vae/models/losses.py")
+    spec = importlib.util.spec_from_file_location("ref_losses", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(42)
+    mu = torch.randn(6, 4, 32, 32, generator=g)
+    sigma = torch.rand(6, 4, 32, 32, generator=g) * 1.5 + 0.05
+    out = {
+        "mu": mu.numpy(), "sigma": sigma.numpy(),
+        "kl_as_called": mod.compute_kl_loss(mu, sigma).numpy(),
+        "kl_sigma_mode": mod.compute_kl_loss(mu, sigma, input_is_logvar=False).numpy(),
+    }
+    t = [torch.tensor(v) for v in (0.31, 12.5, 0.77, 0.2, 1.9)]
+    out["total_ar"] = mod.compute_total_loss(*t, kl_weight=1e-4, perceptual_weight=1.0, adv_weight=0.5,
+                                             ar_gamma=0.5, ar_vae_enabled=True).numpy()
+    out["total_noar"] = mod.compute_total_loss(*t, kl_weight=1e-3, perceptual_weight=1.0, adv_weight=3.0,
+                                               ar_gamma=0.5, ar_vae_enabled=False).numpy()
+    np.savez_compressed(HERE / "losses_ref.npz", **out)
+    print("losses_ref.npz", {k: float(v) for k, v in out.items() if v.ndim == 0})
+
+
+def param_checksum(model):
+    return float(sum(p.detach().double().abs().sum() for p in model.parameters()))
+
+
+def aekl_case(name, cfg, b, h, w, taps):
+    model = aekl_ref.seeded_model(cfg, 1234)
+    x = aekl_ref.synthetic_images(b, h, w, seed=0)
+    with torch.no_grad():
+        mu, sigma = model.encode(x)
+        eps = torch.randn(mu.shape, generator=torch.Generator().manual_seed(7))
+        recon, mu2, sigma2 = model(x, eps)
+        assert torch.equal(mu, mu2)
+        inter = {}
+        hcur = x
+        for i, blk in enumerate(model.encoder.blocks):
+            hcur = blk(hcur)
+            if f"encoder.blocks.{i}" in taps:
+                inter[f"encoder.blocks.{i}"] = hcur.numpy()
+        hcur = model.post_quant_conv(model.sampling(mu, sigma, eps))
+        for i, blk in enumerate(model.decoder.blocks):
+            hcur = blk(hcur)
+            if f"decoder.blocks.{i}" in taps:
+                inter[f"decoder.blocks.{i}"] = hcur.numpy()
+        m64 = aekl_ref.seeded_model(cfg, 1234).double()
+        recon64, mu64, sigma64 = m64(x.double(), eps.double())
+        rdet = model.reconstruct(x)
+    out = dict(eps=eps.numpy(), recon=recon.numpy(), z_mu=mu.numpy(), z_sigma=sigma.numpy(),
+               recon_det=rdet.numpy(), recon64=recon64.float().numpy(), z_mu64=mu64.float().numpy(),
+               z_sigma64=sigma64.float().numpy(),
+               kl_as_called=aekl_ref.kl_loss_ref(mu, sigma).numpy(),
+               kl_sigma_mode=aekl_ref.kl_loss_ref(mu, sigma, input_is_logvar=False).numpy(),
+               l1=aekl_ref.l1_ref(recon, x).numpy(), l2=aekl_ref.l2_ref(recon, x).numpy(),
+               param_checksum=np.float64(param_checksum(model)), x_checksum=np.float64(x.double().abs().sum()))
+    out.update({"tap/" + k: v for k, v in inter.items()})
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(name, "recon", tuple(recon.shape), "fp32-vs-fp64 rel-L2",
+          float((recon - recon64.float()).norm() / recon64.float().norm()))
+
+
+if __name__ == "__main__":
+    if pathlib.Path("/root/reference").exists():
+        ref_losses()
+    aekl_case("aekl_A_64", CFG.AUTOENCODER_DEF_A, 2, 64, 64, {"encoder.blocks.3", "encoder.blocks.13", "decoder.blocks.6"})
+    aekl_case("aekl_A_256", CFG.AUTOENCODER_DEF_A, 1, 256, 256, set())
+    aekl_case("aekl_B_64", CFG.AUTOENCODER_DEF_B, 1, 64, 64, {"encoder.blocks.10"})

@@ -1,0 +1,277 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point vs. a plain PyTorch fp32 statement of the same
+operator on identical (bf16-rounded) inputs.  Tolerances are written next to each check:
+  * bf16-output kernels: the result must sit within ~1 bf16 ulp of the fp32 reference
+    (rel-L2 <= 3e-3, and max-abs <= 2^-7 * max|ref|);
+  * fp32-accumulate / fp32-output kernels: max-abs <= 1e-4 relative to the reference scale.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def _check_bf16(out, ref, what, rel=3e-3, ulp=2.0 ** -7):
+    out, ref = out.float(), ref.float()
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    r = _rel_l2(out, ref)
+    mx = float((out - ref).abs().max())
+    scale = float(ref.abs().max())
+    assert r <= rel, f"{what}: rel-L2 {r:.3e} > {rel}"
+    assert mx <= ulp * scale + 1e-6, f"{what}: max-abs {mx:.3e} vs scale {scale:.3e}"
+
+
+def _rand_act(n, h, w, c, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(n, h, w, c, generator=g).to(DEV).bfloat16()
+
+
+def _rand_conv(cout, cin, k, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(DEV)
+    b = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    return w.bfloat16().float(), b  # weights exactly representable in bf16
+
+
+def _ref_conv(x_nhwc, w, b, mode):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    if mode == 0:
+        y = F.conv2d(x, w, b, padding=1)
+    elif mode == 1:
+        y = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+    elif mode == 2:
+        y = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    else:
+        y = F.conv2d(x, w, b)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.cuda.synchronize()
+
+
+def test_pack_weights(b200):
+    w, _ = _rand_conv(64, 32, 3, 1)
+    p = b200.ops.pack_conv_weight(w, 0)
+    ref = w.permute(2, 3, 0, 1).reshape(9, 64, 32)
+    assert torch.equal(p.float(), ref)
+    p2 = b200.ops.pack_conv_weight(w, 2).float().view(2, 2, 2, 2, 64, 32)
+    rows = {0: [[0], [1, 2]], 1: [[0, 1], [2]]}
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    s = sum(w[:, :, ky, kx] for ky in rows[py][ty] for kx in rows[px][tx])
+                    assert torch.equal(p2[py, px, ty, tx], s.bfloat16().float())
+    lin = torch.randn(128, 128, device=DEV).bfloat16().float()
+    assert torch.equal(b200.ops.pack_conv_weight(lin, 0).float()[0], lin)
+
+
+CONV_CASES = [
+    # (mode, N, H, W, Cin, Cout)
+    (0, 2, 32, 32, 128, 128),
+    (0, 1, 16, 16, 64, 64),
+    (0, 2, 24, 40, 64, 64),      # extents that are not tile multiples
+    (0, 1, 64, 64, 32, 32),
+    (0, 1, 32, 32, 32, 64),
+    (0, 1, 32, 32, 64, 32),
+    (0, 1, 32, 32, 128, 64),
+    (0, 1, 32, 32, 64, 128),
+    (0, 1, 16, 16, 256, 256),
+    (0, 1, 16, 16, 128, 256),
+    (0, 1, 16, 16, 256, 128),
+    (0, 3, 8, 8, 128, 128),      # smaller than one tile
+    (1, 2, 32, 32, 32, 32),
+    (1, 1, 64, 64, 64, 64),
+    (1, 2, 16, 16, 128, 128),
+    (1, 1, 24, 40, 64, 64),
+    (2, 2, 16, 16, 128, 128),
+    (2, 1, 32, 32, 64, 64),
+    (2, 1, 8, 24, 256, 256),
+    (3, 2, 32, 32, 32, 64),
+    (3, 1, 32, 32, 64, 128),
+    (3, 1, 32, 32, 128, 64),
+    (3, 2, 32, 32, 128, 128),
+    (3, 1, 16, 16, 256, 256),
+]
+
+
+@pytest.mark.parametrize("mode,n,h,w,cin,cout", CONV_CASES)
+def test_conv_umma(b200, mode, n, h, w, cin, cout):
+    x = _rand_act(n, h, w, cin, 10 + mode)
+    k = 1 if mode == 3 else 3
+    wt, bias = _rand_conv(cout, cin, k, 20 + cin + cout)
+    wp = b200.ops.pack_conv_weight(wt, 2 if mode == 2 else 0)
+    out = b200.ops.conv_umma(x, wp, bias, mode)
+    ref = _ref_conv(x, wt, bias, mode)
+    assert out.shape == ref.shape
+    # mode 2 pre-sums bf16 weights (one extra rounding per weight) -> slightly looser
+    _check_bf16(out, ref, f"conv mode {mode} {cin}->{cout}", rel=4e-3 if mode == 2 else 3e-3,
+                ulp=2.0 ** -6 if mode == 2 else 2.0 ** -7)
+
+
+@pytest.mark.parametrize("cin,cout,groups", [(128, 128, 16), (64, 64, 16), (32, 32, 16), (64, 128, 32), (256, 256, 32)])
+def test_conv_umma_residual_and_stats(b200, cin, cout, groups):
+    n, h, w = 2, 24, 24
+    x = _rand_act(n, h, w, cin, 3)
+    res = _rand_act(n, h, w, cout, 4)
+    wt, bias = _rand_conv(cout, cin, 3, 5)
+    acc = torch.zeros(n, groups, 2, device=DEV)
+    out = b200.ops.conv_umma(x, b200.ops.pack_conv_weight(wt), bias, 0, residual=res, gn_acc=acc, gn_groups=groups)
+    ref = _ref_conv(x, wt, bias, 0) + res.float()
+    _check_bf16(out, ref, "conv+residual")
+    # statistics are those of the bf16 tensor that was written
+    o = out.float().view(n, h * w, groups, cout // groups)
+    s = o.sum(dim=(1, 3))
+    q = (o * o).sum(dim=(1, 3))
+    assert torch.allclose(acc[..., 0], s, rtol=1e-4, atol=1e-2), float((acc[..., 0] - s).abs().max())
+    assert torch.allclose(acc[..., 1], q, rtol=1e-4, atol=1e-2), float((acc[..., 1] - q).abs().max())
+
+
+@pytest.mark.parametrize("n,h,w,c,groups,silu", [(2, 32, 32, 128, 16, True), (2, 64, 64, 32, 16, True),
+                                                 (1, 48, 16, 64, 16, False), (2, 16, 16, 256, 32, True),
+                                                 (1, 8, 8, 64, 32, True)])
+def test_groupnorm(b200, n, h, w, c, groups, silu):
+    x = (_rand_act(n, h, w, c, 7).float() * 1.7 + 0.3).bfloat16()
+    gamma = torch.randn(c, device=DEV) * 0.5 + 1.0
+    beta = torch.randn(c, device=DEV) * 0.2
+    eps = 1e-6
+    acc = b200.ops.gn_stats(x, groups)
+    xf = x.float().view(n, h * w, groups, c // groups)
+    assert torch.allclose(acc[..., 0], xf.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(acc[..., 1], (xf * xf).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    ss = b200.ops.gn_finalize(acc, gamma, beta, h * w, eps)
+    y = b200.ops.gn_apply(x, ss, silu)
+    ref = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    _check_bf16(y, ref, "groupnorm(+silu)")
+    # fp32-accumulate path: scale/shift against the fp32 statistics, max-abs <= 1e-4 (relative to scale ~1)
+    mean = xf.mean(dim=(1, 3))
+    var = xf.var(dim=(1, 3), unbiased=False)
+    rstd = (var + eps).rsqrt()
+    sc_ref = gamma.view(1, groups, -1) * rstd[..., None]
+    sh_ref = beta.view(1, groups, -1) - mean[..., None] * sc_ref
+    assert float((ss[..., 0].view(n, groups, -1) - sc_ref).abs().max()) <= 1e-4 * float(sc_ref.abs().max())
+    assert float((ss[..., 1].view(n, groups, -1) - sh_ref).abs().max()) <= 1e-4 * max(1.0, float(sh_ref.abs().max()))
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 1, 32, 64, 64), (1, 1, 64, 32, 48), (2, 4, 128, 16, 16), (1, 10, 256, 8, 8)])
+def test_conv_small_cin(b200, n, cin, cout, h, w):
+    x = torch.randn(n, cin, h, w, device=DEV)
+    wt, bias = _rand_conv(cout, cin, 3, 9)
+    out = b200.ops.conv3x3_small_cin(x, wt, bias)
+    ref = F.conv2d(x, wt, bias, padding=1).permute(0, 2, 3, 1)
+    _check_bf16(out, ref, "small_cin")
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,norm", [(2, 32, 1, 64, 64, True), (1, 64, 1, 32, 32, True),
+                                                 (2, 128, 4, 16, 16, True), (1, 256, 10, 8, 8, True),
+                                                 (1, 32, 1, 16, 16, False)])
+def test_conv_small_cout(b200, n, cin, cout, h, w, norm):
+    x = _rand_act(n, h, w, cin, 11)
+    wt, bias = _rand_conv(cout, cin, 3, 12)
+    ss = None
+    xin = x.float().permute(0, 3, 1, 2)
+    if norm:
+        ss = torch.randn(n, cin, 2, device=DEV) * 0.5 + 0.5
+        xin = xin * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]
+    out = b200.ops.conv3x3_small_cout(x, wt, bias, ss)
+    ref = F.conv2d(xin, wt, bias, padding=1)
+    # fp32 accumulate, fp32 out: max-abs <= 1e-4 of the output scale
+    assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_conv1x1_small_and_sigma(b200):
+    x = torch.randn(3, 4, 16, 16, device=DEV) * 8
+    w = torch.randn(4, 4, 1, 1, device=DEV)
+    b = torch.randn(4, device=DEV)
+    mu = b200.ops.conv1x1_small(x, w, b, 0)
+    assert float((mu - F.conv2d(x, w, b)).abs().max()) <= 1e-4 * 30
+    sg = b200.ops.conv1x1_small(x, w * 3, b, 1)
+    ref = torch.exp(torch.clamp(F.conv2d(x, w * 3, b), -30.0, 20.0) / 2)
+    assert torch.allclose(sg, ref, rtol=2e-5, atol=1e-12)
+    assert float(sg.max()) <= math.exp(10.0) * 1.0001 and float(sg.min()) >= math.exp(-15.0) * 0.9999
+
+
+@pytest.mark.parametrize("b,l,d", [(2, 1024, 128), (1, 256, 128), (2, 320, 128), (1, 128, 128), (1, 512, 256),
+                                   (1, 200, 256), (2, 256, 64)])
+def test_attention(b200, b, l, d):
+    g = torch.Generator().manual_seed(l + d)
+    q, k, v = [(torch.randn(b, l, d, generator=g) * s).to(DEV).bfloat16() for s in (1.0, 1.0, 1.0)]
+    out = b200.ops.attention(q, k, v)
+    att = torch.softmax(torch.einsum("bxd,byd->bxy", q.float(), k.float()) * d ** -0.5, dim=-1)
+    ref = torch.einsum("bxy,byd->bxd", att, v.float())
+    # P is rounded to bf16 before PV: allow 2 bf16 ulps of the output scale
+    _check_bf16(out, ref, f"attention L={l} d={d}", rel=6e-3, ulp=2.0 ** -6)
+
+
+def test_attention_peaked(b200):
+    # large-magnitude scores exercise the online-softmax rescaling across key blocks
+    b, l, d = 1, 512, 128
+    g = torch.Generator().manual_seed(5)
+    q = (torch.randn(b, l, d, generator=g) * 4).to(DEV).bfloat16()
+    k = (torch.randn(b, l, d, generator=g) * 4).to(DEV).bfloat16()
+    v = torch.randn(b, l, d, generator=g).to(DEV).bfloat16()
+    out = b200.ops.attention(q, k, v)
+    att = torch.softmax(torch.einsum("bxd,byd->bxy", q.float(), k.float()) * d ** -0.5, dim=-1)
+    ref = torch.einsum("bxy,byd->bxd", att, v.float())
+    _check_bf16(out, ref, "attention peaked", rel=8e-3, ulp=2.0 ** -5)
+
+
+def test_latent_sample(b200, oracle):
+    mu = torch.randn(3, 4, 8, 8, device=DEV)
+    sg = torch.rand(3, 4, 8, 8, device=DEV) + 0.1
+    eps = torch.randn(3, 4, 8, 8, device=DEV)
+    z = b200.ops.latent_sample(mu, sg, eps=eps)
+    assert torch.allclose(z, mu + eps * sg, rtol=1e-6, atol=1e-6)
+    # the product's own generator, pinned against the numpy restatement of Philox4x32-10 + Box-Muller
+    n = mu.numel()
+    z2, e2 = b200.ops.latent_sample(mu, sg, seed=1234, offset=7, return_eps=True)
+    ref = torch.from_numpy(oracle.philox_normal(n, 1234, 7)).to(DEV).view_as(mu)
+    assert float((e2 - ref).abs().max()) <= 2e-4
+    assert torch.allclose(z2, mu + e2 * sg, rtol=1e-6, atol=1e-6)
+    # device-resident state gives the same stream and advances
+    st = torch.tensor([1234, 7], device=DEV, dtype=torch.int64)
+    z3, e3 = b200.ops.latent_sample(mu, sg, rng_dev=st, return_eps=True)
+    assert torch.equal(e3, e2)
+    b200.ops.rng_advance(st)
+    assert st.tolist() == [1234, 8]
+    big = torch.zeros(1 << 20, device=DEV)
+    _, e4 = b200.ops.latent_sample(big, big + 1, seed=99, offset=0, return_eps=True)
+    assert abs(float(e4.mean())) < 5e-3 and abs(float(e4.std()) - 1.0) < 5e-3
+
+
+def test_losses(b200, oracle):
+    g = torch.Generator().manual_seed(0)
+    mu = torch.randn(5, 4, 32, 32, generator=g)
+    sg = torch.rand(5, 4, 32, 32, generator=g) * 2 + 0.01
+    for flag in (True, False):
+        ref = oracle.kl_loss_ref(mu, sg, input_is_logvar=flag)
+        got = b200.compute_kl_loss(mu.to(DEV), sg.to(DEV), input_is_logvar=flag)
+        assert abs(float(got) - float(ref)) <= 1e-3 * abs(float(ref)), (flag, float(got), float(ref))
+    a = torch.randn(3, 1, 64, 64, generator=g)
+    b = torch.randn(3, 1, 64, 64, generator=g)
+    assert abs(float(b200.l1_loss(a.to(DEV), b.to(DEV))) - float(oracle.l1_ref(a, b))) <= 1e-3 * float(oracle.l1_ref(a, b))
+    assert abs(float(b200.mse_loss(a.to(DEV), b.to(DEV))) - float(oracle.l2_ref(a, b))) <= 1e-3 * float(oracle.l2_ref(a, b))
+    # determinism: bit-identical across repeated launches
+    r1 = b200.ops.l1l2(a.to(DEV), b.to(DEV))
+    r2 = b200.ops.l1l2(a.to(DEV), b.to(DEV))
+    assert torch.equal(r1, r2)
+    # reference overflow behaviour is preserved: exp(sigma) with huge sigma -> inf
+    hot = torch.full((1, 4, 4, 4), 200.0)
+    assert math.isinf(float(b200.compute_kl_loss(torch.zeros_like(hot).to(DEV), hot.to(DEV))))
+    assert math.isinf(float(oracle.kl_loss_ref(torch.zeros_like(hot), hot)))
