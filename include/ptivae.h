@@ -15,7 +15,11 @@
  *   - return value: 0 = launched; <0 = argument/shape error (no launch happened):
  *        -1 bad argument, -2 unsupported shape, -3 driver entry point / tensor-map encode failure;
  *     >0 = the cudaError_t reported by the launch;
- *   - activations: bf16 NHWC ("bf16 [N][H][W][C]"), latents/images at the boundary: fp32 NCHW.
+ *   - activations: NHWC [N][H][W][C].  GEMM operands are 16-bit ("h16"): IEEE fp16 when the call's
+ *     f16 flag is non-zero (default of the Python host: 8x finer rounding than bf16 at the same
+ *     tensor-core rate; values are clamped to +-65504), bfloat16 otherwise.  The residual stream between
+ *     blocks is fp32.  Where a tensor may be any of the three, `fmt` is 0 = bf16, 1 = fp16, 2 = fp32.
+ *   - latents / images at the network boundary: fp32 NCHW.
  */
 #ifndef PTIVAE_H_
 #define PTIVAE_H_
@@ -32,51 +36,61 @@ int ptivae_abi_version(void);
  *             UpSample(nearest x2)+postconv 3x3, nin_shortcut 1x1, SABlock.to_q/to_k/to_v/out_proj
  *             (monai 1.5.1 networks/nets/autoencoderkl.py, blocks/selfattention.py; called from
  *             autoencoder.py:114/:139/:151).
- *   in        bf16 [N][H][W][Cin]         Cin in {32, 64k}
- *   w_packed  bf16 [T][Cout][Cin]         from ptivae_pack_conv_weight (T = 9, 1, or 16 for mode 2)
+ *   in        h16 [N][H][W][Cin]          Cin in {32, 64k}
+ *   w_packed  h16 [T][Cout][Cin]          from ptivae_pack_conv_weight (T = 9, 1, or 16 for mode 2)
  *   bias      fp32 [Cout]
- *   residual  bf16, same shape as out, added in the epilogue (may be NULL)
- *   out       bf16 [N][Hout][Wout][Cout]  Cout in {32,64,128,256k}
- *   gn_acc    fp32 [N][gn_groups][2] (sum, sum of squares of the bf16-rounded output), accumulated
- *             with atomics -- must be zeroed by the caller; ignored when gn_groups == 0
+ *   residual  same shape as out, h16 (res_f32 = 0) or fp32 (res_f32 = 1), added in the epilogue; may be NULL
+ *   out       [N][Hout][Wout][Cout], h16 (out_f32 = 0) or fp32 (out_f32 = 1: the residual stream)
+ *   gn_part   fp32 [N][P][gn_groups][2]: per-tile (sum, sum of squares) of the stored output, P =
+ *             ptivae_conv_parts(H, W, mode); plain stores, fixed order (deterministic); ignored when
+ *             gn_groups == 0.  Feed to ptivae_gn_finalize(..., P, ...).
  *   mode      0: 3x3 stride 1 pad 1 (Hout=H)      1: pad right/bottom + 3x3 stride 2 (Hout=H/2, H,W even)
  *             2: nearest x2 upsample + 3x3 pad 1 (Hout=2H)   3: 1x1 */
 int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual, void* out,
-                     float* gn_acc, int gn_groups, int N, int H, int W, int Cin, int Cout, int mode, void* stream);
+                     float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int mode, int out_f32,
+                     int res_f32, int f16, void* stream);
+/* number of statistics partials per image that ptivae_conv_umma writes for this shape */
+int ptivae_conv_parts(int H, int W, int mode);
 
-/* fp32 master weights [Cout][Cin][k][k] -> bf16 UMMA operand [T][Cout][Cin].
+/* fp32 master weights [Cout][Cin][k][k] -> h16 UMMA operand [T][Cout][Cin].
  *   mode 0: T = k*k (k in {1,3}); mode 2: T = 16, the 4-phase x (2x2)-tap decomposition of
  *   nearest-x2-upsample + 3x3 (weights of taps that hit the same low-res pixel are pre-summed). */
-int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, void* stream);
+int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, int f16, void* stream);
 
-/* nn.GroupNorm statistics: acc[n][g] += (sum, sumsq) over the bf16 NHWC tensor x [N][HW][C]. */
-int ptivae_gn_stats(const void* x, float* acc, int N, int HW, int C, int G, void* stream);
-/* acc -> scale_shift fp32 [N][C][2] with scale = gamma*rstd, shift = beta - mean*scale
- * (biased variance, eps inside the sqrt: nn.GroupNorm(eps=norm_eps, affine=True)). */
-int ptivae_gn_finalize(const float* acc, const float* gamma, const float* beta, float* scale_shift, int N, int HW,
-                       int C, int G, float eps, void* stream);
-/* y = act(x*scale + shift): act = SiLU when silu != 0 (AEKLResBlock: F.silu(norm(x))), identity otherwise
- * (SpatialAttentionBlock.norm). x,y bf16 [N][HW][C]. */
-int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, int N, int HW, int C, int silu, void* stream);
+/* nn.GroupNorm statistics, deterministic two-stage form.
+ *   gn_stats: partial[n][p][g] = (sum, sumsq) over pixel chunk p of x [N][HW][C] (storage in_fmt); P = ptivae_gn_stats_parts(N, HW, C) chunks per image.
+ *   gn_finalize: partial [N][P][G][2] -> scale_shift fp32 [N][C][2], scale = gamma*rstd,
+ *             shift = beta - mean*scale (biased variance, eps inside the sqrt:
+ *             nn.GroupNorm(eps=norm_eps, affine=True)); partials are summed in index order.
+ *   gn_apply: y(h16) = act(x*scale + shift); act = SiLU when silu != 0 (AEKLResBlock:
+ *             F.silu(norm(x))), identity otherwise (SpatialAttentionBlock.norm).  raw16 (may be
+ *             NULL) additionally receives x rounded to h16 (the nin_shortcut operand). */
+int ptivae_gn_stats(const void* x, float* partial, int N, int HW, int C, int G, int in_fmt, void* stream);
+int ptivae_gn_stats_parts(int N, int HW, int C);
+int ptivae_gn_finalize(const float* partial, const float* gamma, const float* beta, float* scale_shift, int N, int HW,
+                       int C, int G, int P, float eps, void* stream);
+int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, void* raw16, int N, int HW, int C, int silu,
+                    int in_fmt, int out_f16, void* stream);
 
 /* Thin-end 3x3 s1 p1 convolutions on CUDA cores.
- *   small_cin : x fp32 NCHW [N][Cin<=16][H][W], w fp32 [Cout][Cin][3][3] -> out bf16 NHWC
+ *   small_cin : x fp32 NCHW [N][Cin<=16][H][W], w fp32 [Cout][Cin][3][3] -> out NHWC (storage out_fmt)
  *               (encoder.blocks.0, decoder.blocks.0)
- *   small_cout: x bf16 NHWC, optional fused GroupNorm affine scale_shift [N][Cin][2] (NO activation:
+ *   small_cout: x NHWC (storage in_fmt), optional fused GroupNorm affine scale_shift [N][Cin][2] (NO activation:
  *               encoder.blocks.15/decoder.blocks.15 are bare GroupNorms), zero padding applied after
  *               the norm -> out fp32 NCHW [N][Cout<=16][H][W]  (encoder.blocks.16, decoder.blocks.16) */
 int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int N, int H, int W,
-                             int Cin, int Cout, void* stream);
+                             int Cin, int Cout, int out_fmt, void* stream);
 int ptivae_conv3x3_small_cout(const void* x, const float* w, const float* bias, const float* scale_shift, float* out,
-                              int N, int H, int W, int Cin, int Cout, void* stream);
+                              int N, int H, int W, int Cin, int Cout, int in_fmt, void* stream);
 /* 1x1 conv, fp32 NCHW in/out, Cin,Cout <= 16 (quant_conv_mu, quant_conv_log_sigma, post_quant_conv).
  *   act 0: none;  act 1: exp(clamp(v,-30,20)/2)  == AutoencoderKL.encode's z_sigma. */
 int ptivae_conv1x1_small(const float* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                          int Cout, int act, void* stream);
 
-/* Single-head self-attention core: out = softmax(Q K^T * D^-0.5) V; q,k,v,out bf16 [B][L][D], D in {64,128,256}
+/* Single-head self-attention core: out = softmax(Q K^T * D^-0.5) V; q,k,v,out h16 [B][L][D], D in {64,128,256}
  * (monai SABlock with num_heads = 1, use_flash_attention=False semantics). */
-int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D, void* stream);
+int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D, int f16,
+                         void* stream);
 
 /* AutoencoderKL.sampling: z = mu + sigma*eps.  eps_in != NULL: use the injected noise; else draw
  * eps from Philox4x32-10 (key = seed, counter = (element/4, offset)) + Box-Muller.  eps_out (may be

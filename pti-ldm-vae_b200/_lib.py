@@ -19,15 +19,17 @@ _c_ll, _c_ull = ctypes.c_longlong, ctypes.c_ulonglong
 # symbol -> argtypes ; must list every function include/ptivae.h declares (tests check this)
 SIGNATURES = {
     "ptivae_abi_version": [],
-    "ptivae_conv_umma": [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p],
-    "ptivae_pack_conv_weight": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
-    "ptivae_gn_stats": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
-    "ptivae_gn_finalize": [_c_void_p] * 4 + [_c_int] * 4 + [_c_float, _c_void_p],
-    "ptivae_gn_apply": [_c_void_p] * 3 + [_c_int] * 4 + [_c_void_p],
-    "ptivae_conv3x3_small_cin": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
-    "ptivae_conv3x3_small_cout": [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p],
+    "ptivae_conv_umma": [_c_void_p] * 6 + [_c_int] * 10 + [_c_void_p],
+    "ptivae_conv_parts": [_c_int] * 3,
+    "ptivae_pack_conv_weight": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
+    "ptivae_gn_stats": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
+    "ptivae_gn_stats_parts": [_c_int] * 3,
+    "ptivae_gn_finalize": [_c_void_p] * 4 + [_c_int] * 5 + [_c_float, _c_void_p],
+    "ptivae_gn_apply": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
+    "ptivae_conv3x3_small_cin": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
+    "ptivae_conv3x3_small_cout": [_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p],
     "ptivae_conv1x1_small": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
-    "ptivae_attention_fwd": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
+    "ptivae_attention_fwd": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
     "ptivae_latent_sample": [_c_void_p] * 6 + [_c_ll, _c_ull, _c_ull, _c_void_p],
     "ptivae_rng_advance": [_c_void_p, _c_void_p],
     "ptivae_kl_loss": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],

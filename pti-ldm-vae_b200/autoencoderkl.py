@@ -125,25 +125,32 @@ def _decoder(channels, cin, cout, nres, groups, eps, attn_levels, nonlocal_attn)
 # executor
 # ---------------------------------------------------------------------------------------------
 class _Act:
-    """bf16 NHWC activation + (optional) GroupNorm statistics accumulated by its producer."""
-    __slots__ = ("t", "acc")
+    """NHWC activation (fp32 residual stream, or bf16 GEMM operand) + the GroupNorm statistics
+    partials [N,P,G,2] its producer wrote, if any."""
+    __slots__ = ("t", "part")
 
-    def __init__(self, t, acc=None):
-        self.t, self.acc = t, acc
+    def __init__(self, t, part=None):
+        self.t, self.part = t, part
 
 
 class _Executor:
-    def __init__(self, groups: int, eps: float, fused_stats: bool = True):
+    """Schedules one encoder / decoder stack.  Precision plan: block outputs (the residual stream) are
+    fp32; everything a tensor-core GEMM reads (normalised activations, raw operands of the
+    down/up-sampling and shortcut convs, q/k/v, packed weights) is 16-bit -- fp16 by default, bf16 on
+    request (AutoencoderKL.set_operand_dtype) -- and accumulation is fp32."""
+
+    def __init__(self, groups: int, eps: float, fused_stats: bool = True, operand_dtype=torch.float16):
         self.groups, self.eps, self.fused_stats = groups, eps, fused_stats
+        self.op_dtype = operand_dtype
         self._packed: dict = {}
 
     # -- weights: bf16 UMMA operands cached until the fp32 master changes (optimizer step, load_state_dict, .to())
     def packed(self, w: torch.Tensor, mode: int = 0) -> torch.Tensor:
         key = (id(w), mode)
-        ver = (w.data_ptr(), w._version, w.device)
+        ver = (w.data_ptr(), w._version, w.device, self.op_dtype)
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
-            hit = (ver, ops.pack_conv_weight(w, mode))
+            hit = (ver, ops.pack_conv_weight(w, mode, self.op_dtype))
             self._packed[key] = hit
         return hit[1]
 
@@ -151,54 +158,63 @@ class _Executor:
     def f32(p: torch.Tensor) -> torch.Tensor:
         return p.detach()
 
-    def conv(self, a: _Act, conv: nn.Module, mode: int, residual=None, stats: bool = True) -> _Act:
+    def conv(self, x: torch.Tensor, conv: nn.Module, mode: int, residual=None, stats: bool = True,
+             out_f32: bool = False) -> _Act:
         w = conv.weight
-        cout = w.shape[0]
-        g = self.groups
-        want = stats and self.fused_stats and cout % g == 0 and 32 % (cout // g) == 0
-        acc = torch.zeros((a.t.shape[0], g, 2), device=a.t.device, dtype=torch.float32) if want else None
-        out = ops.conv_umma(a.t, self.packed(w, 2 if mode == 2 else 0), self.f32(conv.bias), mode,
-                            residual=residual, gn_acc=acc, gn_groups=g if want else 0)
-        return _Act(out, acc)
+        cout, g = w.shape[0], self.groups
+        want = stats and self.fused_stats and cout % g == 0 and 32 % (cout // g) == 0 and cout // g >= 2
+        r = ops.conv_umma(x, self.packed(w, 2 if mode == 2 else 0), self.f32(conv.bias), mode, residual=residual,
+                          gn_groups=g if want else 0, out_f32=out_f32)
+        return _Act(*r) if want else _Act(r)
 
     def scale_shift(self, a: _Act, norm: nn.GroupNorm) -> torch.Tensor:
-        acc = a.acc if a.acc is not None else ops.gn_stats(a.t, norm.num_groups)
+        part = a.part if a.part is not None else ops.gn_stats(a.t, norm.num_groups)
         n, c = a.t.shape[0], a.t.shape[-1]
-        hw = a.t.numel() // (n * c)
-        return ops.gn_finalize(acc, self.f32(norm.weight), self.f32(norm.bias), hw, norm.eps)
+        return ops.gn_finalize(part, self.f32(norm.weight), self.f32(norm.bias), a.t.numel() // (n * c), norm.eps)
 
-    def resblock(self, blk: AEKLResBlock, a: _Act) -> _Act:
-        y = _Act(ops.gn_apply(a.t, self.scale_shift(a, blk.norm1), silu=True))
-        h = self.conv(y, blk.conv1.conv, 0)
-        y2 = _Act(ops.gn_apply(h.t, self.scale_shift(h, blk.norm2), silu=True))
-        if isinstance(blk.nin_shortcut, Convolution):
-            sc = self.conv(a, blk.nin_shortcut.conv, 3, stats=False).t
+    def resblock(self, blk: AEKLResBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
+        has_sc = isinstance(blk.nin_shortcut, Convolution)
+        ss1 = self.scale_shift(a, blk.norm1)
+        if has_sc:
+            y, raw = ops.gn_apply(a.t, ss1, silu=True, emit_raw=True, dtype=self.op_dtype)
+            sc = self.conv(raw, blk.nin_shortcut.conv, 3, stats=False, out_f32=True).t
         else:
-            sc = a.t
-        return self.conv(y2, blk.conv2.conv, 0, residual=sc)
+            y, sc = ops.gn_apply(a.t, ss1, silu=True, dtype=self.op_dtype), a.t
+        h = self.conv(y, blk.conv1.conv, 0)                      # 16-bit: only norm2 reads it
+        y2 = ops.gn_apply(h.t, self.scale_shift(h, blk.norm2), silu=True, dtype=self.op_dtype)
+        return self.conv(y2, blk.conv2.conv, 0, residual=sc, stats=stats, out_f32=out_f32)
 
-    def attention(self, blk: SpatialAttentionBlock, a: _Act) -> _Act:
-        xn = _Act(ops.gn_apply(a.t, self.scale_shift(a, blk.norm), silu=False))
+    def attention(self, blk: SpatialAttentionBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
+        xn = ops.gn_apply(a.t, self.scale_shift(a, blk.norm), silu=False, dtype=self.op_dtype)
         q = self.conv(xn, blk.attn.to_q, 3, stats=False).t
         k = self.conv(xn, blk.attn.to_k, 3, stats=False).t
         v = self.conv(xn, blk.attn.to_v, 3, stats=False).t
         n, h, w, c = q.shape
         o = ops.attention(q.view(n, h * w, c), k.view(n, h * w, c), v.view(n, h * w, c)).view(n, h, w, c)
-        return self.conv(_Act(o), blk.attn.out_proj, 3, residual=a.t)
+        return self.conv(o, blk.attn.out_proj, 3, residual=a.t, stats=stats, out_f32=out_f32)
 
     def run_stack(self, blocks: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:
         """x fp32 NCHW -> fp32 NCHW through encoder.blocks / decoder.blocks."""
         first, last_norm, last = blocks[0], blocks[-2], blocks[-1]
-        a = _Act(ops.conv3x3_small_cin(x, self.f32(first.conv.weight), self.f32(first.conv.bias)))
-        for blk in list(blocks)[1:-2]:
+        body = list(blocks)[1:-2]
+
+        def operand_only(i):  # the tensor produced by body[i-1] is read ONLY as a conv operand by body[i]
+            return i < len(body) and isinstance(body[i], (AEKLDownsample, UpSample))
+
+        a = _Act(ops.conv3x3_small_cin(x, self.f32(first.conv.weight), self.f32(first.conv.bias),
+                                       dtype=self.op_dtype if operand_only(0) else torch.float32))
+        for i, blk in enumerate(body):
+            nxt_operand = operand_only(i + 1)
             if isinstance(blk, AEKLResBlock):
-                a = self.resblock(blk, a)
+                a = self.resblock(blk, a, out_f32=not nxt_operand, stats=not nxt_operand)
             elif isinstance(blk, SpatialAttentionBlock):
-                a = self.attention(blk, a)
-            elif isinstance(blk, AEKLDownsample):
-                a = self.conv(a, blk.conv.conv, 1)
-            elif isinstance(blk, UpSample):
-                a = self.conv(a, blk.postconv.conv, 2)
+                a = self.attention(blk, a, out_f32=not nxt_operand, stats=not nxt_operand)
+            elif isinstance(blk, (AEKLDownsample, UpSample)):
+                xin = a.t
+                assert xin.dtype == self.op_dtype, "scheduler bug: down/up-sample operand must be 16-bit"
+                conv = blk.conv.conv if isinstance(blk, AEKLDownsample) else blk.postconv.conv
+                a = self.conv(xin, conv, 1 if isinstance(blk, AEKLDownsample) else 2, out_f32=not nxt_operand,
+                              stats=not nxt_operand)
             else:  # pragma: no cover
                 raise TypeError(f"unexpected block {type(blk)}")
         ss = self.scale_shift(a, last_norm)
@@ -255,18 +271,30 @@ class AutoencoderKL(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("B200 AutoencoderKL runs on CUDA only; there is no CPU fallback "
                                "(the CPU restatement lives in oracle/ and is test-only)")
+        return x.detach().contiguous().float()
+
+    def _check_mode(self) -> None:
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("the backward kernels (SURVEY 8a row a20) are not built yet: call under "
                                       "torch.no_grad() / model.eval() -- forward, encode, decode are inference-only")
-        return x.detach().contiguous().float()
+
+    def set_operand_dtype(self, dtype: torch.dtype) -> None:
+        """Storage format of the tensor-core operands: torch.float16 (default) or torch.bfloat16."""
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("operand dtype must be torch.float16 or torch.bfloat16")
+        self._exec.op_dtype = dtype
 
     def set_fused_stats(self, enabled: bool) -> None:
         """GroupNorm statistics from the producing conv's epilogue (default) vs. a separate pass."""
         self._exec.fused_stats = bool(enabled)
 
     # -- reference API ------------------------------------------------------------------------
-    @torch.no_grad()
     def encode(self, x: torch.Tensor):
+        self._check_mode()
+        with torch.no_grad():
+            return self._encode(x)
+
+    def _encode(self, x: torch.Tensor):
         x = self._prep(x)
         h = self._exec.run_stack(self.encoder.blocks, x)
         mu = ops.conv1x1_small(h, self.quant_conv_mu.conv.weight.detach(), self.quant_conv_mu.conv.bias.detach(), 0)
@@ -287,8 +315,12 @@ class AutoencoderKL(nn.Module):
         self._rng_offset += 1
         return ops.latent_sample(z_mu, z_sigma, seed=torch.initial_seed(), offset=self._rng_offset)
 
-    @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
+        self._check_mode()
+        with torch.no_grad():
+            return self._decode(z)
+
+    def _decode(self, z: torch.Tensor) -> torch.Tensor:
         z = self._prep(z)
         zq = ops.conv1x1_small(z, self.post_quant_conv.conv.weight.detach(), self.post_quant_conv.conv.bias.detach(), 0)
         return self._exec.run_stack(self.decoder.blocks, zq)

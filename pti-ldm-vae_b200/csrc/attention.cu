@@ -20,7 +20,7 @@ namespace ptivae {
 struct AttnArgs {
   int L;
   float scale_log2e;  // D^-0.5 * log2(e)
-  __nv_bfloat16* out;
+  uint16_t* out;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -29,19 +29,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int D, int BKV>
+template <int D, int BKV, bool F16>
 __global__ void __launch_bounds__(192, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
   constexpr int DCH = D / 64;                        // 64-channel chunks of the head dim
-  constexpr int PCH = BKV / 64;                      // 64-key chunks of P
-  constexpr uint32_t Q_BYTES = 128u * D * 2u;
+    constexpr uint32_t Q_BYTES = 128u * D * 2u;
   constexpr uint32_t KV_TILE = uint32_t(BKV) * D * 2u;  // one K (or V) tile
   constexpr uint32_t KV_CHUNK = uint32_t(BKV) * 128u;   // one 64-channel chunk of a K/V tile
   constexpr uint32_t P_BYTES = 128u * BKV * 2u;
   constexpr uint32_t TMEM_COLS = (BKV + D <= 256) ? 256u : 512u;
-  constexpr uint32_t kIdescS = make_idesc_bf16(128, BKV, 0);
-  constexpr uint32_t kIdescO = make_idesc_bf16(128, D, 1);  // B (=V) is MN-major
+  constexpr uint32_t kIdescS = make_idesc_16(128, BKV, F16, 0);
+  constexpr uint32_t kIdescO = make_idesc_16(128, D, F16, 1);  // B (=V) is MN-major
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -191,10 +190,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           uint4 o;
-          o.x = pack_bf16x2(p[u4 * 8 + 0], p[u4 * 8 + 1]);
-          o.y = pack_bf16x2(p[u4 * 8 + 2], p[u4 * 8 + 3]);
-          o.z = pack_bf16x2(p[u4 * 8 + 4], p[u4 * 8 + 5]);
-          o.w = pack_bf16x2(p[u4 * 8 + 6], p[u4 * 8 + 7]);
+          o.x = pack2<F16>(p[u4 * 8 + 0], p[u4 * 8 + 1]);
+          o.y = pack2<F16>(p[u4 * 8 + 2], p[u4 * 8 + 3]);
+          o.z = pack2<F16>(p[u4 * 8 + 4], p[u4 * 8 + 5]);
+          o.w = pack2<F16>(p[u4 * 8 + 6], p[u4 * 8 + 7]);
           const int unit = (c & 1) * 4 + u4;  // 16-byte unit inside the 128-byte row
           *reinterpret_cast<uint4*>(chunk + ((unit ^ (m & 7)) << 4)) = o;
         }
@@ -210,7 +209,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const bool valid = (q0 + m) < L;
-    __nv_bfloat16* optr = args.out + (static_cast<size_t>(b) * L + q0 + m) * D;
+    uint16_t* optr = args.out + (static_cast<size_t>(b) * L + q0 + m) * D;
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
       uint32_t r[32];
@@ -220,10 +219,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[u4 * 8 + 0]) * inv_l, __uint_as_float(r[u4 * 8 + 1]) * inv_l);
-          o.y = pack_bf16x2(__uint_as_float(r[u4 * 8 + 2]) * inv_l, __uint_as_float(r[u4 * 8 + 3]) * inv_l);
-          o.z = pack_bf16x2(__uint_as_float(r[u4 * 8 + 4]) * inv_l, __uint_as_float(r[u4 * 8 + 5]) * inv_l);
-          o.w = pack_bf16x2(__uint_as_float(r[u4 * 8 + 6]) * inv_l, __uint_as_float(r[u4 * 8 + 7]) * inv_l);
+          o.x = pack2<F16>(__uint_as_float(r[u4 * 8 + 0]) * inv_l, __uint_as_float(r[u4 * 8 + 1]) * inv_l);
+          o.y = pack2<F16>(__uint_as_float(r[u4 * 8 + 2]) * inv_l, __uint_as_float(r[u4 * 8 + 3]) * inv_l);
+          o.z = pack2<F16>(__uint_as_float(r[u4 * 8 + 4]) * inv_l, __uint_as_float(r[u4 * 8 + 5]) * inv_l);
+          o.w = pack2<F16>(__uint_as_float(r[u4 * 8 + 6]) * inv_l, __uint_as_float(r[u4 * 8 + 7]) * inv_l);
           *(reinterpret_cast<uint4*>(optr + c * 32) + u4) = o;
         }
       }
@@ -235,33 +234,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int D, int BKV>
+template <int D, int BKV, bool F16>
 static int launch_attn(const void* q, const void* k, const void* v, void* out, int B, int L, cudaStream_t stream) {
   CUtensorMap tmQ, tmK, tmV;
   uint64_t dims[3] = {uint64_t(D), uint64_t(L), uint64_t(B)};
   uint64_t strides[2] = {uint64_t(D) * 2, uint64_t(L) * D * 2};
   uint32_t boxq[3] = {64, 128, 1};
   uint32_t boxkv[3] = {64, BKV, 1};
-  int rc = encode_tmap_bf16(&tmQ, q, 3, dims, strides, boxq, 128);
+  int rc = encode_tmap_16(&tmQ, q, 3, dims, strides, boxq, 128, F16);
   if (rc) return rc;
-  rc = encode_tmap_bf16(&tmK, k, 3, dims, strides, boxkv, 128);
+  rc = encode_tmap_16(&tmK, k, 3, dims, strides, boxkv, 128, F16);
   if (rc) return rc;
-  rc = encode_tmap_bf16(&tmV, v, 3, dims, strides, boxkv, 128);
+  rc = encode_tmap_16(&tmV, v, 3, dims, strides, boxkv, 128, F16);
   if (rc) return rc;
   const size_t smem = 128 * D * 2 + 4 * size_t(BKV) * D * 2 + 128 * BKV * 2 + 1024 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(attn_fwd_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(attn_fwd_kernel<D, BKV, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   AttnArgs a;
   a.L = L;
   a.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(D));
-  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out = static_cast<uint16_t*>(out);
   dim3 grid((L + 127) / 128, B);
-  attn_fwd_kernel<D, BKV><<<grid, 192, smem, stream>>>(tmQ, tmK, tmV, a);
+  attn_fwd_kernel<D, BKV, F16><<<grid, 192, smem, stream>>>(tmQ, tmK, tmV, a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -270,11 +269,14 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
 using namespace ptivae;
 
 extern "C" int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D,
-                                    void* stream_) {
+                                    int f16, void* stream_) {
   if (!q || !k || !v || !out || B <= 0 || L <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (D == 128) return launch_attn<128, 128>(q, k, v, out, B, L, stream);
-  if (D == 256) return launch_attn<256, 64>(q, k, v, out, B, L, stream);
-  if (D == 64) return launch_attn<64, 128>(q, k, v, out, B, L, stream);
+  if (D == 128) return f16 ? launch_attn<128, 128, true>(q, k, v, out, B, L, stream)
+                           : launch_attn<128, 128, false>(q, k, v, out, B, L, stream);
+  if (D == 256) return f16 ? launch_attn<256, 64, true>(q, k, v, out, B, L, stream)
+                           : launch_attn<256, 64, false>(q, k, v, out, B, L, stream);
+  if (D == 64) return f16 ? launch_attn<64, 128, true>(q, k, v, out, B, L, stream)
+                          : launch_attn<64, 128, false>(q, k, v, out, B, L, stream);
   return PTIVAE_ERR_UNSUPPORTED;
 }

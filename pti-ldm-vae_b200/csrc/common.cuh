@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -135,8 +136,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (0 = K)   [16] B major (0 = K, 1 = MN)   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+//   operand format: 0 = F16, 1 = BF16 (A and B always use the same one here)
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, bool f16, uint32_t b_mn_major = 0) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
@@ -177,13 +180,44 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ----------------------------------------------------------------------------- bf16 packing
+// ----------------------------------------------------------------------------- 16-bit operand packing
+// The GEMM operand format is a template flag: F16 = true -> IEEE half (11-bit significand; values are
+// clamped to +-65504 so nothing becomes inf), F16 = false -> bfloat16.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16lo_f(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if constexpr (F16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    return pack_bf16x2(lo, hi);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
+  if constexpr (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    lo = f.x;
+    hi = f.y;
+  } else {
+    lo = bf16lo_f(v);
+    hi = bf16hi_f(v);
+  }
+}
+// value after a round trip through the 16-bit format (what a consumer will read back)
+template <bool F16>
+__device__ __forceinline__ float round16(float x) {
+  if constexpr (F16) return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)));
+  else return __bfloat162float(__float2bfloat16_rn(x));
+}
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 

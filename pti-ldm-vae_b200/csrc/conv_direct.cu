@@ -14,8 +14,8 @@ namespace ptivae {
 __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __restrict__ x,
                                                                 const float* __restrict__ w,  // [Cout][Cin][3][3]
                                                                 const float* __restrict__ bias,
-                                                                __nv_bfloat16* __restrict__ out, int N, int H, int W,
-                                                                int Cin, int Cout) {
+                                                                void* __restrict__ out, int N, int H, int W,
+                                                                int Cin, int Cout, int out_fmt) {
   extern __shared__ float sw[];  // [9*Cin][Cout] then bias [Cout]
   float* sb = sw + 9 * Cin * Cout;
   for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
@@ -59,23 +59,27 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
         }
       }
     }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
-    reinterpret_cast<uint4*>(out)[i] = o;
+    if (out_fmt == 2) {
+      reinterpret_cast<float4*>(out)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else if (out_fmt == 1) {
+      reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2<true>(acc[0], acc[1]), pack2<true>(acc[2], acc[3]),
+                                                    pack2<true>(acc[4], acc[5]), pack2<true>(acc[6], acc[7]));
+    } else {
+      reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2<false>(acc[0], acc[1]), pack2<false>(acc[2], acc[3]),
+                                                    pack2<false>(acc[4], acc[5]), pack2<false>(acc[6], acc[7]));
+    }
   }
 }
 
 // thread -> one output pixel, all COUT channels.  Weights in smem as [tap][ci][COUT] fp32.
 template <int COUT>
-__global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __restrict__ x,
                                                                  const float* __restrict__ w,  // [COUT][Cin][3][3]
                                                                  const float* __restrict__ bias,
                                                                  const float* __restrict__ ss,  // [N][Cin][2] or null
                                                                  float* __restrict__ out, int N, int H, int W,
-                                                                 int Cin) {
+                                                                 int Cin, int in_fmt) {
   extern __shared__ float sw[];  // [9*Cin][COUT], then per-image scale/shift is read from global
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) {
     const int co = i % COUT;
@@ -102,17 +106,24 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __nv_bflo
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = px + kx - 1;
         if (xx < 0 || xx >= W) continue;  // zero padding applies AFTER the norm: skip, do not transform
-        const uint4* xp =
-            reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + yy) * W + xx) * Cin);
+        const size_t pvec = ((static_cast<size_t>(n) * H + yy) * W + xx) * vecs;
         const float* wt = sw + (ky * 3 + kx) * Cin * COUT;
         for (int v = 0; v < vecs; ++v) {
-          const uint4 u = __ldg(xp + v);
-          const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
           float xv[8];
+          if (in_fmt == 2) {
+            const float4* xp = reinterpret_cast<const float4*>(x) + (pvec + v) * 2;
+            const float4 a = __ldg(xp), b = __ldg(xp + 1);
+            xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+          } else {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + pvec + v);
+            const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+            if (in_fmt == 1) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            xv[2 * e] = bf16lo_f(wd[e]);
-            xv[2 * e + 1] = bf16hi_f(wd[e]);
+              for (int e = 0; e < 4; ++e) unpack2<true>(wd[e], xv[2 * e], xv[2 * e + 1]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) unpack2<false>(wd[e], xv[2 * e], xv[2 * e + 1]);
+            }
           }
           if (ssn) {
 #pragma unroll
@@ -162,7 +173,7 @@ __global__ void conv1x1_small_kernel(const float* __restrict__ x, const float* _
 using namespace ptivae;
 
 extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int N, int H,
-                                        int W, int Cin, int Cout, void* stream_) {
+                                        int W, int Cin, int Cout, int out_fmt, void* stream_) {
   if (!x || !w || !bias || !out || N <= 0 || Cin <= 0 || Cin > 16 || Cout % 8 != 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = (static_cast<size_t>(9) * Cin * Cout + Cout) * sizeof(float);
@@ -174,13 +185,13 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
   }
   const size_t total = static_cast<size_t>(N) * H * W * (Cout / 8);
   conv3x3_small_cin_kernel<<<grid_for(total, 256, 148 * 8), 256, smem, stream>>>(
-      x, w, bias, static_cast<__nv_bfloat16*>(out), N, H, W, Cin, Cout);
+      x, w, bias, out, N, H, W, Cin, Cout, out_fmt);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <int COUT>
 static int launch_small_cout(const void* x, const float* w, const float* bias, const float* ss, float* out, int N,
-                             int H, int W, int Cin, cudaStream_t stream) {
+                             int H, int W, int Cin, int in_fmt, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(9) * Cin * COUT * sizeof(float);
   if (smem > 200 * 1024) return PTIVAE_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
@@ -190,22 +201,23 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
   }
   const size_t total = static_cast<size_t>(N) * H * W;
   conv3x3_small_cout_kernel<COUT><<<grid_for(total, 256, 148 * 8), 256, smem, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), w, bias, ss, out, N, H, W, Cin);
+      x, w, bias, ss, out, N, H, W, Cin, in_fmt);
   return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const float* bias, const float* scale_shift,
-                                         float* out, int N, int H, int W, int Cin, int Cout, void* stream_) {
+                                         float* out, int N, int H, int W, int Cin, int Cout, int in_fmt,
+                                         void* stream_) {
   if (!x || !w || !bias || !out || N <= 0 || Cin % 8 != 0 || Cout <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   switch (Cout) {
-    case 1: return launch_small_cout<1>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
-    case 2: return launch_small_cout<2>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
-    case 3: return launch_small_cout<3>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
-    case 4: return launch_small_cout<4>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
-    case 8: return launch_small_cout<8>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
-    case 10: return launch_small_cout<10>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
-    case 16: return launch_small_cout<16>(x, w, bias, scale_shift, out, N, H, W, Cin, stream);
+    case 1: return launch_small_cout<1>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
+    case 2: return launch_small_cout<2>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
+    case 3: return launch_small_cout<3>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
+    case 4: return launch_small_cout<4>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
+    case 8: return launch_small_cout<8>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
+    case 10: return launch_small_cout<10>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
+    case 16: return launch_small_cout<16>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
     default: return PTIVAE_ERR_UNSUPPORTED;
   }
 }

@@ -4,8 +4,9 @@
 // (reference call site
 // /root/reference/src/pti_ldm_vae/models/autoencoder.py:67-79,114).
 //
-// Data layout: activations NHWC bf16, weights packed [tap][Cout][Cin] bf16 (K-major for both UMMA
-// operands), fp32 accumulate, fp32 bias, bf16 output.
+// Data layout: GEMM operands NHWC bf16, weights packed [tap][Cout][Cin] bf16 (K-major for both UMMA
+// operands), fp32 accumulate, fp32 bias; output (and residual) stored bf16 or fp32 -- the residual
+// stream between blocks is fp32 so that 28 blocks of rounding stay inside the z_mu tolerance.
 //   GEMM view:  M = 128 output pixels (a TH x TW = 8 x 16 patch of one image)
 //               N = Cout tile (32..256),  K = taps * Cin, walked tap-major in chunks of KCH channels.
 // The A tile of tap (dy,dx) is ONE TMA box load of the NHWC tensor at (y0+dy, x0+dx): the halo /
@@ -43,15 +44,17 @@ struct ConvArgs {
   int ntaps;         // taps per phase
   int tiles_x, tiles_y;
   int nstages;
-  int gn_groups;     // >0: accumulate per-(n, group) sum/sumsq of the fp32 output into gn_acc
+  int gn_groups;     // >0: write per-(n, tile, group) sum/sumsq of the stored output into gn_part
+  int out_f32;       // output storage: 0 = bf16, 1 = fp32 (residual stream)
+  int res_f32;       // residual storage
   ConvTap taps[4][kMaxTaps];
   const float* bias;
-  const __nv_bfloat16* residual;  // same shape as out, or nullptr
-  __nv_bfloat16* out;
-  float* gn_acc;                  // [N][groups][2]
+  const void* residual;  // same shape as out, or nullptr
+  void* out;
+  float* gn_part;        // [N][P = nphase*tiles_y*tiles_x][groups][2]
 };
 
-template <int KCH, int BN>
+template <int KCH, int BN, bool F16>
 __global__ void __launch_bounds__(192, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvArgs args) {
@@ -60,7 +63,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t kLayout = (KCH == 64) ? kLayoutSW128 : kLayoutSW64;
   constexpr uint32_t kSBO = 8u * KCH * 2u;  // 8 rows of one swizzle atom
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN);
+  constexpr uint32_t kIdesc = make_idesc_16(128, BN, F16);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -70,6 +73,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* spart = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4 warps][<=128 groups][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,8 +148,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int py = (args.os == 2) ? (phase_id >> 1) : 0;
     const int px = (args.os == 2) ? (phase_id & 1) : 0;
     const size_t pix = (static_cast<size_t>(n) * args.Hout + (gy * args.os + py)) * args.Wout + (gx * args.os + px);
-    __nv_bfloat16* optr = args.out + pix * args.Cout + n0;
-    const __nv_bfloat16* rptr = args.residual ? args.residual + pix * args.Cout + n0 : nullptr;
+    const size_t eoff = pix * args.Cout + n0;
+    uint16_t* optr16 = static_cast<uint16_t*>(args.out) + eoff;
+    float* optr32 = static_cast<float*>(args.out) + eoff;
+    const bool has_res = args.residual != nullptr;
+    const uint16_t* rptr16 = static_cast<const uint16_t*>(args.residual) + eoff;
+    const float* rptr32 = static_cast<const float*>(args.residual) + eoff;
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -158,37 +166,54 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(args.bias + n0 + c * 32 + j);
-      if (rptr != nullptr && valid) {
+      if (has_res && valid) {
+        if (args.res_f32) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c * 32) + j4);
-          const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int j8 = 0; j8 < 8; ++j8) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(rptr32 + c * 32) + j8);
+            v[j8 * 4 + 0] += rv.x; v[j8 * 4 + 1] += rv.y; v[j8 * 4 + 2] += rv.z; v[j8 * 4 + 3] += rv.w;
+          }
+        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[j4 * 8 + 2 * e] += bf16lo_f(w[e]);
-            v[j4 * 8 + 2 * e + 1] += bf16hi_f(w[e]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr16 + c * 32) + j4);
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float lo, hi;
+              unpack2<F16>(w[e], lo, hi);
+              v[j4 * 8 + 2 * e] += lo;
+              v[j4 * 8 + 2 * e + 1] += hi;
+            }
           }
         }
       }
       if (valid) {
+        if (args.out_f32) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          uint4 o;
-          o.x = pack_bf16x2(v[j4 * 8 + 0], v[j4 * 8 + 1]);
-          o.y = pack_bf16x2(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-          o.z = pack_bf16x2(v[j4 * 8 + 4], v[j4 * 8 + 5]);
-          o.w = pack_bf16x2(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-          *(reinterpret_cast<uint4*>(optr + c * 32) + j4) = o;
+          for (int j8 = 0; j8 < 8; ++j8)
+            *(reinterpret_cast<float4*>(optr32 + c * 32) + j8) =
+                make_float4(v[j8 * 4 + 0], v[j8 * 4 + 1], v[j8 * 4 + 2], v[j8 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 o;
+            o.x = pack2<F16>(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+            o.y = pack2<F16>(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+            o.z = pack2<F16>(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+            o.w = pack2<F16>(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+            *(reinterpret_cast<uint4*>(optr16 + c * 32) + j4) = o;
+          }
         }
       }
       if (cpg > 0) {
-        // Statistics of the bf16-rounded values the consumer will actually read.
+        // Statistics of the values as stored (bf16-rounded unless the output is the fp32 stream).
         // Transposing butterfly over the 32 pixel lanes: each step halves the live value count,
         // so 31 shuffles per quantity leave lane L holding the column-L total of this warp.
         float s[32], ss[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float b = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+          const float b = valid ? (args.out_f32 ? v[j] : round16<F16>(v[j])) : 0.f;
           s[j] = b;
           ss[j] = b * b;
         }
@@ -211,10 +236,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           b2 += __shfl_xor_sync(0xffffffffu, b2, o);
         }
         if ((lane % cpg) == 0) {
-          const int grp = (n0 + c * 32 + lane) / cpg;
-          atomicAdd(args.gn_acc + (static_cast<size_t>(n) * args.gn_groups + grp) * 2 + 0, a);
-          atomicAdd(args.gn_acc + (static_cast<size_t>(n) * args.gn_groups + grp) * 2 + 1, b2);
+          const int lg = (c * 32 + lane) / cpg;  // group index local to this CTA's BN columns
+          spart[(q * (BN / 2) + lg) * 2 + 0] = a;
+          spart[(q * (BN / 2) + lg) * 2 + 1] = b2;
         }
+      }
+    }
+    if (cpg > 0) {
+      // fixed-order fold of the 4 epilogue warps, then one plain store per (tile, group): no atomics
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;  // 0..127
+      const int ngl = BN / cpg;        // groups covered by this CTA
+      if (e < 2 * ngl) {
+        float t = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) t += spart[(w4 * (BN / 2)) * 2 + e];
+        const int P = gridDim.z * args.tiles_y * args.tiles_x;
+        const int pidx = (phase_id * args.tiles_y + tiy) * args.tiles_x + tix;
+        args.gn_part[((static_cast<size_t>(n) * P + pidx) * args.gn_groups + n0 / cpg) * 2 + e] = t;
       }
     }
   }
@@ -241,8 +280,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle_bytes) {
+int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes, bool f16) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return PTIVAE_ERR_DRIVER;
   cuuint64_t gd[5];
@@ -258,13 +297,13 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PTIVAE_OK : PTIVAE_ERR_DRIVER;
 }
 
-template <int KCH, int BN>
+template <int KCH, int BN, bool F16>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs& a, int N, int nphase,
                        cudaStream_t stream) {
   constexpr int STAGE = (128 + BN) * KCH * 2;
@@ -275,16 +314,16 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs&
   if (stages < 2 && iters >= 2) stages = 2;
   if (stages < 1) stages = 1;
   a.nstages = stages;
-  const size_t smem = size_t(stages) * STAGE + 1024 /*align*/ + (2 * kMaxStages + 1) * 8 + 16;
+  const size_t smem = size_t(stages) * STAGE + 1024 /*align*/ + (2 * kMaxStages + 1) * 8 + 16 + 4 * (BN / 2) * 2 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KCH, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KCH, BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   dim3 grid(a.tiles_x * a.tiles_y * N, a.Cout / BN, nphase);
-  conv_umma_kernel<KCH, BN><<<grid, 192, smem, stream>>>(tmA, tmB, a);
+  conv_umma_kernel<KCH, BN, F16><<<grid, 192, smem, stream>>>(tmA, tmB, a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -292,9 +331,15 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs&
 
 using namespace ptivae;
 
+extern "C" int ptivae_conv_parts(int H, int W, int mode) {
+  if (H <= 0 || W <= 0 || mode < 0 || mode > 3) return PTIVAE_ERR_ARG;
+  const int Ho = mode == 1 ? H / 2 : H, Wo = mode == 1 ? W / 2 : W;
+  return ((Wo + kTW - 1) / kTW) * ((Ho + kTH - 1) / kTH) * (mode == 2 ? 4 : 1);
+}
+
 extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual,
-                                void* out, float* gn_acc, int gn_groups, int N, int H, int W, int Cin, int Cout,
-                                int mode, void* stream_) {
+                                void* out, float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout,
+                                int mode, int out_f32, int res_f32, int f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!in || !w_packed || !bias || !out) return PTIVAE_ERR_ARG;
   if (N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
@@ -302,16 +347,19 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   if (!(Cin == 32 || (Cin % 64 == 0 && Cin <= 1024))) return PTIVAE_ERR_UNSUPPORTED;
   if (!(Cout == 32 || Cout == 64 || Cout == 128 || Cout % 256 == 0)) return PTIVAE_ERR_UNSUPPORTED;
   if (mode == 1 && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;  // even extents only (F.pad(0,1,0,1) + s2)
-  if (gn_groups > 0 && (!gn_acc || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0)) return PTIVAE_ERR_ARG;
+  if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
+    return PTIVAE_ERR_ARG;
 
   ConvArgs a{};
   a.Cin = Cin;
   a.Cout = Cout;
   a.bias = bias;
-  a.residual = static_cast<const __nv_bfloat16*>(residual);
-  a.out = static_cast<__nv_bfloat16*>(out);
-  a.gn_acc = gn_acc;
+  a.residual = residual;
+  a.out = out;
+  a.gn_part = gn_part;
   a.gn_groups = gn_groups;
+  a.out_f32 = out_f32;
+  a.res_f32 = res_f32;
   a.os = 1;
   int nphase = 1, T = 9;
   const int KCH = (Cin == 32) ? 32 : 64;
@@ -360,27 +408,31 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   a.tiles_y = (a.Ho + kTH - 1) / kTH;
 
   CUtensorMap tmA, tmB;
-  int rc = encode_tmap_bf16(&tmA, in, 5, dims, strides, box, KCH * 2);
+  int rc = encode_tmap_16(&tmA, in, 5, dims, strides, box, KCH * 2, f16 != 0);
   if (rc != PTIVAE_OK) return rc;
   const int BN = Cout >= 256 ? 256 : Cout;
   uint64_t wd[3] = {uint64_t(Cin), uint64_t(Cout), uint64_t(T)};
   uint64_t ws[2] = {C2, uint64_t(Cout) * C2};
   uint32_t wb[3] = {static_cast<uint32_t>(KCH), static_cast<uint32_t>(BN), 1};
-  rc = encode_tmap_bf16(&tmB, w_packed, 3, wd, ws, wb, KCH * 2);
+  rc = encode_tmap_16(&tmB, w_packed, 3, wd, ws, wb, KCH * 2, f16 != 0);
   if (rc != PTIVAE_OK) return rc;
 
+#define PTIVAE_CONV_CASE(K, B)                                                              \
+  return f16 ? launch_conv<K, B, true>(tmA, tmB, a, N, nphase, stream)                        \
+             : launch_conv<K, B, false>(tmA, tmB, a, N, nphase, stream)
   if (KCH == 32) {
     switch (BN) {
-      case 32: return launch_conv<32, 32>(tmA, tmB, a, N, nphase, stream);
-      case 64: return launch_conv<32, 64>(tmA, tmB, a, N, nphase, stream);
-      case 128: return launch_conv<32, 128>(tmA, tmB, a, N, nphase, stream);
-      default: return launch_conv<32, 256>(tmA, tmB, a, N, nphase, stream);
+      case 32: PTIVAE_CONV_CASE(32, 32);
+      case 64: PTIVAE_CONV_CASE(32, 64);
+      case 128: PTIVAE_CONV_CASE(32, 128);
+      default: PTIVAE_CONV_CASE(32, 256);
     }
   }
   switch (BN) {
-    case 32: return launch_conv<64, 32>(tmA, tmB, a, N, nphase, stream);
-    case 64: return launch_conv<64, 64>(tmA, tmB, a, N, nphase, stream);
-    case 128: return launch_conv<64, 128>(tmA, tmB, a, N, nphase, stream);
-    default: return launch_conv<64, 256>(tmA, tmB, a, N, nphase, stream);
+    case 32: PTIVAE_CONV_CASE(64, 32);
+    case 64: PTIVAE_CONV_CASE(64, 64);
+    case 128: PTIVAE_CONV_CASE(64, 128);
+    default: PTIVAE_CONV_CASE(64, 256);
   }
+#undef PTIVAE_CONV_CASE
 }

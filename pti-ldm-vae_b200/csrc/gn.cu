@@ -1,22 +1,43 @@
 // GroupNorm pieces (HBM-bound).  Replaces ATen native_group_norm + F.silu issued by
 // AEKLResBlock / SpatialAttentionBlock / the final encoder+decoder norms in monai 1.5.1
 // AutoencoderKL.
-//   gn_stats    : per-(image, group) sum and sum-of-squares of an NHWC bf16 tensor (fp32 accumulate)
-//   gn_finalize : (sum, sumsq) -> per-(image, channel) scale = gamma*rstd, shift = beta - mean*scale
-//                 biased variance, eps inside the sqrt (nn.GroupNorm semantics)
-//   gn_apply    : y = act(x*scale + shift), act in {identity, SiLU}, bf16 out
+//   gn_stats    : per-(image, chunk, group) partial sum / sum-of-squares of an NHWC tensor (bf16 or
+//                 fp32 storage, fp32 accumulate).  No atomics: fixed summation order.
+//   gn_finalize : partials -> per-(image, channel) scale = gamma*rstd, shift = beta - mean*scale
+//                 (biased variance, eps inside the sqrt: nn.GroupNorm semantics), fixed order.
+//   gn_apply    : y = act(x*scale + shift) as a bf16 GEMM operand, act in {identity, SiLU};
+//                 optionally also emits the raw input rounded to bf16 (operand of nin_shortcut).
+// The same partial format [N][P][G][2] is produced by conv_umma's epilogue.
 #include "common.cuh"
 #include "ptivae_internal.h"
 
 namespace ptivae {
 
-// grid (chunks, N); block 256.  Thread t owns one 16-byte vector column (8 channels) and walks pixels.
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ acc,
-                                                       int HW, int C, int G, int pix_per_block) {
-  extern __shared__ float sacc[];  // [G][2]
+// fmt: 0 = bf16, 1 = fp16, 2 = fp32
+__device__ __forceinline__ void load8(const void* base, size_t vec_index, int fmt, float (&v)[8]) {
+  if (fmt == 2) {
+    const float4* p = reinterpret_cast<const float4*>(base) + vec_index * 2;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base) + vec_index);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    if (fmt == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) unpack2<true>(w[e], v[2 * e], v[2 * e + 1]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) unpack2<false>(w[e], v[2 * e], v[2 * e + 1]);
+    }
+  }
+}
+
+// grid (chunks, N); block 256.  Thread t owns one 8-channel vector column and walks pixels.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial,
+                                                       int HW, int C, int G, int pix_per_block, int in_fmt) {
+  __shared__ float sm[256][8];     // per-thread (4 channel pairs) x (sum, sumsq)
+  __shared__ float pairs[256][2];  // per channel pair of the image chunk
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int vecs = C / 8;
   const int v = threadIdx.x % vecs;
   const int prow = threadIdx.x / vecs;
@@ -24,41 +45,63 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(HW, p_begin + pix_per_block);
   float s2[4] = {0.f, 0.f, 0.f, 0.f}, q2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (prow < prows) {
-    const uint4* base = reinterpret_cast<const uint4*>(x + static_cast<size_t>(n) * HW * C) + v;
-    for (int p = p_begin + prow; p < p_end; p += prows) {
-      const uint4 u = __ldg(base + static_cast<size_t>(p) * vecs);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const char* base = reinterpret_cast<const char*>(x) + static_cast<size_t>(n) * HW * C * (in_fmt == 2 ? 4 : 2);
+  for (int p = p_begin + prow; p < p_end; p += prows) {
+    float f[8];
+    load8(base, static_cast<size_t>(p) * vecs + v, in_fmt, f);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float a = bf16lo_f(w[e]), b = bf16hi_f(w[e]);
-        s2[e] += a + b;
-        q2[e] += a * a + b * b;
-      }
+    for (int e = 0; e < 4; ++e) {
+      s2[e] += f[2 * e] + f[2 * e + 1];
+      q2[e] += f[2 * e] * f[2 * e] + f[2 * e + 1] * f[2 * e + 1];
     }
   }
-  const int cpg = C / G;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int grp = (v * 8 + 2 * e) / cpg;
-    atomicAdd(&sacc[2 * grp], s2[e]);
-    atomicAdd(&sacc[2 * grp + 1], q2[e]);
+    sm[threadIdx.x][2 * e] = s2[e];
+    sm[threadIdx.x][2 * e + 1] = q2[e];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
-    atomicAdd(acc + static_cast<size_t>(n) * 2 * G + i, sacc[i]);
+  // fixed-order fold over the pixel rows: thread (v, e) sums rows 0..prows-1
+  const int npairs = vecs * 4;  // channel pairs in C  (<= 256)
+  if (threadIdx.x < npairs) {
+    const int pv = threadIdx.x / 4, pe = threadIdx.x % 4;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < prows; ++r) {
+      a += sm[r * vecs + pv][2 * pe];
+      b += sm[r * vecs + pv][2 * pe + 1];
+    }
+    pairs[threadIdx.x][0] = a;
+    pairs[threadIdx.x][1] = b;
+  }
+  __syncthreads();
+  const int ppg = (C / G) / 2;  // channel pairs per group
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < ppg; ++i) {
+      a += pairs[threadIdx.x * ppg + i][0];
+      b += pairs[threadIdx.x * ppg + i][1];
+    }
+    float* dst = partial + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * G + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
 }
 
-// one thread per (n, c)
-__global__ void gn_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ gamma,
+// one thread per (n, c); sums the P partials of its group in index order
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ scale_shift, int N, int C,
-                                   int G, float inv_count, float eps) {
+                                   int G, int P, float inv_count, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
   const int g = c / (C / G);
-  const float s = acc[(static_cast<size_t>(n) * G + g) * 2 + 0];
-  const float q = acc[(static_cast<size_t>(n) * G + g) * 2 + 1];
+  const float* src = partial + (static_cast<size_t>(n) * P * G + g) * 2;
+  float s = 0.f, q = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(src + static_cast<size_t>(p) * G * 2));
+    s += t.x;
+    q += t.y;
+  }
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
@@ -67,9 +110,10 @@ __global__ void gn_finalize_kernel(const float* __restrict__ acc, const float* _
   scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 1] = beta[c] - mean * sc;
 }
 
-template <bool kSilu>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ ss,
-                                                       uint4* __restrict__ y, size_t total_vecs, int HW, int C) {
+template <bool kSilu, bool F16>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, const float* __restrict__ ss,
+                                                       uint4* __restrict__ y, uint4* __restrict__ raw,
+                                                       size_t total_vecs, int HW, int C, int in_fmt) {
   const int vecs = C / 8;
   const size_t per_img = static_cast<size_t>(HW) * vecs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vecs;
@@ -77,21 +121,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
     const int n = static_cast<int>(i / per_img);
     const int v = static_cast<int>(i % vecs);
     const float4* sp = reinterpret_cast<const float4*>(ss + (static_cast<size_t>(n) * C + v * 8) * 2);
-    const uint4 u = __ldg(x + i);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+    load8(x, i, in_fmt, f);
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float4 p = __ldg(sp + e);  // (scale0, shift0, scale1, shift1)
-      float a = fmaf(bf16lo_f(w[e]), p.x, p.y);
-      float b = fmaf(bf16hi_f(w[e]), p.z, p.w);
+      float a = fmaf(f[2 * e], p.x, p.y);
+      float b = fmaf(f[2 * e + 1], p.z, p.w);
       if (kSilu) {
         a = silu_f(a);
         b = silu_f(b);
       }
-      o[e] = pack_bf16x2(a, b);
+      o[e] = pack2<F16>(a, b);
     }
     y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (raw != nullptr)
+      raw[i] = make_uint4(pack2<F16>(f[0], f[1]), pack2<F16>(f[2], f[3]), pack2<F16>(f[4], f[5]),
+                          pack2<F16>(f[6], f[7]));
   }
 }
 
@@ -99,42 +146,58 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
 
 using namespace ptivae;
 
-extern "C" int ptivae_gn_stats(const void* x, float* acc, int N, int HW, int C, int G, void* stream_) {
-  if (!x || !acc || N <= 0 || HW <= 0 || C % 8 != 0 || G <= 0 || C % G != 0 || (C / G) % 2 != 0 || C / 8 > 256)
-    return PTIVAE_ERR_ARG;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  // enough blocks to fill the machine, at least 64 pixels-rows per block
+static int stats_chunks(int N, int HW, int C, int* ppb_out) {
   int chunks = (148 * 8 + N - 1) / N;
   const int prows = 256 / (C / 8);
   int ppb = (HW + chunks - 1) / chunks;
   if (ppb < prows * 4) ppb = prows * 4;
   chunks = (HW + ppb - 1) / ppb;
+  *ppb_out = ppb;
+  return chunks;
+}
+
+extern "C" int ptivae_gn_stats_parts(int N, int HW, int C) {
+  if (N <= 0 || HW <= 0 || C % 8 != 0 || C / 8 > 64 || 256 % (C / 8) != 0) return PTIVAE_ERR_ARG;
+  int ppb;
+  return stats_chunks(N, HW, C, &ppb);
+}
+
+extern "C" int ptivae_gn_stats(const void* x, float* partial, int N, int HW, int C, int G, int in_fmt,
+                               void* stream_) {
+  if (!x || !partial || N <= 0 || HW <= 0 || C % 8 != 0 || G <= 0 || C % G != 0 || (C / G) % 2 != 0 ||
+      C / 8 > 64 || 256 % (C / 8) != 0 || G > 256 || in_fmt < 0 || in_fmt > 2)
+    return PTIVAE_ERR_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int ppb;
+  const int chunks = stats_chunks(N, HW, C, &ppb);
   dim3 grid(chunks, N);
-  gn_stats_kernel<<<grid, 256, 2 * G * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x), acc, HW, C, G,
-                                                                ppb);
+  gn_stats_kernel<<<grid, 256, 0, stream>>>(x, partial, HW, C, G, ppb, in_fmt);
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int ptivae_gn_finalize(const float* acc, const float* gamma, const float* beta, float* scale_shift, int N,
-                                  int HW, int C, int G, float eps, void* stream_) {
-  if (!acc || !gamma || !beta || !scale_shift || N <= 0 || C % G != 0) return PTIVAE_ERR_ARG;
+extern "C" int ptivae_gn_finalize(const float* partial, const float* gamma, const float* beta, float* scale_shift,
+                                  int N, int HW, int C, int G, int P, float eps, void* stream_) {
+  if (!partial || !gamma || !beta || !scale_shift || N <= 0 || C % G != 0 || P <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
-  gn_finalize_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(acc, gamma, beta, scale_shift, N, C, G, inv, eps);
+  gn_finalize_kernel<<<(N * C + 127) / 128, 128, 0, stream>>>(partial, gamma, beta, scale_shift, N, C, G, P, inv, eps);
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, int N, int HW, int C, int silu,
-                               void* stream_) {
-  if (!x || !scale_shift || !y || N <= 0 || C % 8 != 0) return PTIVAE_ERR_ARG;
+extern "C" int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, void* raw16, int N, int HW, int C,
+                               int silu, int in_fmt, int out_f16, void* stream_) {
+  if (!x || !scale_shift || !y || N <= 0 || C % 8 != 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t total = static_cast<size_t>(N) * HW * (C / 8);
   const int grid = grid_for(total, 256, 148 * 32);
-  if (silu)
-    gn_apply_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), scale_shift,
-                                                    static_cast<uint4*>(y), total, HW, C);
-  else
-    gn_apply_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), scale_shift,
-                                                     static_cast<uint4*>(y), total, HW, C);
+  uint4* yy = static_cast<uint4*>(y);
+  uint4* rr = static_cast<uint4*>(raw16);
+  if (silu) {
+    if (out_f16) gn_apply_kernel<true, true><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
+    else gn_apply_kernel<true, false><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
+  } else {
+    if (out_f16) gn_apply_kernel<false, true><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
+    else gn_apply_kernel<false, false><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
+  }
   return static_cast<int>(cudaGetLastError());
 }

@@ -153,8 +153,8 @@ __global__ void l1l2_final_kernel(const float* __restrict__ partial, float* __re
 // ----------------------------------------------------------------------------- weight packing
 // out[t][co][ci] = sum over source taps selected by mask[t] (bit ky*3+kx) of w[co][ci][ky][kx]
 struct PackMasks { uint32_t m[16]; };
-__global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
-                                   int ksq, int T, PackMasks masks) {
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin,
+                                   int ksq, int T, PackMasks masks, int f16) {
   const size_t total = static_cast<size_t>(T) * Cout * Cin;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -166,7 +166,8 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const uint32_t m = masks.m[t];
     for (int s = 0; s < ksq; ++s)
       if (m & (1u << s)) a += src[s];
-    out[i] = __float2bfloat16_rn(a);
+    if (f16) out[i] = __half_as_ushort(__float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)));
+    else out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(a));
   }
 }
 
@@ -217,7 +218,8 @@ extern "C" int ptivae_l1l2(const float* a, const float* b, float* workspace, flo
 
 // mode 0: plain (T = k*k slabs, tap-major).  mode 2: the 4-phase nearest-x2-upsample decomposition
 // (T = 16 slabs ordered [py][px][ty][tx]; k must be 3).
-extern "C" int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, void* stream_) {
+extern "C" int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, int f16,
+                                       void* stream_) {
   if (!w || !out || Cout <= 0 || Cin <= 0 || !(k == 1 || k == 3) || !(mode == 0 || mode == 2)) return PTIVAE_ERR_ARG;
   if (mode == 2 && k != 3) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -246,7 +248,7 @@ extern "C" int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int 
           }
   }
   const size_t total = static_cast<size_t>(T) * Cout * Cin;
-  pack_conv_w_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), Cout, Cin, k * k,
-                                                               T, pm);
+  pack_conv_w_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, static_cast<uint16_t*>(out), Cout, Cin, k * k, T, pm,
+                                                               f16);
   return static_cast<int>(cudaGetLastError());
 }

@@ -10,6 +10,22 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
+F16 = torch.float16
+_FMT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}   # storage codes of the C ABI
+
+
+def _fmt(t: torch.Tensor) -> int:
+    try:
+        return _FMT[t.dtype]
+    except KeyError:
+        raise _lib.PtivaeError(f"unsupported storage dtype {t.dtype}") from None
+
+
+def _op16(t: torch.Tensor) -> int:
+    """f16 flag of a 16-bit GEMM operand tensor."""
+    if t.dtype not in (BF16, F16):
+        raise _lib.PtivaeError(f"GEMM operands must be float16 or bfloat16, got {t.dtype}")
+    return int(t.dtype == F16)
 
 
 def _stream() -> int:
@@ -45,80 +61,108 @@ def _need_cuda(*ts):
             raise _lib.PtivaeError("ptivae ops need CUDA tensors (there is no CPU path)")
 
 
-def pack_conv_weight(w: torch.Tensor, mode: int = 0) -> torch.Tensor:
-    """fp32 [Cout,Cin,k,k] (or Linear [out,in]) -> bf16 [T,Cout,Cin]."""
+def pack_conv_weight(w: torch.Tensor, mode: int = 0, dtype: torch.dtype = F16) -> torch.Tensor:
+    """fp32 [Cout,Cin,k,k] (or Linear [out,in]) -> 16-bit [T,Cout,Cin]."""
     _need_cuda(w)
     if w.dim() == 2:
         w = w[:, :, None, None]
     w = w.detach().contiguous().float()
     cout, cin, k, _ = w.shape
     t = 16 if mode == 2 else k * k
-    out = torch.empty((t, cout, cin), device=w.device, dtype=BF16)
-    _call("pack_conv_weight", None, 1, _lib.lib().ptivae_pack_conv_weight, _p(w), _p(out), cout, cin, k, mode, _stream())
+    out = torch.empty((t, cout, cin), device=w.device, dtype=dtype)
+    _call("pack_conv_weight", None, 1, _lib.lib().ptivae_pack_conv_weight, _p(w), _p(out), cout, cin, k, mode,
+          _op16(out), _stream())
     return out
+
+
+def conv_parts(h: int, w: int, mode: int) -> int:
+    return _lib.lib().ptivae_conv_parts(h, w, mode)
 
 
 def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode: int, residual=None,
-              gn_acc=None, gn_groups: int = 0) -> torch.Tensor:
-    """x bf16 NHWC [N,H,W,Cin] -> bf16 NHWC.  mode: 0 3x3 s1 | 1 pad+3x3 s2 | 2 up2x+3x3 | 3 1x1."""
+              gn_groups: int = 0, out_f32: bool = False):
+    """x bf16 NHWC [N,H,W,Cin] -> NHWC (bf16, or fp32 when out_f32).  mode: 0 3x3 s1 | 1 pad+3x3 s2 |
+    2 up2x+3x3 | 3 1x1.  Returns out, or (out, stats_partials [N,P,G,2]) when gn_groups > 0."""
     _need_cuda(x, w_packed, bias)
+    f16 = _op16(x)
+    if w_packed.dtype != x.dtype:
+        raise _lib.PtivaeError("activation and packed-weight operand dtypes differ")
     n, h, w, cin = x.shape
     cout = w_packed.shape[1]
     ho, wo = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
-    out = torch.empty((n, ho, wo, cout), device=x.device, dtype=BF16)
-    if residual is not None and residual.shape != out.shape:
-        raise _lib.PtivaeError("residual shape mismatch")
+    out = torch.empty((n, ho, wo, cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
+    res_f32 = 0
+    if residual is not None:
+        if residual.shape != out.shape:
+            raise _lib.PtivaeError("residual shape mismatch")
+        res_f32 = int(residual.dtype == torch.float32)
+        if not res_f32 and residual.dtype != x.dtype:
+            raise _lib.PtivaeError("16-bit residual must use the operand dtype")
+    part = None
+    if gn_groups > 0:
+        part = torch.empty((n, conv_parts(h, w, mode), gn_groups, 2), device=x.device, dtype=torch.float32)
     _call("conv_umma", (mode, n, h, w, cin, cout), 1, _lib.lib().ptivae_conv_umma, _p(x), _p(w_packed), _p(bias),
-          _p(residual), _p(out), _p(gn_acc), gn_groups if gn_acc is not None else 0, n, h, w, cin, cout, mode,
-          _stream())
-    return out
+          _p(residual), _p(out), _p(part), gn_groups, n, h, w, cin, cout, mode, int(out_f32), res_f32, f16, _stream())
+    return (out, part) if gn_groups > 0 else out
 
 
-def gn_stats(x: torch.Tensor, groups: int, acc: torch.Tensor | None = None) -> torch.Tensor:
-    _need_cuda(x)
+def _nhwc_dims(x):
     n, c = x.shape[0], x.shape[-1]
-    hw = x.numel() // (n * c)
-    if acc is None:
-        acc = torch.zeros((n, groups, 2), device=x.device, dtype=torch.float32)
-    _call("gn_stats", (n, hw, c), 1, _lib.lib().ptivae_gn_stats, _p(x), _p(acc), n, hw, c, groups, _stream())
-    return acc
+    return n, x.numel() // (n * c), c
 
 
-def gn_finalize(acc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, eps: float) -> torch.Tensor:
-    n, g, _ = acc.shape
+def gn_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
+    """-> partial statistics [N,P,G,2] (deterministic; feed to gn_finalize)."""
+    _need_cuda(x)
+    n, hw, c = _nhwc_dims(x)
+    parts = _lib.lib().ptivae_gn_stats_parts(n, hw, c)
+    _lib.check(min(parts, 0), "gn_stats_parts")
+    part = torch.empty((n, parts, groups, 2), device=x.device, dtype=torch.float32)
+    _call("gn_stats", (n, hw, c, x.element_size()), 1, _lib.lib().ptivae_gn_stats, _p(x), _p(part), n, hw, c, groups,
+          _fmt(x), _stream())
+    return part
+
+
+def gn_finalize(part: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, eps: float) -> torch.Tensor:
+    n, parts, g, _ = part.shape
     c = gamma.numel()
-    ss = torch.empty((n, c, 2), device=acc.device, dtype=torch.float32)
-    _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(acc), _p(gamma), _p(beta), _p(ss), n, hw, c, g, float(eps),
-                                             _stream())
+    ss = torch.empty((n, c, 2), device=part.device, dtype=torch.float32)
+    _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(part), _p(gamma), _p(beta), _p(ss), n, hw, c, g,
+          parts, float(eps), _stream())
     return ss
 
 
-def gn_apply(x: torch.Tensor, scale_shift: torch.Tensor, silu: bool) -> torch.Tensor:
-    n, c = x.shape[0], x.shape[-1]
-    hw = x.numel() // (n * c)
-    y = torch.empty_like(x)
-    _call("gn_apply", (n, hw, c), 1, _lib.lib().ptivae_gn_apply, _p(x), _p(scale_shift), _p(y), n, hw, c, int(silu), _stream())
-    return y
+def gn_apply(x: torch.Tensor, scale_shift: torch.Tensor, silu: bool, emit_raw: bool = False,
+             dtype: torch.dtype | None = None):
+    """x NHWC (any storage) -> 16-bit operand y (and, if emit_raw, x rounded to that dtype)."""
+    n, hw, c = _nhwc_dims(x)
+    dtype = dtype or (x.dtype if x.dtype != torch.float32 else F16)
+    y = torch.empty(x.shape, device=x.device, dtype=dtype)
+    raw = torch.empty(x.shape, device=x.device, dtype=dtype) if emit_raw else None
+    _call("gn_apply", (n, hw, c, x.element_size(), int(emit_raw)), 1, _lib.lib().ptivae_gn_apply, _p(x),
+          _p(scale_shift), _p(y), _p(raw), n, hw, c, int(silu), _fmt(x), _op16(y), _stream())
+    return (y, raw) if emit_raw else y
 
 
-def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """fp32 NCHW -> bf16 NHWC."""
+def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """fp32 NCHW -> NHWC stored as `dtype` (fp32 stream, or a 16-bit operand)."""
     _need_cuda(x, w, b)
     n, cin, h, wd = x.shape
     cout = w.shape[0]
-    out = torch.empty((n, h, wd, cout), device=x.device, dtype=BF16)
-    _call("conv3x3_small_cin", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x), _p(w), _p(b), _p(out), n, h, wd, cin, cout, _stream())
+    out = torch.empty((n, h, wd, cout), device=x.device, dtype=dtype)
+    _call("conv3x3_small_cin", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x), _p(w), _p(b),
+          _p(out), n, h, wd, cin, cout, _fmt(out), _stream())
     return out
 
 
 def conv3x3_small_cout(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, scale_shift=None) -> torch.Tensor:
-    """bf16 NHWC (+ fused GroupNorm affine) -> fp32 NCHW."""
+    """NHWC bf16|fp32 (+ fused GroupNorm affine) -> fp32 NCHW."""
     _need_cuda(x, w, b)
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     out = torch.empty((n, cout, h, wd), device=x.device, dtype=torch.float32)
-    _call("conv3x3_small_cout", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cout, _p(x), _p(w), _p(b), _p(scale_shift), _p(out), n, h, wd, cin,
-                                                    cout, _stream())
+    _call("conv3x3_small_cout", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cout, _p(x), _p(w), _p(b),
+          _p(scale_shift), _p(out), n, h, wd, cin, cout, _fmt(x), _stream())
     return out
 
 
@@ -137,7 +181,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor
     _need_cuda(q, k, v)
     b, l, d = q.shape
     out = torch.empty_like(q)
-    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), b, l, d, _stream())
+    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), b, l, d,
+          _op16(q), _stream())
     return out
 
 

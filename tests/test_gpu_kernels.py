@@ -1,7 +1,8 @@
 """Per-kernel parity on the GPU: every C-ABI entry point vs. a plain PyTorch fp32 statement of the same
-operator on identical (bf16-rounded) inputs.  Tolerances are written next to each check:
-  * bf16-output kernels: the result must sit within ~1 bf16 ulp of the fp32 reference
-    (rel-L2 <= 3e-3, and max-abs <= 2^-7 * max|ref|);
+operator on identical (16-bit-rounded) inputs, for both operand formats (fp16 = default, bf16).
+Tolerances are written next to each check:
+  * 16-bit-output kernels: the result must sit within ~1 ulp of the fp32 reference
+    (bf16: rel-L2 <= 3e-3, max-abs <= 2^-7 * max|ref|; fp16: 8x tighter);
   * fp32-accumulate / fp32-output kernels: max-abs <= 1e-4 relative to the reference scale.
 """
 import math
@@ -20,6 +21,8 @@ def _rel_l2(a, b):
 
 
 def _check_bf16(out, ref, what, rel=3e-3, ulp=2.0 ** -7):
+    if out.dtype == torch.float16:  # 11-bit significand instead of 8
+        rel, ulp = rel / 8, ulp / 8
     out, ref = out.float(), ref.float()
     assert torch.isfinite(out).all(), f"{what}: non-finite output"
     r = _rel_l2(out, ref)
@@ -29,16 +32,27 @@ def _check_bf16(out, ref, what, rel=3e-3, ulp=2.0 ** -7):
     assert mx <= ulp * scale + 1e-6, f"{what}: max-abs {mx:.3e} vs scale {scale:.3e}"
 
 
+DT = torch.float16  # operand format under test; the fixture below switches it
+
+
+@pytest.fixture(params=[torch.float16, torch.bfloat16], ids=["fp16", "bf16"], autouse=True)
+def _operand_dtype(request):
+    global DT
+    DT = request.param
+    yield
+    DT = torch.float16
+
+
 def _rand_act(n, h, w, c, seed):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    return torch.randn(n, h, w, c, generator=g).to(DEV).bfloat16()
+    return torch.randn(n, h, w, c, generator=g).to(DEV).to(DT)
 
 
 def _rand_conv(cout, cin, k, seed):
     g = torch.Generator(device="cpu").manual_seed(seed)
     w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(DEV)
     b = (torch.randn(cout, generator=g) * 0.1).to(DEV)
-    return w.bfloat16().float(), b  # weights exactly representable in bf16
+    return w.to(DT).float(), b  # weights exactly representable in the operand format
 
 
 def _ref_conv(x_nhwc, w, b, mode):
@@ -64,19 +78,20 @@ def _fp32_reference_math():
 
 def test_pack_weights(b200):
     w, _ = _rand_conv(64, 32, 3, 1)
-    p = b200.ops.pack_conv_weight(w, 0)
+    p = b200.ops.pack_conv_weight(w, 0, DT)
+    assert p.dtype == DT
     ref = w.permute(2, 3, 0, 1).reshape(9, 64, 32)
     assert torch.equal(p.float(), ref)
-    p2 = b200.ops.pack_conv_weight(w, 2).float().view(2, 2, 2, 2, 64, 32)
+    p2 = b200.ops.pack_conv_weight(w, 2, DT).float().view(2, 2, 2, 2, 64, 32)
     rows = {0: [[0], [1, 2]], 1: [[0, 1], [2]]}
     for py in range(2):
         for px in range(2):
             for ty in range(2):
                 for tx in range(2):
                     s = sum(w[:, :, ky, kx] for ky in rows[py][ty] for kx in rows[px][tx])
-                    assert torch.equal(p2[py, px, ty, tx], s.bfloat16().float())
-    lin = torch.randn(128, 128, device=DEV).bfloat16().float()
-    assert torch.equal(b200.ops.pack_conv_weight(lin, 0).float()[0], lin)
+                    assert torch.equal(p2[py, px, ty, tx], s.to(DT).float())
+    lin = torch.randn(128, 128, device=DEV).to(DT).float()
+    assert torch.equal(b200.ops.pack_conv_weight(lin, 0, DT).float()[0], lin)
 
 
 CONV_CASES = [
@@ -113,8 +128,9 @@ def test_conv_umma(b200, mode, n, h, w, cin, cout):
     x = _rand_act(n, h, w, cin, 10 + mode)
     k = 1 if mode == 3 else 3
     wt, bias = _rand_conv(cout, cin, k, 20 + cin + cout)
-    wp = b200.ops.pack_conv_weight(wt, 2 if mode == 2 else 0)
+    wp = b200.ops.pack_conv_weight(wt, 2 if mode == 2 else 0, DT)
     out = b200.ops.conv_umma(x, wp, bias, mode)
+    assert out.dtype == DT
     ref = _ref_conv(x, wt, bias, mode)
     assert out.shape == ref.shape
     # mode 2 pre-sums bf16 weights (one extra rounding per weight) -> slightly looser
@@ -122,38 +138,68 @@ def test_conv_umma(b200, mode, n, h, w, cin, cout):
                 ulp=2.0 ** -6 if mode == 2 else 2.0 ** -7)
 
 
-@pytest.mark.parametrize("cin,cout,groups", [(128, 128, 16), (64, 64, 16), (32, 32, 16), (64, 128, 32), (256, 256, 32)])
-def test_conv_umma_residual_and_stats(b200, cin, cout, groups):
+@pytest.mark.parametrize("cin,cout,groups,out_f32,res_f32", [(128, 128, 16, True, True), (64, 64, 16, False, False),
+                                                             (32, 32, 16, True, True), (64, 128, 32, True, False),
+                                                             (256, 256, 32, False, True)])
+def test_conv_umma_residual_and_stats(b200, cin, cout, groups, out_f32, res_f32):
     n, h, w = 2, 24, 24
     x = _rand_act(n, h, w, cin, 3)
     res = _rand_act(n, h, w, cout, 4)
+    if res_f32:
+        res = res.float() + 1e-3 * torch.randn(n, h, w, cout, device=DEV)
     wt, bias = _rand_conv(cout, cin, 3, 5)
-    acc = torch.zeros(n, groups, 2, device=DEV)
-    out = b200.ops.conv_umma(x, b200.ops.pack_conv_weight(wt), bias, 0, residual=res, gn_acc=acc, gn_groups=groups)
+    out, part = b200.ops.conv_umma(x, b200.ops.pack_conv_weight(wt, 0, DT), bias, 0, residual=res, gn_groups=groups,
+                                   out_f32=out_f32)
     ref = _ref_conv(x, wt, bias, 0) + res.float()
-    _check_bf16(out, ref, "conv+residual")
-    # statistics are those of the bf16 tensor that was written
+    assert out.dtype == (torch.float32 if out_f32 else DT)
+    if out_f32:  # fp32 accumulate + fp32 store: max-abs <= 1e-4 of the output scale
+        assert float((out - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    else:
+        _check_bf16(out, ref, "conv+residual")
+    # statistics are those of the tensor that was written; partials summed in fixed order
+    assert part.shape == (n, b200.ops.conv_parts(h, w, 0), groups, 2)
+    acc = part.sum(dim=1)
     o = out.float().view(n, h * w, groups, cout // groups)
     s = o.sum(dim=(1, 3))
     q = (o * o).sum(dim=(1, 3))
     assert torch.allclose(acc[..., 0], s, rtol=1e-4, atol=1e-2), float((acc[..., 0] - s).abs().max())
     assert torch.allclose(acc[..., 1], q, rtol=1e-4, atol=1e-2), float((acc[..., 1] - q).abs().max())
+    out2, part2 = b200.ops.conv_umma(x, b200.ops.pack_conv_weight(wt, 0, DT), bias, 0, residual=res, gn_groups=groups,
+                                     out_f32=out_f32)
+    assert torch.equal(out, out2) and torch.equal(part, part2), "conv + statistics must be run-to-run deterministic"
 
 
-@pytest.mark.parametrize("n,h,w,c,groups,silu", [(2, 32, 32, 128, 16, True), (2, 64, 64, 32, 16, True),
-                                                 (1, 48, 16, 64, 16, False), (2, 16, 16, 256, 32, True),
-                                                 (1, 8, 8, 64, 32, True)])
-def test_groupnorm(b200, n, h, w, c, groups, silu):
-    x = (_rand_act(n, h, w, c, 7).float() * 1.7 + 0.3).bfloat16()
+@pytest.mark.parametrize("mode,h,w,c", [(1, 32, 32, 64), (2, 16, 16, 128)])
+def test_conv_umma_stats_strided_modes(b200, mode, h, w, c):
+    x = _rand_act(2, h, w, c, 8)
+    wt, bias = _rand_conv(c, c, 3, 9)
+    out, part = b200.ops.conv_umma(x, b200.ops.pack_conv_weight(wt, 2 if mode == 2 else 0, DT), bias, mode, gn_groups=16,
+                                   out_f32=True)
+    assert part.shape[1] == b200.ops.conv_parts(h, w, mode)
+    o = out.view(2, -1, 16, c // 16)
+    assert torch.allclose(part.sum(1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(part.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("n,h,w,c,groups,silu,f32", [(2, 32, 32, 128, 16, True, True), (2, 64, 64, 32, 16, True, False),
+                                                     (1, 48, 16, 64, 16, False, True), (2, 16, 16, 256, 32, True, False),
+                                                     (1, 8, 8, 64, 32, True, True), (3, 40, 24, 128, 32, True, True)])
+def test_groupnorm(b200, n, h, w, c, groups, silu, f32):
+    x = (_rand_act(n, h, w, c, 7).float() * 1.7 + 0.3)
+    x = x + 1e-3 * torch.randn_like(x) if f32 else x.to(DT)
     gamma = torch.randn(c, device=DEV) * 0.5 + 1.0
     beta = torch.randn(c, device=DEV) * 0.2
     eps = 1e-6
-    acc = b200.ops.gn_stats(x, groups)
+    part = b200.ops.gn_stats(x, groups)
+    assert torch.equal(part, b200.ops.gn_stats(x, groups)), "statistics must be deterministic"
+    acc = part.sum(dim=1)
     xf = x.float().view(n, h * w, groups, c // groups)
     assert torch.allclose(acc[..., 0], xf.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(acc[..., 1], (xf * xf).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
-    ss = b200.ops.gn_finalize(acc, gamma, beta, h * w, eps)
-    y = b200.ops.gn_apply(x, ss, silu)
+    ss = b200.ops.gn_finalize(part, gamma, beta, h * w, eps)
+    y, raw = b200.ops.gn_apply(x, ss, silu, emit_raw=True, dtype=DT)
+    assert torch.equal(raw, x.to(DT)) and y.dtype == DT
+    assert torch.equal(y, b200.ops.gn_apply(x, ss, silu, dtype=DT))
     ref = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma, beta, eps)
     if silu:
         ref = F.silu(ref)
@@ -173,16 +219,20 @@ def test_groupnorm(b200, n, h, w, c, groups, silu):
 def test_conv_small_cin(b200, n, cin, cout, h, w):
     x = torch.randn(n, cin, h, w, device=DEV)
     wt, bias = _rand_conv(cout, cin, 3, 9)
-    out = b200.ops.conv3x3_small_cin(x, wt, bias)
+    out = b200.ops.conv3x3_small_cin(x, wt, bias, dtype=DT)
     ref = F.conv2d(x, wt, bias, padding=1).permute(0, 2, 3, 1)
     _check_bf16(out, ref, "small_cin")
+    out32 = b200.ops.conv3x3_small_cin(x, wt, bias)
+    assert float((out32 - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("n,cin,cout,h,w,norm", [(2, 32, 1, 64, 64, True), (1, 64, 1, 32, 32, True),
-                                                 (2, 128, 4, 16, 16, True), (1, 256, 10, 8, 8, True),
-                                                 (1, 32, 1, 16, 16, False)])
-def test_conv_small_cout(b200, n, cin, cout, h, w, norm):
+@pytest.mark.parametrize("n,cin,cout,h,w,norm,f32", [(2, 32, 1, 64, 64, True, True), (1, 64, 1, 32, 32, True, False),
+                                                     (2, 128, 4, 16, 16, True, True), (1, 256, 10, 8, 8, True, True),
+                                                     (1, 32, 1, 16, 16, False, False)])
+def test_conv_small_cout(b200, n, cin, cout, h, w, norm, f32):
     x = _rand_act(n, h, w, cin, 11)
+    if f32:
+        x = x.float() + 1e-3 * torch.randn(n, h, w, cin, device=DEV)
     wt, bias = _rand_conv(cout, cin, 3, 12)
     ss = None
     xin = x.float().permute(0, 3, 1, 2)
@@ -211,11 +261,11 @@ def test_conv1x1_small_and_sigma(b200):
                                    (1, 200, 256), (2, 256, 64)])
 def test_attention(b200, b, l, d):
     g = torch.Generator().manual_seed(l + d)
-    q, k, v = [(torch.randn(b, l, d, generator=g) * s).to(DEV).bfloat16() for s in (1.0, 1.0, 1.0)]
+    q, k, v = [(torch.randn(b, l, d, generator=g) * s).to(DEV).to(DT) for s in (1.0, 1.0, 1.0)]
     out = b200.ops.attention(q, k, v)
     att = torch.softmax(torch.einsum("bxd,byd->bxy", q.float(), k.float()) * d ** -0.5, dim=-1)
     ref = torch.einsum("bxy,byd->bxd", att, v.float())
-    # P is rounded to bf16 before PV: allow 2 bf16 ulps of the output scale
+    # P is rounded to 16 bit before PV: allow 2 ulps of the output scale
     _check_bf16(out, ref, f"attention L={l} d={d}", rel=6e-3, ulp=2.0 ** -6)
 
 
@@ -223,9 +273,9 @@ def test_attention_peaked(b200):
     # large-magnitude scores exercise the online-softmax rescaling across key blocks
     b, l, d = 1, 512, 128
     g = torch.Generator().manual_seed(5)
-    q = (torch.randn(b, l, d, generator=g) * 4).to(DEV).bfloat16()
-    k = (torch.randn(b, l, d, generator=g) * 4).to(DEV).bfloat16()
-    v = torch.randn(b, l, d, generator=g).to(DEV).bfloat16()
+    q = (torch.randn(b, l, d, generator=g) * 4).to(DEV).to(DT)
+    k = (torch.randn(b, l, d, generator=g) * 4).to(DEV).to(DT)
+    v = torch.randn(b, l, d, generator=g).to(DEV).to(DT)
     out = b200.ops.attention(q, k, v)
     att = torch.softmax(torch.einsum("bxd,byd->bxy", q.float(), k.float()) * d ** -0.5, dim=-1)
     ref = torch.einsum("bxy,byd->bxd", att, v.float())
