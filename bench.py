@@ -142,11 +142,16 @@ def classify(name, meta):
         byt = 2.0 * n * (h * w * cin + ho * wo * cout) + 2.0 * taps * cin * cout
         return (f"conv{'3x3' if taps == 9 else '1x1'}_m{mode}_{cin}->{cout}@{h}x{w}", flops, byt)
     if name in ("gn_stats",):
-        n, hw, c = meta
-        return (f"gn_stats_c{c}@{hw}", 0.0, 2.0 * n * hw * c)
+        n, hw, c, esz = meta
+        return (f"gn_stats_c{c}@{hw}", 0.0, float(esz) * n * hw * c)
     if name == "gn_apply":
-        n, hw, c = meta
-        return (f"gn_apply_c{c}@{hw}", 0.0, 4.0 * n * hw * c)
+        n, hw, c, esz, raw = meta
+        return (f"gn_apply_c{c}@{hw}", 0.0, (esz + 2.0 + 2.0 * raw) * n * hw * c)
+    if name == "conv3x3_fused":
+        n, h, w, cin, cout, in_esz, out_esz, res_esz = meta
+        flops = 2.0 * n * h * w * cout * cin * 9
+        byt = n * h * w * (in_esz * cin + (out_esz + res_esz) * cout) + 2.0 * 9 * cin * cout
+        return (f"fused3x3_{cin}->{cout}@{h}x{w}", flops, byt)
     if name == "conv3x3_small_cin":
         n, h, w, cin, cout = meta
         return (f"small_cin_{cin}->{cout}@{h}x{w}", 2.0 * n * h * w * cin * cout * 9, n * h * w * (4.0 * cin + 2.0 * cout))

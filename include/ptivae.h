@@ -41,16 +41,37 @@ int ptivae_abi_version(void);
  *   bias      fp32 [Cout]
  *   residual  same shape as out, h16 (res_f32 = 0) or fp32 (res_f32 = 1), added in the epilogue; may be NULL
  *   out       [N][Hout][Wout][Cout], h16 (out_f32 = 0) or fp32 (out_f32 = 1: the residual stream)
+ *   out16     optional (NULL ok): when out is fp32, an additional h16 copy of it (the operand a following
+ *             nin_shortcut 1x1 conv reads)
  *   gn_part   fp32 [N][P][gn_groups][2]: per-tile (sum, sum of squares) of the stored output, P =
  *             ptivae_conv_parts(H, W, mode); plain stores, fixed order (deterministic); ignored when
  *             gn_groups == 0.  Feed to ptivae_gn_finalize(..., P, ...).
  *   mode      0: 3x3 stride 1 pad 1 (Hout=H)      1: pad right/bottom + 3x3 stride 2 (Hout=H/2, H,W even)
  *             2: nearest x2 upsample + 3x3 pad 1 (Hout=2H)   3: 1x1 */
 int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual, void* out,
-                     float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int mode, int out_f32,
+                     void* out16, float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int mode, int out_f32,
                      int res_f32, int f16, void* stream);
 /* number of statistics partials per image that ptivae_conv_umma writes for this shape */
 int ptivae_conv_parts(int H, int W, int mode);
+
+/* Fused ResBlock convolution: out = conv3x3_s1_p1( act(x*scale + shift) ) + bias (+ residual), tcgen05,
+ * halo-resident: the normalised tensor never exists in HBM and every input byte is read once per tile.
+ *   replaces: AEKLResBlock's  conv1(F.silu(norm1(x)))  and  conv2(F.silu(norm2(h))) + shortcut  pairs
+ *             (monai 1.5.1 networks/nets/autoencoderkl.py AEKLResBlock.forward; via autoencoder.py:114).
+ *   x           NHWC [N][H][W][Cin], storage in_fmt (fp32 stream or the h16 operand format)
+ *   scale_shift fp32 [N][Cin][2] from ptivae_gn_finalize, or NULL (identity prologue); silu != 0 -> SiLU.
+ *               Zero padding is applied AFTER the normalisation, as nn.Conv2d(padding=1) does.
+ *   w_packed    h16 [9][Cout][Cin]; Cin, Cout in {32, 64, 128}
+ *   residual/out/gn_part: as ptivae_conv_umma, with P = ptivae_conv3x3_fused_parts(H, W) (16x16 tiles).
+ *   desc_base_offset: 1 = encode (start>>7)&7 in the shifted operand descriptors' base-offset field. */
+int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, int silu, const void* w_packed,
+                         const float* bias, const void* residual, int res_f32, void* out, int out_f32,
+                         float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,
+                         int desc_base_offset, void* stream);
+int ptivae_conv3x3_fused_parts(int H, int W);
+/* debug only: device buffer (64*32 uint64) that receives CTA 0's per-role clock64 timeline of subsequent
+ * ptivae_conv3x3_fused launches; NULL switches tracing off. */
+int ptivae_debug_set_trace(void* buf);
 
 /* fp32 master weights [Cout][Cin][k][k] -> h16 UMMA operand [T][Cout][Cin].
  *   mode 0: T = k*k (k in {1,3}); mode 2: T = 16, the 4-phase x (2x2)-tap decomposition of

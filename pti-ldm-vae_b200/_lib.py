@@ -19,8 +19,12 @@ _c_ll, _c_ull = ctypes.c_longlong, ctypes.c_ulonglong
 # symbol -> argtypes ; must list every function include/ptivae.h declares (tests check this)
 SIGNATURES = {
     "ptivae_abi_version": [],
-    "ptivae_conv_umma": [_c_void_p] * 6 + [_c_int] * 10 + [_c_void_p],
+    "ptivae_conv_umma": [_c_void_p] * 7 + [_c_int] * 10 + [_c_void_p],
     "ptivae_conv_parts": [_c_int] * 3,
+    "ptivae_conv3x3_fused": [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
+                             _c_int, _c_void_p] + [_c_int] * 8 + [_c_void_p],
+    "ptivae_conv3x3_fused_parts": [_c_int] * 2,
+    "ptivae_debug_set_trace": [_c_void_p],
     "ptivae_pack_conv_weight": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats_parts": [_c_int] * 3,

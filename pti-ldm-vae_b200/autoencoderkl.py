@@ -125,26 +125,34 @@ def _decoder(channels, cin, cout, nres, groups, eps, attn_levels, nonlocal_attn)
 # executor
 # ---------------------------------------------------------------------------------------------
 class _Act:
-    """NHWC activation (fp32 residual stream, or bf16 GEMM operand) + the GroupNorm statistics
-    partials [N,P,G,2] its producer wrote, if any."""
-    __slots__ = ("t", "part")
+    """NHWC activation (fp32 residual stream, or 16-bit GEMM operand), the GroupNorm statistics
+    partials [N,P,G,2] its producer wrote (if any), and an optional 16-bit copy of an fp32 tensor."""
+    __slots__ = ("t", "part", "raw16")
 
-    def __init__(self, t, part=None):
-        self.t, self.part = t, part
+    def __init__(self, t, part=None, raw16=None):
+        self.t, self.part, self.raw16 = t, part, raw16
+
+
+_FUSED_WIDTHS = (32, 64, 128)
 
 
 class _Executor:
     """Schedules one encoder / decoder stack.  Precision plan: block outputs (the residual stream) are
     fp32; everything a tensor-core GEMM reads (normalised activations, raw operands of the
     down/up-sampling and shortcut convs, q/k/v, packed weights) is 16-bit -- fp16 by default, bf16 on
-    request (AutoencoderKL.set_operand_dtype) -- and accumulation is fp32."""
+    request (AutoencoderKL.set_operand_dtype) -- and accumulation is fp32.
+
+    ResBlock convolutions run as ONE kernel each (GroupNorm affine + SiLU prologue, conv, bias,
+    residual, next-norm statistics): ops.conv3x3_fused.  Widths without a fused instantiation (256+)
+    take the unfused route gn_apply -> conv_umma."""
 
     def __init__(self, groups: int, eps: float, fused_stats: bool = True, operand_dtype=torch.float16):
         self.groups, self.eps, self.fused_stats = groups, eps, fused_stats
         self.op_dtype = operand_dtype
+        self.fused_conv = True
         self._packed: dict = {}
 
-    # -- weights: bf16 UMMA operands cached until the fp32 master changes (optimizer step, load_state_dict, .to())
+    # -- weights: 16-bit UMMA operands cached until the fp32 master changes (optimizer step, load_state_dict, .to())
     def packed(self, w: torch.Tensor, mode: int = 0) -> torch.Tensor:
         key = (id(w), mode)
         ver = (w.data_ptr(), w._version, w.device, self.op_dtype)
@@ -158,14 +166,39 @@ class _Executor:
     def f32(p: torch.Tensor) -> torch.Tensor:
         return p.detach()
 
+    def _want_stats(self, cout: int, stats: bool) -> int:
+        g = self.groups
+        ok = stats and self.fused_stats and cout % g == 0 and 32 % (cout // g) == 0 and cout // g >= 2
+        return g if ok else 0
+
     def conv(self, x: torch.Tensor, conv: nn.Module, mode: int, residual=None, stats: bool = True,
-             out_f32: bool = False) -> _Act:
+             out_f32: bool = False, emit16: bool = False) -> _Act:
         w = conv.weight
-        cout, g = w.shape[0], self.groups
-        want = stats and self.fused_stats and cout % g == 0 and 32 % (cout // g) == 0 and cout // g >= 2
+        g = self._want_stats(w.shape[0], stats)
         r = ops.conv_umma(x, self.packed(w, 2 if mode == 2 else 0), self.f32(conv.bias), mode, residual=residual,
-                          gn_groups=g if want else 0, out_f32=out_f32)
-        return _Act(*r) if want else _Act(r)
+                          gn_groups=g, out_f32=out_f32, emit16=emit16)
+        if not isinstance(r, tuple):
+            return _Act(r)
+        out = r[0]
+        part = r[1] if g else None
+        raw16 = r[-1] if emit16 else None
+        return _Act(out, part, raw16)
+
+    def norm_conv3x3(self, a: _Act, norm: nn.GroupNorm, conv: nn.Module, residual=None, stats: bool = True,
+                     out_f32: bool = False) -> _Act:
+        """conv3x3(silu(norm(a))) + bias (+ residual)."""
+        ss = self.scale_shift(a, norm)
+        w = conv.weight
+        cout, cin = w.shape[0], w.shape[1]
+        g = self._want_stats(cout, stats)
+        if self.fused_conv and cin in _FUSED_WIDTHS and cout in _FUSED_WIDTHS:
+            r = ops.conv3x3_fused(a.t, ss, True, self.packed(w), self.f32(conv.bias), residual=residual, gn_groups=g,
+                                  out_f32=out_f32)
+        else:
+            y = ops.gn_apply(a.t, ss, silu=True, dtype=self.op_dtype)
+            r = ops.conv_umma(y, self.packed(w), self.f32(conv.bias), 0, residual=residual, gn_groups=g,
+                              out_f32=out_f32)
+        return _Act(*r) if g else _Act(r)
 
     def scale_shift(self, a: _Act, norm: nn.GroupNorm) -> torch.Tensor:
         part = a.part if a.part is not None else ops.gn_stats(a.t, norm.num_groups)
@@ -173,16 +206,16 @@ class _Executor:
         return ops.gn_finalize(part, self.f32(norm.weight), self.f32(norm.bias), a.t.numel() // (n * c), norm.eps)
 
     def resblock(self, blk: AEKLResBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
-        has_sc = isinstance(blk.nin_shortcut, Convolution)
-        ss1 = self.scale_shift(a, blk.norm1)
-        if has_sc:
-            y, raw = ops.gn_apply(a.t, ss1, silu=True, emit_raw=True, dtype=self.op_dtype)
+        sc = a.t
+        if isinstance(blk.nin_shortcut, Convolution):
+            raw = a.raw16
+            if raw is None:  # producer did not leave a 16-bit copy: make one (identity affine is not needed:
+                # gn_apply's second output is the raw input rounded to the operand format)
+                _, raw = ops.gn_apply(a.t, self.scale_shift(a, blk.norm1), silu=True, emit_raw=True,
+                                      dtype=self.op_dtype)
             sc = self.conv(raw, blk.nin_shortcut.conv, 3, stats=False, out_f32=True).t
-        else:
-            y, sc = ops.gn_apply(a.t, ss1, silu=True, dtype=self.op_dtype), a.t
-        h = self.conv(y, blk.conv1.conv, 0)                      # 16-bit: only norm2 reads it
-        y2 = ops.gn_apply(h.t, self.scale_shift(h, blk.norm2), silu=True, dtype=self.op_dtype)
-        return self.conv(y2, blk.conv2.conv, 0, residual=sc, stats=stats, out_f32=out_f32)
+        h = self.norm_conv3x3(a, blk.norm1, blk.conv1.conv)              # 16-bit: only norm2 reads it
+        return self.norm_conv3x3(h, blk.norm2, blk.conv2.conv, residual=sc, stats=stats, out_f32=out_f32)
 
     def attention(self, blk: SpatialAttentionBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
         xn = ops.gn_apply(a.t, self.scale_shift(a, blk.norm), silu=False, dtype=self.op_dtype)
@@ -201,6 +234,9 @@ class _Executor:
         def operand_only(i):  # the tensor produced by body[i-1] is read ONLY as a conv operand by body[i]
             return i < len(body) and isinstance(body[i], (AEKLDownsample, UpSample))
 
+        def needs_raw16(i):   # body[i] is a ResBlock with a 1x1 shortcut: it wants a 16-bit copy of its input
+            return i < len(body) and isinstance(body[i], AEKLResBlock) and isinstance(body[i].nin_shortcut, Convolution)
+
         a = _Act(ops.conv3x3_small_cin(x, self.f32(first.conv.weight), self.f32(first.conv.bias),
                                        dtype=self.op_dtype if operand_only(0) else torch.float32))
         for i, blk in enumerate(body):
@@ -214,7 +250,7 @@ class _Executor:
                 assert xin.dtype == self.op_dtype, "scheduler bug: down/up-sample operand must be 16-bit"
                 conv = blk.conv.conv if isinstance(blk, AEKLDownsample) else blk.postconv.conv
                 a = self.conv(xin, conv, 1 if isinstance(blk, AEKLDownsample) else 2, out_f32=not nxt_operand,
-                              stats=not nxt_operand)
+                              stats=not nxt_operand, emit16=(not nxt_operand) and needs_raw16(i + 1))
             else:  # pragma: no cover
                 raise TypeError(f"unexpected block {type(blk)}")
         ss = self.scale_shift(a, last_norm)
@@ -283,6 +319,10 @@ class AutoencoderKL(nn.Module):
         if dtype not in (torch.float16, torch.bfloat16):
             raise ValueError("operand dtype must be torch.float16 or torch.bfloat16")
         self._exec.op_dtype = dtype
+
+    def set_fused_conv(self, enabled: bool) -> None:
+        """ResBlock convs as one fused kernel (default) vs. gn_apply + conv_umma."""
+        self._exec.fused_conv = bool(enabled)
 
     def set_fused_stats(self, enabled: bool) -> None:
         """GroupNorm statistics from the producing conv's epilogue (default) vs. a separate pass."""

@@ -47,16 +47,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug traps instead of hanging the GPU box (a hang costs a strike).
+// try_wait carries a suspend-time hint, so a waiting warp SLEEPS until the phase flips (or ~1 ms passes)
+// instead of spinning: the first profile of the fused conv spent 30 % of all issue slots in these loops.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < 4096u; ++it) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(1000000u)
         : "memory");
     if (done) return;
   }
@@ -92,6 +94,12 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3), "r"(c4)
       : "memory");
+}
+
+// Bulk L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16):
+// one instruction pulls a whole halo row HBM -> L2, so the later register loads see L2 latency.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
@@ -153,6 +161,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// Same, with the 64-bit descriptors passed as (lo, hi) halves: the hi halves (LBO/SBO/version/layout) are
+// loop invariants and the lo half is `(addr >> 4) | (lbo << 16)`, so walking K or the taps is ONE 32-bit
+// add per operand instead of rebuilding the descriptor -- the single issuing thread is latency bound.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes = 16) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (lane i <-> TMEM lane base+i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -193,10 +222,9 @@ __device__ __forceinline__ float bf16hi_f(uint32_t v) { return __uint_as_float(v
 template <bool F16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   if constexpr (F16) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;  // one F2FP.SATFINITE: round to nearest, +-inf/overflow clamp to +-65504
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   } else {
     return pack_bf16x2(lo, hi);
   }
@@ -215,7 +243,11 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
 // value after a round trip through the 16-bit format (what a consumer will read back)
 template <bool F16>
 __device__ __forceinline__ float round16(float x) {
-  if constexpr (F16) return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)));
+  if constexpr (F16) {
+    float lo, hi;
+    unpack2<true>(pack2<true>(x, 0.f), lo, hi);
+    return lo;
+  }
   else return __bfloat162float(__float2bfloat16_rn(x));
 }
 

@@ -10,12 +10,15 @@
 
 namespace ptivae {
 
-// thread -> (pixel, 8 consecutive output channels).  Weights staged in smem as [tap][ci][Cout].
+constexpr int kSmallRows = 16;  // image rows walked by one block of the direct kernels
+
+// grid (x-chunks, H / kSmallRows, N): thread -> (x, 8 consecutive output channels); 32-bit index math only.
+// Weights staged in smem as [tap][ci][Cout].
 __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __restrict__ x,
                                                                 const float* __restrict__ w,  // [Cout][Cin][3][3]
                                                                 const float* __restrict__ bias,
-                                                                void* __restrict__ out, int N, int H, int W,
-                                                                int Cin, int Cout, int out_fmt) {
+                                                                void* __restrict__ out, int H, int W, int Cin,
+                                                                int Cout, int out_fmt) {
   extern __shared__ float sw[];  // [9*Cin][Cout] then bias [Cout]
   float* sb = sw + 9 * Cin * Cout;
   for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
@@ -27,60 +30,65 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   const int vecs = Cout / 8;
-  const size_t total = static_cast<size_t>(N) * H * W * vecs;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int px = i / vecs, v = i - px * vecs;
+  if (px >= W) return;
+  const int n = blockIdx.z;
   const size_t plane = static_cast<size_t>(H) * W;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % vecs);
-    const size_t pix = i / vecs;
-    const int px = static_cast<int>(pix % W);
-    const int py = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / plane);
-    float acc[8];
+  // one block walks kSmallRows consecutive rows: the weight staging above and its global latency are paid
+  // once per 16 rows, and two of the three input rows of every step are L1 hits
+  for (int py = blockIdx.y * kSmallRows; py < min(H, (blockIdx.y + 1) * kSmallRows); ++py) {
+  float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[v * 8 + j];
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * plane;
+  for (int j = 0; j < 8; ++j) acc[j] = sb[v * 8 + j];
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * plane;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = py + ky - 1;
-        if (yy < 0 || yy >= H) continue;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= H) continue;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = px + kx - 1;
-          if (xx < 0 || xx >= W) continue;
-          const float xv = __ldg(xp + static_cast<size_t>(yy) * W + xx);
-          const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * Cin + ci) * Cout + v * 8);
-          const float4 w0 = wp[0], w1 = wp[1];
-          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
-        }
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float xv = __ldg(xp + yy * W + xx);
+        const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * Cin + ci) * Cout + v * 8);
+        const float4 w0 = wp[0], w1 = wp[1];
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
       }
     }
-    if (out_fmt == 2) {
-      reinterpret_cast<float4*>(out)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else if (out_fmt == 1) {
-      reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2<true>(acc[0], acc[1]), pack2<true>(acc[2], acc[3]),
-                                                    pack2<true>(acc[4], acc[5]), pack2<true>(acc[6], acc[7]));
-    } else {
-      reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2<false>(acc[0], acc[1]), pack2<false>(acc[2], acc[3]),
-                                                    pack2<false>(acc[4], acc[5]), pack2<false>(acc[6], acc[7]));
-    }
+  }
+  const size_t o = ((static_cast<size_t>(n) * H + py) * W + px) * vecs + v;  // 8-channel vector index
+  if (out_fmt == 2) {
+    reinterpret_cast<float4*>(out)[2 * o] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(out)[2 * o + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else if (out_fmt == 1) {
+    reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<true>(acc[0], acc[1]), pack2<true>(acc[2], acc[3]),
+                                                  pack2<true>(acc[4], acc[5]), pack2<true>(acc[6], acc[7]));
+  } else {
+    reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<false>(acc[0], acc[1]), pack2<false>(acc[2], acc[3]),
+                                                  pack2<false>(acc[4], acc[5]), pack2<false>(acc[6], acc[7]));
+  }
   }
 }
 
-// thread -> one output pixel, all COUT channels.  Weights in smem as [tap][ci][COUT] fp32.
+// grid (x-chunks, H / kSmallRows, N).  LP lanes of a warp share one output pixel; lane `sub` owns the 4-channel units
+// sub, sub+LP, ...  A warp-wide load therefore covers whole contiguous pixel rows (coalesced) and the COUT
+// partial sums are folded with xor-shuffles.  Weights live in smem as [tap][ci][COUT] fp32 (for COUT == 1
+// and one unit per lane they are hoisted into 36 registers); the per-image GroupNorm scale/shift of the
+// lane's channels is hoisted out of the tap loop.  Zero padding applies AFTER the norm (taps outside the
+// image are skipped, not transformed).
 template <int COUT>
 __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __restrict__ x,
                                                                  const float* __restrict__ w,  // [COUT][Cin][3][3]
                                                                  const float* __restrict__ bias,
                                                                  const float* __restrict__ ss,  // [N][Cin][2] or null
-                                                                 float* __restrict__ out, int N, int H, int W,
-                                                                 int Cin, int in_fmt) {
-  extern __shared__ float sw[];  // [9*Cin][COUT], then per-image scale/shift is read from global
+                                                                 float* __restrict__ out, int H, int W, int Cin,
+                                                                 int in_fmt, int lp) {
+  extern __shared__ float sw[];  // [9*Cin][COUT]
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) {
     const int co = i % COUT;
     const int r = i / COUT;
@@ -88,62 +96,77 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
     sw[i] = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap];
   }
   __syncthreads();
-  const size_t plane = static_cast<size_t>(H) * W;
-  const size_t total = static_cast<size_t>(N) * plane;
-  const int vecs = Cin / 8;
-  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
-       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int px = static_cast<int>(pix % W);
-    const int py = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / plane);
-    float acc[COUT];
+  const int units = Cin / 4;
+  const int sub = threadIdx.x % lp;
+  const int px_raw = blockIdx.x * (blockDim.x / lp) + threadIdx.x / lp;
+  const bool live = px_raw < W;
+  const int px = live ? px_raw : W - 1;
+  const int n = blockIdx.z;
+  const size_t esz = in_fmt == 2 ? 4 : 2;
+  const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * esz;
+  const bool one_unit = (units == lp);
+  float wreg[COUT == 1 ? 36 : 1];
+  if (COUT == 1 && one_unit) {
 #pragma unroll
-    for (int j = 0; j < COUT; ++j) acc[j] = __ldg(bias + j);
-    const float* ssn = ss ? ss + static_cast<size_t>(n) * Cin * 2 : nullptr;
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wreg[(COUT == 1) ? t * 4 + c : 0] = sw[t * Cin + sub * 4 + c];
+  }
+  for (int py = blockIdx.y * kSmallRows; py < min(H, (blockIdx.y + 1) * kSmallRows); ++py) {
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+  for (int u = sub; u < units; u += lp) {
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ss != nullptr) {
+      const float4* sp = reinterpret_cast<const float4*>(ss + (static_cast<size_t>(n) * Cin + u * 4) * 2);
+      const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);
+      sc[0] = p0.x; sh[0] = p0.y; sc[1] = p0.z; sh[1] = p0.w;
+      sc[2] = p1.x; sh[2] = p1.y; sc[3] = p1.z; sh[3] = p1.w;
+    }
+#pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = py + ky - 1;
       if (yy < 0 || yy >= H) continue;
+#pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = px + kx - 1;
-        if (xx < 0 || xx >= W) continue;  // zero padding applies AFTER the norm: skip, do not transform
-        const size_t pvec = ((static_cast<size_t>(n) * H + yy) * W + xx) * vecs;
-        const float* wt = sw + (ky * 3 + kx) * Cin * COUT;
-        for (int v = 0; v < vecs; ++v) {
-          float xv[8];
-          if (in_fmt == 2) {
-            const float4* xp = reinterpret_cast<const float4*>(x) + (pvec + v) * 2;
-            const float4 a = __ldg(xp), b = __ldg(xp + 1);
-            xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
-          } else {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + pvec + v);
-            const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
-            if (in_fmt == 1) {
+        if (xx < 0 || xx >= W) continue;
+        const uint8_t* p = img + (static_cast<size_t>(yy) * W + xx) * Cin * esz;
+        float xv[4];
+        if (in_fmt == 2) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p) + u);
+          xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        } else {
+          const uint2 a = __ldg(reinterpret_cast<const uint2*>(p) + u);
+          if (in_fmt == 1) { unpack2<true>(a.x, xv[0], xv[1]); unpack2<true>(a.y, xv[2], xv[3]); }
+          else { unpack2<false>(a.x, xv[0], xv[1]); unpack2<false>(a.y, xv[2], xv[3]); }
+        }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) unpack2<true>(wd[e], xv[2 * e], xv[2 * e + 1]);
-            } else {
+        for (int c = 0; c < 4; ++c) xv[c] = fmaf(xv[c], sc[c], sh[c]);
+        if (COUT == 1 && one_unit) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) unpack2<false>(wd[e], xv[2 * e], xv[2 * e + 1]);
-            }
-          }
-          if (ssn) {
+          for (int c = 0; c < 4; ++c) acc[0] = fmaf(xv[c], wreg[(COUT == 1) ? (ky * 3 + kx) * 4 + c : 0], acc[0]);
+        } else {
+          const float* wt = sw + ((ky * 3 + kx) * Cin + u * 4) * COUT;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float2 p = __ldg(reinterpret_cast<const float2*>(ssn) + v * 8 + e);
-              xv[e] = fmaf(xv[e], p.x, p.y);
-            }
-          }
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float* wr = wt + (v * 8 + e) * COUT;
-#pragma unroll
-            for (int j = 0; j < COUT; ++j) acc[j] = fmaf(xv[e], wr[j], acc[j]);
-          }
+            for (int j = 0; j < COUT; ++j) acc[j] = fmaf(xv[c], wt[c * COUT + j], acc[j]);
         }
       }
     }
-    const size_t rem = pix % plane;
+  }
+  for (int o = lp >> 1; o > 0; o >>= 1) {
 #pragma unroll
-    for (int j = 0; j < COUT; ++j) out[(static_cast<size_t>(n) * COUT + j) * plane + rem] = acc[j];
+    for (int j = 0; j < COUT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (live && sub == 0) {
+    const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+    for (int j = 0; j < COUT; ++j)
+      out[(static_cast<size_t>(n) * COUT + j) * plane + static_cast<size_t>(py) * W + px] = acc[j] + __ldg(bias + j);
+  }
   }
 }
 
@@ -183,9 +206,9 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  const size_t total = static_cast<size_t>(N) * H * W * (Cout / 8);
-  conv3x3_small_cin_kernel<<<grid_for(total, 256, 148 * 8), 256, smem, stream>>>(
-      x, w, bias, out, N, H, W, Cin, Cout, out_fmt);
+  if (H > 65535 || N > 65535) return PTIVAE_ERR_UNSUPPORTED;
+  dim3 grid((W * (Cout / 8) + 255) / 256, (H + kSmallRows - 1) / kSmallRows, N);
+  conv3x3_small_cin_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -199,9 +222,12 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  const size_t total = static_cast<size_t>(N) * H * W;
-  conv3x3_small_cout_kernel<COUT><<<grid_for(total, 256, 148 * 8), 256, smem, stream>>>(
-      x, w, bias, ss, out, N, H, W, Cin, in_fmt);
+  int lp = Cin / 4;  // lanes per pixel: one 4-channel unit each, capped at a warp
+  if (lp > 32) lp = 32;
+  if ((lp & (lp - 1)) || (Cin / 4) % lp != 0 || H > 65535 || N > 65535) return PTIVAE_ERR_UNSUPPORTED;
+  const int ppb = 256 / lp;
+  dim3 grid((W + ppb - 1) / ppb, (H + kSmallRows - 1) / kSmallRows, N);
+  conv3x3_small_cout_kernel<COUT><<<grid, 256, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, in_fmt, lp);
   return static_cast<int>(cudaGetLastError());
 }
 

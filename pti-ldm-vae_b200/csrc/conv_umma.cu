@@ -20,6 +20,7 @@
 // warps 2..5 = epilogue (TMEM -> registers -> +bias (+residual) -> bf16 -> global, optional
 // per-(image, group) sum / sum-of-squares for the NEXT GroupNorm).
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptivae_internal.h"
 
 namespace ptivae {
@@ -51,6 +52,7 @@ struct ConvArgs {
   const float* bias;
   const void* residual;  // same shape as out, or nullptr
   void* out;
+  void* out16;           // optional extra 16-bit copy of the output (when out is fp32), or nullptr
   float* gn_part;        // [N][P = nphase*tiles_y*tiles_x][groups][2]
 };
 
@@ -74,6 +76,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* spart = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4 warps][<=128 groups][2]
+  float* escr = spart + 4 * (BN / 2) * 2;                       // [4 warps][32 rows][16 fp32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,153 +110,72 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int t = it / KC, kc = it - t * KC;
-        const int s = it % nstages;
-        const uint32_t ph = (it / nstages) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < args.ntaps; ++t) {
         const ConvTap tap = args.taps[phase_id][t];
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        tma_load_5d(sa, &tmA, &full_bar[s], tap.cmul * args.Cin + kc * KCH, x0 + tap.dx, tap.pz, y0 + tap.dy, n);
-        tma_load_3d(sa + A_BYTES, &tmB, &full_bar[s], kc * KCH, n0, tap.wtap);
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          tma_load_5d(sa, &tmA, &full_bar[s], tap.cmul * args.Cin + kc * KCH, x0 + tap.dx, tap.pz, y0 + tap.dy, n);
+          tma_load_3d(sa + A_BYTES, &tmB, &full_bar[s], kc * KCH, n0, tap.wtap);
+          if (++s == nstages) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      const uint32_t hi = desc_hi(kSBO, kLayout);
+      const uint32_t lo0 = desc_lo(smem_u32(smem));
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % nstages;
-        const uint32_t ph = (it / nstages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t a_lo = lo0 + ((s * STAGE_BYTES) >> 4);
+        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < KCH / 16; ++k) {
-          const uint64_t adesc = make_smem_desc(sa + k * 32, 16, kSBO, kLayout);
-          const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, kSBO, kLayout);
-          umma_bf16(tmem_base, adesc, bdesc, kIdesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16_lohi(tmem_base, a_lo + 2 * k, hi, b_lo + 2 * k, hi, kIdesc, accum);
+          accum = 1;
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        if (++s == nstages) { s = 0; ph ^= 1u; }
       }
       umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ---------------- epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int ty = m / kTW, tx = m % kTW;
-    const int gy = y0 + ty, gx = x0 + tx;
-    const bool valid = (gy < args.Ho) && (gx < args.Wo);
     const int py = (args.os == 2) ? (phase_id >> 1) : 0;
     const int px = (args.os == 2) ? (phase_id & 1) : 0;
-    const size_t pix = (static_cast<size_t>(n) * args.Hout + (gy * args.os + py)) * args.Wout + (gx * args.os + px);
-    const size_t eoff = pix * args.Cout + n0;
-    uint16_t* optr16 = static_cast<uint16_t*>(args.out) + eoff;
-    float* optr32 = static_cast<float*>(args.out) + eoff;
-    const bool has_res = args.residual != nullptr;
-    const uint16_t* rptr16 = static_cast<const uint16_t*>(args.residual) + eoff;
-    const float* rptr32 = static_cast<const float*>(args.residual) + eoff;
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    auto rowfn = [&](int, int r, long long& off, bool& valid) {
+      const int m = q * 32 + r;
+      const int gy = y0 + m / kTW, gx = x0 + m % kTW;
+      valid = (gy < args.Ho) && (gx < args.Wo);
+      off = ((static_cast<long long>(n) * args.Hout + (gy * args.os + py)) * args.Wout + (gx * args.os + px)) *
+                args.Cout + n0;
+    };
     const int cpg = args.gn_groups > 0 ? args.Cout / args.gn_groups : 0;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(args.bias + n0 + c * 32 + j);
-      if (has_res && valid) {
-        if (args.res_f32) {
-#pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
-            const float4 rv = __ldg(reinterpret_cast<const float4*>(rptr32 + c * 32) + j8);
-            v[j8 * 4 + 0] += rv.x; v[j8 * 4 + 1] += rv.y; v[j8 * 4 + 2] += rv.z; v[j8 * 4 + 3] += rv.w;
-          }
-        } else {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr16 + c * 32) + j4);
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float lo, hi;
-              unpack2<F16>(w[e], lo, hi);
-              v[j4 * 8 + 2 * e] += lo;
-              v[j4 * 8 + 2 * e + 1] += hi;
-            }
-          }
-        }
-      }
-      if (valid) {
-        if (args.out_f32) {
-#pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8)
-            *(reinterpret_cast<float4*>(optr32 + c * 32) + j8) =
-                make_float4(v[j8 * 4 + 0], v[j8 * 4 + 1], v[j8 * 4 + 2], v[j8 * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 o;
-            o.x = pack2<F16>(v[j4 * 8 + 0], v[j4 * 8 + 1]);
-            o.y = pack2<F16>(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-            o.z = pack2<F16>(v[j4 * 8 + 4], v[j4 * 8 + 5]);
-            o.w = pack2<F16>(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-            *(reinterpret_cast<uint4*>(optr16 + c * 32) + j4) = o;
-          }
-        }
-      }
-      if (cpg > 0) {
-        // Statistics of the values as stored (bf16-rounded unless the output is the fp32 stream).
-        // Transposing butterfly over the 32 pixel lanes: each step halves the live value count,
-        // so 31 shuffles per quantity leave lane L holding the column-L total of this warp.
-        float s[32], ss[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float b = valid ? (args.out_f32 ? v[j] : round16<F16>(v[j])) : 0.f;
-          s[j] = b;
-          ss[j] = b * b;
-        }
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const bool upper = (lane & step) != 0;
-#pragma unroll
-          for (int i = 0; i < step; ++i) {
-            const float send_s = upper ? s[i] : s[i + step];
-            const float keep_s = upper ? s[i + step] : s[i];
-            const float send_q = upper ? ss[i] : ss[i + step];
-            const float keep_q = upper ? ss[i + step] : ss[i];
-            s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, step);
-            ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, step);
-          }
-        }
-        float a = s[0], b2 = ss[0];  // column (c*32 + lane)
-        for (int o = 1; o < cpg && o < 32; o <<= 1) {  // fold the cpg adjacent columns of one group
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          b2 += __shfl_xor_sync(0xffffffffu, b2, o);
-        }
-        if ((lane % cpg) == 0) {
-          const int lg = (c * 32 + lane) / cpg;  // group index local to this CTA's BN columns
-          spart[(q * (BN / 2) + lg) * 2 + 0] = a;
-          spart[(q * (BN / 2) + lg) * 2 + 1] = b2;
-        }
-      }
-    }
+    float* spart_w = spart + q * (BN / 2) * 2;
+    EpiOut e;
+    e.bias = args.bias + n0; e.residual = args.residual; e.out = args.out; e.out16 = args.out16;
+    e.out_f32 = args.out_f32; e.res_f32 = args.res_f32; e.cpg = cpg;
+    epilogue_tile<F16, BN, 1>(tmem_base + (static_cast<uint32_t>(q * 32) << 16), 0, escr + q * 512, e, rowfn, spart_w,
+                              lane, tmem_full_bar, 0);
     if (cpg > 0) {
       // fixed-order fold of the 4 epilogue warps, then one plain store per (tile, group): no atomics
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 64;  // 0..127
-      const int ngl = BN / cpg;        // groups covered by this CTA
-      if (e < 2 * ngl) {
+      const int ei = threadIdx.x - 64;  // 0..127
+      const int ngl = BN / cpg;         // groups covered by this CTA
+      if (ei < 2 * ngl) {
         float t = 0.f;
 #pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) t += spart[(w4 * (BN / 2)) * 2 + e];
+        for (int w4 = 0; w4 < 4; ++w4) t += spart[(w4 * (BN / 2)) * 2 + ei];
         const int P = gridDim.z * args.tiles_y * args.tiles_x;
         const int pidx = (phase_id * args.tiles_y + tiy) * args.tiles_x + tix;
-        args.gn_part[((static_cast<size_t>(n) * P + pidx) * args.gn_groups + n0 / cpg) * 2 + e] = t;
+        args.gn_part[((static_cast<size_t>(n) * P + pidx) * args.gn_groups + n0 / cpg) * 2 + ei] = t;
       }
     }
   }
@@ -314,7 +236,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs&
   if (stages < 2 && iters >= 2) stages = 2;
   if (stages < 1) stages = 1;
   a.nstages = stages;
-  const size_t smem = size_t(stages) * STAGE + 1024 /*align*/ + (2 * kMaxStages + 1) * 8 + 16 + 4 * (BN / 2) * 2 * 4;
+  const size_t smem = size_t(stages) * STAGE + 1024 /*align*/ + (2 * kMaxStages + 1) * 8 + 16 + 4 * (BN / 2) * 2 * 4 + 4 * 512 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KCH, BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -338,8 +260,8 @@ extern "C" int ptivae_conv_parts(int H, int W, int mode) {
 }
 
 extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual,
-                                void* out, float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout,
-                                int mode, int out_f32, int res_f32, int f16, void* stream_) {
+                                void* out, void* out16, float* gn_part, int gn_groups, int N, int H, int W, int Cin,
+                                int Cout, int mode, int out_f32, int res_f32, int f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!in || !w_packed || !bias || !out) return PTIVAE_ERR_ARG;
   if (N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
@@ -356,6 +278,7 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   a.bias = bias;
   a.residual = residual;
   a.out = out;
+  a.out16 = out_f32 ? out16 : nullptr;
   a.gn_part = gn_part;
   a.gn_groups = gn_groups;
   a.out_f32 = out_f32;

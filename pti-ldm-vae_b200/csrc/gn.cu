@@ -87,27 +87,39 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
   }
 }
 
-// one thread per (n, c); sums the P partials of its group in index order
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale_shift, int N, int C,
-                                   int G, int P, float inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i % C;
-  const int g = c / (C / G);
-  const float* src = partial + (static_cast<size_t>(n) * P * G + g) * 2;
+// one warp per (n, g): lanes stride over the P partials, fixed-pattern shuffle reduction (deterministic),
+// then the first C/G lanes (looping if C/G > 32) write scale/shift of the group's channels.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          float* __restrict__ scale_shift, int N, int C, int G, int P,
+                                                          float inv_count, float eps) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= N * G) return;
+  const int n = wid / G, g = wid - n * G;
+  const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * G + g;
   float s = 0.f, q = 0.f;
-  for (int p = 0; p < P; ++p) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(src + static_cast<size_t>(p) * G * 2));
+  for (int p = lane; p < P; p += 32) {
+    const float2 t = __ldg(src + static_cast<size_t>(p) * G);
     s += t.x;
     q += t.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
-  const float sc = gamma[c] * rstd;
-  scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 0] = sc;
-  scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 1] = beta[c] - mean * sc;
+  const int cpg = C / G;
+  for (int j = lane; j < cpg; j += 32) {
+    const int c = g * cpg + j;
+    const float sc = gamma[c] * rstd;
+    scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 0] = sc;
+    scale_shift[(static_cast<size_t>(n) * C + c) * 2 + 1] = beta[c] - mean * sc;
+  }
 }
 
 template <bool kSilu, bool F16>
@@ -180,7 +192,8 @@ extern "C" int ptivae_gn_finalize(const float* partial, const float* gamma, cons
   if (!partial || !gamma || !beta || !scale_shift || N <= 0 || C % G != 0 || P <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
-  gn_finalize_kernel<<<(N * C + 127) / 128, 128, 0, stream>>>(partial, gamma, beta, scale_shift, N, C, G, P, inv, eps);
+  gn_finalize_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(partial, gamma, beta, scale_shift, N, C, G, P, inv,
+                                                                   eps);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -80,9 +80,10 @@ def conv_parts(h: int, w: int, mode: int) -> int:
 
 
 def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode: int, residual=None,
-              gn_groups: int = 0, out_f32: bool = False):
+              gn_groups: int = 0, out_f32: bool = False, emit16: bool = False):
     """x bf16 NHWC [N,H,W,Cin] -> NHWC (bf16, or fp32 when out_f32).  mode: 0 3x3 s1 | 1 pad+3x3 s2 |
-    2 up2x+3x3 | 3 1x1.  Returns out, or (out, stats_partials [N,P,G,2]) when gn_groups > 0."""
+    2 up2x+3x3 | 3 1x1.  Returns out, or (out, stats_partials [N,P,G,2]) when gn_groups > 0; with
+    emit16 (fp32 output only) a 16-bit copy of out is appended to the returned tuple."""
     _need_cuda(x, w_packed, bias)
     f16 = _op16(x)
     if w_packed.dtype != x.dtype:
@@ -101,8 +102,44 @@ def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode:
     part = None
     if gn_groups > 0:
         part = torch.empty((n, conv_parts(h, w, mode), gn_groups, 2), device=x.device, dtype=torch.float32)
+    out16 = torch.empty(out.shape, device=x.device, dtype=x.dtype) if (emit16 and out_f32) else None
     _call("conv_umma", (mode, n, h, w, cin, cout), 1, _lib.lib().ptivae_conv_umma, _p(x), _p(w_packed), _p(bias),
-          _p(residual), _p(out), _p(part), gn_groups, n, h, w, cin, cout, mode, int(out_f32), res_f32, f16, _stream())
+          _p(residual), _p(out), _p(out16), _p(part), gn_groups, n, h, w, cin, cout, mode, int(out_f32), res_f32, f16,
+          _stream())
+    r = (out, part) if gn_groups > 0 else (out,)
+    if emit16:
+        r = r + (out16,)
+    return r if len(r) > 1 else r[0]
+
+
+FUSED_DESC_BASE_OFFSET = 0   # measured on B200: shifted operand descriptors need base_offset = 0 (the swizzle
+                             # phase comes from absolute smem address bits); 1 is kept only for the probe
+
+
+def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tensor, bias: torch.Tensor,
+                  residual=None, gn_groups: int = 0, out_f32: bool = False):
+    """out = conv3x3(act(x*scale+shift)) + bias (+ residual); x NHWC fp32 or 16-bit, weights 16-bit."""
+    _need_cuda(x, w_packed, bias)
+    n, h, w, cin = x.shape
+    cout = w_packed.shape[1]
+    f16 = _op16(w_packed)
+    if x.dtype != torch.float32 and x.dtype != w_packed.dtype:
+        raise _lib.PtivaeError("16-bit input must use the packed-weight dtype")
+    out = torch.empty((n, h, w, cout), device=x.device, dtype=torch.float32 if out_f32 else w_packed.dtype)
+    res_f32 = 0
+    if residual is not None:
+        if residual.shape != out.shape:
+            raise _lib.PtivaeError("residual shape mismatch")
+        res_f32 = int(residual.dtype == torch.float32)
+    part = None
+    if gn_groups > 0:
+        part = torch.empty((n, _lib.lib().ptivae_conv3x3_fused_parts(h, w), gn_groups, 2), device=x.device,
+                           dtype=torch.float32)
+    meta = (n, h, w, cin, cout, x.element_size(), out.element_size(),
+            0 if residual is None else residual.element_size())
+    _call("conv3x3_fused", meta, 1, _lib.lib().ptivae_conv3x3_fused, _p(x), _fmt(x), _p(scale_shift), int(silu),
+          _p(w_packed), _p(bias), _p(residual), res_f32, _p(out), int(out_f32), _p(part), gn_groups, n, h, w, cin,
+          cout, f16, FUSED_DESC_BASE_OFFSET, _stream())
     return (out, part) if gn_groups > 0 else out
 
 

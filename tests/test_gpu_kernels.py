@@ -215,6 +215,56 @@ def test_groupnorm(b200, n, h, w, c, groups, silu, f32):
     assert float((ss[..., 1].view(n, groups, -1) - sh_ref).abs().max()) <= 1e-4 * max(1.0, float(sh_ref.abs().max()))
 
 
+FUSED_CASES = [
+    # (N, H, W, Cin, Cout, in_f32, norm, silu, res, out_f32, groups)
+    (2, 32, 32, 128, 128, True, True, True, True, True, 16),
+    (1, 16, 16, 128, 128, False, True, True, False, False, 16),
+    (2, 40, 24, 64, 64, True, True, True, True, True, 16),     # extents not multiples of the tile
+    (1, 64, 64, 32, 32, True, True, True, True, True, 16),
+    (1, 32, 32, 32, 64, True, True, True, False, False, 16),
+    (1, 32, 32, 64, 32, False, True, True, True, True, 16),
+    (1, 32, 32, 128, 64, True, True, False, False, True, 16),
+    (1, 32, 32, 64, 128, True, False, False, True, True, 32),
+    (3, 8, 8, 128, 128, True, True, True, True, True, 16),      # image smaller than one tile
+    (5, 48, 48, 64, 64, False, True, True, True, True, 16),     # > 1 tile per CTA not needed, many tiles
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,in_f32,norm,silu,res,out_f32,groups", FUSED_CASES)
+def test_conv3x3_fused(b200, n, h, w, cin, cout, in_f32, norm, silu, res, out_f32, groups):
+    x = _rand_act(n, h, w, cin, 31).float() * 1.5 + 0.2
+    x = x + 1e-3 * torch.randn_like(x) if in_f32 else x.to(DT)
+    wt, bias = _rand_conv(cout, cin, 3, 32)
+    ss = None
+    xin = x.float().permute(0, 3, 1, 2)
+    if norm:
+        ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
+        xin = xin * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]
+        if silu:
+            xin = F.silu(xin)
+    xin = xin.to(DT).float()          # the operand the tensor cores see
+    r = None
+    if res:
+        r = torch.randn(n, h, w, cout, device=DEV)
+    ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r
+    out, part = b200.ops.conv3x3_fused(x, ss, silu, b200.ops.pack_conv_weight(wt, 0, DT), bias, residual=r,
+                                       gn_groups=groups, out_f32=out_f32)
+    if out_f32:
+        # operand rounding can flip (silu differs in the last ulp): allow 1 ulp of the operand format on the sum
+        _check_bf16(out.to(DT), ref, "fused conv (fp32 out)")
+    else:
+        _check_bf16(out, ref, "fused conv")
+    o = out.float().view(n, h * w, groups, cout // groups)
+    acc = part.sum(dim=1)
+    assert torch.allclose(acc[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(acc[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    out2, part2 = b200.ops.conv3x3_fused(x, ss, silu, b200.ops.pack_conv_weight(wt, 0, DT), bias, residual=r,
+                                         gn_groups=groups, out_f32=out_f32)
+    assert torch.equal(out, out2) and torch.equal(part, part2)
+
+
 @pytest.mark.parametrize("n,cin,cout,h,w", [(2, 1, 32, 64, 64), (1, 1, 64, 32, 48), (2, 4, 128, 16, 16), (1, 10, 256, 8, 8)])
 def test_conv_small_cin(b200, n, cin, cout, h, w):
     x = torch.randn(n, cin, h, w, device=DEV)

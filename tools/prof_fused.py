@@ -1,0 +1,45 @@
+"""Fused-conv micro-benchmark + CTA-0 role timeline.  usage: prof_fused.py [trace]"""
+import sys, pathlib, math
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import torch
+import _pkg
+b200 = _pkg.load(); ops = b200.ops; lib = b200._lib.lib()
+trace = len(sys.argv) > 1 and sys.argv[1] == "trace"
+cases = [(64, 256, 256, 32, 32, True), (64, 256, 256, 32, 32, False), (64, 64, 64, 128, 128, True), (64, 128, 128, 64, 64, True)]
+for (n, h, w, cin, cout, conv2) in cases:
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, h, w, cin, device="cuda", dtype=torch.float32 if not conv2 else torch.float16)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).cuda()
+    wp = ops.pack_conv_weight(wt, 0, torch.float16)
+    bias = torch.randn(cout, generator=g).cuda()
+    ss = torch.randn(n, cin, 2, device="cuda")
+    res = torch.randn(n, h, w, cout, device="cuda") if conv2 else None
+    def run():
+        return ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=16, out_f32=conv2)
+    for _ in range(2): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    fl = 2.0 * n * h * w * cin * cout * 9
+    by = n * h * w * (x.element_size() * cin + (4 if conv2 else 2) * cout + (4 * cout if conv2 else 0))
+    print(f"{cin}->{cout}@{h} conv{'2' if conv2 else '1'}: {ms:.3f} ms  {fl/ms/1e9:.0f} TF  {by/ms/1e6:.0f} GB/s", flush=True)
+    if trace:
+        buf = torch.zeros(64 * 32, device="cuda", dtype=torch.int64)
+        lib.ptivae_debug_set_trace(buf.data_ptr())
+        run(); torch.cuda.synchronize()
+        lib.ptivae_debug_set_trace(None)
+        t = buf.view(64, 32).cpu()
+        t0 = int(t[0, 0])
+        names = ["xf_start", "xf_end", "mma_start", "mma_issued", "epi_start", "epi_end"]
+        print("   tile " + " ".join(f"{nm:>10s}" for nm in names))
+        for i in range(0, 7):
+            print(f"   {i:4d} " + " ".join(f"{int(t[i, k]) - t0:10d}" for k in range(6)))
+        for i in (3, 4):
+            e0 = int(t[i, 4])
+            print(f"   tile {i} epilogue detail (rel. to epi_start): acc_ready {int(t[i,6])-e0}  slab1: ld_done {int(t[i,7])-e0} sts_done {int(t[i,8])-e0} stores_done {int(t[i,9])-e0}  slab_end[0..3] " + " ".join(str(int(t[i, 10 + k]) - e0) for k in range(4)))
+            m0 = int(t[i, 2])
+            print(f"   tile {i} mma detail (rel. to mma_start): wait-done " + " ".join(str(int(t[i, 14 + k]) - m0) for k in range(9)))
+            print(f"   tile {i}                               committed " + " ".join(str(int(t[i, 23 + k]) - m0) for k in range(9)))
