@@ -5,17 +5,17 @@
 // Versus conv_umma.cu (one TMA box per tap => every activation byte crosses L2->SMEM 9 times, and the
 // normalised tensor makes an extra round trip through HBM) this kernel is HALO-RESIDENT:
 //   * a persistent CTA owns a 16x16 output patch (two M=128 UMMA blocks); its 18x18xCin halo is read
-//     from global memory ONCE by 8 transform warps, normalised (x*scale+shift, SiLU) in registers and
+//     from global memory ONCE by the transform warps, normalised (x*scale+shift, SiLU) in registers and
 //     written as the 16-bit UMMA operand into shared memory in the K-major swizzled layout.  Out-of-
 //     image halo pixels are written as zeros AFTER the transform (the reference pads silu(norm(x)));
 //   * the 9 taps are 9 *shifted UMMA descriptors* into that one buffer (start address moves by whole
-//     128-byte pixel rows; the 8-row groups are one output row each, SBO = halo pitch);
-//   * weights stream through a TMA ring; operand buffer and TMEM accumulators are double buffered so
-//     transform(t+1) | MMA(t) | epilogue(t-1) overlap.
-// Roles (448 threads): warps 0-7 transform, warps 8-11 epilogue, warp 12 TMEM alloc + MMA issuer, warp 13
-// weight TMA producer.  The order matters: the warp scheduler favours the highest warp id among eligible
-// warps, and the ALU-heavy transform warps are always eligible -- with them on top (first layout) the
-// epilogue warps needed ~20 cycles per instruction.  Critical, latency-bound roles get the high ids.
+//     128-byte pixel rows; the 8-row groups are one output row each, SBO = halo pitch).  Measured on
+//     B200: the swizzle phase comes from absolute smem address bits, base_offset must stay 0;
+//   * weights are SMEM-resident for the whole kernel when 9*Cin*Cout*2 B fits next to the operand
+//     buffers (the MMA thread then issues a tile's MMAs back to back), else they stream through a TMA ring;
+//   * operand buffer and TMEM accumulators are double buffered: transform(t+1) | MMA(t) | epilogue(t-1).
+// Warp roles: [0,NTW) transform, [NTW,NTW+NEW) epilogue, then the MMA issuer (+TMEM alloc), then the
+// weight TMA producer.  Cin = 32 runs two CTAs per SM (4+4 warps each); wider layers one CTA with 8+8.
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptivae_internal.h"
@@ -25,19 +25,16 @@ namespace ptivae {
 constexpr int kFT = 16;            // tile edge (output pixels)
 constexpr int kHP = kFT + 2;       // halo pitch (pixels per halo row)
 constexpr int kHaloPix = kHP * kHP;
-constexpr int kNumTransformWarps = 8;
-constexpr int kFusedThreads = (6 + kNumTransformWarps) * 32;
 constexpr int kMaxBStages = 8;
+constexpr uint32_t kSmemMax = 232448;  // 227 KB opt-in maximum per block
 
 struct FusedArgs {
   int N, H, W;
   int tiles_x, tiles_y, num_tiles;
-  int in_fmt;      // 0 bf16, 1 fp16, 2 fp32
   int silu;
   int out_f32, res_f32;
   int gn_groups;
   int nstages;
-  int desc_base_offset;  // 1: put (start>>7)&7 into the descriptor's base-offset field
   const void* x;
   const float* scale_shift;  // [N][CIN][2] or nullptr (identity prologue)
   const float* bias;
@@ -47,27 +44,38 @@ struct FusedArgs {
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 ([tile][32] slots), or nullptr
 };
 
-#define PTIVAE_TRACE(slot)                                                                         \
-  do {                                                                                             \
+#define PTIVAE_TRACE(slot)                                                                            \
+  do {                                                                                                \
     if (args.trace != nullptr && blockIdx.x == 0 && it < 64) args.trace[it * 32 + (slot)] = clock64(); \
   } while (0)
 
-__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout,
-                                                      int use_base_offset) {
-  uint64_t d = make_smem_desc(saddr, 16, sbo_bytes, layout);
-  if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
-  return d;
-}
+// Per-shape configuration.
+template <int CIN, int COUT>
+struct FusedCfg {
+  static constexpr int KCH = CIN >= 64 ? 64 : 32;   // channels per K chunk (swizzle span)
+  static constexpr int NCH = CIN / KCH;
+  static constexpr uint32_t LB = KCH * 2;           // bytes per operand line (one pixel, one chunk)
+  static constexpr uint32_t CHUNK = ((kHaloPix * LB + 1023u) / 1024u) * 1024u;
+  static constexpr uint32_t OPBUF = NCH * CHUNK;
+  static constexpr uint32_t SLAB = uint32_t(COUT) * LB;   // one (tap, chunk) weight slab
+  static constexpr uint32_t WBYTES = 9u * NCH * SLAB;     // all weights
+  static constexpr bool TWO_CTAS = (CIN == 32);
+  static constexpr int NTW = TWO_CTAS ? 4 : 8;            // transform warps
+  static constexpr int NEW = TWO_CTAS ? 4 : 8;            // epilogue warps (8: one quartet per M block)
+  static constexpr int THREADS = (NTW + NEW + 2) * 32;
+  static constexpr uint32_t FIXED = 1024 /*align*/ + 2 * OPBUF + NEW * (COUT / 2) * 2 * 4 /*spart*/ +
+                                    NEW * 512 * 4 /*epilogue scratch*/ + (2 * kMaxBStages + 8) * 8 + 16;
+  static constexpr uint32_t BUDGET = TWO_CTAS ? 113u * 1024u : kSmemMax;
+  static constexpr bool RESB = FIXED + WBYTES <= BUDGET;  // weights resident in smem
+};
 
 template <int CIN, int COUT, bool F16, bool IN32>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(FusedCfg<CIN, COUT>::THREADS, FusedCfg<CIN, COUT>::TWO_CTAS ? 2 : 1)
 conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs args) {
-  constexpr int KCH = CIN >= 64 ? 64 : 32;          // channels per K chunk
-  constexpr int NCH = CIN / KCH;
-  constexpr uint32_t LB = KCH * 2;                  // bytes per operand line (one pixel, one chunk)
-  constexpr uint32_t CHUNK = ((kHaloPix * LB + 1023u) / 1024u) * 1024u;
-  constexpr uint32_t OPBUF = NCH * CHUNK;
-  constexpr uint32_t SLAB = uint32_t(COUT) * LB;    // one (tap, chunk) weight slab
+  using Cfg = FusedCfg<CIN, COUT>;
+  constexpr int KCH = Cfg::KCH, NCH = Cfg::NCH, NTW = Cfg::NTW, NEW = Cfg::NEW;
+  constexpr uint32_t LB = Cfg::LB, CHUNK = Cfg::CHUNK, OPBUF = Cfg::OPBUF, SLAB = Cfg::SLAB;
+  constexpr bool RESB = Cfg::RESB;
   constexpr uint32_t kLayout = (KCH == 64) ? kLayoutSW128 : kLayoutSW64;
   constexpr uint32_t kSBO_A = kHP * LB;             // next output row = next halo row
   constexpr uint32_t kSBO_B = 8u * LB;
@@ -75,17 +83,17 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
   constexpr uint32_t TMEM_COLS = 4 * COUT;          // 2 accumulator stages x 2 M blocks
   constexpr int VPP = CIN / 8;                      // 16-byte operand vectors per pixel
   constexpr int UPC = KCH / 8;                      // vectors per pixel per chunk
+  constexpr int W_MMA = NTW + NEW, W_PROD = NTW + NEW + 1;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   uint8_t* opbuf = smem;                                   // [2][NCH][CHUNK]
-  uint8_t* bring = opbuf + 2 * OPBUF;                      // [nstages][SLAB]
+  uint8_t* bring = opbuf + 2 * OPBUF;                      // resident: [9*NCH][SLAB]; ring: [nstages][SLAB]
   const int nstages = args.nstages;
-  float* ss_s = reinterpret_cast<float*>(bring + nstages * SLAB);  // [2][CIN*2]
-  float* spart = ss_s + 2 * CIN * 2;                       // [4][COUT/2][2]
-  float* escr = spart + 4 * (COUT / 2) * 2;                // [4 warps][32 rows][16 fp32] epilogue scratch
-  uint64_t* bars = reinterpret_cast<uint64_t*>(escr + 4 * 512);
+  float* spart = reinterpret_cast<float*>(bring + (RESB ? 9 * NCH : nstages) * SLAB);  // [NEW][COUT/2][2]
+  float* escr = spart + NEW * (COUT / 2) * 2;              // [NEW warps][32 rows][16 fp32] epilogue scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(escr + NEW * 512);
   uint64_t* b_full = bars;                    // [kMaxBStages]
   uint64_t* b_empty = bars + kMaxBStages;     // [kMaxBStages]
   uint64_t* op_full = bars + 2 * kMaxBStages;   // [2]
@@ -96,52 +104,63 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 13 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < nstages; ++s) {
+    for (int s = 0; s < kMaxBStages; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&op_full[i], kNumTransformWarps * 32);
+      mbar_init(&op_full[i], NTW * 32);
       mbar_init(&op_empty[i], 1);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], NEW * 32);
     }
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tiles_per_img = args.tiles_x * args.tiles_y;
 
-  if (warp == 13) {
+  if (warp == W_PROD) {
     // ------------------------------------------------------------------ weight TMA producer
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      if constexpr (RESB) {
+        mbar_expect_tx(&b_full[0], Cfg::WBYTES);
         for (int tap = 0; tap < 9; ++tap)
-          for (int kc = 0; kc < NCH; ++kc) {
-            mbar_wait(&b_empty[s], ph ^ 1u);
-            mbar_expect_tx(&b_full[s], SLAB);
-            tma_load_3d(bring + s * SLAB, &tmB, &b_full[s], kc * KCH, 0, tap);
-            if (++s == nstages) { s = 0; ph ^= 1u; }
-          }
+          for (int kc = 0; kc < NCH; ++kc)
+            tma_load_3d(bring + (tap * NCH + kc) * SLAB, &tmB, &b_full[0], kc * KCH, 0, tap);
+      } else {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+          for (int tap = 0; tap < 9; ++tap)
+            for (int kc = 0; kc < NCH; ++kc) {
+              mbar_wait(&b_empty[s], ph ^ 1u);
+              mbar_expect_tx(&b_full[s], SLAB);
+              tma_load_3d(bring + s * SLAB, &tmB, &b_full[s], kc * KCH, 0, tap);
+              if (++s == nstages) { s = 0; ph ^= 1u; }
+            }
+        }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     // The issuing thread is latency bound: descriptors are (lo, hi) halves, hi is invariant and lo moves
     // by compile-time constants inside the unrolled (k, M-block) loops.
     if (lane == 0) {
-      const uint32_t a_hi = desc_hi(kSBO_A, kLayout) | (0u);
+      const uint32_t a_hi = desc_hi(kSBO_A, kLayout);
       const uint32_t b_hi = desc_hi(kSBO_B, kLayout);
       const uint32_t bring_lo = desc_lo(smem_u32(bring));
       int s = 0, it = 0;
       uint32_t ph = 0;
+      if constexpr (RESB) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t ph2 = (it >> 1) & 1;
@@ -154,27 +173,32 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
         uint32_t accum = 0;
 #pragma unroll 1
         for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll 1
+#pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
             for (int kc = 0; kc < NCH; ++kc) {
-              mbar_wait(&b_full[s], ph);
-              tc_fence_after();
-              if (kc == 0) PTIVAE_TRACE(14 + ky * 3 + kx);
-              const uint32_t b_lo = bring_lo + ((s * SLAB) >> 4);
+              uint32_t b_lo;
+              if constexpr (RESB) {
+                b_lo = bring_lo + ((((ky * 3 + kx) * NCH + kc) * SLAB) >> 4);
+              } else {
+                mbar_wait(&b_full[s], ph);
+                tc_fence_after();
+                b_lo = bring_lo + ((s * SLAB) >> 4);
+              }
               const uint32_t a_lo = a_lo_tile + ((kc * CHUNK + (ky * kHP + kx) * LB) >> 4);
 #pragma unroll
               for (int k = 0; k < KCH / 16; ++k) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
-                  umma_f16_lohi(acc + mb * COUT, a_lo + ((mb * 8 * LB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
-                                kIdesc, accum);
+                  umma_f16_lohi(acc + mb * COUT, a_lo + ((mb * 8 * LB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4),
+                                b_hi, kIdesc, accum);
                 }
                 accum = 1;
               }
-              umma_commit(&b_empty[s]);
-              if (kc == NCH - 1) PTIVAE_TRACE(23 + ky * 3 + kx);
-              if (++s == nstages) { s = 0; ph ^= 1u; }
+              if constexpr (!RESB) {
+                umma_commit(&b_empty[s]);
+                if (++s == nstages) { s = 0; ph ^= 1u; }
+              }
             }
           }
         }
@@ -183,23 +207,27 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
         PTIVAE_TRACE(3);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= NTW) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
+    // NEW == 4: each warp drains both M blocks of its TMEM lane quarter; NEW == 8: warps [NTW,NTW+4) take
+    // M block 0 and [NTW+4,NTW+8) M block 1.
+    const int ew = warp - NTW;             // 0 .. NEW-1
+    const int q = warp & 3;                // TMEM lane quarter (hardware: warp id % 4)
+    const int mb0 = (NEW == 8) ? (ew >> 2) : 0;
+    constexpr int NMB = (NEW == 8) ? 1 : 2;
     const int cpg = args.gn_groups > 0 ? COUT / args.gn_groups : 0;
-    float* scr_w = escr + q * 512;
-    float* spart_w = spart + q * (COUT / 2) * 2;
+    float* scr_w = escr + ew * 512;
+    float* spart_w = spart + ew * (COUT / 2) * 2;
     EpiOut e;
     e.bias = args.bias; e.residual = args.residual; e.out = args.out; e.out16 = nullptr;
     e.out_f32 = args.out_f32; e.res_f32 = args.res_f32; e.cpg = cpg;
-    // residual rows of a tile, HBM -> L2, two tiles ahead (same reasoning as in the transform role)
+    // residual rows of a tile, HBM -> L2, two tiles ahead (one bulk prefetch per row)
     auto prefetch_res = [&](int t) {
-      if (args.residual == nullptr || m >= kFT || t >= args.num_tiles) return;
+      if (args.residual == nullptr || ew != 0 || lane >= kFT || t >= args.num_tiles) return;
       const int n = t / tiles_per_img;
       const int trem = t - n * tiles_per_img;
       const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
-      const int gy = tiy * kFT + m;
+      const int gy = tiy * kFT + lane;
       const int xs = tix * kFT, xe = min(xs + kFT, args.W);
       if (gy >= args.H) return;
       const uint32_t eb = args.res_f32 ? 4u : 2u;
@@ -217,45 +245,45 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
       const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
       prefetch_res(t + 2 * gridDim.x);
       const long long tile_base = ((static_cast<long long>(n) * args.H + tiy * kFT) * args.W + tix * kFT) * COUT;
-      auto rowfn = [&](int mb, int r, long long& off, bool& valid) {
-        const int mm = q * 32 + r;                       // accumulator row -> pixel (mm >> 3, mb*8 + (mm & 7))
-        const int dy = mm >> 3, dx = mb * 8 + (mm & 7);
+      auto rowfn = [&](int mbi, int r, long long& off, bool& valid) {
+        const int mm = q * 32 + r;                 // accumulator row -> pixel (mm >> 3, mb*8 + (mm & 7))
+        const int dy = mm >> 3, dx = (mb0 + mbi) * 8 + (mm & 7);
         valid = (tiy * kFT + dy < args.H) && (tix * kFT + dx < args.W);
         off = tile_base + static_cast<long long>(dy * args.W + dx) * COUT;
       };
-      if (warp == 8 && lane == 0) PTIVAE_TRACE(4);
-      const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 2 * COUT;
-      epilogue_tile<F16, COUT, 2>(tcol, COUT, scr_w, e, rowfn, spart_w, lane, &acc_full[b], (it >> 1) & 1,
-                                  (args.trace != nullptr && blockIdx.x == 0 && it < 64 && warp == 8 && lane == 0)
-                                      ? args.trace + it * 32 + 6 : nullptr);
+      if (ew == 0 && lane == 0) PTIVAE_TRACE(4);
+      const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 2 * COUT + mb0 * COUT;
+      epilogue_tile<F16, COUT, NMB>(tcol, COUT, scr_w, e, rowfn, spart_w, lane, &acc_full[b], (it >> 1) & 1,
+                                    (args.trace != nullptr && blockIdx.x == 0 && it < 64 && ew == 0 && lane == 0)
+                                        ? args.trace + it * 32 + 6 : nullptr);
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);
-      if (warp == 8 && lane == 0) PTIVAE_TRACE(5);
+      if (ew == 0 && lane == 0) PTIVAE_TRACE(5);
       if (cpg > 0) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int ei = threadIdx.x - 256;
+        asm volatile("bar.sync 1, %0;" ::"n"(NEW * 32) : "memory");
+        const int ei = threadIdx.x - NTW * 32;
         const int ngl = COUT / cpg;
         if (ei < 2 * ngl) {
           float tsum = 0.f;
 #pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) tsum += spart[(w4 * (COUT / 2)) * 2 + ei];
+          for (int w8 = 0; w8 < NEW; ++w8) tsum += spart[(w8 * (COUT / 2)) * 2 + ei];
           args.gn_part[((static_cast<size_t>(n) * tiles_per_img + trem) * args.gn_groups) * 2 + ei] = tsum;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NEW * 32) : "memory");
       }
     }
   } else {
     // ------------------------------------------------------------------ transform producers
     // Thread tt owns the fixed 8-channel unit u = tt % VPP of the halo pixels L = tt / VPP + k * LS, so
-    // its operand-buffer chunk, swizzle row phase and scale/shift registers are loop invariants.
+    // its operand-buffer chunk, swizzle column and scale/shift registers are loop invariants.
     // Software pipelined: the raw global loads of batch i+1 (also across tile boundaries) are in flight
     // while batch i is normalised, activated, packed and stored to the swizzled operand buffer.
-    const int tt = threadIdx.x;                          // 0 .. NT-1 (warps 0-7)
-    constexpr int NT = kNumTransformWarps * 32;
+    const int tt = threadIdx.x;                          // 0 .. NT-1
+    constexpr int NT = NTW * 32;
     constexpr int LS = NT / VPP;                         // halo-pixel stride between a thread's vectors
     constexpr int VPT = (kHaloPix + LS - 1) / LS;        // vectors per thread per tile
-    constexpr int UNR = 4;
+    constexpr int UNR = IN32 ? 2 : 4;                    // raw vectors per batch (register budget)
     constexpr int NB = (VPT + UNR - 1) / UNR;
     const bool has_norm = args.scale_shift != nullptr;
     const bool do_silu = args.silu != 0;
@@ -389,35 +417,36 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 template <int CIN, int COUT, bool F16, bool IN32>
 static int launch_fused(const CUtensorMap& tmB, FusedArgs& a, cudaStream_t stream) {
-  constexpr int KCH = CIN >= 64 ? 64 : 32;
-  constexpr int LB = KCH * 2;
-  constexpr size_t CHUNK = ((size_t(kHaloPix) * LB + 1023) / 1024) * 1024;
-  constexpr size_t OPBUF = (CIN / KCH) * CHUNK;
-  constexpr size_t SLAB = size_t(COUT) * LB;
-  const size_t fixed = 1024 + 2 * OPBUF + 2 * CIN * 2 * 4 + 4 * (COUT / 2) * 2 * 4 + 4 * 512 * 4 +
-                       (2 * kMaxBStages + 8) * 8 + 16;
-  int stages = static_cast<int>((232448 - fixed) / SLAB);  // 227 KB opt-in maximum per block
-  if (stages > kMaxBStages) stages = kMaxBStages;
-  if (stages < 2) return PTIVAE_ERR_UNSUPPORTED;
-  a.nstages = stages;
-  const size_t smem = fixed + stages * SLAB;
+  using Cfg = FusedCfg<CIN, COUT>;
+  size_t smem;
+  if (Cfg::RESB) {
+    a.nstages = 1;
+    smem = Cfg::FIXED + Cfg::WBYTES;
+  } else {
+    int stages = static_cast<int>((Cfg::BUDGET - Cfg::FIXED) / Cfg::SLAB);
+    if (stages > kMaxBStages) stages = kMaxBStages;
+    if (stages < 2) return PTIVAE_ERR_UNSUPPORTED;
+    a.nstages = stages;
+    smem = Cfg::FIXED + size_t(stages) * Cfg::SLAB;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_fused_kernel<CIN, COUT, F16, IN32>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax));
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  conv3x3_fused_kernel<CIN, COUT, F16, IN32><<<grid, kFusedThreads, smem, stream>>>(tmB, a);
+  const int slots = sms * (Cfg::TWO_CTAS ? 2 : 1);
+  const int grid = a.num_tiles < slots ? a.num_tiles : slots;
+  conv3x3_fused_kernel<CIN, COUT, F16, IN32><<<grid, Cfg::THREADS, smem, stream>>>(tmB, a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -442,6 +471,7 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                                     void* out, int out_f32, float* gn_part, int gn_groups, int N, int H, int W,
                                     int Cin, int Cout, int f16, int desc_base_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  (void)desc_base_offset;  // kept in the ABI for the hardware probe; the answer is 0 (see file header)
   if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   if (in_fmt != 2 && in_fmt != (f16 ? 1 : 0)) return PTIVAE_ERR_ARG;  // 16-bit input must use the operand format
   if (!(Cin == 32 || Cin == 64 || Cin == 128) || !(Cout == 32 || Cout == 64 || Cout == 128)) return PTIVAE_ERR_UNSUPPORTED;
@@ -452,8 +482,7 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
   a.tiles_x = (W + kFT - 1) / kFT;
   a.tiles_y = (H + kFT - 1) / kFT;
   a.num_tiles = N * a.tiles_x * a.tiles_y;
-  a.in_fmt = in_fmt; a.silu = silu; a.out_f32 = out_f32; a.res_f32 = res_f32; a.gn_groups = gn_groups;
-  a.desc_base_offset = desc_base_offset;
+  a.silu = silu; a.out_f32 = out_f32; a.res_f32 = res_f32; a.gn_groups = gn_groups;
   a.trace = g_fused_trace;
   a.x = x; a.scale_shift = scale_shift; a.bias = bias; a.residual = residual; a.out = out; a.gn_part = gn_part;
   const int KCH = Cin >= 64 ? 64 : 32;
@@ -463,8 +492,8 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
   uint32_t wb[3] = {static_cast<uint32_t>(KCH), static_cast<uint32_t>(Cout), 1};
   int rc = encode_tmap_16(&tmB, w_packed, 3, wd, ws, wb, KCH * 2, f16 != 0);
   if (rc != PTIVAE_OK) return rc;
-#define PTIVAE_FUSED_CASE(CI, CO)                                                   \
-  if (Cin == CI && Cout == CO)                                                      \
+#define PTIVAE_FUSED_CASE(CI, CO)                                                                    \
+  if (Cin == CI && Cout == CO)                                                                       \
     return f16 ? (in_fmt == 2 ? launch_fused<CI, CO, true, true>(tmB, a, stream)                     \
                               : launch_fused<CI, CO, true, false>(tmB, a, stream))                   \
                : (in_fmt == 2 ? launch_fused<CI, CO, false, true>(tmB, a, stream)                    \
