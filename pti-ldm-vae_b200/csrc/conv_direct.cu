@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
   const int n = blockIdx.z;
   const size_t esz = in_fmt == 2 ? 4 : 2;
   const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * esz;
+  // HBM -> L2 bulk prefetch of every input row this block will touch (its x range +-1, rows y0-1 .. y0+R):
+  // the per-row loads below are then L2 hits instead of exposed DRAM latency (the kernel is latency bound).
+  {
+    const int ppb = blockDim.x / lp;
+    const int xs = max(static_cast<int>(blockIdx.x) * ppb - 1, 0), xe = min(static_cast<int>(blockIdx.x + 1) * ppb + 1, W);
+    const int ry = static_cast<int>(blockIdx.y) * kSmallRows - 1 + static_cast<int>(threadIdx.x);
+    if (threadIdx.x < kSmallRows + 2 && ry >= 0 && ry < H && xe > xs)
+      l2_prefetch_bulk(img + (static_cast<size_t>(ry) * W + xs) * Cin * esz, static_cast<uint32_t>((xe - xs) * Cin * esz));
+  }
   const bool one_unit = (units == lp);
   float wreg[COUT == 1 ? 36 : 1];
   if (COUT == 1 && one_unit) {
@@ -167,6 +176,78 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
     for (int j = 0; j < COUT; ++j)
       out[(static_cast<size_t>(n) * COUT + j) * plane + static_cast<size_t>(py) * W + px] = acc[j] + __ldg(bias + j);
   }
+  }
+}
+
+// Single-output-channel 3x3 conv (the decoder's final conv: GroupNorm affine, no activation, 32|64 -> 1).
+// out(y,x) = sum_taps sum_c w[tap][c] * n(y+dy, x+dx, c) is evaluated as per-pixel tap dot products
+//   p[tap](y,x) = sum_c w[tap][c] * n(y,x,c)           (every input pixel is read from HBM exactly once)
+// staged in shared memory for an 18x18 halo of a 16x16 output tile, followed by a 9-point gather
+//   out(y,x) = bias + sum_tap p[tap](y+dy, x+dx).
+// Out-of-image halo pixels contribute p = 0: the zero padding applies to the normalised tensor.
+constexpr int kC1T = 16, kC1H = kC1T + 2;
+__global__ void __launch_bounds__(256) conv3x3_cout1_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ ss, float* __restrict__ out,
+                                                            int H, int W, int Cin, int in_fmt) {
+  extern __shared__ float c1s[];
+  float* swt = c1s;                       // [9][Cin] weights, tap-major
+  float* sss = swt + 9 * Cin;             // [Cin][2] scale/shift of this image (identity when ss == null)
+  float* sp = sss + 2 * Cin;              // [9][kC1H*kC1H] tap partials
+  const int n = blockIdx.z;
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+    const int tap = i / Cin, ci = i - tap * Cin;
+    swt[i] = w[ci * 9 + tap];             // w is [1][Cin][3][3]
+  }
+  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
+    sss[2 * i] = ss ? ss[(static_cast<size_t>(n) * Cin + i) * 2] : 1.f;
+    sss[2 * i + 1] = ss ? ss[(static_cast<size_t>(n) * Cin + i) * 2 + 1] : 0.f;
+  }
+  __syncthreads();
+  const int y0 = blockIdx.y * kC1T - 1, x0 = blockIdx.x * kC1T - 1;
+  const size_t esz = in_fmt == 2 ? 4 : 2;
+  const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * esz;
+  for (int hp = threadIdx.x; hp < kC1H * kC1H; hp += blockDim.x) {
+    const int hy = hp / kC1H, hx = hp - hy * kC1H;
+    const int gy = y0 + hy, gx = x0 + hx;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    if (static_cast<unsigned>(gy) < static_cast<unsigned>(H) && static_cast<unsigned>(gx) < static_cast<unsigned>(W)) {
+      const uint8_t* p = img + (static_cast<size_t>(gy) * W + gx) * Cin * esz;
+      for (int c4 = 0; c4 < Cin / 4; ++c4) {
+        float v[4];
+        if (in_fmt == 2) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p) + c4);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+          const uint2 a = __ldg(reinterpret_cast<const uint2*>(p) + c4);
+          if (in_fmt == 1) { unpack2<true>(a.x, v[0], v[1]); unpack2<true>(a.y, v[2], v[3]); }
+          else { unpack2<false>(a.x, v[0], v[1]); unpack2<false>(a.y, v[2], v[3]); }
+        }
+        const float4 s0 = reinterpret_cast<const float4*>(sss)[2 * c4], s1 = reinterpret_cast<const float4*>(sss)[2 * c4 + 1];
+        v[0] = fmaf(v[0], s0.x, s0.y); v[1] = fmaf(v[1], s0.z, s0.w);
+        v[2] = fmaf(v[2], s1.x, s1.y); v[3] = fmaf(v[3], s1.z, s1.w);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 wv = reinterpret_cast<const float4*>(swt + t * Cin)[c4];   // warp-uniform: broadcast
+          acc[t] = fmaf(v[0], wv.x, fmaf(v[1], wv.y, fmaf(v[2], wv.z, fmaf(v[3], wv.w, acc[t]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) sp[t * (kC1H * kC1H) + hp] = acc[t];
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / kC1T, tx = threadIdx.x % kC1T;
+  const int gy = blockIdx.y * kC1T + ty, gx = blockIdx.x * kC1T + tx;
+  if (gy < H && gx < W) {
+    float o = __ldg(bias);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) o += sp[(ky * 3 + kx) * (kC1H * kC1H) + (ty + ky) * kC1H + tx + kx];
+    out[(static_cast<size_t>(n) * H + gy) * W + gx] = o;
   }
 }
 
@@ -236,6 +317,12 @@ extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const fl
                                          void* stream_) {
   if (!x || !w || !bias || !out || N <= 0 || Cin % 8 != 0 || Cout <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (Cout == 1 && Cin % 4 == 0 && Cin <= 512 && H <= 65535 * kC1T && N <= 65535) {
+    const size_t smem = (static_cast<size_t>(9) * Cin + 2 * Cin + 9 * kC1H * kC1H) * sizeof(float);
+    dim3 grid((W + kC1T - 1) / kC1T, (H + kC1T - 1) / kC1T, N);
+    conv3x3_cout1_kernel<<<grid, 256, smem, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, in_fmt);
+    return static_cast<int>(cudaGetLastError());
+  }
   switch (Cout) {
     case 1: return launch_small_cout<1>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);
     case 2: return launch_small_cout<2>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);

@@ -59,18 +59,19 @@ struct FusedCfg {
   static constexpr uint32_t OPBUF = NCH * CHUNK;
   static constexpr uint32_t SLAB = uint32_t(COUT) * LB;   // one (tap, chunk) weight slab
   static constexpr uint32_t WBYTES = 9u * NCH * SLAB;     // all weights
-  static constexpr bool TWO_CTAS = (CIN == 32);
+  static constexpr bool TWO_CTAS = (CIN == 32);           // small CTAs (4+4 warps), several per SM
+  static constexpr int CTAS = TWO_CTAS ? 2 : 1;           // CTAs per SM (3 with a 64-register cap spills: slower)
   static constexpr int NTW = TWO_CTAS ? 4 : 8;            // transform warps
   static constexpr int NEW = TWO_CTAS ? 4 : 8;            // epilogue warps (8: one quartet per M block)
   static constexpr int THREADS = (NTW + NEW + 2) * 32;
   static constexpr uint32_t FIXED = 1024 /*align*/ + 2 * OPBUF + NEW * (COUT / 2) * 2 * 4 /*spart*/ +
                                     NEW * 512 * 4 /*epilogue scratch*/ + (2 * kMaxBStages + 8) * 8 + 16;
-  static constexpr uint32_t BUDGET = TWO_CTAS ? 113u * 1024u : kSmemMax;
+  static constexpr uint32_t BUDGET = CTAS == 3 ? 74u * 1024u : (CTAS == 2 ? 113u * 1024u : kSmemMax);
   static constexpr bool RESB = FIXED + WBYTES <= BUDGET;  // weights resident in smem
 };
 
 template <int CIN, int COUT, bool F16, bool IN32>
-__global__ void __launch_bounds__(FusedCfg<CIN, COUT>::THREADS, FusedCfg<CIN, COUT>::TWO_CTAS ? 2 : 1)
+__global__ void __launch_bounds__(FusedCfg<CIN, COUT>::THREADS, FusedCfg<CIN, COUT>::CTAS)
 conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs args) {
   using Cfg = FusedCfg<CIN, COUT>;
   constexpr int KCH = Cfg::KCH, NCH = Cfg::NCH, NTW = Cfg::NTW, NEW = Cfg::NEW;
@@ -444,7 +445,7 @@ static int launch_fused(const CUtensorMap& tmB, FusedArgs& a, cudaStream_t strea
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int slots = sms * (Cfg::TWO_CTAS ? 2 : 1);
+  const int slots = sms * Cfg::CTAS;
   const int grid = a.num_tiles < slots ? a.num_tiles : slots;
   conv3x3_fused_kernel<CIN, COUT, F16, IN32><<<grid, Cfg::THREADS, smem, stream>>>(tmB, a);
   return static_cast<int>(cudaGetLastError());

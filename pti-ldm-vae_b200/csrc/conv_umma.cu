@@ -57,7 +57,7 @@ struct ConvArgs {
 };
 
 template <int KCH, int BN, bool F16>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 3)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvArgs args) {
   constexpr uint32_t A_BYTES = 128u * KCH * 2u;
@@ -230,7 +230,9 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs&
                        cudaStream_t stream) {
   constexpr int STAGE = (128 + BN) * KCH * 2;
   const int iters = a.ntaps * (a.Cin / KCH);
-  int stages = (100 * 1024) / STAGE;            // aim for 2 CTAs per SM
+  // These launches are one tile per CTA and latency bound (TMA fill + epilogue drain), so co-residency is
+  // what hides it: aim for 3 CTAs per SM (<= ~72 KB each) rather than a deep pipeline.
+  int stages = (62 * 1024) / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > iters) stages = iters;
   if (stages < 2 && iters >= 2) stages = 2;
