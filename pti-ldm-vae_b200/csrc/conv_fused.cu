@@ -254,9 +254,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
       };
       if (ew == 0 && lane == 0) PTIVAE_TRACE(4);
       const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 2 * COUT + mb0 * COUT;
-      epilogue_tile<F16, COUT, NMB>(tcol, COUT, scr_w, e, rowfn, spart_w, lane, &acc_full[b], (it >> 1) & 1,
-                                    (args.trace != nullptr && blockIdx.x == 0 && it < 64 && ew == 0 && lane == 0)
-                                        ? args.trace + it * 32 + 6 : nullptr);
+      epilogue_tile<F16, COUT, NMB>(tcol, COUT, scr_w, e, rowfn, spart_w, lane, &acc_full[b], (it >> 1) & 1);
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);

@@ -46,7 +46,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 template <bool F16, int NC, int NMB, class RowFn>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t blk_stride, float* scr, const EpiOut& e,
                                               RowFn rowfn, float* spart_w, int lane, uint64_t* full_bar,
-                                              uint32_t parity, unsigned long long* trace = nullptr) {
+                                              uint32_t parity) {
   constexpr int SPB = NC / 16;       // slabs per block
   constexpr int F = NMB * SPB;       // flat slab count
   const int q = lane & 3;            // which 4-channel unit of the 16-column slab
@@ -94,18 +94,26 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t blk_strid
   mbar_wait(full_bar, parity);
   tc_fence_after();
   __syncwarp();
-  if (trace) trace[0] = clock64();
 #pragma unroll 1
   for (int f = 0; f < F; ++f) {
     const int mb = f / SPB, c0 = (f - mb * SPB) * 16;
     float4 rcur[4];
+    long long off4[4];
+    bool ok4[4];
 #pragma unroll
-    for (int st = 0; st < 4; ++st) rcur[st] = rnext[st];
+    for (int st = 0; st < 4; ++st) {
+      rcur[st] = rnext[st];
+      long long off = roff[0][st];     // select this block's row offsets once per slab (no dynamic indexing)
+#pragma unroll
+      for (int k = 1; k < NMB; ++k) off = (mb == k) ? roff[k][st] : off;
+      off4[st] = off + c0;
+      ok4[st] = (rmask >> (mb * 4 + st) & 1u) != 0;
+    }
     uint32_t acc[16];
     tmem_ld16(taddr + mb * blk_stride + c0, acc);
     if (f + 1 < F) prefetch(f + 1);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + c0) + q);   // early: off the critical path
     tmem_ld_wait();
-    if (trace && f == 1) trace[1] = clock64();
     {
       float4* row = reinterpret_cast<float4*>(scr + lane * 16);
       const int x = (lane >> 1) & 3;
@@ -115,36 +123,52 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t blk_strid
                                  __uint_as_float(acc[4 * u + 2]), __uint_as_float(acc[4 * u + 3]));
     }
     __syncwarp();
-    if (trace && f == 1) trace[2] = clock64();
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + c0) + q);
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    // four independent row-steps: all shared loads first, then the math, then the stores (explicit ILP --
+    // the first version let the compiler chain the steps through one register set: ~225 cycles per step)
+    float4 v[4];
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
       const int r = st * 8 + rsub;
-      float4 v = reinterpret_cast<const float4*>(scr + r * 16)[q ^ ((r >> 1) & 3)];
-      v.x += b4.x + rcur[st].x; v.y += b4.y + rcur[st].y; v.z += b4.z + rcur[st].z; v.w += b4.w + rcur[st].w;
-      if (rmask >> (mb * 4 + st) & 1u) {
-        long long off = roff[0][st];
+      v[st] = reinterpret_cast<const float4*>(scr + r * 16)[q ^ ((r >> 1) & 3)];
+    }
 #pragma unroll
-        for (int k = 1; k < NMB; ++k) off = (mb == k) ? roff[k][st] : off;
-        off += c0;
-        if (e.out_f32) {
-          *reinterpret_cast<float4*>(static_cast<float*>(e.out) + off) = v;
-          if (e.out16 != nullptr)
-            *reinterpret_cast<uint2*>(static_cast<uint16_t*>(e.out16) + off) =
-                make_uint2(pack2<F16>(v.x, v.y), pack2<F16>(v.z, v.w));
-        } else {
-          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(e.out) + off) =
-              make_uint2(pack2<F16>(v.x, v.y), pack2<F16>(v.z, v.w));
-          // statistics are those of the values a consumer reads back
-          v.x = round16<F16>(v.x); v.y = round16<F16>(v.y); v.z = round16<F16>(v.z); v.w = round16<F16>(v.w);
-        }
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-        s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+    for (int st = 0; st < 4; ++st) {
+      v[st].x += b4.x + rcur[st].x; v[st].y += b4.y + rcur[st].y;
+      v[st].z += b4.z + rcur[st].z; v[st].w += b4.w + rcur[st].w;
+    }
+    if (e.out_f32) {
+#pragma unroll
+      for (int st = 0; st < 4; ++st)
+        if (ok4[st]) *reinterpret_cast<float4*>(static_cast<float*>(e.out) + off4[st]) = v[st];
+      if (e.out16 != nullptr) {
+#pragma unroll
+        for (int st = 0; st < 4; ++st)
+          if (ok4[st])
+            *reinterpret_cast<uint2*>(static_cast<uint16_t*>(e.out16) + off4[st]) =
+                make_uint2(pack2<F16>(v[st].x, v[st].y), pack2<F16>(v[st].z, v[st].w));
+      }
+    } else {
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        const uint2 pk = make_uint2(pack2<F16>(v[st].x, v[st].y), pack2<F16>(v[st].z, v[st].w));
+        if (ok4[st]) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(e.out) + off4[st]) = pk;
+        // statistics are those of the values a consumer reads back
+        unpack2<F16>(pk.x, v[st].x, v[st].y);
+        unpack2<F16>(pk.y, v[st].z, v[st].w);
+      }
+    }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e.cpg > 0) {
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        const float m = ok4[st] ? 1.f : 0.f;
+        const float a0 = v[st].x * m, a1 = v[st].y * m, a2 = v[st].z * m, a3 = v[st].w * m;
+        s[0] += a0; s[1] += a1; s[2] += a2; s[3] += a3;
+        s2[0] = fmaf(a0, a0, s2[0]); s2[1] = fmaf(a1, a1, s2[1]);
+        s2[2] = fmaf(a2, a2, s2[2]); s2[3] = fmaf(a3, a3, s2[3]);
       }
     }
     __syncwarp();  // scratch is rewritten by the next slab
-    if (trace && f == 1) trace[3] = clock64();
     if (e.cpg > 0) {
       // fold the 8 row-lanes that share this 4-channel unit (fixed pattern -> deterministic)
 #pragma unroll
@@ -174,7 +198,6 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t blk_strid
         }
       }
     }
-    if (trace && f < 4) trace[4 + f] = clock64();
   }
 }
 

@@ -38,8 +38,6 @@ for (n, h, w, cin, cout, conv2) in cases:
         for i in range(0, 7):
             print(f"   {i:4d} " + " ".join(f"{int(t[i, k]) - t0:10d}" for k in range(6)))
         for i in (3, 4):
-            e0 = int(t[i, 4])
-            print(f"   tile {i} epilogue detail (rel. to epi_start): acc_ready {int(t[i,6])-e0}  slab1: ld_done {int(t[i,7])-e0} sts_done {int(t[i,8])-e0} stores_done {int(t[i,9])-e0}  slab_end[0..3] " + " ".join(str(int(t[i, 10 + k]) - e0) for k in range(4)))
             m0 = int(t[i, 2])
             print(f"   tile {i} mma detail (rel. to mma_start): wait-done " + " ".join(str(int(t[i, 14 + k]) - m0) for k in range(9)))
             print(f"   tile {i}                               committed " + " ".join(str(int(t[i, 23 + k]) - m0) for k in range(9)))
