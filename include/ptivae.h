@@ -63,11 +63,12 @@ int ptivae_conv_parts(int H, int W, int mode);
  *               Zero padding is applied AFTER the normalisation, as nn.Conv2d(padding=1) does.
  *   w_packed    h16 [9][Cout][Cin]; Cin, Cout in {32, 64, 128}
  *   residual/out/gn_part: as ptivae_conv_umma, with P = ptivae_conv3x3_fused_parts(H, W) (16x16 tiles).
- *   desc_base_offset: 1 = encode (start>>7)&7 in the shifted operand descriptors' base-offset field. */
+ *   impl: 0 = auto; 1 = register-staged kernel (all shapes); 2 = TMA-staged kernel (Cin,Cout <= 64, fp16
+ *         operands, fp32 residual; returns -2 for anything else).  Both produce the same results. */
 int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, int silu, const void* w_packed,
                          const float* bias, const void* residual, int res_f32, void* out, int out_f32,
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,
-                         int desc_base_offset, void* stream);
+                         int impl, void* stream);
 int ptivae_conv3x3_fused_parts(int H, int W);
 /* debug only: device buffer (64*32 uint64) that receives CTA 0's per-role clock64 timeline of subsequent
  * ptivae_conv3x3_fused launches; NULL switches tracing off. */

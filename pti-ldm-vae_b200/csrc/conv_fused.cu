@@ -470,12 +470,19 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                                     void* out, int out_f32, float* gn_part, int gn_groups, int N, int H, int W,
                                     int Cin, int Cout, int f16, int desc_base_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  (void)desc_base_offset;  // kept in the ABI for the hardware probe; the answer is 0 (see file header)
+  const int impl = desc_base_offset;  // 0 = auto, 1 = register-staged kernel (this file), 2 = TMA-staged (conv_tma.cu)
+  if (impl < 0 || impl > 2) return PTIVAE_ERR_ARG;
   if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   if (in_fmt != 2 && in_fmt != (f16 ? 1 : 0)) return PTIVAE_ERR_ARG;  // 16-bit input must use the operand format
   if (!(Cin == 32 || Cin == 64 || Cin == 128) || !(Cout == 32 || Cout == 64 || Cout == 128)) return PTIVAE_ERR_UNSUPPORTED;
   if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
     return PTIVAE_ERR_ARG;
+  if (impl != 1) {
+    FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
+                N, H, W, Cin, Cout, f16, g_fused_trace, impl == 2};
+    const int rc = conv3x3_tma_launch(c, stream);
+    if (rc != PTIVAE_ERR_UNSUPPORTED || impl == 2) return rc;
+  }
   FusedArgs a{};
   a.N = N; a.H = H; a.W = W;
   a.tiles_x = (W + kFT - 1) / kFT;

@@ -225,6 +225,31 @@ int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   return r == CUDA_SUCCESS ? PTIVAE_OK : PTIVAE_ERR_DRIVER;
 }
 
+int encode_tmap(CUtensorMap* map, const void* base, int dtype, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return PTIVAE_ERR_DRIVER;
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_bytes[i - 1];
+  }
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMapDataType dt = dtype == 2   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                        : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(map, dt, rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PTIVAE_OK : PTIVAE_ERR_DRIVER;
+}
+
 template <int KCH, int BN, bool F16>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs& a, int N, int nphase,
                        cudaStream_t stream) {

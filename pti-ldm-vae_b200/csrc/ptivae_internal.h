@@ -10,6 +10,19 @@ namespace ptivae {
 int encode_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes, bool f16);
 
+// dtype: 0 = bf16, 1 = fp16, 2 = fp32
+int encode_tmap(CUtensorMap* map, const void* base, int dtype, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
+struct FusedCall {   // arguments of ptivae_conv3x3_fused, shared by its two implementations
+  const void* x; int in_fmt; const float* scale_shift; int silu; const void* w_packed; const float* bias;
+  const void* residual; int res_f32; void* out; int out_f32; float* gn_part; int gn_groups;
+  int N, H, W, Cin, Cout, f16; unsigned long long* trace; bool force;
+};
+// TMA-staged implementation (conv_tma.cu): returns PTIVAE_ERR_UNSUPPORTED (-2) if the shape/mode has no
+// instantiation, so the caller can fall back to the register-staged kernel.
+int conv3x3_tma_launch(const FusedCall& c, cudaStream_t stream);
+
 inline int grid_for(size_t work_items, int block, int max_blocks = 148 * 16) {
   size_t g = (work_items + block - 1) / block;
   if (g > static_cast<size_t>(max_blocks)) g = max_blocks;

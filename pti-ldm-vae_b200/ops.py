@@ -112,8 +112,7 @@ def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode:
     return r if len(r) > 1 else r[0]
 
 
-FUSED_DESC_BASE_OFFSET = 0   # measured on B200: shifted operand descriptors need base_offset = 0 (the swizzle
-                             # phase comes from absolute smem address bits); 1 is kept only for the probe
+FUSED_IMPL = 0   # 0 auto | 1 register-staged conv_fused.cu | 2 TMA-staged conv_tma.cu (tests force each)
 
 
 def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tensor, bias: torch.Tensor,
@@ -139,7 +138,7 @@ def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tens
             0 if residual is None else residual.element_size())
     _call("conv3x3_fused", meta, 1, _lib.lib().ptivae_conv3x3_fused, _p(x), _fmt(x), _p(scale_shift), int(silu),
           _p(w_packed), _p(bias), _p(residual), res_f32, _p(out), int(out_f32), _p(part), gn_groups, n, h, w, cin,
-          cout, f16, FUSED_DESC_BASE_OFFSET, _stream())
+          cout, f16, FUSED_IMPL, _stream())
     return (out, part) if gn_groups > 0 else out
 
 

@@ -230,6 +230,56 @@ FUSED_CASES = [
 ]
 
 
+# shapes/modes that have a TMA-staged instantiation (conv_tma.cu): ResBlock conv1 (fp32 in, 16-bit out), conv2 to the
+# fp32 stream (16-bit in, fp32 residual, fp32 out) and conv2 to a 16-bit operand; fp16 operands, Cin/Cout <= 64
+TMA_CASES = [
+    # (N, H, W, Cin, Cout, in_f32, res, out_f32, groups)
+    (2, 32, 32, 32, 32, True, False, False, 16),
+    (2, 32, 32, 32, 32, False, True, True, 16),
+    (1, 48, 40, 32, 32, False, True, False, 16),     # edge tiles (extents not multiples of 16)
+    (2, 24, 24, 64, 64, True, False, False, 16),
+    (3, 40, 24, 64, 64, False, True, True, 32),
+    (1, 32, 32, 32, 64, True, False, False, 16),
+    (1, 32, 32, 64, 32, True, False, False, 16),
+    (2, 16, 16, 64, 32, False, True, True, 16),
+    (1, 8, 8, 32, 64, False, True, False, 32),       # image smaller than a tile
+    (9, 64, 64, 32, 32, False, True, True, 16),      # several tiles per CTA on any SM count >= 16
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,in_f32,res,out_f32,groups", TMA_CASES)
+def test_conv3x3_fused_tma(b200, n, h, w, cin, cout, in_f32, res, out_f32, groups):
+    if DT != torch.float16:
+        pytest.skip("the TMA-staged kernel is instantiated for fp16 operands only")
+    x = _rand_act(n, h, w, cin, 41).float() * 1.5 + 0.2
+    x = x + 1e-3 * torch.randn_like(x) if in_f32 else x.to(DT)
+    wt, bias = _rand_conv(cout, cin, 3, 42)
+    ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
+    xin = F.silu(x.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
+    r = torch.randn(n, h, w, cout, device=DEV) if res else None
+    ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r
+    wp = b200.ops.pack_conv_weight(wt, 0, DT)
+    outs = {}
+    try:
+        for impl in (2, 1):
+            b200.ops.FUSED_IMPL = impl
+            out, part = b200.ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+            out2, part2 = b200.ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+            assert torch.equal(out, out2) and torch.equal(part, part2), f"impl {impl} not deterministic"
+            _check_bf16(out.to(DT), ref, f"fused conv impl={impl}")
+            o = out.float().view(n, h * w, groups, cout // groups)
+            acc = part.sum(dim=1)
+            assert torch.allclose(acc[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2), impl
+            assert torch.allclose(acc[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2), impl
+            outs[impl] = out.float()
+    finally:
+        b200.ops.FUSED_IMPL = 0
+    # both implementations compute the same thing (fp32 add order differs by at most an ulp or a 16-bit flip)
+    assert float((outs[1] - outs[2]).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,in_f32,norm,silu,res,out_f32,groups", FUSED_CASES)
 def test_conv3x3_fused(b200, n, h, w, cin, cout, in_f32, norm, silu, res, out_f32, groups):
     x = _rand_act(n, h, w, cin, 31).float() * 1.5 + 0.2

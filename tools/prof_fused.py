@@ -5,7 +5,9 @@ import torch
 import _pkg
 b200 = _pkg.load(); ops = b200.ops; lib = b200._lib.lib()
 trace = len(sys.argv) > 1 and sys.argv[1] == "trace"
-cases = [(64, 256, 256, 32, 32, True), (64, 256, 256, 32, 32, False), (64, 64, 64, 128, 128, True), (64, 128, 128, 64, 64, True)]
+if len(sys.argv) > 2: ops.FUSED_IMPL = int(sys.argv[2])
+print("FUSED_IMPL", ops.FUSED_IMPL)
+cases = [(64, 256, 256, 32, 32, True), (64, 256, 256, 32, 32, False), (64, 64, 64, 128, 128, True), (64, 128, 128, 64, 64, True), (64, 128, 128, 64, 64, False), (64, 256, 256, 64, 32, False), (64, 128, 128, 32, 64, False)]
 for (n, h, w, cin, cout, conv2) in cases:
     g = torch.Generator().manual_seed(1)
     x = torch.randn(n, h, w, cin, device="cuda", dtype=torch.float32 if not conv2 else torch.float16)
@@ -36,7 +38,7 @@ for (n, h, w, cin, cout, conv2) in cases:
         names = ["xf_start", "xf_end", "mma_start", "mma_issued", "epi_start", "epi_end"]
         print("   tile " + " ".join(f"{nm:>10s}" for nm in names))
         for i in range(0, 7):
-            print(f"   {i:4d} " + " ".join(f"{int(t[i, k]) - t0:10d}" for k in range(6)))
+            print(f"   {i:4d} " + " ".join(f"{int(t[i, k]) - t0:10d}" for k in range(6)) + "   | os_ready acc_ready drained: " + " ".join(f"{int(t[i, k]) - int(t[i, 4]):7d}" for k in (6, 7, 8, 9, 10)))
         for i in (3, 4):
             m0 = int(t[i, 2])
             print(f"   tile {i} mma detail (rel. to mma_start): wait-done " + " ".join(str(int(t[i, 14 + k]) - m0) for k in range(9)))
