@@ -133,6 +133,23 @@ int ptivae_kl_loss(const float* mu, const float* t, float* workspace, float* out
  *   n % 4 == 0, 16-byte aligned inputs; workspace: 2*1184 floats. */
 int ptivae_l1l2(const float* a, const float* b, float* workspace, float* out, long long n, void* stream);
 
+/* latent_vectors = z_mu.mean((2,3)) (vae_scripts/train_vae.py:387-389): x fp32 [BC][HW] -> out [BC]. */
+int ptivae_spatial_mean(const float* x, float* out, int BC, int HW, void* stream);
+
+/* compute_ar_vae_loss (/root/reference/src/pti_ldm_vae/models/losses.py:69-166) on the device.
+ *   zbar [B][C] fp32 latent vectors; attrs [L][B] attribute values; channel [L] latent channel per attribute;
+ *   delta [L]; pairs: NULL = all ordered pairs i != j ("all" mode), else int32 [P][2] explicit (i, j) pairs
+ *   ("subset" mode: the host samples them exactly as the reference does).
+ *   loss_per_attr [L] = mean over pairs with a_j != a_i of (tanh(delta*(z_j-z_i)) - sign(a_j-a_i))^2 (0 if none),
+ *   pair_count [L] = number of such pairs, total[0] = sum of loss_per_attr. */
+int ptivae_ar_vae_loss(const float* zbar, const float* attrs, const int* channel, const float* delta, const int* pairs,
+                       int P, int B, int C, int L, float* loss_per_attr, int* pair_count, float* total, void* stream);
+
+/* y [B][O] = act(x [B][I] * W[O][I]^T + b): nn.Linear (+activation) of LatentRegressor
+ * (/root/reference/src/pti_ldm_vae/models/regression_head.py:30-78).  act: 0 none, 1 relu, 2 gelu, 3 leaky_relu, 4 elu. */
+int ptivae_linear_act(const float* x, const float* w, const float* bias, float* y, int B, int I, int O, int act,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

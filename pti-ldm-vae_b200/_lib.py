@@ -38,6 +38,9 @@ SIGNATURES = {
     "ptivae_rng_advance": [_c_void_p, _c_void_p],
     "ptivae_kl_loss": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
     "ptivae_l1l2": [_c_void_p] * 4 + [_c_ll, _c_void_p],
+    "ptivae_spatial_mean": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+    "ptivae_ar_vae_loss": [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p] * 4,
+    "ptivae_linear_act": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
 }
 
 _lib = None

@@ -34,3 +34,68 @@ def compute_total_loss(recons_loss, kl_loss, perceptual_loss, adv_gen_loss, ar_l
     if ar_vae_enabled:
         total = total + ar_gamma * ar_loss
     return total
+
+
+def compute_ar_vae_loss(latent_vectors: torch.Tensor, attributes: dict, attribute_latent_mapping: dict, pairwise_mode: str,
+                        subset_pairs, delta_global):
+    """Attribute-regularised VAE loss with the reference's signature, validation and return tuple
+    (/root/reference/src/pti_ldm_vae/models/losses.py:69-166): ``(total_loss, losses_per_attr, pair_counts, deltas_per_attr)``.
+    All attributes are evaluated by ONE kernel (no host pair lists in "all" mode, one device->host read for the
+    pair counts instead of two syncs per attribute).  "subset" mode samples pairs on the host with
+    ``random.sample`` exactly like the reference, so a seeded ``random`` gives the same pairs."""
+    if latent_vectors.dim() == 4:
+        latent_vectors = ops.spatial_mean(latent_vectors)
+    elif latent_vectors.dim() != 2:
+        raise ValueError(f"Expected latent shape [B, C] or [B, C, H, W], got {latent_vectors.shape}")
+    latent_vectors = latent_vectors.detach().contiguous().float()
+    batch_size, latent_dim = latent_vectors.shape
+    if pairwise_mode not in {"all", "subset"}:
+        raise ValueError(f"pairwise must be 'all' or 'subset', got {pairwise_mode}")
+    if pairwise_mode == "subset" and (subset_pairs is None or subset_pairs <= 0):
+        raise ValueError("subset_pairs must be a positive integer when pairwise='subset'")
+    dev = latent_vectors.device
+    names, chans, deltas, rows = [], [], [], []
+    for attr_name, mapping in attribute_latent_mapping.items():
+        target_latent = int(mapping["latent_channel"])
+        if target_latent >= latent_dim:
+            raise ValueError(f"Latent channel {target_latent} for attribute {attr_name} exceeds latent size {latent_dim}")
+        attr_values = attributes.get(attr_name)
+        if attr_values is None:
+            raise KeyError(f"Missing attribute values for {attr_name} in batch.")
+        delta_attr = mapping.get("delta")
+        if delta_attr is None and delta_global and delta_global.get("enabled", False):
+            delta_attr = delta_global.get("value")
+        if delta_attr is None:
+            raise ValueError(f"Delta not provided for {attr_name} and no delta_global fallback.")
+        names.append(attr_name)
+        chans.append(target_latent)
+        deltas.append(float(delta_attr))
+        rows.append(torch.as_tensor(attr_values, dtype=torch.float32).to(dev).reshape(-1))
+    if not names:
+        return torch.tensor(0.0, device=dev), {}, {}, {}
+    zero = torch.tensor(0.0, device=dev)
+    if batch_size < 2:
+        return zero, {n: zero.clone() for n in names}, {n: 0 for n in names}, dict(zip(names, deltas))
+    attrs = torch.stack(rows).contiguous()
+    ch = torch.tensor(chans, device=dev, dtype=torch.int32)
+    dl = torch.tensor(deltas, device=dev, dtype=torch.float32)
+    if pairwise_mode == "all":
+        loss, cnt, tot = ops.ar_vae_loss(latent_vectors, attrs, ch, dl, None)
+        cnt_h = cnt.tolist()
+        total = tot[0]
+        per = loss
+    else:
+        import random
+        all_pairs = [(i, j) for i in range(batch_size) for j in range(batch_size) if i != j]
+        per_list, cnt_h = [], []
+        for k in range(len(names)):           # the reference draws a fresh sample per attribute, in mapping order
+            pairs = random.sample(all_pairs, min(len(all_pairs), int(subset_pairs)))
+            pt = torch.tensor(pairs, device=dev, dtype=torch.int32).contiguous()
+            l1, c1, _ = ops.ar_vae_loss(latent_vectors, attrs[k:k + 1].contiguous(), ch[k:k + 1].contiguous(),
+                                        dl[k:k + 1].contiguous(), pt)
+            per_list.append(l1[0])
+            cnt_h.append(int(c1[0]))
+        per = torch.stack(per_list)
+        total = per.sum()
+    return (total, {n: per[k] for k, n in enumerate(names)}, {n: int(cnt_h[k]) for k, n in enumerate(names)},
+            dict(zip(names, deltas)))

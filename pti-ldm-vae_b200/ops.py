@@ -258,3 +258,42 @@ def l1l2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty(2, device=a.device, dtype=torch.float32)
     _call("l1l2", None, 2, _lib.lib().ptivae_l1l2, _p(a), _p(b), _p(ws), _p(out), a.numel(), _stream())
     return out
+
+
+def spatial_mean(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 -> [B,C] (mean over H,W)."""
+    _need_cuda(x)
+    x = x.detach().contiguous().float()
+    b, c = x.shape[:2]
+    out = torch.empty((b, c), device=x.device, dtype=torch.float32)
+    _call("spatial_mean", None, 1, _lib.lib().ptivae_spatial_mean, _p(x), _p(out), b * c, x.numel() // (b * c), _stream())
+    return out
+
+
+def ar_vae_loss(zbar: torch.Tensor, attrs: torch.Tensor, channel: torch.Tensor, delta: torch.Tensor, pairs=None):
+    """zbar [B,C], attrs [L,B], channel int32 [L], delta [L], pairs int32 [P,2] | None -> (per-attr loss [L], counts int32 [L], total [1])."""
+    _need_cuda(zbar, attrs, channel, delta)
+    b, c = zbar.shape
+    l = attrs.shape[0]
+    loss = torch.empty(l, device=zbar.device, dtype=torch.float32)
+    cnt = torch.empty(l, device=zbar.device, dtype=torch.int32)
+    tot = torch.empty(1, device=zbar.device, dtype=torch.float32)
+    _call("ar_vae_loss", None, 2, _lib.lib().ptivae_ar_vae_loss, _p(zbar), _p(attrs), _p(channel), _p(delta), _p(pairs),
+          0 if pairs is None else pairs.shape[0], b, c, l, _p(loss), _p(cnt), _p(tot), _stream())
+    return loss, cnt, tot
+
+
+_ACTS = {None: 0, "none": 0, "relu": 1, "gelu": 2, "leaky_relu": 3, "elu": 4}
+
+
+def linear_act(x: torch.Tensor, w: torch.Tensor, b, act: str | None = None) -> torch.Tensor:
+    """fp32 [B,I] x [O,I]^T + b, optional activation -> [B,O]."""
+    _need_cuda(x, w)
+    x = x.detach().contiguous().float()
+    w = w.detach().contiguous().float()
+    bsz, i = x.shape
+    o = w.shape[0]
+    y = torch.empty((bsz, o), device=x.device, dtype=torch.float32)
+    _call("linear_act", None, 1, _lib.lib().ptivae_linear_act, _p(x), _p(w), _p(None if b is None else b.detach()), _p(y),
+          bsz, i, o, _ACTS[act], _stream())
+    return y

@@ -45,8 +45,53 @@ def ref_losses():
                                              ar_gamma=0.5, ar_vae_enabled=True).numpy()
     out["total_noar"] = mod.compute_total_loss(*t, kl_weight=1e-3, perceptual_weight=1.0, adv_weight=3.0,
                                                ar_gamma=0.5, ar_vae_enabled=False).numpy()
+    # AR-VAE loss of the reference itself ("all" pairs and a seeded "subset")
+    import random
+    zb = torch.randn(12, 10, generator=g)
+    attrs = {f"a{k}": torch.randint(20, 200, (12,), generator=g).float() for k in range(3)}
+    attrs["a1"][3] = attrs["a1"][7]              # ties -> sign 0 pairs are dropped
+    mapping = {"a0": {"latent_channel": 0, "delta": 1.0}, "a1": {"latent_channel": 4}, "a2": {"latent_channel": 9, "delta": 0.25}}
+    dg = {"enabled": True, "value": 2.0}
+    tot, per, cnt, dl = mod.compute_ar_vae_loss(zb, attrs, mapping, "all", None, dg)
+    out.update({"ar_z": zb.numpy(), "ar_total": tot.numpy(), "ar_per": np.array([float(per[k]) for k in mapping]),
+                "ar_cnt": np.array([cnt[k] for k in mapping]), "ar_delta": np.array([dl[k] for k in mapping])})
+    for k, v in attrs.items():
+        out["ar_attr_" + k] = v.numpy()
+    random.seed(123)
+    tot, per, cnt, _ = mod.compute_ar_vae_loss(zb, attrs, mapping, "subset", 40, dg)
+    out.update({"ars_total": tot.numpy(), "ars_per": np.array([float(per[k]) for k in mapping]),
+                "ars_cnt": np.array([cnt[k] for k in mapping])})
+    z4 = torch.randn(5, 10, 4, 4, generator=g)
+    tot4, _, _, _ = mod.compute_ar_vae_loss(z4, {k: v[:5] for k, v in attrs.items()}, mapping, "all", None, dg)
+    out.update({"ar_z4": z4.numpy(), "ar_total4": tot4.numpy()})
     np.savez_compressed(HERE / "losses_ref.npz", **out)
     print("losses_ref.npz", {k: float(v) for k, v in out.items() if v.ndim == 0})
+
+
+def ref_regressor():
+    """LatentRegressor of the reference itself (regression_head.py imports pti_ldm_vae.models.autoencoder, which
+    needs MONAI: stub that module, the class under test is pure torch)."""
+    import types
+    stub = types.ModuleType("pti_ldm_vae.models.autoencoder")
+    stub.VAEModel = object
+    for name in ("pti_ldm_vae", "pti_ldm_vae.models"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pti_ldm_vae.models.autoencoder"] = stub
+    p = pathlib.Path("/root/reference/src/pti_ldm_vae/models/regression_head.py")
+    spec = importlib.util.spec_from_file_location("ref_reg", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    for tag, act, drop in (("relu", "relu", 0.1), ("gelu", "gelu", 0.0), ("lrelu", "leaky_relu", 0.0), ("elu", "elu", 0.0)):
+        torch.manual_seed(77)
+        reg = mod.LatentRegressor(in_features=4096, hidden_dims=[256, 32], output_dim=6, dropout=drop, activation=act).eval()
+        x = torch.randn(5, 4096, generator=torch.Generator().manual_seed(5))
+        with torch.no_grad():
+            out[tag] = reg(x).numpy()
+        out[tag + "_keys"] = np.array(list(reg.state_dict().keys()))
+    out["x"] = x.numpy()
+    np.savez_compressed(HERE / "regressor_ref.npz", **out)
+    print("regressor_ref.npz", {k: v.shape for k, v in out.items() if not k.endswith("_keys")})
 
 
 def param_checksum(model):
@@ -91,6 +136,7 @@ def aekl_case(name, cfg, b, h, w, taps):
 if __name__ == "__main__":
     if pathlib.Path("/root/reference").exists():
         ref_losses()
+        ref_regressor()
     aekl_case("aekl_A_64", CFG.AUTOENCODER_DEF_A, 2, 64, 64, {"encoder.blocks.3", "encoder.blocks.13", "decoder.blocks.6"})
     aekl_case("aekl_A_256", CFG.AUTOENCODER_DEF_A, 1, 256, 256, set())
     aekl_case("aekl_B_64", CFG.AUTOENCODER_DEF_B, 1, 64, 64, {"encoder.blocks.10"})

@@ -130,3 +130,54 @@ def test_graph_replay_matches_eager(b200, oracle):
     torch.cuda.synchronize()
     assert not torch.equal(r1, r2), "noise must be fresh on every replay"
     vae.autoencoder._rng_dev = None
+
+
+AR_MAPPING = {"a0": {"latent_channel": 0, "delta": 1.0}, "a1": {"latent_channel": 4}, "a2": {"latent_channel": 9, "delta": 0.25}}
+AR_DG = {"enabled": True, "value": 2.0}
+
+
+def test_ar_vae_loss_matches_reference_golden(b200, oracle):
+    """compute_ar_vae_loss (row a17) vs outputs of the reference's own function (tests/golden/losses_ref.npz)."""
+    import random
+    g = np.load(GOLD / "losses_ref.npz")
+    z = torch.from_numpy(g["ar_z"]).to(DEV)
+    attrs = {k: torch.from_numpy(g["ar_attr_" + k]) for k in AR_MAPPING}          # CPU tensors, as a DataLoader yields
+    tot, per, cnt, dl = b200.compute_ar_vae_loss(z, attrs, AR_MAPPING, "all", None, AR_DG)
+    assert abs(float(tot) - float(g["ar_total"])) <= TOL_LOSS * float(g["ar_total"])
+    assert np.allclose([float(per[k]) for k in AR_MAPPING], g["ar_per"], rtol=TOL_LOSS)
+    assert [cnt[k] for k in AR_MAPPING] == list(g["ar_cnt"]) and [dl[k] for k in AR_MAPPING] == list(g["ar_delta"])
+    random.seed(123)
+    tot, per, cnt, _ = b200.compute_ar_vae_loss(z, attrs, AR_MAPPING, "subset", 40, AR_DG)
+    assert abs(float(tot) - float(g["ars_total"])) <= TOL_LOSS * float(g["ars_total"])
+    assert [cnt[k] for k in AR_MAPPING] == list(g["ars_cnt"])
+    z4 = torch.from_numpy(g["ar_z4"]).to(DEV)
+    tot4, _, _, _ = b200.compute_ar_vae_loss(z4, {k: v[:5] for k, v in attrs.items()}, AR_MAPPING, "all", None, AR_DG)
+    assert abs(float(tot4) - float(g["ar_total4"])) <= TOL_LOSS * float(g["ar_total4"])
+    # all attribute values equal -> no valid pair -> zero loss, zero count (reference semantics)
+    t0, p0, c0, _ = b200.compute_ar_vae_loss(z, {"a0": torch.ones(12)}, {"a0": {"latent_channel": 0, "delta": 1.0}}, "all", None, None)
+    assert float(t0) == 0.0 and c0["a0"] == 0
+
+
+def test_regressor_matches_reference_golden(b200, oracle):
+    """LatentRegressor (row a18) vs outputs of the reference's own class; VAELatentRegressor end to end vs the oracle."""
+    g = np.load(GOLD / "regressor_ref.npz")
+    x = torch.from_numpy(g["x"]).to(DEV)
+    for tag, act, drop in (("relu", "relu", 0.1), ("gelu", "gelu", 0.0), ("lrelu", "leaky_relu", 0.0), ("elu", "elu", 0.0)):
+        torch.manual_seed(77)
+        reg = b200.LatentRegressor(4096, [256, 32], 6, dropout=drop, activation=act).to(DEV).eval()
+        out = reg(x)
+        ref = torch.from_numpy(g[tag])
+        assert float((out.cpu() - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), tag   # fp32 path
+    cfg = b200.config.AUTOENCODER_DEF_A
+    ref_vae, vae = _models(b200, oracle, cfg)
+    torch.manual_seed(3)
+    head = b200.LatentRegressor(4 * 8 * 8, [64, 16], 6, dropout=0.1).to(DEV).eval()
+    head_ref = oracle.LatentRegressorRef(4 * 8 * 8, [64, 16], 6, dropout=0.1).eval()
+    head_ref.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
+    assert b200.VAELatentRegressor.infer_flat_dim_from_patch(vae, (64, 64), torch.device(DEV)) == 256
+    model = b200.VAELatentRegressor(vae, head, latent_dim=256)
+    imgs = oracle.synthetic_images(3, 64, 64, seed=9)
+    with torch.no_grad():
+        want = head_ref(torch.flatten(ref_vae.encode(imgs)[0], 1))
+    got = model(imgs.to(DEV)).cpu()
+    assert float((got - want).norm() / want.norm()) <= TOL_LATENT
