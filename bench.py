@@ -151,13 +151,17 @@ def classify(name, meta):
         n, h, w, cin, cout, in_esz, out_esz, res_esz = meta
         flops = 2.0 * n * h * w * cout * cin * 9
         byt = n * h * w * (in_esz * cin + (out_esz + res_esz) * cout) + 2.0 * 9 * cin * cout
-        return (f"fused3x3_{cin}->{cout}@{h}x{w}", flops, byt)
+        return (f"fused3x3_{cin}->{cout}@{h}x{w}_in{in_esz}_res{res_esz}_out{out_esz}", flops, byt)
+    if name == "up2x_conv3x3":
+        n, h, w, c, e16 = meta
+        return (f"up2x_conv3x3_{c}@{h}x{w}", 2.0 * n * 4 * h * w * c * c * 9,      # nominal direct-form count
+                n * h * w * c * (2.0 + 4 * (4.0 + 2.0 * e16)) + 2.0 * 16 * c * c)
     if name == "conv3x3_small_cin":
-        n, h, w, cin, cout = meta
-        return (f"small_cin_{cin}->{cout}@{h}x{w}", 2.0 * n * h * w * cin * cout * 9, n * h * w * (4.0 * cin + 2.0 * cout))
+        n, h, w, cin, cout, oesz = meta
+        return (f"small_cin_{cin}->{cout}@{h}x{w}", 2.0 * n * h * w * cin * cout * 9, n * h * w * (4.0 * cin + float(oesz) * cout))
     if name == "conv3x3_small_cout":
-        n, h, w, cin, cout = meta
-        return (f"small_cout_{cin}->{cout}@{h}x{w}", 2.0 * n * h * w * cin * cout * 9, n * h * w * (2.0 * cin + 4.0 * cout))
+        n, h, w, cin, cout, iesz = meta
+        return (f"small_cout_{cin}->{cout}@{h}x{w}", 2.0 * n * h * w * cin * cout * 9, n * h * w * (float(iesz) * cin + 4.0 * cout))
     if name == "attention_fwd":
         b, l, d = meta
         return (f"attention_L{l}_d{d}", 4.0 * b * l * l * d, 8.0 * b * l * d)
@@ -176,9 +180,11 @@ def kernel_breakdown(model, x, passes: int):
         torch.cuda.synchronize()
         for name, meta, e0, e1 in ops.PROFILE:
             key, fl, by = classify(name, meta)
-            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": fl, "bytes": by})
+            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})   # sums over launches
             a["ms"] += e0.elapsed_time(e1)
             a["launches"] += 1
+            a["flops"] += fl
+            a["bytes"] += by
         ops.PROFILE = None
     return agg
 
@@ -281,16 +287,16 @@ def run_b200(args) -> None:
         agg = kernel_breakdown(vae.autoencoder, x_dev, passes=2)
         tot_ms = sum(a["ms"] for a in agg.values())
         top_key, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        avg_s = top["ms"] / top["launches"] * 1e-3
+        tot_s = top["ms"] * 1e-3
         ai = top["flops"] / max(top["bytes"], 1.0)
         ridge = peaks.get("bf16_tflops_sustained", 1400.0) * 1e12 / (peaks.get("hbm_gbs", 6650.0) * 1e9)
         if top["flops"] > 0 and ai >= ridge:
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            roof = {"bound": "tensor", "achieved": top["flops"] / avg_s / 1e12, "peak": peak, "unit": "TFLOP/s"}
+            roof = {"bound": "tensor", "achieved": top["flops"] / tot_s / 1e12, "peak": peak, "unit": "TFLOP/s"}
             roof["peak_source"] = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
         else:
             peak = peaks.get("hbm_gbs", 6650.0)
-            roof = {"bound": "hbm", "achieved": top["bytes"] / avg_s / 1e9, "peak": peak, "unit": "GB/s"}
+            roof = {"bound": "hbm", "achieved": top["bytes"] / tot_s / 1e9, "peak": peak, "unit": "GB/s"}
             roof["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
         roof["frac"] = roof["achieved"] / roof["peak"]
         # DRAM traffic per launch of that kernel class from the committed ncu --set full capture, if any
@@ -302,10 +308,11 @@ def run_b200(args) -> None:
         roof["share_of_step"] = top["ms"] / tot_ms
         roof["avg_launch_ms"] = top["ms"] / top["launches"]
         roof["launches_per_step"] = top["launches"] // 2
+        roof["algorithmic_bytes_per_launch"] = top["bytes"] / top["launches"]
         model_tflops = GFLOP_PER_IMG_A256 * (S / 256.0) ** 2 * 1e9 * value / world / 1e12 if S == 256 else None
         breakdown = {k: {"ms_per_step": v["ms"] / 2, "launches": v["launches"] // 2,
-                         "tflops": (v["flops"] * v["launches"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None,
-                         "gbs": v["bytes"] * v["launches"] / (v["ms"] * 1e-3) / 1e9}
+                         "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None,
+                         "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
         out_dir = ROOT / "gpurun_out"
         out_dir.mkdir(exist_ok=True)

@@ -70,6 +70,18 @@ int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, in
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,
                          int impl, void* stream);
 int ptivae_conv3x3_fused_parts(int H, int W);
+/* Nearest x2 upsample + 3x3 conv (pad 1) in one halo-resident kernel: out = conv3x3(upsample2x(x)) + bias.
+ *   replaces: monai UpSample(mode="nontrainable", interp_mode="nearest") + its post-conv inside the decoder
+ *             (monai 1.5.1 networks/nets/autoencoderkl.py Decoder; via autoencoder.py:151), for the widths where
+ *             it beats ptivae_conv_umma mode 2: C in {64, 128}, fp16 operands (anything else returns -2).
+ *   x         h16 [N][H][W][C] raw operand (no normalisation: the producer stored the operand format)
+ *   w_packed  h16 [16][C][C] from ptivae_pack_conv_weight(mode = 2) (4 phases x 2x2 pre-summed taps)
+ *   out       fp32 [N][2H][2W][C] (the residual stream);  out16: optional h16 copy (NULL ok)
+ *   gn_part   fp32 [N][P][gn_groups][2] statistics of the stored fp32 values, P = ptivae_up2x_conv3x3_parts(H, W)
+ *             (one partial per 16x16 low-res tile); ignored when gn_groups == 0 */
+int ptivae_up2x_conv3x3(const void* x, const void* w_packed, const float* bias, float* out, void* out16,
+                        float* gn_part, int gn_groups, int N, int H, int W, int C, int f16, void* stream);
+int ptivae_up2x_conv3x3_parts(int H, int W);
 /* debug only: device buffer (64*32 uint64) that receives CTA 0's per-role clock64 timeline of subsequent
  * ptivae_conv3x3_fused launches; NULL switches tracing off. */
 int ptivae_debug_set_trace(void* buf);

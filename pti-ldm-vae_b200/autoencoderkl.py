@@ -175,8 +175,11 @@ class _Executor:
              out_f32: bool = False, emit16: bool = False) -> _Act:
         w = conv.weight
         g = self._want_stats(w.shape[0], stats)
-        r = ops.conv_umma(x, self.packed(w, 2 if mode == 2 else 0), self.f32(conv.bias), mode, residual=residual,
-                          gn_groups=g, out_f32=out_f32, emit16=emit16)
+        if mode == 2 and out_f32 and residual is None and self.fused_conv and ops.up2x_supported(x):
+            r = ops.up2x_conv3x3(x, self.packed(w, 2), self.f32(conv.bias), gn_groups=g, emit16=emit16)
+        else:
+            r = ops.conv_umma(x, self.packed(w, 2 if mode == 2 else 0), self.f32(conv.bias), mode, residual=residual,
+                              gn_groups=g, out_f32=out_f32, emit16=emit16)
         if not isinstance(r, tuple):
             return _Act(r)
         out = r[0]
@@ -241,10 +244,12 @@ class _Executor:
                                        dtype=self.op_dtype if operand_only(0) else torch.float32))
         for i, blk in enumerate(body):
             nxt_operand = operand_only(i + 1)
+            # the last body tensor is read only by the final norm + conv: 16-bit storage (statistics still needed)
+            to_stream = not (nxt_operand or i + 1 == len(body))
             if isinstance(blk, AEKLResBlock):
-                a = self.resblock(blk, a, out_f32=not nxt_operand, stats=not nxt_operand)
+                a = self.resblock(blk, a, out_f32=to_stream, stats=not nxt_operand)
             elif isinstance(blk, SpatialAttentionBlock):
-                a = self.attention(blk, a, out_f32=not nxt_operand, stats=not nxt_operand)
+                a = self.attention(blk, a, out_f32=to_stream, stats=not nxt_operand)
             elif isinstance(blk, (AEKLDownsample, UpSample)):
                 xin = a.t
                 assert xin.dtype == self.op_dtype, "scheduler bug: down/up-sample operand must be 16-bit"

@@ -179,75 +179,180 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
   }
 }
 
-// Single-output-channel 3x3 conv (the decoder's final conv: GroupNorm affine, no activation, 32|64 -> 1).
-// out(y,x) = sum_taps sum_c w[tap][c] * n(y+dy, x+dx, c) is evaluated as per-pixel tap dot products
-//   p[tap](y,x) = sum_c w[tap][c] * n(y,x,c)           (every input pixel is read from HBM exactly once)
-// staged in shared memory for an 18x18 halo of a 16x16 output tile, followed by a 9-point gather
-//   out(y,x) = bias + sum_tap p[tap](y+dy, x+dx).
-// Out-of-image halo pixels contribute p = 0: the zero padding applies to the normalised tensor.
-constexpr int kC1T = 16, kC1H = kC1T + 2;
-__global__ void __launch_bounds__(256) conv3x3_cout1_kernel(const void* __restrict__ x, const float* __restrict__ w,
-                                                            const float* __restrict__ bias,
-                                                            const float* __restrict__ ss, float* __restrict__ out,
-                                                            int H, int W, int Cin, int in_fmt) {
-  extern __shared__ float c1s[];
-  float* swt = c1s;                       // [9][Cin] weights, tap-major
-  float* sss = swt + 9 * Cin;             // [Cin][2] scale/shift of this image (identity when ss == null)
-  float* sp = sss + 2 * Cin;              // [9][kC1H*kC1H] tap partials
+// Single-input-channel 3x3 conv (the encoder's first conv, 1 -> 32|64): thread -> (x, 8 consecutive output
+// channels) walking kSmallRows image rows.  The first version read its weights from shared memory inside the
+// tap loop (2 LDS.128 per 8 FMAs: the LSU pipe, not HBM, bounded it at 1.1 TB/s); here the thread's 72 weights
+// live in registers and the 3x3 input window slides down the rows (3 new loads per row).
+__global__ void __launch_bounds__(256) conv3x3_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, void* __restrict__ out,
+                                                           int H, int W, int Cout, int out_fmt) {
+  const int vecs = Cout / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int px = i / vecs, v = i - px * vecs;
+  if (px >= W) return;
   const int n = blockIdx.z;
-  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
-    const int tap = i / Cin, ci = i - tap * Cin;
-    swt[i] = w[ci * 9 + tap];             // w is [1][Cin][3][3]
-  }
-  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
-    sss[2 * i] = ss ? ss[(static_cast<size_t>(n) * Cin + i) * 2] : 1.f;
-    sss[2 * i + 1] = ss ? ss[(static_cast<size_t>(n) * Cin + i) * 2 + 1] : 0.f;
-  }
-  __syncthreads();
-  const int y0 = blockIdx.y * kC1T - 1, x0 = blockIdx.x * kC1T - 1;
-  const size_t esz = in_fmt == 2 ? 4 : 2;
-  const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * esz;
-  for (int hp = threadIdx.x; hp < kC1H * kC1H; hp += blockDim.x) {
-    const int hy = hp / kC1H, hx = hp - hy * kC1H;
-    const int gy = y0 + hy, gx = x0 + hx;
-    float acc[9];
+  float wr[9][8], br[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-    if (static_cast<unsigned>(gy) < static_cast<unsigned>(H) && static_cast<unsigned>(gx) < static_cast<unsigned>(W)) {
-      const uint8_t* p = img + (static_cast<size_t>(gy) * W + gx) * Cin * esz;
-      for (int c4 = 0; c4 < Cin / 4; ++c4) {
-        float v[4];
-        if (in_fmt == 2) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p) + c4);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        } else {
-          const uint2 a = __ldg(reinterpret_cast<const uint2*>(p) + c4);
-          if (in_fmt == 1) { unpack2<true>(a.x, v[0], v[1]); unpack2<true>(a.y, v[2], v[3]); }
-          else { unpack2<false>(a.x, v[0], v[1]); unpack2<false>(a.y, v[2], v[3]); }
-        }
-        const float4 s0 = reinterpret_cast<const float4*>(sss)[2 * c4], s1 = reinterpret_cast<const float4*>(sss)[2 * c4 + 1];
-        v[0] = fmaf(v[0], s0.x, s0.y); v[1] = fmaf(v[1], s0.z, s0.w);
-        v[2] = fmaf(v[2], s1.x, s1.y); v[3] = fmaf(v[3], s1.z, s1.w);
+  for (int j = 0; j < 8; ++j) {
+    br[j] = __ldg(bias + v * 8 + j);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 wv = reinterpret_cast<const float4*>(swt + t * Cin)[c4];   // warp-uniform: broadcast
-          acc[t] = fmaf(v[0], wv.x, fmaf(v[1], wv.y, fmaf(v[2], wv.z, fmaf(v[3], wv.w, acc[t]))));
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) sp[t * (kC1H * kC1H) + hp] = acc[t];
+    for (int t = 0; t < 9; ++t) wr[t][j] = __ldg(w + (v * 8 + j) * 9 + t);   // w is [Cout][1][3][3]
   }
-  __syncthreads();
-  const int ty = threadIdx.x / kC1T, tx = threadIdx.x % kC1T;
-  const int gy = blockIdx.y * kC1T + ty, gx = blockIdx.x * kC1T + tx;
-  if (gy < H && gx < W) {
-    float o = __ldg(bias);
+  const float* xp = x + static_cast<size_t>(n) * H * W;
+  const int r0 = blockIdx.y * kSmallRows, r1 = min(H, r0 + kSmallRows);
+  const bool hl = px > 0, hr = px + 1 < W;
+  auto load_row = [&](int yy, float (&r)[3]) {
+    const bool ok = yy >= 0 && yy < H;
+    const float* q = xp + static_cast<size_t>(ok ? yy : 0) * W + px;
+    r[0] = (ok && hl) ? __ldg(q - 1) : 0.f;
+    r[1] = ok ? __ldg(q) : 0.f;
+    r[2] = (ok && hr) ? __ldg(q + 1) : 0.f;
+  };
+  float win[3][3], nxt[3];
+  load_row(r0 - 1, win[0]);
+  load_row(r0, win[1]);
+  load_row(r0 + 1, win[2]);
+  for (int py = r0; py < r1; ++py) {
+    load_row(py + 2, nxt);        // one row ahead of its use: its latency hides behind this row's 72 FMAs
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) o += sp[(ky * 3 + kx) * (kC1H * kC1H) + (ty + ky) * kC1H + tx + kx];
-    out[(static_cast<size_t>(n) * H + gy) * W + gx] = o;
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[ky][kx], wr[ky * 3 + kx][j], acc[j]);
+    const size_t o = ((static_cast<size_t>(n) * H + py) * W + px) * vecs + v;  // 8-channel vector index
+    if (out_fmt == 2) {
+      reinterpret_cast<float4*>(out)[2 * o] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(out)[2 * o + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else if (out_fmt == 1) {
+      reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<true>(acc[0], acc[1]), pack2<true>(acc[2], acc[3]),
+                                                    pack2<true>(acc[4], acc[5]), pack2<true>(acc[6], acc[7]));
+    } else {
+      reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<false>(acc[0], acc[1]), pack2<false>(acc[2], acc[3]),
+                                                    pack2<false>(acc[4], acc[5]), pack2<false>(acc[6], acc[7]));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; win[2][k] = nxt[k]; }
+  }
+}
+
+// Few-output-channel 3x3 conv (the final conv of each stack: GroupNorm affine, no activation, C -> 1|4|...).
+// One launch plane per output channel (grid.z = N * Cout; the extra passes over the input are L2 hits).
+//   out(y,x) = sum_taps sum_c w[tap][c] * n(y+dy, x+dx, c) is evaluated as per-pixel tap dot products
+//   p[tap](y,x) = sum_c w[tap][c] * n(y,x,c)           (every input pixel is read exactly once per plane)
+// staged in shared memory for the 18x34 halo of a 16x32 output tile, followed by a 9-point gather
+//   out(y,x) = bias + sum_tap p[tap](y+dy, x+dx).
+// LP = Cin/8 lanes share a pixel: each owns 8 channels whose 72 weights and scale/shift stay in registers (the
+// first version re-read them from shared memory per pixel: 72 LDS.128 per 288 FMAs, LSU bound at 0.8 TB/s),
+// a warp-wide load covers 32/LP whole pixels (coalesced), and the 9 partial sums fold with xor-shuffles.
+// Out-of-image halo pixels contribute p = 0: the zero padding applies to the normalised tensor.
+constexpr int kFcTW = 32, kFcTH = 16, kFcHW = kFcTW + 2, kFcHH = kFcTH + 2, kFcHalo = kFcHW * kFcHH;
+constexpr int kFcVT = 4;   // vertically stacked tiles per block (amortises the weight registers' fill)
+template <int FMT>         // 0 bf16 | 1 fp16 | 2 fp32 input
+__global__ void __launch_bounds__(256, 2) conv3x3_fewcout_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias,
+                                                                 const float* __restrict__ ss, float* __restrict__ out,
+                                                                 int H, int W, int Cin, int Cout, int lp) {
+  __shared__ float sp[9 * kFcHalo];       // [tap][halo pixel] tap partials
+  const int n = blockIdx.z / Cout, co = blockIdx.z - n * Cout;
+  const int sub = threadIdx.x % lp;       // this thread's 8-channel unit (blockDim.x % lp == 0)
+  const int c0 = sub * 8;
+  float wr[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float* wp = w + (static_cast<size_t>(co) * Cin + c0 + j) * 9;   // w is [Cout][Cin][3][3]
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][j] = __ldg(wp + t);
+    sc[j] = ss ? __ldg(ss + (static_cast<size_t>(n) * Cin + c0 + j) * 2) : 1.f;
+    sh[j] = ss ? __ldg(ss + (static_cast<size_t>(n) * Cin + c0 + j) * 2 + 1) : 0.f;
+  }
+  constexpr int ESZ = FMT == 2 ? 4 : 2;
+  const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * ESZ + c0 * ESZ;
+  const float b0 = __ldg(bias + co);
+  float* oplane = out + (static_cast<size_t>(n) * Cout + co) * H * W;
+  const int x0 = blockIdx.x * kFcTW - 1;
+  const int items = kFcHalo * lp;
+  {  // HBM -> L2 bulk prefetch of every input row segment this block reads (all channels of the x range)
+    const int ry = static_cast<int>(blockIdx.y) * kFcVT * kFcTH - 1 + static_cast<int>(threadIdx.x);
+    const int xs = max(x0, 0), xe = min(x0 + kFcHW, W);
+    if (threadIdx.x < kFcVT * kFcTH + 2 && ry >= 0 && ry < H && sub == 0)
+      l2_prefetch_bulk(static_cast<const uint8_t*>(x) + ((static_cast<size_t>(n) * H + ry) * W + xs) * Cin * ESZ,
+                       static_cast<uint32_t>((xe - xs) * Cin * ESZ));
+  }
+  for (int vt = 0; vt < kFcVT; ++vt) {
+    const int ty0 = (blockIdx.y * kFcVT + vt) * kFcTH;
+    if (ty0 >= H) break;
+    const int y0 = ty0 - 1;
+    // batches of UB independent 16|32-byte loads per thread are in flight before any arithmetic: the first version
+    // (one load, then 80 dependent FMAs, per iteration) was DRAM-latency bound at 0.9 TB/s
+    constexpr int UB = FMT == 2 ? 2 : 4;
+    for (int it0 = 0; it0 < items; it0 += UB * blockDim.x) {   // uniform trip count: the shuffles need whole warps
+      uint4 raw[UB][FMT == 2 ? 2 : 1];
+      bool ok[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int hp = (it0 + u * blockDim.x + threadIdx.x) / lp;
+        const int hy = hp / kFcHW, hx = hp - hy * kFcHW;
+        const int gy = y0 + hy, gx = x0 + hx;
+        ok[u] = hp < kFcHalo && static_cast<unsigned>(gy) < static_cast<unsigned>(H) &&
+                static_cast<unsigned>(gx) < static_cast<unsigned>(W);
+        if (ok[u]) {
+          const uint4* p = reinterpret_cast<const uint4*>(img + (static_cast<size_t>(gy) * W + gx) * Cin * ESZ);
+          raw[u][0] = __ldg(p);
+          if constexpr (FMT == 2) raw[u][1] = __ldg(p + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int hp = (it0 + u * blockDim.x + threadIdx.x) / lp;
+        float acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+        if (ok[u]) {
+          float v[8];
+          if constexpr (FMT == 2) {
+            v[0] = __uint_as_float(raw[u][0].x); v[1] = __uint_as_float(raw[u][0].y);
+            v[2] = __uint_as_float(raw[u][0].z); v[3] = __uint_as_float(raw[u][0].w);
+            v[4] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].x); v[5] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].y);
+            v[6] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].z); v[7] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].w);
+          } else {
+            unpack2<FMT == 1>(raw[u][0].x, v[0], v[1]); unpack2<FMT == 1>(raw[u][0].y, v[2], v[3]);
+            unpack2<FMT == 1>(raw[u][0].z, v[4], v[5]); unpack2<FMT == 1>(raw[u][0].w, v[6], v[7]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+#pragma unroll
+          for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t] = fmaf(v[j], wr[t][j], acc[t]);
+        }
+        for (int o = lp >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (sub == 0 && hp < kFcHalo) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) sp[t * kFcHalo + hp] = acc[t];
+        }
+      }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kFcTW * kFcTH; q += blockDim.x) {
+      const int ty = q / kFcTW, tx = q - ty * kFcTW;
+      const int gy = ty0 + ty, gx = blockIdx.x * kFcTW + tx;
+      if (gy < H && gx < W) {
+        float o = b0;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) o += sp[(ky * 3 + kx) * kFcHalo + (ty + ky) * kFcHW + tx + kx];
+        oplane[static_cast<size_t>(gy) * W + gx] = o;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -289,6 +394,10 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
   }
   if (H > 65535 || N > 65535) return PTIVAE_ERR_UNSUPPORTED;
   dim3 grid((W * (Cout / 8) + 255) / 256, (H + kSmallRows - 1) / kSmallRows, N);
+  if (Cin == 1) {
+    conv3x3_cin1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, out, H, W, Cout, out_fmt);
+    return static_cast<int>(cudaGetLastError());
+  }
   conv3x3_small_cin_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt);
   return static_cast<int>(cudaGetLastError());
 }
@@ -317,11 +426,17 @@ extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const fl
                                          void* stream_) {
   if (!x || !w || !bias || !out || N <= 0 || Cin % 8 != 0 || Cout <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (Cout == 1 && Cin % 4 == 0 && Cin <= 512 && H <= 65535 * kC1T && N <= 65535) {
-    const size_t smem = (static_cast<size_t>(9) * Cin + 2 * Cin + 9 * kC1H * kC1H) * sizeof(float);
-    dim3 grid((W + kC1T - 1) / kC1T, (H + kC1T - 1) / kC1T, N);
-    conv3x3_cout1_kernel<<<grid, 256, smem, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, in_fmt);
-    return static_cast<int>(cudaGetLastError());
+  const int lp = Cin / 8;   // lanes per pixel of the tap-partial kernel: power of two, at most a warp
+  if (Cin % 8 == 0 && lp <= 32 && (lp & (lp - 1)) == 0 && in_fmt >= 0 && in_fmt <= 2) {
+    const long long gz = static_cast<long long>(N) * Cout;
+    const int gy = (H + kFcTH * kFcVT - 1) / (kFcTH * kFcVT);
+    if (gz <= 65535 && gy <= 65535) {
+      dim3 grid((W + kFcTW - 1) / kFcTW, gy, static_cast<unsigned>(gz));
+      if (in_fmt == 2) conv3x3_fewcout_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout, lp);
+      else if (in_fmt == 1) conv3x3_fewcout_kernel<1><<<grid, 256, 0, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout, lp);
+      else conv3x3_fewcout_kernel<0><<<grid, 256, 0, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout, lp);
+      return static_cast<int>(cudaGetLastError());
+    }
   }
   switch (Cout) {
     case 1: return launch_small_cout<1>(x, w, bias, scale_shift, out, N, H, W, Cin, in_fmt, stream);

@@ -112,6 +112,32 @@ def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode:
     return r if len(r) > 1 else r[0]
 
 
+def up2x_supported(x: torch.Tensor) -> bool:
+    """Shapes/dtypes the halo-resident upsample kernel instantiates (others: conv_umma mode 2)."""
+    return x.dtype == F16 and x.shape[-1] in (64, 128)
+
+
+def up2x_conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_groups: int = 0, emit16: bool = False):
+    """conv3x3(nearest_upsample_2x(x)) + bias.  x fp16 NHWC [N,H,W,C] -> fp32 NHWC [N,2H,2W,C]; returns out,
+    (out, partials [N,P,G,2]) with gn_groups > 0, and the fp16 copy of out appended when emit16."""
+    _need_cuda(x, w_packed, bias)
+    if w_packed.dtype != x.dtype:
+        raise _lib.PtivaeError("activation and packed-weight operand dtypes differ")
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.float32)
+    out16 = torch.empty(out.shape, device=x.device, dtype=x.dtype) if emit16 else None
+    part = None
+    if gn_groups > 0:
+        part = torch.empty((n, _lib.lib().ptivae_up2x_conv3x3_parts(h, w), gn_groups, 2), device=x.device,
+                           dtype=torch.float32)
+    _call("up2x_conv3x3", (n, h, w, c, int(emit16)), 1, _lib.lib().ptivae_up2x_conv3x3, _p(x), _p(w_packed), _p(bias),
+          _p(out), _p(out16), _p(part), gn_groups, n, h, w, c, _op16(x), _stream())
+    r = (out, part) if gn_groups > 0 else (out,)
+    if emit16:
+        r = r + (out16,)
+    return r if len(r) > 1 else r[0]
+
+
 FUSED_IMPL = 0   # 0 auto | 1 register-staged conv_fused.cu | 2 TMA-staged conv_tma.cu (tests force each)
 
 
@@ -186,7 +212,7 @@ def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: 
     n, cin, h, wd = x.shape
     cout = w.shape[0]
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=dtype)
-    _call("conv3x3_small_cin", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x), _p(w), _p(b),
+    _call("conv3x3_small_cin", (n, h, wd, cin, cout, out.element_size()), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x), _p(w), _p(b),
           _p(out), n, h, wd, cin, cout, _fmt(out), _stream())
     return out
 
@@ -197,7 +223,7 @@ def conv3x3_small_cout(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, scale_
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     out = torch.empty((n, cout, h, wd), device=x.device, dtype=torch.float32)
-    _call("conv3x3_small_cout", (n, h, wd, cin, cout), 1, _lib.lib().ptivae_conv3x3_small_cout, _p(x), _p(w), _p(b),
+    _call("conv3x3_small_cout", (n, h, wd, cin, cout, x.element_size()), 1, _lib.lib().ptivae_conv3x3_small_cout, _p(x), _p(w), _p(b),
           _p(scale_shift), _p(out), n, h, wd, cin, cout, _fmt(x), _stream())
     return out
 

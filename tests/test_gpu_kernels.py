@@ -181,6 +181,36 @@ def test_conv_umma_stats_strided_modes(b200, mode, h, w, c):
     assert torch.allclose(part.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("n,h,w,c,groups,emit16", [(2, 16, 16, 64, 32, True), (1, 32, 48, 64, 16, False), (2, 24, 40, 64, 32, True),
+                                                   (2, 16, 16, 128, 32, True), (1, 40, 24, 128, 16, False), (3, 8, 8, 128, 32, True),
+                                                   (1, 64, 64, 128, 32, True), (1, 20, 9, 64, 0, True)])
+def test_up2x_conv3x3(b200, n, h, w, c, groups, emit16):
+    """Halo-resident upsample+conv vs F.interpolate(nearest) + conv2d; statistics and the 16-bit copy of the stored values."""
+    if DT != torch.float16:
+        pytest.skip("fp16 operands only (bf16 takes conv_umma mode 2)")
+    x = _rand_act(n, h, w, c, 21)
+    wt, bias = _rand_conv(c, c, 3, 22)
+    wp = b200.ops.pack_conv_weight(wt, 2, DT)
+    r = b200.ops.up2x_conv3x3(x, wp, bias, gn_groups=groups, emit16=emit16)
+    r = r if isinstance(r, tuple) else (r,)
+    out = r[0]
+    ref = _ref_conv(x, wt, bias, 2)
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    _check_bf16(out, ref, f"up2x {c}", rel=4e-3, ulp=2.0 ** -6)      # pre-summed 16-bit weights: as conv_umma mode 2
+    old = b200.ops.conv_umma(x, wp, bias, 2, out_f32=True)
+    assert float((out - old).abs().max()) <= 1e-4 * max(1.0, float(old.abs().max())), "same operands, fp32 accumulate"
+    if emit16:
+        assert torch.equal(r[-1], out.to(DT))
+    if groups:
+        part = r[1]
+        assert part.shape == (n, ((h + 15) // 16) * ((w + 15) // 16), groups, 2)
+        o = out.view(n, -1, groups, c // groups)
+        assert torch.allclose(part.sum(1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(part.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+        r2 = b200.ops.up2x_conv3x3(x, wp, bias, gn_groups=groups, emit16=emit16)
+        assert torch.equal(r2[0], out) and torch.equal(r2[1], part), "deterministic"
+
+
 @pytest.mark.parametrize("n,h,w,c,groups,silu,f32", [(2, 32, 32, 128, 16, True, True), (2, 64, 64, 32, 16, True, False),
                                                      (1, 48, 16, 64, 16, False, True), (2, 16, 16, 256, 32, True, False),
                                                      (1, 8, 8, 64, 32, True, True), (3, 40, 24, 128, 32, True, True)])
@@ -315,7 +345,8 @@ def test_conv3x3_fused(b200, n, h, w, cin, cout, in_f32, norm, silu, res, out_f3
     assert torch.equal(out, out2) and torch.equal(part, part2)
 
 
-@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 1, 32, 64, 64), (1, 1, 64, 32, 48), (2, 4, 128, 16, 16), (1, 10, 256, 8, 8)])
+@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 1, 32, 64, 64), (1, 1, 64, 32, 48), (2, 4, 128, 16, 16), (1, 10, 256, 8, 8),
+                                           (1, 1, 32, 37, 50)])
 def test_conv_small_cin(b200, n, cin, cout, h, w):
     x = torch.randn(n, cin, h, w, device=DEV)
     wt, bias = _rand_conv(cout, cin, 3, 9)
@@ -328,7 +359,8 @@ def test_conv_small_cin(b200, n, cin, cout, h, w):
 
 @pytest.mark.parametrize("n,cin,cout,h,w,norm,f32", [(2, 32, 1, 64, 64, True, True), (1, 64, 1, 32, 32, True, False),
                                                      (2, 128, 4, 16, 16, True, True), (1, 256, 10, 8, 8, True, True),
-                                                     (1, 32, 1, 16, 16, False, False)])
+                                                     (1, 32, 1, 16, 16, False, False), (1, 32, 1, 40, 70, True, False),
+                                                     (2, 64, 2, 100, 36, True, True)])
 def test_conv_small_cout(b200, n, cin, cout, h, w, norm, f32):
     x = _rand_act(n, h, w, cin, 11)
     if f32:

@@ -1,0 +1,86 @@
+"""Event-timed micro-benchmarks of single ops at the bench shapes: bench_ops.py [name ...]"""
+import sys, pathlib, math
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import torch
+import _pkg
+b200 = _pkg.load(); ops = b200.ops
+N = 64
+DT = torch.float16
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def cout1():
+    x = torch.randn(N, 256, 256, 32, device="cuda").to(DT); w = torch.randn(1, 32, 3, 3, device="cuda"); b = torch.randn(1, device="cuda")
+    ss = torch.randn(N, 32, 2, device="cuda")
+    return timeit(lambda: ops.conv3x3_small_cout(x, w, b, ss)), x.numel() * 2 + N * 65536 * 4
+
+
+def cout4():
+    x = torch.randn(N, 32, 32, 128, device="cuda"); w = torch.randn(4, 128, 3, 3, device="cuda"); b = torch.randn(4, device="cuda")
+    ss = torch.randn(N, 128, 2, device="cuda")
+    return timeit(lambda: ops.conv3x3_small_cout(x, w, b, ss)), x.numel() * 4
+
+
+def cin1():
+    x = torch.randn(N, 1, 256, 256, device="cuda"); w = torch.randn(32, 1, 3, 3, device="cuda"); b = torch.randn(32, device="cuda")
+    return timeit(lambda: ops.conv3x3_small_cin(x, w, b)), N * 65536 * 32 * 4
+
+
+def cin4():
+    x = torch.randn(N, 4, 32, 32, device="cuda"); w = torch.randn(128, 4, 3, 3, device="cuda"); b = torch.randn(128, device="cuda")
+    return timeit(lambda: ops.conv3x3_small_cin(x, w, b)), N * 1024 * 128 * 4
+
+
+def up(c, hw, emit16):
+    x = torch.randn(N, hw, hw, c, device="cuda").to(DT)
+    w = torch.randn(c, c, 3, 3, device="cuda") / math.sqrt(9 * c); b = torch.randn(c, device="cuda")
+    wp = ops.pack_conv_weight(w, 2, DT)
+    by = x.numel() * 2 + N * 4 * hw * hw * c * (4 + (2 if emit16 else 0))
+    return timeit(lambda: ops.conv_umma(x, wp, b, 2, gn_groups=32, out_f32=True, emit16=emit16)), by
+
+
+def up_new(c, hw, emit16):
+    x = torch.randn(N, hw, hw, c, device="cuda").to(DT)
+    w = torch.randn(c, c, 3, 3, device="cuda") / math.sqrt(9 * c); b = torch.randn(c, device="cuda")
+    wp = ops.pack_conv_weight(w, 2, DT)
+    by = x.numel() * 2 + N * 4 * hw * hw * c * (4 + (2 if emit16 else 0))
+    return timeit(lambda: ops.up2x_conv3x3(x, wp, b, gn_groups=32, emit16=emit16)), by
+
+
+def fused(cin, cout, hw, conv2, out32=True):
+    x = torch.randn(N, hw, hw, cin, device="cuda", dtype=DT if conv2 else torch.float32)
+    wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda") / math.sqrt(9 * cin), 0, DT)
+    bias = torch.randn(cout, device="cuda"); ss = torch.randn(N, cin, 2, device="cuda")
+    res = torch.randn(N, hw, hw, cout, device="cuda") if conv2 else None
+    o32 = bool(conv2 and out32)
+    by = x.numel() * x.element_size() + N * hw * hw * cout * ((4 if o32 else 2) + (4 if conv2 else 0))
+    return timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=32, out_f32=o32)), by
+
+
+CASES = {
+    "cout1": cout1, "cout4": cout4, "cin1": cin1, "cin4": cin4,
+    "up64": lambda: up(64, 128, True), "up128": lambda: up(128, 64, True), "up128s": lambda: up(128, 32, False),
+    "upn64": lambda: up_new(64, 128, True), "upn128": lambda: up_new(128, 64, True), "upn128s": lambda: up_new(128, 32, False),
+    "f32c1": lambda: fused(32, 32, 256, 0), "f32c2": lambda: fused(32, 32, 256, 1),
+    "f64c1": lambda: fused(64, 64, 128, 0), "f64c2": lambda: fused(64, 64, 128, 1), "f64c2h": lambda: fused(64, 64, 128, 1, False),
+    "f6432": lambda: fused(64, 32, 256, 0), "f12864": lambda: fused(128, 64, 128, 0),
+    "f128c1": lambda: fused(128, 128, 64, 0), "f128c2": lambda: fused(128, 128, 64, 1),
+    "f128c1s": lambda: fused(128, 128, 32, 0), "f128c2s": lambda: fused(128, 128, 32, 1),
+}
+for name in (sys.argv[1:] or list(CASES)):
+    try:
+        ms, by = CASES[name]()
+        print(f"{name:10s} {ms:8.4f} ms  {by / ms / 1e6:8.1f} GB/s", flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(f"{name:10s} failed: {e}", flush=True)
