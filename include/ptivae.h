@@ -63,8 +63,9 @@ int ptivae_conv_parts(int H, int W, int mode);
  *               Zero padding is applied AFTER the normalisation, as nn.Conv2d(padding=1) does.
  *   w_packed    h16 [9][Cout][Cin]; Cin, Cout in {32, 64, 128}
  *   residual/out/gn_part: as ptivae_conv_umma, with P = ptivae_conv3x3_fused_parts(H, W) (16x16 tiles).
- *   impl: 0 = auto; 1 = register-staged kernel (all shapes); 2 = TMA-staged kernel (Cin,Cout <= 64, fp16
- *         operands, fp32 residual; returns -2 for anything else).  Both produce the same results. */
+ *   impl: 0 = auto; 1 = register-staged kernel (all shapes, both operand formats); 2 = TMA-staged kernel
+ *         (Cin,Cout <= 64); 3 = chunk-pipelined TMA kernel (all widths).  2 and 3 need fp16 operands and an fp32
+ *         residual and return -2 otherwise.  All implementations produce the same results. */
 int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, int silu, const void* w_packed,
                          const float* bias, const void* residual, int res_f32, void* out, int out_f32,
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,

@@ -470,8 +470,9 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                                     void* out, int out_f32, float* gn_part, int gn_groups, int N, int H, int W,
                                     int Cin, int Cout, int f16, int desc_base_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int impl = desc_base_offset;  // 0 = auto, 1 = register-staged kernel (this file), 2 = TMA-staged (conv_tma.cu)
-  if (impl < 0 || impl > 2) return PTIVAE_ERR_ARG;
+  // 0 = auto, 1 = register-staged kernel (this file), 2 = TMA-staged (conv_tma.cu), 3 = chunk-pipelined TMA (conv_tma2.cu)
+  const int impl = desc_base_offset;
+  if (impl < 0 || impl > 3) return PTIVAE_ERR_ARG;
   if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   if (in_fmt != 2 && in_fmt != (f16 ? 1 : 0)) return PTIVAE_ERR_ARG;  // 16-bit input must use the operand format
   if (!(Cin == 32 || Cin == 64 || Cin == 128) || !(Cout == 32 || Cout == 64 || Cout == 128)) return PTIVAE_ERR_UNSUPPORTED;
@@ -480,8 +481,14 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
   if (impl != 1) {
     FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
                 N, H, W, Cin, Cout, f16, g_fused_trace, impl == 2};
-    const int rc = conv3x3_tma_launch(c, stream);
-    if (rc != PTIVAE_ERR_UNSUPPORTED || impl == 2) return rc;
+    if (impl == 3) return conv3x3_tma2_launch(c, stream);
+    if (impl == 2) return conv3x3_tma_launch(c, stream);
+    // auto: measured winners (B200, batch 64) -- the chunk-pipelined kernel for every shape with a 128-wide side
+    // and for 64->64 with a residual; the single-buffer kernel (12 transform warps) for the 32-wide layers
+    const bool wide = Cin == 128 || Cout == 128 || (Cin == 64 && Cout == 64 && residual != nullptr);
+    int rc = wide ? conv3x3_tma2_launch(c, stream) : conv3x3_tma_launch(c, stream);
+    if (rc == PTIVAE_ERR_UNSUPPORTED) rc = wide ? conv3x3_tma_launch(c, stream) : conv3x3_tma2_launch(c, stream);
+    if (rc != PTIVAE_ERR_UNSUPPORTED) return rc;
   }
   FusedArgs a{};
   a.N = N; a.H = H; a.W = W;

@@ -1,0 +1,615 @@
+// Second TMA-staged implementation of the fused GroupNorm(+SiLU) -> 3x3 conv -> (+bias, +residual, statistics)
+// kernel, for the shapes conv_tma.cu cannot hold in shared memory (everything with 64 or 128 channels on a
+// side).  Same math, same shifted-descriptor MMA loop; the data movement is re-cut into smaller pieces so that
+// every stage stays double buffered inside 227 KB:
+//   * OPERAND: the UMMA operand lives in 64-channel CHUNK buffers (18x18 pixels x 128 B, 128B-swizzled) that are
+//     produced, consumed and recycled independently (MMA order: chunk outer, tap inner), so a 128-channel
+//     layer pipelines transform(chunk 1) | MMA(chunk 0) inside ONE tile with only two buffers;
+//   * 16-bit input (ResBlock conv2): the halo chunk is TMA-loaded with the operand swizzle straight into its
+//     chunk buffer and normalised + SiLU'd IN PLACE (no staging buffer at all);
+//   * fp32 input (ResBlock conv1): raw halo blocks of 32 or 16 channels stream through a small ring and are
+//     converted into the chunk buffer;
+//   * OUTPUT: units of 128 pixels (one M block) x 32 channels.  Two epilogue teams (4 warps each = the four TMEM
+//     lane quarters; team = M block) own two unit slots each: the fp32 residual of the NEXT unit is already in
+//     flight (TMA) while the current one is drained TMEM -> +bias +residual -> swizzled slot -> ONE TMA tensor
+//     store (image edges clipped by the TMA unit);
+//   * GroupNorm statistics of the stored values: column sums over the warp's own 32 rows of the slot
+//     (conflict-free 16-byte loads), folded in fixed order -- deterministic, no atomics.
+// Warp roles (608 threads): 0-7 epilogue teams, 8-15 transform, 16 MMA issuer (+TMEM), 17 halo TMA producer,
+// 18 weight TMA producer.
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "ptivae_internal.h"
+
+namespace ptivae {
+namespace tma4 {
+
+constexpr int kT = 16, kHP = kT + 2, kHalo = kHP * kHP;
+constexpr int NTEAM = 2, NEW = NTEAM * 4, NTW = 8;
+constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
+constexpr int kThreads = (NEW + NTW + 3) * 32;
+constexpr int NT = NTW * 32;
+constexpr uint32_t kSmemMax = 232448;
+constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
+
+template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+struct Cfg {
+  static constexpr int KCH = CIN >= 64 ? 64 : 32;
+  static constexpr int NCH = CIN / KCH;
+  static constexpr uint32_t LB = KCH * 2;
+  static constexpr uint32_t CHUNK = r1k(kHalo * LB);
+  static constexpr uint32_t SLAB = uint32_t(COUT) * LB;
+  static constexpr uint32_t WBYTES = 9u * NCH * SLAB;
+  static constexpr bool SEP_RS = RES && !OUT32;               // fp32 residual staged beside a 16-bit output unit
+  static constexpr uint32_t OLB = OUT32 ? 128 : 64;           // bytes per output line (32 channels)
+  static constexpr uint32_t OSLOT = 128 * OLB;
+  static constexpr uint32_t RSLOT = SEP_RS ? 128 * 128 : 0;
+  static constexpr uint32_t SLOT = OSLOT + RSLOT;
+  static constexpr int NOB = COUT / 32;                       // units per M block
+  static constexpr uint32_t MISC = 1024 + NEW * COUT * 2 * 4 + COUT * 4 + 64 * 8 + 64;
+  static constexpr uint32_t FIXED = MISC + NTEAM * 2 * SLOT;
+  // ---- variable part: chunk buffers, raw-input ring (fp32 input only), weights (resident or ring)
+  static constexpr uint32_t xs_block(int xc) { return r1k(kHalo * xc * 4); }
+  static constexpr uint32_t total(int nbuf, int xc, int nxs, bool resb, int nst) {
+    return FIXED + nbuf * CHUNK + (IN32 ? nxs * xs_block(xc) : 0u) + (resb ? WBYTES : nst * SLAB);
+  }
+  struct Pick { int nbuf, xc, nxs, nst; bool resb, ok; };
+  static constexpr Pick pick() {
+    // preference: double-buffered chunks > (fp32 input) at least one tile of raw blocks in flight > resident weights
+    const int nbufs[2] = {2 * NCH, NCH};
+    for (int bi = 0; bi < 2; ++bi) {
+      const int nbuf = nbufs[bi];
+      if (nbuf < 2) continue;
+      if (!IN32) {
+        if (total(nbuf, 32, 0, true, 0) <= kSmemMax) return {nbuf, 32, 0, 1, true, true};
+        if (total(nbuf, 32, 0, false, 4) <= kSmemMax) return {nbuf, 32, 0, 4, false, true};
+        if (total(nbuf, 32, 0, false, 3) <= kSmemMax) return {nbuf, 32, 0, 3, false, true};
+        if (total(nbuf, 32, 0, false, 2) <= kSmemMax) return {nbuf, 32, 0, 2, false, true};
+      } else {
+        const int per_tile32 = CIN / 32;
+        for (int nxs = (per_tile32 < 4 ? per_tile32 * 2 : 4); nxs >= 2; --nxs) {
+          if (nxs > 4) continue;
+          if (total(nbuf, 32, nxs, true, 0) <= kSmemMax) return {nbuf, 32, nxs, 1, true, true};
+          if (total(nbuf, 32, nxs, false, 3) <= kSmemMax) return {nbuf, 32, nxs, 3, false, true};
+        }
+        for (int nxs = 4; nxs >= 2; --nxs) {
+          if (total(nbuf, 16, nxs, false, 3) <= kSmemMax) return {nbuf, 16, nxs, 3, false, true};
+          if (total(nbuf, 16, nxs, false, 2) <= kSmemMax) return {nbuf, 16, nxs, 2, false, true};
+        }
+        if (total(nbuf, 32, 1, false, 2) <= kSmemMax) return {nbuf, 32, 1, 2, false, true};
+      }
+    }
+    return {0, 32, 0, 0, false, false};
+  }
+  static constexpr Pick P = pick();
+  static constexpr bool FITS = P.ok;
+  static constexpr int NBUF = P.nbuf, XC = P.xc, NXS = P.nxs, NST = P.nst;
+  static constexpr bool RESB = P.resb;
+  static constexpr uint32_t XSB = IN32 ? xs_block(P.xc) : 0u;
+  static constexpr uint32_t SMEM = total(P.nbuf, P.xc, P.nxs, P.resb, P.nst);
+};
+
+struct Args {
+  int N, H, W;
+  int tiles_x, tiles_y, num_tiles;
+  int silu;
+  int gn_groups;
+  const float* scale_shift;  // [N][CIN][2] or nullptr
+  const float* bias;
+  float* gn_part;            // [N][tiles][groups][2]
+};
+
+template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
+  using C = Cfg<CIN, COUT, IN32, RES, OUT32>;
+  constexpr bool F16 = true;
+  constexpr int KCH = C::KCH, NCH = C::NCH, NBUF = C::NBUF, XC = C::XC, NXS = C::NXS, NST = C::NST, NOB = C::NOB;
+  constexpr uint32_t LB = C::LB, CHUNK = C::CHUNK, SLAB = C::SLAB, OLB = C::OLB;
+  constexpr bool RESB = C::RESB, SEP_RS = C::SEP_RS;
+  constexpr uint32_t kLayout = (KCH == 64) ? kLayoutSW128 : kLayoutSW64;
+  constexpr uint32_t kSBO_A = kHP * LB, kSBO_B = 8u * LB;
+  constexpr uint32_t kIdesc = make_idesc_16(128, COUT, F16);
+  constexpr uint32_t TMEM_COLS = 4 * COUT;
+  constexpr int UPC = KCH / 8;                  // 16-byte vectors per operand line
+  constexpr int NPIECE = IN32 ? CIN / XC : NCH; // input pieces per tile
+  constexpr int PPC = IN32 ? KCH / XC : 1;      // pieces per chunk
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* opbuf = smem;                                    // [NBUF][CHUNK]
+  uint8_t* xs = opbuf + NBUF * CHUNK;                       // [NXS][XSB] raw fp32 halo blocks
+  uint8_t* slots = xs + (IN32 ? NXS * C::XSB : 0u);         // [NTEAM][2][SLOT]
+  uint8_t* wts = slots + NTEAM * 2 * C::SLOT;               // resident [9*NCH][SLAB] | ring [NST][SLAB]
+  float* colsum = reinterpret_cast<float*>(wts + (RESB ? C::WBYTES : NST * SLAB));   // [NEW][COUT][2]
+  float* sbias = colsum + NEW * COUT * 2;                   // [COUT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
+  uint64_t* b_full = bars;             // [4]
+  uint64_t* b_empty = bars + 4;        // [4]
+  uint64_t* in_full = bars + 8;        // [4] 16-bit input: chunk landed (TMA)   | fp32 input: raw block landed
+  uint64_t* in_empty = bars + 12;      // [4] fp32 input: raw block consumed
+  uint64_t* op_full = bars + 16;       // [4] chunk transformed
+  uint64_t* op_empty = bars + 20;      // [4] chunk consumed by the MMAs
+  uint64_t* acc_full = bars + 24;      // [2]
+  uint64_t* acc_empty = bars + 26;     // [2]
+  uint64_t* res_full = bars + 28;      // [NTEAM][2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == W_IN && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO);
+    if (RES) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], NT);
+      mbar_init(&op_full[s], NT);
+      mbar_init(&op_empty[s], 1);
+      mbar_init(&res_full[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], NEW * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sbias[i] = args.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int tiles_per_img = args.tiles_x * args.tiles_y;
+
+  if (warp == W_W) {
+    // ------------------------------------------------------------------ weights (order: chunk outer, tap inner)
+    if (lane == 0) {
+      if constexpr (RESB) {
+        mbar_expect_tx(&b_full[0], C::WBYTES);
+        for (int kc = 0; kc < NCH; ++kc)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_3d(wts + (kc * 9 + tap) * SLAB, &tmW, &b_full[0], kc * KCH, 0, tap);
+      } else {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x)
+          for (int kc = 0; kc < NCH; ++kc)
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[s], ph ^ 1u);
+              mbar_expect_tx(&b_full[s], SLAB);
+              tma_load_3d(wts + s * SLAB, &tmW, &b_full[s], kc * KCH, 0, tap);
+              if (++s == NST) { s = 0; ph ^= 1u; }
+            }
+      }
+    }
+  } else if (warp == W_IN) {
+    // ------------------------------------------------------------------ input halo pieces (TMA loads)
+    if (lane == 0) {
+      int pq = 0;   // global piece counter
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+        const int n = t / tiles_per_img;
+        const int trem = t - n * tiles_per_img;
+        const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
+        for (int p = 0; p < NPIECE; ++p, ++pq) {
+          if constexpr (IN32) {
+            const int s = pq % NXS;
+            mbar_wait(&in_empty[s], ((pq / NXS) & 1) ^ 1u);
+            mbar_expect_tx(&in_full[s], kHalo * XC * 4);
+            tma_load_4d(xs + s * C::XSB, &tmX, &in_full[s], p * XC, tix * kT - 1, tiy * kT - 1, n);
+          } else {
+            const int s = pq % NBUF;   // the chunk buffer itself
+            mbar_wait(&op_empty[s], ((pq / NBUF) & 1) ^ 1u);
+            mbar_expect_tx(&in_full[s], kHalo * LB);
+            tma_load_4d(opbuf + s * CHUNK, &tmX, &in_full[s], p * KCH, tix * kT - 1, tiy * kT - 1, n);
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t a_hi = desc_hi(kSBO_A, kLayout);
+      const uint32_t b_hi = desc_hi(kSBO_B, kLayout);
+      const uint32_t w_lo = desc_lo(smem_u32(wts));
+      int s = 0, it = 0, cq = 0;
+      uint32_t ph = 0;
+      if constexpr (RESB) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        const int st = it & 1;
+        mbar_wait(&acc_empty[st], ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + st * 2 * COUT;
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int kc = 0; kc < NCH; ++kc, ++cq) {
+          const int cb = cq % NBUF;
+          mbar_wait(&op_full[cb], (cq / NBUF) & 1);
+          tc_fence_after();
+          const uint32_t a_lo_chunk = desc_lo(smem_u32(opbuf + cb * CHUNK));
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            uint32_t b_lo;
+            if constexpr (RESB) {
+              b_lo = w_lo + (((kc * 9 + tap) * SLAB) >> 4);
+            } else {
+              mbar_wait(&b_full[s], ph);
+              tc_fence_after();
+              b_lo = w_lo + ((s * SLAB) >> 4);
+            }
+            const uint32_t a_lo = a_lo_chunk + (((ky * kHP + kx) * LB) >> 4);
+#pragma unroll
+            for (int k = 0; k < KCH / 16; ++k) {
+#pragma unroll
+              for (int mb = 0; mb < 2; ++mb)
+                umma_f16_lohi(acc + mb * COUT, a_lo + ((mb * 8 * LB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
+                              kIdesc, accum);
+              accum = 1;
+            }
+            if constexpr (!RESB) {
+              umma_commit(&b_empty[s]);
+              if (++s == NST) { s = 0; ph ^= 1u; }
+            }
+          }
+          umma_commit(&op_empty[cb]);
+        }
+        umma_commit(&acc_full[st]);
+      }
+    }
+  } else if (warp >= W_TR0) {
+    // ------------------------------------------------------------------ transform
+    const int tt = threadIdx.x - W_TR0 * 32;
+    const bool has_norm = args.scale_shift != nullptr;
+    const bool do_silu = args.silu != 0;
+    constexpr int VPL = IN32 ? XC / 8 : UPC;     // 8-channel vectors per pixel per piece
+    constexpr int LS = NT / VPL;                 // pixel stride between a thread's vectors
+    constexpr int VPT = (kHalo + LS - 1) / LS;
+    const int u = tt % VPL, Lbase = tt / VPL;
+    int pq = 0, cq = 0;
+    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      const int n = t / tiles_per_img;
+      const int trem = t - n * tiles_per_img;
+      const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
+      const int y0 = tiy * kT - 1, x0 = tix * kT - 1;
+      const bool interior = y0 >= 0 && x0 >= 0 && y0 + kHP <= args.H && x0 + kHP <= args.W;   // uniform per tile
+#pragma unroll 1
+      for (int p = 0; p < NPIECE; ++p, ++pq) {
+        const int c0 = p * (IN32 ? XC : KCH) + u * 8;    // this thread's first channel in the piece
+        float4 sp[4];
+        if (has_norm) {
+          const float4* src = reinterpret_cast<const float4*>(args.scale_shift + (static_cast<size_t>(n) * CIN + c0) * 2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sp[e] = __ldg(src + e);
+        }
+        const int cb = cq % NBUF;
+        const uint8_t* src_base;
+        if constexpr (IN32) {
+          const int s = pq % NXS;
+          if (p % PPC == 0) mbar_wait(&op_empty[cb], ((cq / NBUF) & 1) ^ 1u);   // chunk buffer free (MMAs done)
+          mbar_wait(&in_full[s], (pq / NXS) & 1);
+          src_base = xs + s * C::XSB + u * 32;
+        } else {
+          mbar_wait(&in_full[cb], (cq / NBUF) & 1);                             // raw chunk landed in place
+          src_base = nullptr;
+        }
+        uint8_t* ob = opbuf + cb * CHUNK;
+        const uint32_t uu = IN32 ? static_cast<uint32_t>((p % PPC) * VPL + u) : static_cast<uint32_t>(u);   // 16-byte column in the line
+#pragma unroll 2
+        for (int k = 0; k < VPT; ++k) {
+          const int L = Lbase + k * LS;
+          if (L >= kHalo) break;
+          bool inb = true;
+          if (!interior) {
+            const int hy = (L * 3641) >> 16, hx = L - hy * kHP;
+            inb = static_cast<unsigned>(y0 + hy) < static_cast<unsigned>(args.H) &&
+                  static_cast<unsigned>(x0 + hx) < static_cast<unsigned>(args.W);
+          }
+          const uint32_t sw = (KCH == 64) ? ((uu ^ (L & 7)) << 4) : ((uu ^ ((L >> 1) & 3)) << 4);
+          uint4* dst = reinterpret_cast<uint4*>(ob + L * LB + sw);
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);   // out-of-image halo stays exactly zero (padding AFTER the norm)
+          if (inb) {
+            float f[8];
+            if constexpr (IN32) {
+              const uint4* src = reinterpret_cast<const uint4*>(src_base + L * (XC * 4));
+              const uint4 lo = src[0], hi = src[1];
+              f[0] = __uint_as_float(lo.x); f[1] = __uint_as_float(lo.y); f[2] = __uint_as_float(lo.z); f[3] = __uint_as_float(lo.w);
+              f[4] = __uint_as_float(hi.x); f[5] = __uint_as_float(hi.y); f[6] = __uint_as_float(hi.z); f[7] = __uint_as_float(hi.w);
+            } else {
+              const uint4 lo = *dst;
+              unpack2<F16>(lo.x, f[0], f[1]); unpack2<F16>(lo.y, f[2], f[3]);
+              unpack2<F16>(lo.z, f[4], f[5]); unpack2<F16>(lo.w, f[6], f[7]);
+            }
+            if (has_norm) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = fmaf(f[2 * e], sp[e].x, sp[e].y);
+                float c = fmaf(f[2 * e + 1], sp[e].z, sp[e].w);
+                if (do_silu) {
+                  a = __fdividef(a, 1.0f + __expf(-a));
+                  c = __fdividef(c, 1.0f + __expf(-c));
+                }
+                f[2 * e] = a;
+                f[2 * e + 1] = c;
+              }
+            }
+            o = make_uint4(pack2<F16>(f[0], f[1]), pack2<F16>(f[2], f[3]), pack2<F16>(f[4], f[5]), pack2<F16>(f[6], f[7]));
+          }
+          *dst = o;
+        }
+        if constexpr (IN32) mbar_arrive(&in_empty[pq % NXS]);
+        if ((p + 1) % PPC == 0) {     // chunk complete
+          fence_proxy_async_smem();
+          mbar_arrive(&op_full[cb]);
+          ++cq;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue teams (team = M block)
+    const int team = warp >> 2, ew = warp & 3;      // ew == TMEM lane quarter
+    const int m = ew * 32 + lane;                   // accumulator row = pixel (m >> 3, team*8 + (m & 7)) of the tile
+    const int mb = team;
+    const bool leader = (ew == 0 && lane == 0);
+    const int cpg = args.gn_groups > 0 ? COUT / args.gn_groups : 0;
+    const int bar_id = 1 + team;
+    uint8_t* tslots = slots + team * 2 * C::SLOT;
+    uint64_t* rfull = res_full + team * 2;
+    float* cs = colsum + warp * COUT * 2;
+    const int my_tiles = (args.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int total_units = my_tiles * NOB;
+    // residual of unit q (tile q / NOB, channel block q % NOB) -> slot q & 1   (leader only)
+    auto issue_res = [&](int q) {
+      if constexpr (RES) {
+        const int ti = q / NOB, ob = q - ti * NOB;
+        const int t = blockIdx.x + ti * gridDim.x;
+        const int n = t / tiles_per_img;
+        const int trem = t - n * tiles_per_img;
+        const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
+        uint8_t* dst = tslots + (q & 1) * C::SLOT + (SEP_RS ? C::OSLOT : 0u);
+        if (tix * kT + mb * 8 < args.W) {
+          mbar_expect_tx(&rfull[q & 1], 128 * 128);
+          tma_load_4d(dst, &tmR, &rfull[q & 1], ob * 32, tix * kT + mb * 8, tiy * kT, n);
+        } else {
+          mbar_arrive(&rfull[q & 1]);    // M block wholly outside the image: nothing to load (nothing is stored either)
+        }
+      }
+    };
+    if (leader && total_units > 0) issue_res(0);
+    int q = 0, it = 0;
+    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+      const int st = it & 1;
+      const int n = t / tiles_per_img;
+      const int trem = t - n * tiles_per_img;
+      const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
+      const int x0 = tix * kT + mb * 8, y0 = tiy * kT;
+      mbar_wait(&acc_full[st], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ob = 0; ob < NOB; ++ob, ++q) {
+        uint8_t* oslot = tslots + (q & 1) * C::SLOT;
+        uint8_t* rslot = oslot + (SEP_RS ? C::OSLOT : 0u);
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * 2 * COUT + mb * COUT + ob * 32, acc);
+        if (leader) {
+          if constexpr (RES) {
+            tma_store_wait_read();                     // store of unit q-1 has drained the other slot
+            if (q + 1 < total_units) issue_res(q + 1);   // next unit's residual: in flight during this unit
+          } else {
+            tma_store_wait_read1();                    // store of unit q-2 has drained this unit's slot
+          }
+        }
+        __syncwarp();
+        tmem_ld_wait();
+        if (ob == NOB - 1) {                          // all of this tile's accumulator columns are in registers
+          tc_fence_before();
+          mbar_arrive(&acc_empty[st]);
+        }
+        if constexpr (RES) mbar_wait(&rfull[q & 1], (q >> 1) & 1);
+        else asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // slot free (leader saw store q-2 drained in unit q-1)
+        {
+          const uint8_t* rl = rslot + m * 128;
+          uint8_t* ol = oslot + m * OLB;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = reinterpret_cast<const float4*>(sbias + ob * 32)[j];   // broadcast
+            float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
+            float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
+            if constexpr (RES) {
+              const float4 rv = *reinterpret_cast<const float4*>(rl + ((j ^ (m & 7)) << 4));
+              v0 += rv.x; v1 += rv.y; v2 += rv.z; v3 += rv.w;
+            }
+            if constexpr (OUT32) {
+              *reinterpret_cast<float4*>(ol + ((j ^ (m & 7)) << 4)) = make_float4(v0, v1, v2, v3);
+            } else {
+              acc[4 * j + 0] = pack2<F16>(v0, v1);
+              acc[4 * j + 1] = pack2<F16>(v2, v3);
+            }
+          }
+          if constexpr (!OUT32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4)) =
+                  make_uint4(acc[8 * j + 0], acc[8 * j + 1], acc[8 * j + 4], acc[8 * j + 5]);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // unit written by all four warps
+        if (leader && x0 < args.W) {
+          tma_store_4d(&tmO, oslot, ob * 32, x0, y0, n);
+          tma_store_commit();
+        }
+        if (cpg > 0) {
+          // column sums of the stored values over this warp's own 32 rows (lane = (row sub-index, 16-byte chunk))
+          constexpr int LPR = OLB / 16, RPI = 32 / LPR, CPC = OUT32 ? 4 : 8;
+          const int rsub = lane / LPR, j = lane % LPR;
+          float s[CPC], s2[CPC];
+#pragma unroll
+          for (int k = 0; k < CPC; ++k) s[k] = s2[k] = 0.f;
+          uint4 w[32 / RPI];
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            const int r = ew * 32 + i * RPI + rsub;
+            const int sw = OUT32 ? (r & 7) : ((r >> 1) & 3);
+            const bool ok = (y0 + (r >> 3) < args.H) && (x0 + (r & 7) < args.W);
+            w[i] = ok ? *reinterpret_cast<const uint4*>(oslot + r * OLB + ((j ^ sw) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            float x[CPC];
+            if constexpr (OUT32) {
+              x[0] = __uint_as_float(w[i].x); x[1] = __uint_as_float(w[i].y);
+              x[2] = __uint_as_float(w[i].z); x[3] = __uint_as_float(w[i].w);
+            } else {
+              unpack2<F16>(w[i].x, x[0], x[1]); unpack2<F16>(w[i].y, x[2], x[3]);
+              unpack2<F16>(w[i].z, x[4 % CPC], x[5 % CPC]); unpack2<F16>(w[i].w, x[6 % CPC], x[7 % CPC]);
+            }
+#pragma unroll
+            for (int k = 0; k < CPC; ++k) {
+              s[k] += x[k];
+              s2[k] = fmaf(x[k], x[k], s2[k]);
+            }
+          }
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) {       // fold the row sub-lanes (fixed pattern)
+#pragma unroll
+            for (int k = 0; k < CPC; ++k) {
+              s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+            }
+          }
+          if (rsub == 0) {
+#pragma unroll
+            for (int k = 0; k < CPC; ++k) {
+              const int c = ob * 32 + j * CPC + k;
+              cs[c * 2] = s[k];
+              cs[c * 2 + 1] = s2[k];
+            }
+          }
+        }
+      }
+      if (cpg > 0) {
+        asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
+        const int ei = threadIdx.x;                 // epilogue warps are warps 0 .. NEW-1
+        if (ei < 2 * args.gn_groups) {
+          const int g = ei >> 1, k = ei & 1;
+          float tsum = 0.f;
+          for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+#pragma unroll
+            for (int w8 = 0; w8 < NEW; ++w8) tsum += colsum[(w8 * COUT + c) * 2 + k];
+          args.gn_part[((static_cast<size_t>(n) * tiles_per_img + trem) * args.gn_groups + g) * 2 + k] = tsum;
+        }
+        asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+static int launch(const FusedCall& c, cudaStream_t stream) {
+  using C = Cfg<CIN, COUT, IN32, RES, OUT32>;
+  if constexpr (!C::FITS) {
+    return PTIVAE_ERR_UNSUPPORTED;
+  } else {
+    Args a{};
+    a.N = c.N; a.H = c.H; a.W = c.W;
+    a.tiles_x = (c.W + kT - 1) / kT;
+    a.tiles_y = (c.H + kT - 1) / kT;
+    a.num_tiles = c.N * a.tiles_x * a.tiles_y;
+    a.silu = c.silu; a.gn_groups = c.gn_groups; a.scale_shift = c.scale_shift; a.bias = c.bias; a.gn_part = c.gn_part;
+    CUtensorMap tmX, tmW, tmR, tmO;
+    const uint64_t H = c.H, W = c.W, N = c.N;
+    if (IN32) {  // raw fp32 halo blocks: dims (C, W, H, N), box (XC, 18, 18, 1), dense
+      uint64_t d[4] = {uint64_t(CIN), W, H, N};
+      uint64_t s[3] = {uint64_t(CIN) * 4, W * CIN * 4, H * W * CIN * 4};
+      uint32_t b[4] = {uint32_t(C::XC), kHP, kHP, 1};
+      int rc = encode_tmap(&tmX, c.x, 2, 4, d, s, b, 0);
+      if (rc) return rc;
+    } else {     // 16-bit halo chunks with the operand swizzle
+      uint64_t d[4] = {uint64_t(CIN), W, H, N};
+      uint64_t s[3] = {uint64_t(CIN) * 2, W * CIN * 2, H * W * CIN * 2};
+      uint32_t b[4] = {uint32_t(C::KCH), kHP, kHP, 1};
+      int rc = encode_tmap(&tmX, c.x, 1, 4, d, s, b, C::LB);
+      if (rc) return rc;
+    }
+    {  // weights [9][Cout][Cin] fp16
+      uint64_t d[3] = {uint64_t(CIN), uint64_t(COUT), 9};
+      uint64_t s[2] = {uint64_t(CIN) * 2, uint64_t(COUT) * CIN * 2};
+      uint32_t b[3] = {uint32_t(C::KCH), uint32_t(COUT), 1};
+      int rc = encode_tmap(&tmW, c.w_packed, 1, 3, d, s, b, C::LB);
+      if (rc) return rc;
+    }
+    {  // output unit: box (32 channels, 8 pixels, 16 rows, 1), swizzle = line bytes
+      const uint64_t esz = OUT32 ? 4 : 2;
+      uint64_t d[4] = {uint64_t(COUT), W, H, N};
+      uint64_t s[3] = {uint64_t(COUT) * esz, W * COUT * esz, H * W * COUT * esz};
+      uint32_t b[4] = {32, 8, kT, 1};
+      int rc = encode_tmap(&tmO, c.out, OUT32 ? 2 : 1, 4, d, s, b, C::OLB);
+      if (rc) return rc;
+    }
+    if (RES) {
+      uint64_t d[4] = {uint64_t(COUT), W, H, N};
+      uint64_t s[3] = {uint64_t(COUT) * 4, W * COUT * 4, H * W * COUT * 4};
+      uint32_t b[4] = {32, 8, kT, 1};
+      int rc = encode_tmap(&tmR, c.residual, 2, 4, d, s, b, 128);
+      if (rc) return rc;
+    } else {
+      tmR = tmO;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_set = true;
+    }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, a);
+    return static_cast<int>(cudaGetLastError());
+  }
+}
+
+template <int CIN, int COUT>
+static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
+  const bool in32 = c.in_fmt == 2, res = c.residual != nullptr, out32 = c.out_f32 != 0;
+  if (in32 && !res && !out32) return launch<CIN, COUT, true, false, false>(c, stream);   // ResBlock conv1
+  if (!in32 && res && out32) return launch<CIN, COUT, false, true, true>(c, stream);     // ResBlock conv2 -> stream
+  if (!in32 && res && !out32) return launch<CIN, COUT, false, true, false>(c, stream);   // conv2 -> 16-bit operand
+  return PTIVAE_ERR_UNSUPPORTED;
+}
+
+}  // namespace tma4
+
+int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream) {
+  if (!c.f16) return PTIVAE_ERR_UNSUPPORTED;                           // fp16 operands only
+  if (c.residual != nullptr && !c.res_f32) return PTIVAE_ERR_UNSUPPORTED;
+  if (2 * c.gn_groups > tma4::NEW * 32) return PTIVAE_ERR_UNSUPPORTED;
+#define PTIVAE_T2_CASE(CI, CO) \
+  if (c.Cin == CI && c.Cout == CO) return tma4::dispatch_mode<CI, CO>(c, stream)
+  PTIVAE_T2_CASE(32, 32);
+  PTIVAE_T2_CASE(32, 64);
+  PTIVAE_T2_CASE(64, 32);
+  PTIVAE_T2_CASE(64, 64);
+  PTIVAE_T2_CASE(64, 128);
+  PTIVAE_T2_CASE(128, 64);
+  PTIVAE_T2_CASE(128, 128);
+#undef PTIVAE_T2_CASE
+  return PTIVAE_ERR_UNSUPPORTED;
+}
+
+}  // namespace ptivae

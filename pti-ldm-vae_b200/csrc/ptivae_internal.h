@@ -22,6 +22,8 @@ struct FusedCall {   // arguments of ptivae_conv3x3_fused, shared by its two imp
 // TMA-staged implementation (conv_tma.cu): returns PTIVAE_ERR_UNSUPPORTED (-2) if the shape/mode has no
 // instantiation, so the caller can fall back to the register-staged kernel.
 int conv3x3_tma_launch(const FusedCall& c, cudaStream_t stream);
+// chunk-pipelined TMA implementation (conv_tma2.cu): all widths in {32, 64, 128}; same contract
+int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream);
 
 inline int grid_for(size_t work_items, int block, int max_blocks = 148 * 16) {
   size_t g = (work_items + block - 1) / block;

@@ -310,6 +310,46 @@ def test_conv3x3_fused_tma(b200, n, h, w, cin, cout, in_f32, res, out_f32, group
     assert float((outs[1] - outs[2]).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
 
 
+TMA2_SHAPES = [(32, 32), (32, 64), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128)]
+TMA2_MODES = [(True, False, False), (False, True, True), (False, True, False)]    # (in_f32, res, out_f32): conv1 | conv2 | conv2 -> operand
+
+
+@pytest.mark.parametrize("cin,cout", TMA2_SHAPES)
+@pytest.mark.parametrize("in_f32,res,out_f32", TMA2_MODES)
+@pytest.mark.parametrize("n,h,w,groups", [(2, 32, 32, 32), (1, 40, 24, 16), (5, 48, 48, 32)])
+def test_conv3x3_fused_tma2(b200, cin, cout, in_f32, res, out_f32, n, h, w, groups):
+    """Chunk-pipelined TMA kernel (impl 3) vs the fp32 reference and vs the register-staged kernel (impl 1)."""
+    if DT != torch.float16:
+        pytest.skip("the TMA-staged kernels are instantiated for fp16 operands only")
+    groups = min(groups, cout // 2)
+    x = _rand_act(n, h, w, cin, 51).float() * 1.5 + 0.2
+    x = x + 1e-3 * torch.randn_like(x) if in_f32 else x.to(DT)
+    wt, bias = _rand_conv(cout, cin, 3, 52)
+    ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
+    xin = F.silu(x.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
+    r = torch.randn(n, h, w, cout, device=DEV) if res else None
+    ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r
+    wp = b200.ops.pack_conv_weight(wt, 0, DT)
+    outs = {}
+    try:
+        for impl in (3, 1):
+            b200.ops.FUSED_IMPL = impl
+            out, part = b200.ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+            out2, part2 = b200.ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+            assert torch.equal(out, out2) and torch.equal(part, part2), f"impl {impl} not deterministic"
+            _check_bf16(out.to(DT), ref, f"fused conv impl={impl}")
+            o = out.float().view(n, h * w, groups, cout // groups)
+            acc = part.sum(dim=1)
+            assert torch.allclose(acc[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2), impl
+            assert torch.allclose(acc[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2), impl
+            outs[impl] = out.float()
+    finally:
+        b200.ops.FUSED_IMPL = 0
+    assert float((outs[1] - outs[3]).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,in_f32,norm,silu,res,out_f32,groups", FUSED_CASES)
 def test_conv3x3_fused(b200, n, h, w, cin, cout, in_f32, norm, silu, res, out_f32, groups):
     x = _rand_act(n, h, w, cin, 31).float() * 1.5 + 0.2

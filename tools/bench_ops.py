@@ -58,26 +58,29 @@ def up_new(c, hw, emit16):
     return timeit(lambda: ops.up2x_conv3x3(x, wp, b, gn_groups=32, emit16=emit16)), by
 
 
-def fused(cin, cout, hw, conv2, out32=True):
+def fused(cin, cout, hw, conv2, out32=True, impl=0):
+    ops.FUSED_IMPL = impl
     x = torch.randn(N, hw, hw, cin, device="cuda", dtype=DT if conv2 else torch.float32)
     wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda") / math.sqrt(9 * cin), 0, DT)
     bias = torch.randn(cout, device="cuda"); ss = torch.randn(N, cin, 2, device="cuda")
     res = torch.randn(N, hw, hw, cout, device="cuda") if conv2 else None
     o32 = bool(conv2 and out32)
     by = x.numel() * x.element_size() + N * hw * hw * cout * ((4 if o32 else 2) + (4 if conv2 else 0))
-    return timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=32, out_f32=o32)), by
+    return timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=min(32, cout // 2), out_f32=o32)), by
 
 
 CASES = {
     "cout1": cout1, "cout4": cout4, "cin1": cin1, "cin4": cin4,
     "up64": lambda: up(64, 128, True), "up128": lambda: up(128, 64, True), "up128s": lambda: up(128, 32, False),
     "upn64": lambda: up_new(64, 128, True), "upn128": lambda: up_new(128, 64, True), "upn128s": lambda: up_new(128, 32, False),
-    "f32c1": lambda: fused(32, 32, 256, 0), "f32c2": lambda: fused(32, 32, 256, 1),
-    "f64c1": lambda: fused(64, 64, 128, 0), "f64c2": lambda: fused(64, 64, 128, 1), "f64c2h": lambda: fused(64, 64, 128, 1, False),
-    "f6432": lambda: fused(64, 32, 256, 0), "f12864": lambda: fused(128, 64, 128, 0),
-    "f128c1": lambda: fused(128, 128, 64, 0), "f128c2": lambda: fused(128, 128, 64, 1),
-    "f128c1s": lambda: fused(128, 128, 32, 0), "f128c2s": lambda: fused(128, 128, 32, 1),
+    "f32c1": lambda impl=0: fused(32, 32, 256, 0, impl=impl), "f32c2": lambda impl=0: fused(32, 32, 256, 1, impl=impl),
+    "f64c1": lambda impl=0: fused(64, 64, 128, 0, impl=impl), "f64c2": lambda impl=0: fused(64, 64, 128, 1, impl=impl), "f64c2h": lambda impl=0: fused(64, 64, 128, 1, False, impl=impl),
+    "f6432": lambda impl=0: fused(64, 32, 256, 0, impl=impl), "f12864": lambda impl=0: fused(128, 64, 128, 0, impl=impl),
+    "f128c1": lambda impl=0: fused(128, 128, 64, 0, impl=impl), "f128c2": lambda impl=0: fused(128, 128, 64, 1, impl=impl),
+    "f128c1s": lambda impl=0: fused(128, 128, 32, 0, impl=impl), "f128c2s": lambda impl=0: fused(128, 128, 32, 1, impl=impl),
 }
+for _k in ("f32c1", "f32c2", "f64c1", "f64c2", "f64c2h", "f6432", "f12864", "f128c1", "f128c2", "f128c1s", "f128c2s"):
+    CASES[_k + "@3"] = (lambda f: (lambda: f(impl=3)))(CASES[_k])
 for name in (sys.argv[1:] or list(CASES)):
     try:
         ms, by = CASES[name]()
