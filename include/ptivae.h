@@ -109,12 +109,15 @@ int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, void* raw1
 
 /* Thin-end 3x3 s1 p1 convolutions on CUDA cores.
  *   small_cin : x fp32 NCHW [N][Cin<=16][H][W], w fp32 [Cout][Cin][3][3] -> out NHWC (storage out_fmt)
- *               (encoder.blocks.0, decoder.blocks.0)
+ *               (encoder.blocks.0, decoder.blocks.0).  gn_groups > 0: also writes the GroupNorm statistics partials
+ *               of the stored values, gn_part fp32 [N][P][gn_groups][2], P = ptivae_conv3x3_small_cin_parts(H, W,
+ *               Cout); fused only for Cin == 1 (returns -2 otherwise: use ptivae_gn_stats)
  *   small_cout: x NHWC (storage in_fmt), optional fused GroupNorm affine scale_shift [N][Cin][2] (NO activation:
  *               encoder.blocks.15/decoder.blocks.15 are bare GroupNorms), zero padding applied after
  *               the norm -> out fp32 NCHW [N][Cout<=16][H][W]  (encoder.blocks.16, decoder.blocks.16) */
-int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int N, int H, int W,
-                             int Cin, int Cout, int out_fmt, void* stream);
+int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, float* gn_part,
+                             int gn_groups, int N, int H, int W, int Cin, int Cout, int out_fmt, void* stream);
+int ptivae_conv3x3_small_cin_parts(int H, int W, int Cout);
 int ptivae_conv3x3_small_cout(const void* x, const float* w, const float* bias, const float* scale_shift, float* out,
                               int N, int H, int W, int Cin, int Cout, int in_fmt, void* stream);
 /* 1x1 conv, fp32 NCHW in/out, Cin,Cout <= 16 (quant_conv_mu, quant_conv_log_sigma, post_quant_conv).

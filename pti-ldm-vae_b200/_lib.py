@@ -32,7 +32,8 @@ SIGNATURES = {
     "ptivae_gn_stats_parts": [_c_int] * 3,
     "ptivae_gn_finalize": [_c_void_p] * 4 + [_c_int] * 5 + [_c_float, _c_void_p],
     "ptivae_gn_apply": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
-    "ptivae_conv3x3_small_cin": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
+    "ptivae_conv3x3_small_cin": [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p],
+    "ptivae_conv3x3_small_cin_parts": [_c_int] * 3,
     "ptivae_conv3x3_small_cout": [_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p],
     "ptivae_conv1x1_small": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
     "ptivae_attention_fwd": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],

@@ -240,8 +240,12 @@ class _Executor:
         def needs_raw16(i):   # body[i] is a ResBlock with a 1x1 shortcut: it wants a 16-bit copy of its input
             return i < len(body) and isinstance(body[i], AEKLResBlock) and isinstance(body[i].nin_shortcut, Convolution)
 
-        a = _Act(ops.conv3x3_small_cin(x, self.f32(first.conv.weight), self.f32(first.conv.bias),
-                                       dtype=self.op_dtype if operand_only(0) else torch.float32))
+        cw = first.conv.weight
+        g0 = self.groups if (self.fused_stats and not operand_only(0) and
+                             ops.small_cin_stats_supported(cw.shape[1], cw.shape[0], self.groups)) else 0
+        r0 = ops.conv3x3_small_cin(x, self.f32(cw), self.f32(first.conv.bias),
+                                   dtype=self.op_dtype if operand_only(0) else torch.float32, gn_groups=g0)
+        a = _Act(*r0) if g0 else _Act(r0)
         for i, blk in enumerate(body):
             nxt_operand = operand_only(i + 1)
             # the last body tensor is read only by the final norm + conv: 16-bit storage (statistics still needed)

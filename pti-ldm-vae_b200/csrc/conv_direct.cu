@@ -183,14 +183,23 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
 // channels) walking kSmallRows image rows.  The first version read its weights from shared memory inside the
 // tap loop (2 LDS.128 per 8 FMAs: the LSU pipe, not HBM, bounded it at 1.1 TB/s); here the thread's 72 weights
 // live in registers and the 3x3 input window slides down the rows (3 new loads per row).
-__global__ void __launch_bounds__(256) conv3x3_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// Optional GroupNorm statistics of the STORED values (gn_part [N][P = gridDim.y*gridDim.x][groups][2], channels
+// per group in {1,2,4,8}, Cout/8 a power of two <= 32): per-thread sums over its rows, xor-shuffle fold over the
+// lanes that share a channel octet, fixed-order fold over the 8 warps -- plain stores, deterministic.
+__global__ void __launch_bounds__(256, 2) conv3x3_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, void* __restrict__ out,
-                                                           int H, int W, int Cout, int out_fmt) {
+                                                           int H, int W, int Cout, int out_fmt,
+                                                           float* __restrict__ gn_part, int gn_groups) {
+  __shared__ float red[8][32][16];     // [warp][lane-of-octet][sum x8, sumsq x8]
   const int vecs = Cout / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int px = i / vecs, v = i - px * vecs;
-  if (px >= W) return;
+  const int px_raw = i / vecs, v = i - px_raw * vecs;
+  const bool live = px_raw < W;
+  const int px = live ? px_raw : W - 1;
   const int n = blockIdx.z;
+  float st[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) st[k] = 0.f;
   float wr[9][8], br[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(256) conv3x3_cin1_kernel(const float* __restri
   }
   const float* xp = x + static_cast<size_t>(n) * H * W;
   const int r0 = blockIdx.y * kSmallRows, r1 = min(H, r0 + kSmallRows);
-  const bool hl = px > 0, hr = px + 1 < W;
+  const bool hl = px > 0, hr = px + 1 < W;   // (threads beyond the row end recompute pixel W-1 and store nothing)
   auto load_row = [&](int yy, float (&r)[3]) {
     const bool ok = yy >= 0 && yy < H;
     const float* q = xp + static_cast<size_t>(ok ? yy : 0) * W + px;
@@ -225,17 +234,57 @@ __global__ void __launch_bounds__(256) conv3x3_cin1_kernel(const float* __restri
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[ky][kx], wr[ky * 3 + kx][j], acc[j]);
     const size_t o = ((static_cast<size_t>(n) * H + py) * W + px) * vecs + v;  // 8-channel vector index
     if (out_fmt == 2) {
-      reinterpret_cast<float4*>(out)[2 * o] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(out)[2 * o + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else if (out_fmt == 1) {
-      reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<true>(acc[0], acc[1]), pack2<true>(acc[2], acc[3]),
-                                                    pack2<true>(acc[4], acc[5]), pack2<true>(acc[6], acc[7]));
+      if (live) {
+        reinterpret_cast<float4*>(out)[2 * o] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(out)[2 * o + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
     } else {
-      reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<false>(acc[0], acc[1]), pack2<false>(acc[2], acc[3]),
-                                                    pack2<false>(acc[4], acc[5]), pack2<false>(acc[6], acc[7]));
+      uint4 pk;
+      if (out_fmt == 1) {
+        pk = make_uint4(pack2<true>(acc[0], acc[1]), pack2<true>(acc[2], acc[3]), pack2<true>(acc[4], acc[5]),
+                        pack2<true>(acc[6], acc[7]));
+        unpack2<true>(pk.x, acc[0], acc[1]); unpack2<true>(pk.y, acc[2], acc[3]);
+        unpack2<true>(pk.z, acc[4], acc[5]); unpack2<true>(pk.w, acc[6], acc[7]);
+      } else {
+        pk = make_uint4(pack2<false>(acc[0], acc[1]), pack2<false>(acc[2], acc[3]), pack2<false>(acc[4], acc[5]),
+                        pack2<false>(acc[6], acc[7]));
+        unpack2<false>(pk.x, acc[0], acc[1]); unpack2<false>(pk.y, acc[2], acc[3]);
+        unpack2<false>(pk.z, acc[4], acc[5]); unpack2<false>(pk.w, acc[6], acc[7]);
+      }
+      if (live) reinterpret_cast<uint4*>(out)[o] = pk;
+    }
+    if (gn_groups > 0 && live) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        st[j] += acc[j];
+        st[8 + j] = fmaf(acc[j], acc[j], st[8 + j]);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; win[2][k] = nxt[k]; }
+  }
+  if (gn_groups > 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = vecs; o < 32; o <<= 1) {         // lanes lane % vecs == v share a channel octet
+#pragma unroll
+      for (int k = 0; k < 16; ++k) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);
+    }
+    if (lane < vecs) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) red[warp][lane][k] = st[k];
+    }
+    __syncthreads();
+    // blockDim.x % vecs == 0 and 32 % vecs == 0: lane l of every warp holds octet l (vecs <= 32)
+    const int cpg = Cout / gn_groups;
+    const int t = threadIdx.x;                    // one thread per (group, sum | sumsq)
+    if (t < 2 * gn_groups) {
+      const int g = t >> 1, k = t & 1;
+      float a = 0.f;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+        for (int w8 = 0; w8 < 8; ++w8) a += red[w8][c >> 3][k * 8 + (c & 7)];
+      const size_t p = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+      gn_part[((static_cast<size_t>(n) * gridDim.y * gridDim.x + p) * gn_groups + g) * 2 + k] = a;
+    }
   }
 }
 
@@ -381,9 +430,21 @@ __global__ void conv1x1_small_kernel(const float* __restrict__ x, const float* _
 
 using namespace ptivae;
 
-extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, int N, int H,
-                                        int W, int Cin, int Cout, int out_fmt, void* stream_) {
-  if (!x || !w || !bias || !out || N <= 0 || Cin <= 0 || Cin > 16 || Cout % 8 != 0) return PTIVAE_ERR_ARG;
+extern "C" int ptivae_conv3x3_small_cin_parts(int H, int W, int Cout) {
+  if (H <= 0 || W <= 0 || Cout <= 0 || Cout % 8 != 0) return PTIVAE_ERR_ARG;
+  return ((W * (Cout / 8) + 255) / 256) * ((H + kSmallRows - 1) / kSmallRows);
+}
+
+extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* out, float* gn_part,
+                                        int gn_groups, int N, int H, int W, int Cin, int Cout, int out_fmt,
+                                        void* stream_) {
+  if (!x || !w || !bias || !out || N <= 0 || Cin <= 0 || Cin > 16 || Cout % 8 != 0 || gn_groups < 0) return PTIVAE_ERR_ARG;
+  if (gn_groups > 0) {
+    if (!gn_part || Cout % gn_groups != 0) return PTIVAE_ERR_ARG;
+    const int vecs = Cout / 8, cpg = Cout / gn_groups;
+    // fused statistics: single input channel, octet count a power of two <= 32, groups inside an octet
+    if (Cin != 1 || vecs > 32 || (vecs & (vecs - 1)) || 8 % cpg != 0 || 2 * gn_groups > 256) return PTIVAE_ERR_UNSUPPORTED;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = (static_cast<size_t>(9) * Cin * Cout + Cout) * sizeof(float);
   if (smem > 200 * 1024) return PTIVAE_ERR_UNSUPPORTED;
@@ -395,7 +456,7 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
   if (H > 65535 || N > 65535) return PTIVAE_ERR_UNSUPPORTED;
   dim3 grid((W * (Cout / 8) + 255) / 256, (H + kSmallRows - 1) / kSmallRows, N);
   if (Cin == 1) {
-    conv3x3_cin1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, out, H, W, Cout, out_fmt);
+    conv3x3_cin1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, out, H, W, Cout, out_fmt, gn_part, gn_groups);
     return static_cast<int>(cudaGetLastError());
   }
   conv3x3_small_cin_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt);

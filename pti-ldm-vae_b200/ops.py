@@ -206,15 +206,28 @@ def gn_apply(x: torch.Tensor, scale_shift: torch.Tensor, silu: bool, emit_raw: b
     return (y, raw) if emit_raw else y
 
 
-def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """fp32 NCHW -> NHWC stored as `dtype` (fp32 stream, or a 16-bit operand)."""
+def small_cin_stats_supported(cin: int, cout: int, groups: int) -> bool:
+    """Shapes for which conv3x3_small_cin also emits GroupNorm statistics partials."""
+    vecs = cout // 8
+    return (cin == 1 and groups > 0 and cout % 8 == 0 and cout % groups == 0 and vecs <= 32 and vecs & (vecs - 1) == 0
+            and 8 % (cout // groups) == 0 and 2 * groups <= 256)
+
+
+def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: torch.dtype = torch.float32,
+                      gn_groups: int = 0):
+    """fp32 NCHW -> NHWC stored as `dtype` (fp32 stream, or a 16-bit operand).  With gn_groups > 0 (see
+    small_cin_stats_supported) returns (out, statistics partials [N,P,G,2] of the stored values)."""
     _need_cuda(x, w, b)
     n, cin, h, wd = x.shape
     cout = w.shape[0]
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=dtype)
-    _call("conv3x3_small_cin", (n, h, wd, cin, cout, out.element_size()), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x), _p(w), _p(b),
-          _p(out), n, h, wd, cin, cout, _fmt(out), _stream())
-    return out
+    part = None
+    if gn_groups > 0:
+        part = torch.empty((n, _lib.lib().ptivae_conv3x3_small_cin_parts(h, wd, cout), gn_groups, 2), device=x.device,
+                           dtype=torch.float32)
+    _call("conv3x3_small_cin", (n, h, wd, cin, cout, out.element_size()), 1, _lib.lib().ptivae_conv3x3_small_cin, _p(x),
+          _p(w), _p(b), _p(out), _p(part), gn_groups, n, h, wd, cin, cout, _fmt(out), _stream())
+    return (out, part) if gn_groups > 0 else out
 
 
 def conv3x3_small_cout(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, scale_shift=None) -> torch.Tensor:

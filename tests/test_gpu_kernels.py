@@ -395,6 +395,17 @@ def test_conv_small_cin(b200, n, cin, cout, h, w):
     _check_bf16(out, ref, "small_cin")
     out32 = b200.ops.conv3x3_small_cin(x, wt, bias)
     assert float((out32 - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+    for groups in (32, 16, 8):
+        if not b200.ops.small_cin_stats_supported(cin, cout, groups):
+            continue
+        for dt in (torch.float32, DT):
+            o, part = b200.ops.conv3x3_small_cin(x, wt, bias, dtype=dt, gn_groups=groups)
+            assert torch.equal(o, b200.ops.conv3x3_small_cin(x, wt, bias, dtype=dt))
+            of = o.float().view(n, h * w, groups, cout // groups)
+            acc = part.sum(dim=1)
+            assert torch.allclose(acc[..., 0], of.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+            assert torch.allclose(acc[..., 1], (of * of).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+            assert torch.equal(part, b200.ops.conv3x3_small_cin(x, wt, bias, dtype=dt, gn_groups=groups)[1])
 
 
 @pytest.mark.parametrize("n,cin,cout,h,w,norm,f32", [(2, 32, 1, 64, 64, True, True), (1, 64, 1, 32, 32, True, False),

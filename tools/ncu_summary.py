@@ -1,0 +1,25 @@
+"""Key metrics + stall mix of one .ncu-rep (raw page) as text: ncu_summary.py report.ncu-rep"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
+        "launch__shared_mem_per_block_dynamic"]
+for w in want:
+    if w in hdr:
+        i = hdr.index(w)
+        print("%-78s %18s %s" % (w, vals[i][:90], units[i]))
+st = {}
+for i, h in enumerate(hdr):
+    if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+        try:
+            st[h[len("smsp__pcsamp_warps_issue_stalled_"):]] = float(vals[i].replace(",", ""))
+        except ValueError:
+            pass
+tot = sum(st.values()) or 1.0
+print("stall mix (pc sampling): " + ", ".join("%s %.0f %%" % (k, 100 * v / tot) for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:7]))
