@@ -86,7 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_O = tmem_base + BKV;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       mbar_expect_tx(q_full, Q_BYTES);
       for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * (128 * 128), &tmQ, q_full, c * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
@@ -103,7 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       mbar_wait(q_full, 0);
       for (int j = 0; j < nkv; ++j) {
         const int s = j & 1;

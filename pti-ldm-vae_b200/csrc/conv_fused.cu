@@ -128,7 +128,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
 
   if (warp == W_PROD) {
     // ------------------------------------------------------------------ weight TMA producer
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       if constexpr (RESB) {
         mbar_expect_tx(&b_full[0], Cfg::WBYTES);
         for (int tap = 0; tap < 9; ++tap)
@@ -152,7 +152,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap tmB, const FusedArgs ar
     // ------------------------------------------------------------------ MMA issuer
     // The issuing thread is latency bound: descriptors are (lo, hi) halves, hi is invariant and lo moves
     // by compile-time constants inside the unrolled (k, M-block) loops.
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       const uint32_t a_hi = desc_hi(kSBO_A, kLayout);
       const uint32_t b_hi = desc_hi(kSBO_B, kLayout);
       const uint32_t bring_lo = desc_lo(smem_u32(bring));
@@ -485,7 +485,8 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
     if (impl == 2) return conv3x3_tma_launch(c, stream);
     // auto: measured winners (B200, batch 64) -- the chunk-pipelined kernel for every shape with a 128-wide side
     // and for 64->64 with a residual; the single-buffer kernel (12 transform warps) for the 32-wide layers
-    const bool wide = Cin == 128 || Cout == 128 || (Cin == 64 && Cout == 64 && residual != nullptr);
+    const bool wide = Cin == 128 || Cout == 128 || (Cin == 64 && Cout == 64 && residual != nullptr) ||
+                      (Cin == 64 && Cout == 32);
     int rc = wide ? conv3x3_tma2_launch(c, stream) : conv3x3_tma_launch(c, stream);
     if (rc == PTIVAE_ERR_UNSUPPORTED) rc = wide ? conv3x3_tma_launch(c, stream) : conv3x3_tma2_launch(c, stream);
     if (rc != PTIVAE_ERR_UNSUPPORTED) return rc;

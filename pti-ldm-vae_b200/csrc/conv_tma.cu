@@ -154,7 +154,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
   if (warp == W_PRODB) {
     // ------------------------------------------------------------------ weights
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       if constexpr (RESB) {
         mbar_expect_tx(&b_full[0], C::WBYTES);
         for (int tap = 0; tap < 9; ++tap)
@@ -175,7 +175,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else if (warp == W_PROD) {
     // ------------------------------------------------------------------ raw halo tiles (TMA loads)
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       int it = 0;
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
         const int n = t / tiles_per_img;
@@ -193,7 +193,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // (TMA), waits until the epilogue warps have added the accumulators in place, drains the tile with one TMA
     // tensor store (image edges clipped by the TMA unit) and recycles the buffer for tile k + RO.  The
     // epilogue warps never wait on a store.
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       auto tile_xy = [&](int k, int& n, int& x0, int& y0) {
         const int t = blockIdx.x + k * gridDim.x;
         n = t / tiles_per_img;
@@ -237,7 +237,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (as in conv_fused.cu)
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       const uint32_t a_hi = desc_hi(kSBO_A, kLayout);
       const uint32_t b_hi = desc_hi(kSBO_B, kLayout);
       const uint32_t w_lo = desc_lo(smem_u32(wts));
@@ -499,7 +499,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (inb) {
           float f[8];
           const uint4* src = reinterpret_cast<const uint4*>(xb + L * (CIN * C::IESZ));
-          if constexpr (IN32) {
+          if constexpr (IN32 && CIN == 32) {
+            // 128-byte raw lines are TMA-swizzled: the quarter-warp's 16-byte reads hit distinct banks
+            const uint8_t* line = xs + s * C::XS_BYTES + L * 128;
+            const uint4 lo = *reinterpret_cast<const uint4*>(line + (((2 * u) ^ (L & 7)) << 4));
+            const uint4 hi = *reinterpret_cast<const uint4*>(line + (((2 * u + 1) ^ (L & 7)) << 4));
+            f[0] = __uint_as_float(lo.x); f[1] = __uint_as_float(lo.y); f[2] = __uint_as_float(lo.z); f[3] = __uint_as_float(lo.w);
+            f[4] = __uint_as_float(hi.x); f[5] = __uint_as_float(hi.y); f[6] = __uint_as_float(hi.z); f[7] = __uint_as_float(hi.w);
+          } else if constexpr (IN32) {
             const uint4 lo = src[0], hi = src[1];
             f[0] = __uint_as_float(lo.x); f[1] = __uint_as_float(lo.y); f[2] = __uint_as_float(lo.z); f[3] = __uint_as_float(lo.w);
             f[4] = __uint_as_float(hi.x); f[5] = __uint_as_float(hi.y); f[6] = __uint_as_float(hi.z); f[7] = __uint_as_float(hi.w);
@@ -562,7 +569,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     uint64_t d[4] = {uint64_t(CIN), W, H, N};
     uint64_t s[3] = {uint64_t(CIN) * C::IESZ, W * CIN * C::IESZ, H * W * CIN * C::IESZ};
     uint32_t b[4] = {uint32_t(CIN), kHP, kHP, 1};
-    int rc = encode_tmap(&tmX, c.x, IN32 ? 2 : 1, 4, d, s, b, 0);
+    int rc = encode_tmap(&tmX, c.x, IN32 ? 2 : 1, 4, d, s, b, (IN32 && CIN == 32) ? 128 : 0);
     if (rc) return rc;
   }
   {  // weights [9][Cout][Cin] fp16

@@ -15,8 +15,8 @@
 //     store (image edges clipped by the TMA unit);
 //   * GroupNorm statistics of the stored values: column sums over the warp's own 32 rows of the slot
 //     (conflict-free 16-byte loads), folded in fixed order -- deterministic, no atomics.
-// Warp roles (608 threads): 0-7 epilogue teams, 8-15 transform, 16 MMA issuer (+TMEM), 17 halo TMA producer,
-// 18 weight TMA producer.
+// Warp roles: 0-7 epilogue teams, then 8 (or 12) transform warps, the MMA issuer (+TMEM), the halo TMA producer
+// and the weight TMA producer (608 or 736 threads).
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptivae_internal.h"
@@ -25,10 +25,11 @@ namespace ptivae {
 namespace tma4 {
 
 constexpr int kT = 16, kHP = kT + 2, kHalo = kHP * kHP;
-constexpr int NTEAM = 2, NEW = NTEAM * 4, NTW = 8;
-constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
-constexpr int kThreads = (NEW + NTW + 3) * 32;
-constexpr int NT = NTW * 32;
+constexpr int NTEAM = 2, NEW = NTEAM * 4;
+constexpr int W_TR0 = NEW;   // transform warps [NEW, NEW + NTW), then the MMA issuer and the two TMA producers
+// transform warps: 12 where the transform is the widest stage (64-channel fp32 input into a narrow output), else 8
+template <int CIN, int COUT, bool IN32>
+constexpr int ntw() { return (IN32 && CIN == 64 && COUT == 32) ? 12 : 8; }
 constexpr uint32_t kSmemMax = 232448;
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 
@@ -54,29 +55,39 @@ struct Cfg {
     return FIXED + nbuf * CHUNK + (IN32 ? nxs * xs_block(xc) : 0u) + (resb ? WBYTES : nst * SLAB);
   }
   struct Pick { int nbuf, xc, nxs, nst; bool resb, ok; };
+  // weights for a given rest-of-the-budget: resident if they fit, else the deepest ring (<= 8 stages, <= 64 KB):
+  // a slab is consumed in 0.2-0.3 us but takes ~0.7 us to arrive from L2, so a shallow ring starves the MMAs
+  // (measured: 64->32 with 3 stages of 4 KB ran at 0.29 us per slab instead of 0.17)
+  static constexpr Pick weights(int nbuf, int xc, int nxs, int min_nst) {
+    if (total(nbuf, xc, nxs, true, 0) <= kSmemMax) return {nbuf, xc, nxs, 1, true, true};
+    for (int nst = 8; nst >= min_nst; --nst)
+      if (nst * SLAB <= 65536u && total(nbuf, xc, nxs, false, nst) <= kSmemMax) return {nbuf, xc, nxs, nst, false, true};
+    return {0, 32, 0, 0, false, false};
+  }
   static constexpr Pick pick() {
-    // preference: double-buffered chunks > (fp32 input) at least one tile of raw blocks in flight > resident weights
+    // preference: double-buffered chunks > (fp32 input) a tile's worth of raw blocks in flight > weight-ring depth
     const int nbufs[2] = {2 * NCH, NCH};
-    for (int bi = 0; bi < 2; ++bi) {
-      const int nbuf = nbufs[bi];
-      if (nbuf < 2) continue;
-      if (!IN32) {
-        if (total(nbuf, 32, 0, true, 0) <= kSmemMax) return {nbuf, 32, 0, 1, true, true};
-        if (total(nbuf, 32, 0, false, 4) <= kSmemMax) return {nbuf, 32, 0, 4, false, true};
-        if (total(nbuf, 32, 0, false, 3) <= kSmemMax) return {nbuf, 32, 0, 3, false, true};
-        if (total(nbuf, 32, 0, false, 2) <= kSmemMax) return {nbuf, 32, 0, 2, false, true};
-      } else {
-        const int per_tile32 = CIN / 32;
-        for (int nxs = (per_tile32 < 4 ? per_tile32 * 2 : 4); nxs >= 2; --nxs) {
-          if (nxs > 4) continue;
-          if (total(nbuf, 32, nxs, true, 0) <= kSmemMax) return {nbuf, 32, nxs, 1, true, true};
-          if (total(nbuf, 32, nxs, false, 3) <= kSmemMax) return {nbuf, 32, nxs, 3, false, true};
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0 insists on a ring of >= 3 stages
+      const int min_nst = pass == 0 ? 3 : 2;
+      for (int bi = 0; bi < 2; ++bi) {
+        const int nbuf = nbufs[bi];
+        if (nbuf < 2) continue;
+        if (!IN32) {
+          const Pick p = weights(nbuf, 32, 0, min_nst);
+          if (p.ok) return p;
+        } else {
+          const int per_tile32 = CIN / 32;
+          for (int nxs = (per_tile32 < 4 ? per_tile32 * 2 : 4); nxs >= 2; --nxs) {
+            const Pick p = weights(nbuf, 32, nxs, min_nst);
+            if (p.ok) return p;
+          }
+          for (int nxs = 4; nxs >= 2; --nxs) {
+            const Pick p = weights(nbuf, 16, nxs, min_nst);
+            if (p.ok) return p;
+          }
+          const Pick p = weights(nbuf, 32, 1, min_nst);
+          if (p.ok) return p;
         }
-        for (int nxs = 4; nxs >= 2; --nxs) {
-          if (total(nbuf, 16, nxs, false, 3) <= kSmemMax) return {nbuf, 16, nxs, 3, false, true};
-          if (total(nbuf, 16, nxs, false, 2) <= kSmemMax) return {nbuf, 16, nxs, 2, false, true};
-        }
-        if (total(nbuf, 32, 1, false, 2) <= kSmemMax) return {nbuf, 32, 1, 2, false, true};
       }
     }
     return {0, 32, 0, 0, false, false};
@@ -97,14 +108,22 @@ struct Args {
   const float* scale_shift;  // [N][CIN][2] or nullptr
   const float* bias;
   float* gn_part;            // [N][tiles][groups][2]
+  unsigned long long* trace; // debug timeline of CTA 0 ([tile][32] slots) or nullptr
 };
 
+#define TMA4_TRACE(it, slot)                                                                             \
+  do {                                                                                                   \
+    if (args.trace != nullptr && blockIdx.x == 0 && (it) < 64) args.trace[(it) * 32 + (slot)] = clock64(); \
+  } while (0)
+
 template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((NEW + ntw<CIN, COUT, IN32>() + 3) * 32, 1)
 conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
   using C = Cfg<CIN, COUT, IN32, RES, OUT32>;
   constexpr bool F16 = true;
+  constexpr int NTW = ntw<CIN, COUT, IN32>(), NT = NTW * 32;
+  constexpr int W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
   constexpr int KCH = C::KCH, NCH = C::NCH, NBUF = C::NBUF, XC = C::XC, NXS = C::NXS, NST = C::NST, NOB = C::NOB;
   constexpr uint32_t LB = C::LB, CHUNK = C::CHUNK, SLAB = C::SLAB, OLB = C::OLB;
   constexpr bool RESB = C::RESB, SEP_RS = C::SEP_RS;
@@ -126,16 +145,16 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   float* colsum = reinterpret_cast<float*>(wts + (RESB ? C::WBYTES : NST * SLAB));   // [NEW][COUT][2]
   float* sbias = colsum + NEW * COUT * 2;                   // [COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
-  uint64_t* b_full = bars;             // [4]
-  uint64_t* b_empty = bars + 4;        // [4]
-  uint64_t* in_full = bars + 8;        // [4] 16-bit input: chunk landed (TMA)   | fp32 input: raw block landed
-  uint64_t* in_empty = bars + 12;      // [4] fp32 input: raw block consumed
-  uint64_t* op_full = bars + 16;       // [4] chunk transformed
-  uint64_t* op_empty = bars + 20;      // [4] chunk consumed by the MMAs
-  uint64_t* acc_full = bars + 24;      // [2]
-  uint64_t* acc_empty = bars + 26;     // [2]
-  uint64_t* res_full = bars + 28;      // [NTEAM][2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 32);
+  uint64_t* b_full = bars;             // [8]
+  uint64_t* b_empty = bars + 8;        // [8]
+  uint64_t* in_full = bars + 16;       // [4] 16-bit input: chunk landed (TMA)   | fp32 input: raw block landed
+  uint64_t* in_empty = bars + 20;      // [4] fp32 input: raw block consumed
+  uint64_t* op_full = bars + 24;       // [4] chunk transformed
+  uint64_t* op_empty = bars + 28;      // [4] chunk consumed by the MMAs
+  uint64_t* acc_full = bars + 32;      // [2]
+  uint64_t* acc_empty = bars + 34;     // [2]
+  uint64_t* res_full = bars + 36;      // [NTEAM][2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 40);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -144,9 +163,11 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmO);
     if (RES) tma_prefetch_desc(&tmR);
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&in_full[s], 1);
       mbar_init(&in_empty[s], NT);
       mbar_init(&op_full[s], NT);
@@ -169,7 +190,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   if (warp == W_W) {
     // ------------------------------------------------------------------ weights (order: chunk outer, tap inner)
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       if constexpr (RESB) {
         mbar_expect_tx(&b_full[0], C::WBYTES);
         for (int kc = 0; kc < NCH; ++kc)
@@ -190,7 +211,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp == W_IN) {
     // ------------------------------------------------------------------ input halo pieces (TMA loads)
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       int pq = 0;   // global piece counter
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
         const int n = t / tiles_per_img;
@@ -213,7 +234,9 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // elect.sync (not lane == 0): ptxas then knows a single thread runs this region and emits each UTCHMMA
+    // straight; under a plain lane test it wraps every MMA in an ELECT/branch loop (~90 cycles per MMA, measured)
+    if (elect_one()) {
       const uint32_t a_hi = desc_hi(kSBO_A, kLayout);
       const uint32_t b_hi = desc_hi(kSBO_B, kLayout);
       const uint32_t w_lo = desc_lo(smem_u32(wts));
@@ -234,6 +257,8 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const int cb = cq % NBUF;
           mbar_wait(&op_full[cb], (cq / NBUF) & 1);
           tc_fence_after();
+          if (kc == 0) TMA4_TRACE(it, 2);
+          TMA4_TRACE(it, 22 + kc);
           const uint32_t a_lo_chunk = desc_lo(smem_u32(opbuf + cb * CHUNK));
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -263,6 +288,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           umma_commit(&op_empty[cb]);
         }
         umma_commit(&acc_full[st]);
+        TMA4_TRACE(it, 3);
       }
     }
   } else if (warp >= W_TR0) {
@@ -274,8 +300,9 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     constexpr int LS = NT / VPL;                 // pixel stride between a thread's vectors
     constexpr int VPT = (kHalo + LS - 1) / LS;
     const int u = tt % VPL, Lbase = tt / VPL;
-    int pq = 0, cq = 0;
+    int pq = 0, cq = 0, it = -1;
     for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      ++it;
       const int n = t / tiles_per_img;
       const int trem = t - n * tiles_per_img;
       const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
@@ -296,10 +323,14 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const int s = pq % NXS;
           if (p % PPC == 0) mbar_wait(&op_empty[cb], ((cq / NBUF) & 1) ^ 1u);   // chunk buffer free (MMAs done)
           mbar_wait(&in_full[s], (pq / NXS) & 1);
-          src_base = xs + s * C::XSB + u * 32;
+          src_base = xs;
         } else {
           mbar_wait(&in_full[cb], (cq / NBUF) & 1);                             // raw chunk landed in place
           src_base = nullptr;
+        }
+        if (tt == 0) {
+          if (p == 0) TMA4_TRACE(it, 0);
+          TMA4_TRACE(it, 14 + (p & 3));
         }
         uint8_t* ob = opbuf + cb * CHUNK;
         const uint32_t uu = IN32 ? static_cast<uint32_t>((p % PPC) * VPL + u) : static_cast<uint32_t>(u);   // 16-byte column in the line
@@ -319,8 +350,12 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           if (inb) {
             float f[8];
             if constexpr (IN32) {
-              const uint4* src = reinterpret_cast<const uint4*>(src_base + L * (XC * 4));
-              const uint4 lo = src[0], hi = src[1];
+              // raw blocks are TMA-swizzled (line = XC*4 bytes): consecutive pixels land on different banks, so
+              // the two 16-byte reads of a quarter-warp are conflict-free (dense lines: 2-way conflicts, measured)
+              const uint8_t* line = xs + (pq % NXS) * C::XSB + L * (XC * 4);
+              const uint32_t xsw = (XC == 32) ? (L & 7) : ((L >> 1) & 3);
+              const uint4 lo = *reinterpret_cast<const uint4*>(line + (((2 * u) ^ xsw) << 4));
+              const uint4 hi = *reinterpret_cast<const uint4*>(line + (((2 * u + 1) ^ xsw) << 4));
               f[0] = __uint_as_float(lo.x); f[1] = __uint_as_float(lo.y); f[2] = __uint_as_float(lo.z); f[3] = __uint_as_float(lo.w);
               f[4] = __uint_as_float(hi.x); f[5] = __uint_as_float(hi.y); f[6] = __uint_as_float(hi.z); f[7] = __uint_as_float(hi.w);
             } else {
@@ -346,6 +381,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           *dst = o;
         }
         if constexpr (IN32) mbar_arrive(&in_empty[pq % NXS]);
+        if (tt == 0) {
+          TMA4_TRACE(it, 18 + (p & 3));
+          if (p == NPIECE - 1) TMA4_TRACE(it, 1);
+        }
         if ((p + 1) % PPC == 0) {     // chunk complete
           fence_proxy_async_smem();
           mbar_arrive(&op_full[cb]);
@@ -391,8 +430,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int trem = t - n * tiles_per_img;
       const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
       const int x0 = tix * kT + mb * 8, y0 = tiy * kT;
+      if (threadIdx.x == 0) TMA4_TRACE(it, 4);
       mbar_wait(&acc_full[st], (it >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) TMA4_TRACE(it, 6);
 #pragma unroll 1
       for (int ob = 0; ob < NOB; ++ob, ++q) {
         uint8_t* oslot = tslots + (q & 1) * C::SLOT;
@@ -447,6 +488,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tma_store_4d(&tmO, oslot, ob * 32, x0, y0, n);
           tma_store_commit();
         }
+        if (threadIdx.x == 0 && ob == 0) TMA4_TRACE(it, 7);
         if (cpg > 0) {
           // column sums of the stored values over this warp's own 32 rows (lane = (row sub-index, 16-byte chunk))
           constexpr int LPR = OLB / 16, RPI = 32 / LPR, CPC = OUT32 ? 4 : 8;
@@ -509,6 +551,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
       }
+      if (threadIdx.x == 0) TMA4_TRACE(it, 5);
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
@@ -530,13 +573,14 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     a.tiles_y = (c.H + kT - 1) / kT;
     a.num_tiles = c.N * a.tiles_x * a.tiles_y;
     a.silu = c.silu; a.gn_groups = c.gn_groups; a.scale_shift = c.scale_shift; a.bias = c.bias; a.gn_part = c.gn_part;
+    a.trace = c.trace;
     CUtensorMap tmX, tmW, tmR, tmO;
     const uint64_t H = c.H, W = c.W, N = c.N;
-    if (IN32) {  // raw fp32 halo blocks: dims (C, W, H, N), box (XC, 18, 18, 1), dense
+    if (IN32) {  // raw fp32 halo blocks: dims (C, W, H, N), box (XC, 18, 18, 1), swizzle = line bytes
       uint64_t d[4] = {uint64_t(CIN), W, H, N};
       uint64_t s[3] = {uint64_t(CIN) * 4, W * CIN * 4, H * W * CIN * 4};
       uint32_t b[4] = {uint32_t(C::XC), kHP, kHP, 1};
-      int rc = encode_tmap(&tmX, c.x, 2, 4, d, s, b, 0);
+      int rc = encode_tmap(&tmX, c.x, 2, 4, d, s, b, C::XC * 4);
       if (rc) return rc;
     } else {     // 16-bit halo chunks with the operand swizzle
       uint64_t d[4] = {uint64_t(CIN), W, H, N};
@@ -579,6 +623,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    constexpr int kThreads = (NEW + ntw<CIN, COUT, IN32>() + 3) * 32;
     conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, a);
     return static_cast<int>(cudaGetLastError());
   }

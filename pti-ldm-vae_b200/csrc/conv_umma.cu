@@ -109,7 +109,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < args.ntaps; ++t) {
@@ -125,7 +125,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       const uint32_t hi = desc_hi(kSBO, kLayout);
       const uint32_t lo0 = desc_lo(smem_u32(smem));
       int s = 0;

@@ -112,7 +112,7 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   if (warp == W_W) {
     // ------------------------------------------------------------------ weight ring: 16 (phase, tap) x NCH slabs per tile
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x)
@@ -126,7 +126,7 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp == W_IN) {
     // ------------------------------------------------------------------ halo tiles: straight into the operand buffer
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       int it = 0;
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
         const int n = t / tiles_per_img;
@@ -141,7 +141,7 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       const uint32_t a_hi = desc_hi(kSBO_A, kLayoutSW128);
       const uint32_t b_hi = desc_hi(kSBO_B, kLayoutSW128);
       const uint32_t w_lo = desc_lo(smem_u32(wring));

@@ -7,8 +7,12 @@ b200 = _pkg.load(); ops = b200.ops; lib = b200._lib.lib()
 trace = len(sys.argv) > 1 and sys.argv[1] == "trace"
 if len(sys.argv) > 2: ops.FUSED_IMPL = int(sys.argv[2])
 print("FUSED_IMPL", ops.FUSED_IMPL)
+only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
 cases = [(64, 256, 256, 32, 32, True), (64, 256, 256, 32, 32, False), (64, 64, 64, 128, 128, True), (64, 128, 128, 64, 64, True), (64, 128, 128, 64, 64, False), (64, 256, 256, 64, 32, False), (64, 128, 128, 32, 64, False)]
+cases += [(64, 64, 64, 128, 128, False), (64, 128, 128, 128, 64, False), (64, 32, 32, 128, 128, True)]
 for (n, h, w, cin, cout, conv2) in cases:
+    if only and f"{cin}-{cout}-{h}-{int(conv2)}" not in only:
+        continue
     g = torch.Generator().manual_seed(1)
     x = torch.randn(n, h, w, cin, device="cuda", dtype=torch.float32 if not conv2 else torch.float16)
     wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).cuda()
@@ -40,6 +44,9 @@ for (n, h, w, cin, cout, conv2) in cases:
         for i in range(0, 7):
             print(f"   {i:4d} " + " ".join(f"{int(t[i, k]) - t0:10d}" for k in range(6)) + "   | os_ready acc_ready drained: " + " ".join(f"{int(t[i, k]) - int(t[i, 4]):7d}" for k in (6, 7, 8, 9, 10)))
         for i in (3, 4):
+            x0 = int(t[i, 0])
+            print(f"   tile {i} transform pieces (rel. to xf_start) start: " + " ".join(str(int(t[i, 14 + k]) - x0) for k in range(4)) + "  end: " + " ".join(str(int(t[i, 18 + k]) - x0) for k in range(4)) + "  | mma chunk ready (rel. mma_start): " + " ".join(str(int(t[i, 22 + k]) - int(t[i, 2])) for k in range(2)))
+        for i in (3, 4) if ops.FUSED_IMPL != 3 else ():
             m0 = int(t[i, 2])
             print(f"   tile {i} mma detail (rel. to mma_start): wait-done " + " ".join(str(int(t[i, 14 + k]) - m0) for k in range(9)))
             print(f"   tile {i}                               committed " + " ".join(str(int(t[i, 23 + k]) - m0) for k in range(9)))
