@@ -292,101 +292,99 @@ __global__ void __launch_bounds__(256, 2) conv3x3_cin1_kernel(const float* __res
 // One launch plane per output channel (grid.z = N * Cout; the extra passes over the input are L2 hits).
 //   out(y,x) = sum_taps sum_c w[tap][c] * n(y+dy, x+dx, c) is evaluated as per-pixel tap dot products
 //   p[tap](y,x) = sum_c w[tap][c] * n(y,x,c)           (every input pixel is read exactly once per plane)
-// staged in shared memory for the 18x34 halo of a 16x32 output tile, followed by a 9-point gather
+// staged in shared memory for the 18x66 halo of a 16x64 output tile, followed by a 9-point gather
 //   out(y,x) = bias + sum_tap p[tap](y+dy, x+dx).
-// LP = Cin/8 lanes share a pixel: each owns 8 channels whose 72 weights and scale/shift stay in registers (the
-// first version re-read them from shared memory per pixel: 72 LDS.128 per 288 FMAs, LSU bound at 0.8 TB/s),
-// a warp-wide load covers 32/LP whole pixels (coalesced), and the 9 partial sums fold with xor-shuffles.
-// Out-of-image halo pixels contribute p = 0: the zero padding applies to the normalised tensor.
-constexpr int kFcTW = 32, kFcTH = 16, kFcHW = kFcTW + 2, kFcHH = kFcTH + 2, kFcHalo = kFcHW * kFcHH;
-constexpr int kFcVT = 4;   // vertically stacked tiles per block (amortises the weight registers' fill)
-template <int FMT>         // 0 bf16 | 1 fp16 | 2 fp32 input
-__global__ void __launch_bounds__(256, 2) conv3x3_fewcout_kernel(const void* __restrict__ x, const float* __restrict__ w,
-                                                                 const float* __restrict__ bias,
-                                                                 const float* __restrict__ ss, float* __restrict__ out,
-                                                                 int H, int W, int Cin, int Cout, int lp) {
-  __shared__ float sp[9 * kFcHalo];       // [tap][halo pixel] tap partials
+// The GroupNorm affine is folded into the block's weights (one image per block): w'[tap][c] = w*scale[n][c] and
+// K[tap] = sum_c w*shift[n][c], so p = sum_c w'*x + K for in-image pixels and 0 outside (zero padding applies to
+// the normalised tensor).  A thread owns FOUR halo pixels: each broadcast LDS.128 of weights feeds 16 FMAs.
+// History (ncu): weights re-read per pixel = LSU bound (0.32 ms at 32->1, 256^2 x 64); 4 lanes per pixel with
+// register weights and a shuffle fold = issue bound at 257 instructions per lane-pixel (0.26 ms); this form
+// issues ~90 per pixel-octet.
+constexpr int kFcTW = 64, kFcTH = 16, kFcHW = kFcTW + 2, kFcHH = kFcTH + 2, kFcHalo = kFcHW * kFcHH;   // 1188 = 4 * 297
+constexpr int kFcQ = kFcHalo / 4;     // halo pixels per thread-slot
+constexpr int kFcThreads = 160;       // two rounds cover the 297 slots
+constexpr int kFcVT = 2;              // vertically stacked tiles per block (amortises the weight fold)
+template <int FMT>                    // 0 bf16 | 1 fp16 | 2 fp32 input
+__global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias,
+                                                                     const float* __restrict__ ss, float* __restrict__ out,
+                                                                     int H, int W, int Cin, int Cout) {
+  extern __shared__ float fsm[];
+  float* sp = fsm;                        // [9][kFcHalo] tap partials
+  float* sw = sp + 9 * kFcHalo;           // [Cin/8][9][8] folded weights, octet-major
+  float* sk = sw + 9 * Cin;               // [9] folded shift constants (+ padding)
   const int n = blockIdx.z / Cout, co = blockIdx.z - n * Cout;
-  const int sub = threadIdx.x % lp;       // this thread's 8-channel unit (blockDim.x % lp == 0)
-  const int c0 = sub * 8;
-  float wr[9][8], sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float* wp = w + (static_cast<size_t>(co) * Cin + c0 + j) * 9;   // w is [Cout][Cin][3][3]
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wr[t][j] = __ldg(wp + t);
-    sc[j] = ss ? __ldg(ss + (static_cast<size_t>(n) * Cin + c0 + j) * 2) : 1.f;
-    sh[j] = ss ? __ldg(ss + (static_cast<size_t>(n) * Cin + c0 + j) * 2 + 1) : 0.f;
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+    const int oct = i / 72, r = i - oct * 72, t = r >> 3, j = r & 7;
+    const int c = oct * 8 + j;
+    const float sc = ss ? __ldg(ss + (static_cast<size_t>(n) * Cin + c) * 2) : 1.f;
+    sw[i] = __ldg(w + (static_cast<size_t>(co) * Cin + c) * 9 + t) * sc;          // w is [Cout][Cin][3][3]
   }
+  if (threadIdx.x < 9) {
+    float k = 0.f;
+    if (ss)
+      for (int c = 0; c < Cin; ++c)
+        k = fmaf(__ldg(w + (static_cast<size_t>(co) * Cin + c) * 9 + threadIdx.x), __ldg(ss + (static_cast<size_t>(n) * Cin + c) * 2 + 1), k);
+    sk[threadIdx.x] = k;
+  }
+  __syncthreads();
   constexpr int ESZ = FMT == 2 ? 4 : 2;
-  const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * ESZ + c0 * ESZ;
+  const uint8_t* img = static_cast<const uint8_t*>(x) + static_cast<size_t>(n) * H * W * Cin * ESZ;
   const float b0 = __ldg(bias + co);
   float* oplane = out + (static_cast<size_t>(n) * Cout + co) * H * W;
   const int x0 = blockIdx.x * kFcTW - 1;
-  const int items = kFcHalo * lp;
-  {  // HBM -> L2 bulk prefetch of every input row segment this block reads (all channels of the x range)
-    const int ry = static_cast<int>(blockIdx.y) * kFcVT * kFcTH - 1 + static_cast<int>(threadIdx.x);
-    const int xs = max(x0, 0), xe = min(x0 + kFcHW, W);
-    if (threadIdx.x < kFcVT * kFcTH + 2 && ry >= 0 && ry < H && sub == 0)
-      l2_prefetch_bulk(static_cast<const uint8_t*>(x) + ((static_cast<size_t>(n) * H + ry) * W + xs) * Cin * ESZ,
-                       static_cast<uint32_t>((xe - xs) * Cin * ESZ));
-  }
+  const int noct = Cin / 8;
   for (int vt = 0; vt < kFcVT; ++vt) {
     const int ty0 = (blockIdx.y * kFcVT + vt) * kFcTH;
     if (ty0 >= H) break;
     const int y0 = ty0 - 1;
-    // batches of UB independent 16|32-byte loads per thread are in flight before any arithmetic: the first version
-    // (one load, then 80 dependent FMAs, per iteration) was DRAM-latency bound at 0.9 TB/s
-    constexpr int UB = FMT == 2 ? 2 : 4;
-    for (int it0 = 0; it0 < items; it0 += UB * blockDim.x) {   // uniform trip count: the shuffles need whole warps
-      uint4 raw[UB][FMT == 2 ? 2 : 1];
-      bool ok[UB];
+    for (int slot = threadIdx.x; slot < kFcQ; slot += blockDim.x) {
+      const uint8_t* pp[4];
+      bool ok[4];
 #pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int hp = (it0 + u * blockDim.x + threadIdx.x) / lp;
+      for (int q = 0; q < 4; ++q) {
+        const int hp = slot + q * kFcQ;
         const int hy = hp / kFcHW, hx = hp - hy * kFcHW;
         const int gy = y0 + hy, gx = x0 + hx;
-        ok[u] = hp < kFcHalo && static_cast<unsigned>(gy) < static_cast<unsigned>(H) &&
-                static_cast<unsigned>(gx) < static_cast<unsigned>(W);
-        if (ok[u]) {
-          const uint4* p = reinterpret_cast<const uint4*>(img + (static_cast<size_t>(gy) * W + gx) * Cin * ESZ);
-          raw[u][0] = __ldg(p);
-          if constexpr (FMT == 2) raw[u][1] = __ldg(p + 1);
-        }
+        ok[q] = static_cast<unsigned>(gy) < static_cast<unsigned>(H) && static_cast<unsigned>(gx) < static_cast<unsigned>(W);
+        pp[q] = img + (static_cast<size_t>(ok[q] ? gy : 0) * W + (ok[q] ? gx : 0)) * Cin * ESZ;
       }
+      float acc[4][9];
 #pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int hp = (it0 + u * blockDim.x + threadIdx.x) / lp;
-        float acc[9];
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-        if (ok[u]) {
-          float v[8];
+        for (int t = 0; t < 9; ++t) acc[q][t] = 0.f;
+      for (int oct = 0; oct < noct; ++oct) {
+        float v[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
           if constexpr (FMT == 2) {
-            v[0] = __uint_as_float(raw[u][0].x); v[1] = __uint_as_float(raw[u][0].y);
-            v[2] = __uint_as_float(raw[u][0].z); v[3] = __uint_as_float(raw[u][0].w);
-            v[4] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].x); v[5] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].y);
-            v[6] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].z); v[7] = __uint_as_float(raw[u][FMT == 2 ? 1 : 0].w);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pp[q]) + 2 * oct);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pp[q]) + 2 * oct + 1);
+            v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w; v[q][4] = b.x; v[q][5] = b.y; v[q][6] = b.z; v[q][7] = b.w;
           } else {
-            unpack2<FMT == 1>(raw[u][0].x, v[0], v[1]); unpack2<FMT == 1>(raw[u][0].y, v[2], v[3]);
-            unpack2<FMT == 1>(raw[u][0].z, v[4], v[5]); unpack2<FMT == 1>(raw[u][0].w, v[6], v[7]);
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(pp[q]) + oct);
+            unpack2<FMT == 1>(a.x, v[q][0], v[q][1]); unpack2<FMT == 1>(a.y, v[q][2], v[q][3]);
+            unpack2<FMT == 1>(a.z, v[q][4], v[q][5]); unpack2<FMT == 1>(a.w, v[q][6], v[q][7]);
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-#pragma unroll
-          for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t] = fmaf(v[j], wr[t][j], acc[t]);
         }
-        for (int o = lp >> 1; o > 0; o >>= 1) {
+        const float4* wo = reinterpret_cast<const float4*>(sw + oct * 72);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-        }
-        if (sub == 0 && hp < kFcHalo) {
+        for (int t = 0; t < 9; ++t) {
+          const float4 w0 = wo[2 * t], w1 = wo[2 * t + 1];     // warp-uniform address: broadcast
 #pragma unroll
-          for (int t = 0; t < 9; ++t) sp[t * kFcHalo + hp] = acc[t];
+          for (int q = 0; q < 4; ++q) {
+            float a = acc[q][t];
+            a = fmaf(v[q][0], w0.x, a); a = fmaf(v[q][1], w0.y, a); a = fmaf(v[q][2], w0.z, a); a = fmaf(v[q][3], w0.w, a);
+            a = fmaf(v[q][4], w1.x, a); a = fmaf(v[q][5], w1.y, a); a = fmaf(v[q][6], w1.z, a); a = fmaf(v[q][7], w1.w, a);
+            acc[q][t] = a;
+          }
         }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) sp[t * kFcHalo + slot + q * kFcQ] = ok[q] ? acc[q][t] + sk[t] : 0.f;
     }
     __syncthreads();
     for (int q = threadIdx.x; q < kFcTW * kFcTH; q += blockDim.x) {
@@ -487,16 +485,25 @@ extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const fl
                                          void* stream_) {
   if (!x || !w || !bias || !out || N <= 0 || Cin % 8 != 0 || Cout <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int lp = Cin / 8;   // lanes per pixel of the tap-partial kernel: power of two, at most a warp
-  if (Cin % 8 == 0 && lp <= 32 && (lp & (lp - 1)) == 0 && in_fmt >= 0 && in_fmt <= 2) {
+  if (Cin % 8 == 0 && Cin <= 256 && in_fmt >= 0 && in_fmt <= 2) {   // tap-partial kernel (weights folded per image)
     const long long gz = static_cast<long long>(N) * Cout;
     const int gy = (H + kFcTH * kFcVT - 1) / (kFcTH * kFcVT);
     if (gz <= 65535 && gy <= 65535) {
       dim3 grid((W + kFcTW - 1) / kFcTW, gy, static_cast<unsigned>(gz));
-      if (in_fmt == 2) conv3x3_fewcout_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout, lp);
-      else if (in_fmt == 1) conv3x3_fewcout_kernel<1><<<grid, 256, 0, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout, lp);
-      else conv3x3_fewcout_kernel<0><<<grid, 256, 0, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout, lp);
-      return static_cast<int>(cudaGetLastError());
+      const size_t smem = (static_cast<size_t>(9) * kFcHalo + 9 * Cin + 16) * sizeof(float);
+      auto go = [&](auto kern) -> int {
+        static bool attr_set = false;
+        if (!attr_set) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+          if (e != cudaSuccess) return static_cast<int>(e);
+          attr_set = true;
+        }
+        kern<<<grid, kFcThreads, smem, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout);
+        return static_cast<int>(cudaGetLastError());
+      };
+      if (in_fmt == 2) return go(conv3x3_fewcout_kernel<2>);
+      if (in_fmt == 1) return go(conv3x3_fewcout_kernel<1>);
+      return go(conv3x3_fewcout_kernel<0>);
     }
   }
   switch (Cout) {

@@ -72,11 +72,13 @@ def test_forward_matches_golden(b200, oracle, name, cfgname, b, h, w, fused_stat
     assert _rel_l2(rdet, torch.from_numpy(gold["recon_det"])) <= tol_recon
 
 
-def test_forward_matches_oracle_live(b200, oracle):
-    """Fresh seeds (not the golden ones), odd-ish extent, oracle evaluated in this process."""
+@pytest.mark.parametrize("b,h,w", [(3, 96, 160), (2, 40, 56), (5, 8, 8), (1, 136, 24)])
+def test_forward_matches_oracle_live(b200, oracle, b, h, w):
+    """Fresh seeds (not the golden ones), extents whose pyramid levels are not tile multiples (40x56 -> 5x7 at the
+    bottom; 8x8 -> a 1x1 latent), oracle evaluated in this process."""
     cfg = b200.config.AUTOENCODER_DEF_A
     ref, vae = _models(b200, oracle, cfg)
-    x = oracle.synthetic_images(3, 96, 160, seed=11)
+    x = oracle.synthetic_images(b, h, w, seed=11)
     with torch.no_grad():
         mu_r, sg_r = ref.encode(x)
         eps = torch.randn(mu_r.shape, generator=torch.Generator().manual_seed(3))
