@@ -483,10 +483,9 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                 N, H, W, Cin, Cout, f16, g_fused_trace, impl == 2};
     if (impl == 3) return conv3x3_tma2_launch(c, stream);
     if (impl == 2) return conv3x3_tma_launch(c, stream);
-    // auto: measured winners (B200, batch 64) -- the chunk-pipelined kernel for every shape with a 128-wide side
-    // and for 64->64 with a residual; the single-buffer kernel (12 transform warps) for the 32-wide layers
-    const bool wide = Cin == 128 || Cout == 128 || (Cin == 64 && Cout == 64 && residual != nullptr) ||
-                      (Cin == 64 && Cout == 32);
+    // auto: measured winners (B200, batch 64) -- the chunk-pipelined kernel for every shape with >= 64 input
+    // channels or 128 output channels; the whole-tile kernel for the 32-channel-input layers
+    const bool wide = Cin >= 64 || Cout == 128;
     int rc = wide ? conv3x3_tma2_launch(c, stream) : conv3x3_tma_launch(c, stream);
     if (rc == PTIVAE_ERR_UNSUPPORTED) rc = wide ? conv3x3_tma_launch(c, stream) : conv3x3_tma2_launch(c, stream);
     if (rc != PTIVAE_ERR_UNSUPPORTED) return rc;

@@ -29,7 +29,7 @@ constexpr int NTEAM = 2, NEW = NTEAM * 4;
 constexpr int W_TR0 = NEW;   // transform warps [NEW, NEW + NTW), then the MMA issuer and the two TMA producers
 // transform warps: 12 where the transform is the widest stage (64-channel fp32 input into a narrow output), else 8
 template <int CIN, int COUT, bool IN32>
-constexpr int ntw() { return (IN32 && CIN == 64 && COUT == 32) ? 12 : 8; }
+constexpr int ntw() { return (IN32 && CIN >= 64) ? 12 : 8; }
 constexpr uint32_t kSmemMax = 232448;
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 

@@ -183,3 +183,47 @@ def test_regressor_matches_reference_golden(b200, oracle):
         want = head_ref(torch.flatten(ref_vae.encode(imgs)[0], 1))
     got = model(imgs.to(DEV)).cpu()
     assert float((got - want).norm() / want.norm()) <= TOL_LATENT
+
+
+@pytest.mark.parametrize("hw", [384, 512])
+def test_regression_sweep_extents(b200, oracle, hw):
+    """BASELINE configs[4] (reg_edente_from_dente sweep, 256^2-512^2): deterministic encode -> flatten -> MLP and
+    reconstruct_deterministic at the larger extents (attention L = 2304 / 4096), vs the oracle evaluated here."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    ref_vae, vae = _models(b200, oracle, cfg)
+    lat = 4 * (hw // 8) ** 2
+    torch.manual_seed(5)
+    head = b200.LatentRegressor(lat, [256, 32], 6, dropout=0.1).to(DEV).eval()
+    head_ref = oracle.LatentRegressorRef(lat, [256, 32], 6, dropout=0.1).eval()
+    head_ref.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
+    model = b200.VAELatentRegressor(vae, head, latent_dim=lat)
+    x = oracle.synthetic_images(1, hw, hw, seed=13)
+    with torch.no_grad():
+        mu_r, _ = ref_vae.encode(x)
+        want = head_ref(torch.flatten(mu_r, 1))
+        rec_r = ref_vae.decode(mu_r)
+    got = model(x.to(DEV)).cpu()
+    assert float((got - want).norm() / want.norm()) <= TOL_LATENT
+    assert _rel_l2(vae.encode_deterministic(x.to(DEV)), mu_r) <= TOL_LATENT
+    assert _rel_l2(vae.reconstruct_deterministic(x.to(DEV)), rec_r) <= TOL_RECON
+
+
+def test_config_b_full_extent_and_ar_loss(b200, oracle):
+    """BASELINE configs[3] (ar_vae_dente: latent 10, channels 64/128/256, attention L = 4096 d = 256) at 256^2:
+    forward parity with the oracle and the AR loss on its z_mu."""
+    cfg = b200.config.AUTOENCODER_DEF_B
+    ref, vae = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(2, 256, 256, seed=17)
+    with torch.no_grad():
+        mu_r, sg_r = ref.encode(x)
+        eps = torch.randn(mu_r.shape, generator=torch.Generator().manual_seed(4))
+        rec_r, _, _ = ref(x, eps)
+    rec, mu, sg = vae.autoencoder(x.to(DEV), eps.to(DEV))
+    assert mu.shape == (2, 10, 64, 64)
+    assert _rel_l2(mu, mu_r) <= TOL_LATENT and _rel_l2(sg, sg_r) <= TOL_LATENT
+    assert _rel_l2(rec, rec_r) <= TOL_RECON
+    attrs = {"w": torch.tensor([31.0, 120.0]), "h": torch.tensor([77.0, 20.0])}
+    mapping = {"w": {"latent_channel": 0, "delta": 1.0}, "h": {"latent_channel": 7, "delta": 2.0}}
+    t_ref, _, c_ref, _ = oracle.ar_vae_loss_ref(mu_r, attrs, mapping, "all", None, None)
+    t_got, _, c_got, _ = b200.compute_ar_vae_loss(mu, attrs, mapping, "all", None, None)
+    assert c_got == c_ref and abs(float(t_got) - float(t_ref)) <= 5e-3 * max(1e-3, abs(float(t_ref)))
