@@ -166,6 +166,24 @@ int ptivae_ar_vae_loss(const float* zbar, const float* attrs, const int* channel
 int ptivae_linear_act(const float* x, const float* w, const float* bias, float* y, int B, int I, int O, int act,
                       void* stream);
 
+/* ---- callers either side of the hot path --------------------------------------------------
+ * Per-sample evaluation metrics of evaluate_vae.py in one pass:
+ *   replaces: compute_psnr / compute_ssim (src/pti_ldm_vae/utils/eval_metrics.py:6-63) and the per-sample MSE/MAE
+ *             of vae_scripts/evaluate_vae.py:87-98 (torch.clamp(.,0,1) of both images first when do_clamp != 0)
+ *   pred, target fp32 NCHW [B][C][H][W];  window: `win` (odd, <= 15) fp32 taps of the separable SSIM window
+ *   (the reference's 11-tap Gaussian, sigma 1.5, normalised); zero padding as conv2d(padding = win/2)
+ *   out fp32 [B][4] = (mse, mae, psnr, ssim);  workspace: ptivae_eval_metrics_workspace(B, C, H, W) bytes */
+int ptivae_eval_metrics(const float* pred, const float* target, const float* window, int win, float* out,
+                        void* workspace, int B, int C, int H, int W, int do_clamp, float lo, float hi,
+                        float data_range, float k1, float k2, void* stream);
+int ptivae_eval_metrics_workspace(int B, int C, int H, int W);
+/* LocalNormalizeByMask (src/pti_ldm_vae/data/transforms.py:8-32) for a batch on the device: per image, z-score
+ * with the mean / population std of the NON-ZERO pixels (std <= 1e-5 -> 1), zero pixels stay exactly 0.
+ *   x, out fp32 [B][per_img];  stats: optional fp32 [B][2] (mean, std used);  workspace:
+ *   ptivae_local_normalize_workspace(B) bytes (fp64 partial sums, fixed order) */
+int ptivae_local_normalize(const float* x, float* out, float* stats, void* workspace, int B, int per_img, void* stream);
+int ptivae_local_normalize_workspace(int B);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,7 +1,7 @@
 """pti-ldm-vae_b200: the B200-native hot path of Sukikui/PTI-LDM-VAE (AutoencoderKL
 encode -> reparameterised sample -> decode, latent head, KL / L1 / L2) behind the reference's
 ``VAEModel`` API.  Import name: ``pti_ldm_vae_b200`` (see _pkg.py at the repo root)."""
-from . import _lib, config, losses, ops, parallel  # noqa: F401
+from . import _lib, config, eval_metrics, losses, ops, parallel, transforms  # noqa: F401
 from .autoencoderkl import AutoencoderKL, B200AutoencoderKL  # noqa: F401
 from .graph import GraphedVAE  # noqa: F401
 from .loader import load_vae_model  # noqa: F401

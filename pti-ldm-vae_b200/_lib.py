@@ -27,6 +27,10 @@ SIGNATURES = {
     "ptivae_up2x_conv3x3": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],
     "ptivae_up2x_conv3x3_parts": [_c_int] * 2,
     "ptivae_debug_set_trace": [_c_void_p],
+    "ptivae_eval_metrics": [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 2 + [_c_int] * 5 + [_c_float] * 5 + [_c_void_p],
+    "ptivae_eval_metrics_workspace": [_c_int] * 4,
+    "ptivae_local_normalize": [_c_void_p] * 4 + [_c_int] * 2 + [_c_void_p],
+    "ptivae_local_normalize_workspace": [_c_int],
     "ptivae_pack_conv_weight": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats_parts": [_c_int] * 3,

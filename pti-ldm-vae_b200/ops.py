@@ -336,3 +336,40 @@ def linear_act(x: torch.Tensor, w: torch.Tensor, b, act: str | None = None) -> t
     _call("linear_act", None, 1, _lib.lib().ptivae_linear_act, _p(x), _p(w), _p(None if b is None else b.detach()), _p(y),
           bsz, i, o, _ACTS[act], _stream())
     return y
+
+
+def eval_metrics(pred: torch.Tensor, target: torch.Tensor, window: torch.Tensor, clamp=(0.0, 1.0), data_range: float = 1.0,
+                 k1: float = 0.01, k2: float = 0.03) -> torch.Tensor:
+    """fp32 NCHW pred/target -> [B,4] = per-sample (mse, mae, psnr, ssim); `clamp` = (lo, hi) applied to both images
+    first, or None.  window: fp32 taps of the separable SSIM window (odd length <= 15)."""
+    _need_cuda(pred, target, window)
+    if pred.shape != target.shape or pred.dim() != 4 or pred.dtype != torch.float32 or target.dtype != torch.float32:
+        raise _lib.PtivaeError("eval_metrics needs two fp32 NCHW tensors of the same shape")
+    pred, target, window = pred.contiguous(), target.contiguous(), window.contiguous().float()
+    b, c, h, w = pred.shape
+    out = torch.empty((b, 4), device=pred.device, dtype=torch.float32)
+    nbytes = _lib.lib().ptivae_eval_metrics_workspace(b, c, h, w)
+    if nbytes < 0:
+        _lib.check(nbytes, "eval_metrics_workspace")
+    ws = torch.empty(nbytes, device=pred.device, dtype=torch.uint8)
+    lo, hi = clamp if clamp is not None else (0.0, 0.0)
+    _call("eval_metrics", (b, c, h, w), 2, _lib.lib().ptivae_eval_metrics, _p(pred), _p(target), _p(window), window.numel(),
+          _p(out), _p(ws), b, c, h, w, int(clamp is not None), float(lo), float(hi), float(data_range), float(k1), float(k2),
+          _stream())
+    return out
+
+
+def local_normalize(x: torch.Tensor, return_stats: bool = False):
+    """Batch of fp32 images [B, ...] -> z-score over each image's non-zero pixels, zeros stay zero."""
+    _need_cuda(x)
+    if x.dtype != torch.float32:
+        raise _lib.PtivaeError("local_normalize needs an fp32 tensor")
+    x = x.contiguous()
+    b = x.shape[0]
+    per = x.numel() // b
+    out = torch.empty_like(x)
+    stats = torch.empty((b, 2), device=x.device, dtype=torch.float32) if return_stats else None
+    ws = torch.empty(_lib.lib().ptivae_local_normalize_workspace(b), device=x.device, dtype=torch.uint8)
+    _call("local_normalize", (b, per), 2, _lib.lib().ptivae_local_normalize, _p(x), _p(out), _p(stats), _p(ws), b, per,
+          _stream())
+    return (out, stats) if return_stats else out

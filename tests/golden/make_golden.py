@@ -133,10 +133,48 @@ def aekl_case(name, cfg, b, h, w, taps):
           float((recon - recon64.float()).norm() / recon64.float().norm()))
 
 
+def ref_metrics():
+    """Outputs of the reference's OWN eval metrics (utils/eval_metrics.py) and LocalNormalizeByMask
+    (data/transforms.py; tifffile stubbed, it is only used by the TIFF reader) -> metrics_ref.npz."""
+    import types
+    spec = importlib.util.spec_from_file_location("ref_evalm", "/root/reference/src/pti_ldm_vae/utils/eval_metrics.py")
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    sys.modules.setdefault("tifffile", types.ModuleType("tifffile"))
+    spec = importlib.util.spec_from_file_location("ref_tf", "/root/reference/src/pti_ldm_vae/data/transforms.py")
+    tf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tf)
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for tag, (b, c, h, w) in {"a": (3, 1, 70, 50), "b": (2, 1, 256, 256), "c": (4, 1, 33, 64)}.items():
+        img = torch.rand(b, c, h, w, generator=g) * 1.2 - 0.1            # some values outside [0, 1]
+        img[..., : w // 4] = 0.0
+        rec = img + 0.05 * torch.randn(b, c, h, w, generator=g)
+        rc, ic = torch.clamp(rec, 0.0, 1.0), torch.clamp(img, 0.0, 1.0)
+        out[f"{tag}_img"], out[f"{tag}_rec"] = img.numpy(), rec.numpy()
+        out[f"{tag}_psnr"] = em.compute_psnr(rc, ic).numpy()
+        out[f"{tag}_ssim"] = em.compute_ssim(rc, ic).numpy()
+        out[f"{tag}_mse"] = torch.mean((rc - ic) ** 2, dim=(1, 2, 3)).numpy()
+        out[f"{tag}_mae"] = torch.mean(torch.abs(rc - ic), dim=(1, 2, 3)).numpy()
+        out[f"{tag}_psnr_raw"] = em.compute_psnr(rec, img, data_range=2.0).numpy()
+        out[f"{tag}_ssim_raw"] = em.compute_ssim(rec, img, data_range=2.0, k1=0.02, k2=0.05).numpy()
+    norm = tf.LocalNormalizeByMask()
+    raw = torch.rand(5, 1, 96, 80, generator=g) * 200.0 + 20.0
+    raw[:, :, :, :30] = 0.0                                               # background band
+    raw[1, :, 40:, :] = 0.0
+    raw[3] = 0.0
+    raw[3, 0, 10:20, 40:50] = 7.0                                         # constant foreground: std <= 1e-5 -> 1
+    out["ln_raw"] = raw.numpy()
+    out["ln_out"] = np.stack([norm(raw[i].numpy().copy()) for i in range(5) if i != 4] + [norm(raw[4].clone())])
+    np.savez_compressed(HERE / "metrics_ref.npz", **out)
+    print("metrics_ref: ssim", out["a_ssim"], "psnr", out["a_psnr"])
+
+
 if __name__ == "__main__":
     if pathlib.Path("/root/reference").exists():
         ref_losses()
         ref_regressor()
+        ref_metrics()
     aekl_case("aekl_A_64", CFG.AUTOENCODER_DEF_A, 2, 64, 64, {"encoder.blocks.3", "encoder.blocks.13", "decoder.blocks.6"})
     aekl_case("aekl_A_256", CFG.AUTOENCODER_DEF_A, 1, 256, 256, set())
     aekl_case("aekl_B_64", CFG.AUTOENCODER_DEF_B, 1, 64, 64, {"encoder.blocks.10"})

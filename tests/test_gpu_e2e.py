@@ -227,3 +227,31 @@ def test_config_b_full_extent_and_ar_loss(b200, oracle):
     t_ref, _, c_ref, _ = oracle.ar_vae_loss_ref(mu_r, attrs, mapping, "all", None, None)
     t_got, _, c_got, _ = b200.compute_ar_vae_loss(mu, attrs, mapping, "all", None, None)
     assert c_got == c_ref and abs(float(t_got) - float(t_ref)) <= 5e-3 * max(1e-3, abs(float(t_ref)))
+
+
+def test_eval_metrics_and_local_normalisation_match_reference_golden(b200, oracle):
+    """fused PSNR/SSIM/MSE/MAE and the device LocalNormalizeByMask vs outputs of the
+    reference's own functions (tests/golden/metrics_ref.npz)."""
+    from pti_ldm_vae_b200 import eval_metrics, transforms
+    g = np.load(GOLD / "metrics_ref.npz")
+    for tag in "abc":
+        img, rec = torch.from_numpy(g[f"{tag}_img"]).to(DEV), torch.from_numpy(g[f"{tag}_rec"]).to(DEV)
+        m = eval_metrics.compute_eval_metrics(rec, img)
+        assert np.allclose(m["psnr"].cpu().numpy(), g[f"{tag}_psnr"], atol=1e-3)
+        assert np.allclose(m["ssim"].cpu().numpy(), g[f"{tag}_ssim"], atol=1e-4)
+        assert np.allclose(m["mse"].cpu().numpy(), g[f"{tag}_mse"], rtol=1e-4)
+        assert np.allclose(m["mae"].cpu().numpy(), g[f"{tag}_mae"], rtol=1e-4)
+        assert np.allclose(eval_metrics.compute_psnr(rec, img, 2.0).cpu().numpy(), g[f"{tag}_psnr_raw"], atol=1e-3)
+        assert np.allclose(eval_metrics.compute_ssim(rec, img, 2.0, 0.02, 0.05).cpu().numpy(), g[f"{tag}_ssim_raw"], atol=1e-4)
+        m2 = eval_metrics.compute_eval_metrics(rec, img)
+        assert all(torch.equal(m[k], m2[k]) for k in m), "deterministic"
+    raw = torch.from_numpy(g["ln_raw"]).to(DEV)
+    out = transforms.LocalNormalizeByMask()(raw)
+    assert np.allclose(out.cpu().numpy(), g["ln_out"], rtol=1e-5, atol=2e-5)
+    assert (out[:, :, :, :30] == 0).all() and float(out[3].abs().max()) == 0.0
+    single = transforms.LocalNormalizeByMask()(raw[0, 0])
+    assert torch.equal(single, out[0, 0])
+    d = transforms.ApplyLocalNormd(["image"])({"image": raw.clone(), "other": 1})
+    assert torch.equal(d["image"], out) and d["other"] == 1
+    with pytest.raises(b200._lib.PtivaeError):
+        eval_metrics.compute_psnr(rec.cpu(), img.cpu())
