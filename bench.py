@@ -152,6 +152,11 @@ def classify(name, meta):
         flops = 2.0 * n * h * w * cout * cin * 9
         byt = n * h * w * (in_esz * cin + (out_esz + res_esz) * cout) + 2.0 * 9 * cin * cout
         return (f"fused3x3_{cin}->{cout}@{h}x{w}_in{in_esz}_res{res_esz}_out{out_esz}", flops, byt)
+    if name == "conv3x3_fused_sc":
+        n, h, w, cin, cout, in_esz, out_esz, _, sc = meta
+        flops = 2.0 * n * h * w * cout * (cin * 9 + sc)
+        byt = n * h * w * (in_esz * cin + 2.0 * sc + out_esz * cout) + 2.0 * cout * (9 * cin + sc)
+        return (f"fused3x3+sc{sc}_{cin}->{cout}@{h}x{w}", flops, byt)
     if name == "up2x_conv3x3":
         n, h, w, c, e16 = meta
         return (f"up2x_conv3x3_{c}@{h}x{w}", 2.0 * n * 4 * h * w * c * c * 9,      # nominal direct-form count

@@ -71,6 +71,16 @@ int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, in
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,
                          int impl, void* stream);
 int ptivae_conv3x3_fused_parts(int H, int W);
+/* conv2 of an AEKLResBlock whose nin_shortcut is a 1x1 conv, with that shortcut fused into the same accumulators:
+ *   out = conv3x3_s1_p1( act(h*scale + shift) ) + W_sc * x + bias      (fp32 stream out, no residual tensor)
+ *   replaces: `return self.nin_shortcut(x) + h` of AEKLResBlock.forward together with its conv2.
+ *   h         h16 [N][H][W][Cin];  sc_x: h16 [N][H][W][sc_cin] = the block input in the operand format
+ *   sc_w_packed h16 [1][Cout][sc_cin] (ptivae_pack_conv_weight of the 1x1);  bias = conv2.bias + nin_shortcut.bias
+ *   instantiated for (Cin, Cout, sc_cin) in {(32,32,64), (64,64,32)}, fp16 operands; -2 otherwise (callers then
+ *   run the shortcut as its own ptivae_conv_umma and pass it as the residual of ptivae_conv3x3_fused) */
+int ptivae_conv3x3_fused_sc(const void* h, const float* scale_shift, int silu, const void* w_packed, const float* bias,
+                            const void* sc_x, const void* sc_w_packed, int sc_cin, void* out, int out_f32,
+                            float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16, void* stream);
 /* Nearest x2 upsample + 3x3 conv (pad 1) in one halo-resident kernel: out = conv3x3(upsample2x(x)) + bias.
  *   replaces: monai UpSample(mode="nontrainable", interp_mode="nearest") + its post-conv inside the decoder
  *             (monai 1.5.1 networks/nets/autoencoderkl.py Decoder; via autoencoder.py:151), for the widths where

@@ -166,6 +166,16 @@ class _Executor:
     def f32(p: torch.Tensor) -> torch.Tensor:
         return p.detach()
 
+    def bias_sum(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """a + b of two bias vectors, cached until either master changes (fused conv2 + shortcut)."""
+        key = (id(a), id(b), "bias_sum")
+        ver = (a.data_ptr(), a._version, b.data_ptr(), b._version, a.device)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, (a.detach() + b.detach()).contiguous())
+            self._packed[key] = hit
+        return hit[1]
+
     def _want_stats(self, cout: int, stats: bool) -> int:
         g = self.groups
         ok = stats and self.fused_stats and cout % g == 0 and 32 % (cout // g) == 0 and cout // g >= 2
@@ -216,6 +226,15 @@ class _Executor:
                 # gn_apply's second output is the raw input rounded to the operand format)
                 _, raw = ops.gn_apply(a.t, self.scale_shift(a, blk.norm1), silu=True, emit_raw=True,
                                       dtype=self.op_dtype)
+            w2, wsc = blk.conv2.conv.weight, blk.nin_shortcut.conv.weight
+            if self.fused_conv and out_f32 and ops.fused_sc_supported(raw.dtype, w2.shape[1], w2.shape[0], wsc.shape[1]):
+                # conv2 and the 1x1 shortcut accumulate into the same TMEM tile: no shortcut tensor in HBM at all
+                h = self.norm_conv3x3(a, blk.norm1, blk.conv1.conv)
+                g = self._want_stats(w2.shape[0], stats)
+                r = ops.conv3x3_fused_sc(h.t, self.scale_shift(h, blk.norm2), True, self.packed(w2),
+                                         self.bias_sum(blk.conv2.conv.bias, blk.nin_shortcut.conv.bias), raw,
+                                         self.packed(wsc), gn_groups=g)
+                return _Act(*r) if g else _Act(r)
             sc = self.conv(raw, blk.nin_shortcut.conv, 3, stats=False, out_f32=True).t
         h = self.norm_conv3x3(a, blk.norm1, blk.conv1.conv)              # 16-bit: only norm2 reads it
         return self.norm_conv3x3(h, blk.norm2, blk.conv2.conv, residual=sc, stats=stats, out_f32=out_f32)

@@ -480,6 +480,19 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
   return static_cast<int>(cudaGetLastError());
 }
 
+template <int FMT>
+static int launch_fewcout(dim3 grid, size_t smem, const void* x, const float* w, const float* bias, const float* ss,
+                          float* out, int H, int W, int Cin, int Cout, cudaStream_t stream) {
+  static bool attr_set = false;   // one flag per instantiation (the three kernels share a function-pointer type)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_fewcout_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  conv3x3_fewcout_kernel<FMT><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout);
+  return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const float* bias, const float* scale_shift,
                                          float* out, int N, int H, int W, int Cin, int Cout, int in_fmt,
                                          void* stream_) {
@@ -491,19 +504,9 @@ extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const fl
     if (gz <= 65535 && gy <= 65535) {
       dim3 grid((W + kFcTW - 1) / kFcTW, gy, static_cast<unsigned>(gz));
       const size_t smem = (static_cast<size_t>(9) * kFcHalo + 9 * Cin + 16) * sizeof(float);
-      auto go = [&](auto kern) -> int {
-        static bool attr_set = false;
-        if (!attr_set) {
-          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-          if (e != cudaSuccess) return static_cast<int>(e);
-          attr_set = true;
-        }
-        kern<<<grid, kFcThreads, smem, stream>>>(x, w, bias, scale_shift, out, H, W, Cin, Cout);
-        return static_cast<int>(cudaGetLastError());
-      };
-      if (in_fmt == 2) return go(conv3x3_fewcout_kernel<2>);
-      if (in_fmt == 1) return go(conv3x3_fewcout_kernel<1>);
-      return go(conv3x3_fewcout_kernel<0>);
+      if (in_fmt == 2) return launch_fewcout<2>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, stream);
+      if (in_fmt == 1) return launch_fewcout<1>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, stream);
+      return launch_fewcout<0>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, stream);
     }
   }
   switch (Cout) {

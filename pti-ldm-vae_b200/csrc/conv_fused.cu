@@ -521,3 +521,21 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
 #undef PTIVAE_FUSED_CASE
   return PTIVAE_ERR_UNSUPPORTED;
 }
+
+// conv2 of a ResBlock whose shortcut is a 1x1 conv, with that shortcut fused in:
+//   out = conv3x3(act(h * scale + shift)) + W_sc * x + bias       (bias = conv2.bias + shortcut.bias, added by the caller)
+// Only the chunk-pipelined TMA kernel implements it (-2 otherwise: run the shortcut as its own conv and pass it as residual).
+extern "C" int ptivae_conv3x3_fused_sc(const void* h, const float* scale_shift, int silu, const void* w_packed,
+                                       const float* bias, const void* sc_x, const void* sc_w_packed, int sc_cin, void* out,
+                                       int out_f32, float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout,
+                                       int f16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!h || !w_packed || !bias || !out || !sc_x || !sc_w_packed || N <= 0 || H <= 0 || W <= 0 || sc_cin <= 0) return PTIVAE_ERR_ARG;
+  if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
+    return PTIVAE_ERR_ARG;
+  if (!f16 || !out_f32) return PTIVAE_ERR_UNSUPPORTED;
+  FusedCall c{h, 1, scale_shift, silu, w_packed, bias, nullptr, 0, out, out_f32, gn_part, gn_groups,
+              N, H, W, Cin, Cout, f16, g_fused_trace, false};
+  c.sc_x = sc_x; c.sc_w = sc_w_packed; c.sc_cin = sc_cin;
+  return conv3x3_tma2_launch(c, stream);
+}

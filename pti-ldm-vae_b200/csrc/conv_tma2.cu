@@ -33,7 +33,7 @@ constexpr int ntw() { return (IN32 && CIN >= 64) ? 12 : 8; }
 constexpr uint32_t kSmemMax = 232448;
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+template <int CIN, int COUT, bool IN32, bool RES, bool OUT32, int SC = 0>
 struct Cfg {
   static constexpr int KCH = CIN >= 64 ? 64 : 32;
   static constexpr int NCH = CIN / KCH;
@@ -48,7 +48,11 @@ struct Cfg {
   static constexpr uint32_t SLOT = OSLOT + RSLOT;
   static constexpr int NOB = COUT / 32;                       // units per M block
   static constexpr uint32_t MISC = 1024 + NEW * COUT * 2 * 4 + COUT * 4 + 64 * 8 + 64;
-  static constexpr uint32_t FIXED = MISC + NTEAM * 2 * SLOT;
+  // fused 1x1 shortcut (SC = its input channels, 32 or 64): two raw halo chunks of the block input + its weights
+  static constexpr uint32_t LBS = SC * 2;
+  static constexpr uint32_t SCHUNK = SC ? r1k(kHalo * LBS) : 0u;
+  static constexpr uint32_t SWBYTES = uint32_t(COUT) * LBS;
+  static constexpr uint32_t FIXED = MISC + NTEAM * 2 * SLOT + 2 * SCHUNK + SWBYTES;
   // ---- variable part: chunk buffers, raw-input ring (fp32 input only), weights (resident or ring)
   static constexpr uint32_t xs_block(int xc) { return r1k(kHalo * xc * 4); }
   static constexpr uint32_t total(int nbuf, int xc, int nxs, bool resb, int nst) {
@@ -116,11 +120,13 @@ struct Args {
     if (args.trace != nullptr && blockIdx.x == 0 && (it) < 64) args.trace[(it) * 32 + (slot)] = clock64(); \
   } while (0)
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+template <int CIN, int COUT, bool IN32, bool RES, bool OUT32, int SC>
 __global__ void __launch_bounds__((NEW + ntw<CIN, COUT, IN32>() + 3) * 32, 1)
 conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
-  using C = Cfg<CIN, COUT, IN32, RES, OUT32>;
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                    const __grid_constant__ CUtensorMap tmXs, const __grid_constant__ CUtensorMap tmWs, const Args args) {
+  using C = Cfg<CIN, COUT, IN32, RES, OUT32, SC>;
+  static_assert(SC == 0 || (!RES && !IN32), "the fused shortcut replaces the residual of a 16-bit-input conv2");
   constexpr bool F16 = true;
   constexpr int NTW = ntw<CIN, COUT, IN32>(), NT = NTW * 32;
   constexpr int W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
@@ -141,7 +147,9 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint8_t* opbuf = smem;                                    // [NBUF][CHUNK]
   uint8_t* xs = opbuf + NBUF * CHUNK;                       // [NXS][XSB] raw fp32 halo blocks
   uint8_t* slots = xs + (IN32 ? NXS * C::XSB : 0u);         // [NTEAM][2][SLOT]
-  uint8_t* wts = slots + NTEAM * 2 * C::SLOT;               // resident [9*NCH][SLAB] | ring [NST][SLAB]
+  uint8_t* scbuf = slots + NTEAM * 2 * C::SLOT;             // [2][SCHUNK] raw halo chunks of the block input (shortcut)
+  uint8_t* scw = scbuf + 2 * C::SCHUNK;                     // [COUT][SC] shortcut weights (resident)
+  uint8_t* wts = scw + C::SWBYTES;                          // resident [9*NCH][SLAB] | ring [NST][SLAB]
   float* colsum = reinterpret_cast<float*>(wts + (RESB ? C::WBYTES : NST * SLAB));   // [NEW][COUT][2]
   float* sbias = colsum + NEW * COUT * 2;                   // [COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
@@ -154,7 +162,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* acc_full = bars + 32;      // [2]
   uint64_t* acc_empty = bars + 34;     // [2]
   uint64_t* res_full = bars + 36;      // [NTEAM][2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 40);
+  uint64_t* sc_full = bars + 40;       // [2] shortcut chunk landed
+  uint64_t* sc_empty = bars + 42;      // [2] shortcut chunk consumed
+  uint64_t* scw_full = bars + 44;      // shortcut weights landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 46);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -177,7 +188,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], NEW * 32);
+      mbar_init(&sc_full[i], 1);
+      mbar_init(&sc_empty[i], 1);
     }
+    mbar_init(scw_full, 1);
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
@@ -191,6 +205,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == W_W) {
     // ------------------------------------------------------------------ weights (order: chunk outer, tap inner)
     if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
+      if constexpr (SC != 0) {
+        mbar_expect_tx(scw_full, C::SWBYTES);
+        tma_load_3d(scw, &tmWs, scw_full, 0, 0, 0);
+      }
       if constexpr (RESB) {
         mbar_expect_tx(&b_full[0], C::WBYTES);
         for (int kc = 0; kc < NCH; ++kc)
@@ -212,8 +230,8 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else if (warp == W_IN) {
     // ------------------------------------------------------------------ input halo pieces (TMA loads)
     if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
-      int pq = 0;   // global piece counter
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      int pq = 0, it = 0;   // global piece counter, tile counter
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
         const int n = t / tiles_per_img;
         const int trem = t - n * tiles_per_img;
         const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
@@ -229,6 +247,12 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_expect_tx(&in_full[s], kHalo * LB);
             tma_load_4d(opbuf + s * CHUNK, &tmX, &in_full[s], p * KCH, tix * kT - 1, tiy * kT - 1, n);
           }
+        }
+        if constexpr (SC != 0) {   // raw halo of the block input for the fused 1x1 shortcut (only its centre tap is used)
+          const int sb = it & 1;
+          mbar_wait(&sc_empty[sb], ((it >> 1) & 1) ^ 1u);
+          mbar_expect_tx(&sc_full[sb], kHalo * C::LBS);
+          tma_load_4d(scbuf + sb * C::SCHUNK, &tmXs, &sc_full[sb], 0, tix * kT - 1, tiy * kT - 1, n);
         }
       }
     }
@@ -286,6 +310,25 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
           }
           umma_commit(&op_empty[cb]);
+        }
+        if constexpr (SC != 0) {
+          // shortcut: D += x_raw(centre tap) * W_sc -- one more "tap" whose operand is the raw block input
+          constexpr uint32_t LBS = C::LBS;
+          constexpr uint32_t kLayoutS = (SC == 64) ? kLayoutSW128 : kLayoutSW64;
+          const int sb = it & 1;
+          if (it == 0) mbar_wait(scw_full, 0);
+          mbar_wait(&sc_full[sb], (it >> 1) & 1);
+          tc_fence_after();
+          const uint32_t as_hi = desc_hi(kHP * LBS, kLayoutS), bs_hi = desc_hi(8u * LBS, kLayoutS);
+          const uint32_t as_lo = desc_lo(smem_u32(scbuf + sb * C::SCHUNK)) + (((kHP + 1) * LBS) >> 4);
+          const uint32_t bs_lo = desc_lo(smem_u32(scw));
+#pragma unroll
+          for (int k = 0; k < SC / 16; ++k)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+              umma_f16_lohi(acc + mb * COUT, as_lo + ((mb * 8 * LBS + k * 32) >> 4), as_hi, bs_lo + ((k * 32) >> 4), bs_hi,
+                            kIdesc, 1u);
+          umma_commit(&sc_empty[sb]);
         }
         umma_commit(&acc_full[st]);
         TMA4_TRACE(it, 3);
@@ -561,9 +604,9 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+template <int CIN, int COUT, bool IN32, bool RES, bool OUT32, int SC = 0>
 static int launch(const FusedCall& c, cudaStream_t stream) {
-  using C = Cfg<CIN, COUT, IN32, RES, OUT32>;
+  using C = Cfg<CIN, COUT, IN32, RES, OUT32, SC>;
   if constexpr (!C::FITS) {
     return PTIVAE_ERR_UNSUPPORTED;
   } else {
@@ -574,7 +617,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     a.num_tiles = c.N * a.tiles_x * a.tiles_y;
     a.silu = c.silu; a.gn_groups = c.gn_groups; a.scale_shift = c.scale_shift; a.bias = c.bias; a.gn_part = c.gn_part;
     a.trace = c.trace;
-    CUtensorMap tmX, tmW, tmR, tmO;
+    CUtensorMap tmX, tmW, tmR, tmO, tmXs, tmWs;
     const uint64_t H = c.H, W = c.W, N = c.N;
     if (IN32) {  // raw fp32 halo blocks: dims (C, W, H, N), box (XC, 18, 18, 1), swizzle = line bytes
       uint64_t d[4] = {uint64_t(CIN), W, H, N};
@@ -613,9 +656,24 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     } else {
       tmR = tmO;
     }
+    if (SC != 0) {   // shortcut operand (raw 16-bit block input, halo box) and its [Cout][SC] weights
+      uint64_t d[4] = {uint64_t(SC), W, H, N};
+      uint64_t s[3] = {uint64_t(SC) * 2, W * SC * 2, H * W * SC * 2};
+      uint32_t b[4] = {uint32_t(SC), kHP, kHP, 1};
+      int rc = encode_tmap(&tmXs, c.sc_x, 1, 4, d, s, b, SC * 2);
+      if (rc) return rc;
+      uint64_t wd[3] = {uint64_t(SC), uint64_t(COUT), 1};
+      uint64_t ws[2] = {uint64_t(SC) * 2, uint64_t(COUT) * SC * 2};
+      uint32_t wb[3] = {uint32_t(SC), uint32_t(COUT), 1};
+      rc = encode_tmap(&tmWs, c.sc_w, 1, 3, wd, ws, wb, SC * 2);
+      if (rc) return rc;
+    } else {
+      tmXs = tmX;
+      tmWs = tmW;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32>,
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax));
       if (e != cudaSuccess) return static_cast<int>(e);
       attr_set = true;
@@ -624,7 +682,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     constexpr int kThreads = (NEW + ntw<CIN, COUT, IN32>() + 3) * 32;
-    conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, a);
+    conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, tmXs, tmWs, a);
     return static_cast<int>(cudaGetLastError());
   }
 }
@@ -632,6 +690,16 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
 template <int CIN, int COUT>
 static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
   const bool in32 = c.in_fmt == 2, res = c.residual != nullptr, out32 = c.out_f32 != 0;
+  if (c.sc_x != nullptr) {   // conv2 with the block's 1x1 shortcut fused in (no residual tensor at all)
+    if (in32 || res || !out32 || !c.sc_w) return PTIVAE_ERR_UNSUPPORTED;
+    if constexpr (CIN == 32 && COUT == 32) {
+      if (c.sc_cin == 64) return launch<32, 32, false, false, true, 64>(c, stream);
+    }
+    if constexpr (CIN == 64 && COUT == 64) {
+      if (c.sc_cin == 32) return launch<64, 64, false, false, true, 32>(c, stream);
+    }
+    return PTIVAE_ERR_UNSUPPORTED;
+  }
   if (in32 && !res && !out32) return launch<CIN, COUT, true, false, false>(c, stream);   // ResBlock conv1
   if (!in32 && res && out32) return launch<CIN, COUT, false, true, true>(c, stream);     // ResBlock conv2 -> stream
   if (!in32 && res && !out32) return launch<CIN, COUT, false, true, false>(c, stream);   // conv2 -> 16-bit operand

@@ -18,6 +18,9 @@ struct FusedCall {   // arguments of ptivae_conv3x3_fused, shared by its two imp
   const void* x; int in_fmt; const float* scale_shift; int silu; const void* w_packed; const float* bias;
   const void* residual; int res_f32; void* out; int out_f32; float* gn_part; int gn_groups;
   int N, H, W, Cin, Cout, f16; unsigned long long* trace; bool force;
+  const void* sc_x = nullptr;   // fused 1x1 shortcut: raw 16-bit block input [N][H][W][sc_cin] ...
+  const void* sc_w = nullptr;   // ... its packed weights [1][Cout][sc_cin] (conv_tma2.cu only)
+  int sc_cin = 0;
 };
 // TMA-staged implementation (conv_tma.cu): returns PTIVAE_ERR_UNSUPPORTED (-2) if the shape/mode has no
 // instantiation, so the caller can fall back to the register-staged kernel.

@@ -168,6 +168,31 @@ def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tens
     return (out, part) if gn_groups > 0 else out
 
 
+def fused_sc_supported(dtype: torch.dtype, cin: int, cout: int, sc_cin: int) -> bool:
+    """(conv2 Cin, Cout, shortcut Cin) combinations for which conv2 + 1x1 shortcut run as one kernel."""
+    return dtype == F16 and (cin, cout, sc_cin) in ((32, 32, 64), (64, 64, 32))
+
+
+def conv3x3_fused_sc(h: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tensor, bias: torch.Tensor,
+                     sc_x: torch.Tensor, sc_w_packed: torch.Tensor, gn_groups: int = 0):
+    """out = conv3x3(act(h*scale+shift)) + conv1x1(sc_x) + bias as ONE kernel (bias = sum of both conv biases).
+    h, sc_x fp16 NHWC; returns the fp32 stream tensor, or (out, statistics partials) with gn_groups > 0."""
+    _need_cuda(h, w_packed, bias, sc_x, sc_w_packed)
+    n, hh, w, cin = h.shape
+    cout = w_packed.shape[1]
+    if sc_x.shape[:3] != h.shape[:3] or sc_x.dtype != h.dtype or sc_w_packed.shape != (1, cout, sc_x.shape[-1]):
+        raise _lib.PtivaeError("shortcut operand / weight shape mismatch")
+    out = torch.empty((n, hh, w, cout), device=h.device, dtype=torch.float32)
+    part = None
+    if gn_groups > 0:
+        part = torch.empty((n, _lib.lib().ptivae_conv3x3_fused_parts(hh, w), gn_groups, 2), device=h.device, dtype=torch.float32)
+    meta = (n, hh, w, cin, cout, h.element_size(), 4, 0, sc_x.shape[-1])
+    _call("conv3x3_fused_sc", meta, 1, _lib.lib().ptivae_conv3x3_fused_sc, _p(h), _p(scale_shift), int(silu), _p(w_packed),
+          _p(bias), _p(sc_x), _p(sc_w_packed), sc_x.shape[-1], _p(out), 1, _p(part), gn_groups, n, hh, w, cin, cout, _op16(h),
+          _stream())
+    return (out, part) if gn_groups > 0 else out
+
+
 def _nhwc_dims(x):
     n, c = x.shape[0], x.shape[-1]
     return n, x.numel() // (n * c), c

@@ -350,6 +350,35 @@ def test_conv3x3_fused_tma2(b200, cin, cout, in_f32, res, out_f32, n, h, w, grou
     assert float((outs[1] - outs[3]).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("c,sc", [(32, 64), (64, 32)])
+@pytest.mark.parametrize("n,h,w,groups", [(2, 32, 32, 16), (1, 40, 24, 16), (5, 48, 48, 32)])
+def test_conv3x3_fused_shortcut(b200, c, sc, n, h, w, groups):
+    """conv2 + fused 1x1 shortcut vs conv2d + conv2d in fp32, and vs the two-kernel route (shortcut conv -> residual)."""
+    if DT != torch.float16:
+        pytest.skip("fp16 operands only")
+    groups = min(groups, c // 2)
+    hh = (_rand_act(n, h, w, c, 61).float() * 1.5 + 0.2).to(DT)
+    xr = _rand_act(n, h, w, sc, 62)
+    wt, bias = _rand_conv(c, c, 3, 63)
+    wsc, bsc = _rand_conv(c, sc, 1, 64)
+    ss = (torch.randn(n, c, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
+    xin = F.silu(hh.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
+    ref = (F.conv2d(xin, wt, bias, padding=1) + F.conv2d(xr.float().permute(0, 3, 1, 2), wsc, bsc)).permute(0, 2, 3, 1)
+    assert b200.ops.fused_sc_supported(hh.dtype, c, c, sc)
+    wp, wscp = b200.ops.pack_conv_weight(wt, 0, DT), b200.ops.pack_conv_weight(wsc, 0, DT)
+    out, part = b200.ops.conv3x3_fused_sc(hh, ss, True, wp, bias + bsc, xr, wscp, gn_groups=groups)
+    out2, part2 = b200.ops.conv3x3_fused_sc(hh, ss, True, wp, bias + bsc, xr, wscp, gn_groups=groups)
+    assert torch.equal(out, out2) and torch.equal(part, part2)
+    _check_bf16(out.to(DT), ref, "fused conv + shortcut")
+    o = out.view(n, h * w, groups, c // groups)
+    acc = part.sum(dim=1)
+    assert torch.allclose(acc[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(acc[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    scv = b200.ops.conv_umma(xr, wscp, bsc, 3, out_f32=True)
+    two, _ = b200.ops.conv3x3_fused(hh, ss, True, wp, bias, residual=scv, gn_groups=groups, out_f32=True)
+    assert float((out - two).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,in_f32,norm,silu,res,out_f32,groups", FUSED_CASES)
 def test_conv3x3_fused(b200, n, h, w, cin, cout, in_f32, norm, silu, res, out_f32, groups):
     x = _rand_act(n, h, w, cin, 31).float() * 1.5 + 0.2
