@@ -3,7 +3,7 @@ encode -> reparameterised sample -> decode, latent head, KL / L1 / L2) behind th
 ``VAEModel`` API.  Import name: ``pti_ldm_vae_b200`` (see _pkg.py at the repo root)."""
 from . import _lib, config, eval_metrics, losses, ops, parallel, transforms  # noqa: F401
 from .autoencoderkl import AutoencoderKL, B200AutoencoderKL  # noqa: F401
-from .graph import GraphedVAE  # noqa: F401
+from .graph import GraphedVAE, PipelinedVAE  # noqa: F401
 from .loader import load_vae_model  # noqa: F401
 from .losses import compute_ar_vae_loss, compute_kl_loss, compute_total_loss, l1_loss, mse_loss  # noqa: F401
 from .regression_head import LatentRegressor, VAELatentRegressor  # noqa: F401

@@ -255,3 +255,22 @@ def test_eval_metrics_and_local_normalisation_match_reference_golden(b200, oracl
     assert torch.equal(d["image"], out) and d["other"] == 1
     with pytest.raises(b200._lib.PtivaeError):
         eval_metrics.compute_psnr(rec.cpu(), img.cpu())
+
+
+def test_pipelined_host_streaming_matches_serial(b200, oracle):
+    """PipelinedVAE (H2D || replay || D2H over double buffers) returns, for every batch of a stream of different
+    batches, exactly what the serial GraphedVAE call returns."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    _, vae = _models(b200, oracle, cfg)
+    g = b200.GraphedVAE(vae, 2, 64, 64, mode="reconstruct")
+    xs = [oracle.synthetic_images(2, 64, 64, seed=100 + i).pin_memory() for i in range(7)]
+    want = [g(x.to(DEV)).clone().cpu() for x in xs]
+    pipe = b200.PipelinedVAE(g)
+    outs = [torch.empty(2, 1, 64, 64).pin_memory() for _ in xs]
+    for x, o in zip(xs, outs):
+        pipe.submit(x, o)
+    pipe.synchronize()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
+    with pytest.raises(ValueError):
+        pipe.submit(torch.zeros(2, 1, 64, 64), outs[0])
