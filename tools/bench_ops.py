@@ -69,7 +69,17 @@ def fused(cin, cout, hw, conv2, out32=True, impl=0):
     return timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=min(32, cout // 2), out_f32=o32)), by
 
 
+def fused_sc(c, sc, hw):
+    h = torch.randn(N, hw, hw, c, device="cuda").to(DT); xr = torch.randn(N, hw, hw, sc, device="cuda").to(DT)
+    wp = ops.pack_conv_weight(torch.randn(c, c, 3, 3, device="cuda") / math.sqrt(9 * c), 0, DT)
+    wsc = ops.pack_conv_weight(torch.randn(c, sc, 1, 1, device="cuda") / math.sqrt(sc), 0, DT)
+    bias = torch.randn(c, device="cuda"); ss = torch.randn(N, c, 2, device="cuda")
+    by = h.numel() * 2 + xr.numel() * 2 + N * hw * hw * c * 4
+    return timeit(lambda: ops.conv3x3_fused_sc(h, ss, True, wp, bias, xr, wsc, gn_groups=min(32, c // 2))), by
+
+
 CASES = {
+    "f32c2sc": lambda: fused_sc(32, 64, 256), "f64c2sc": lambda: fused_sc(64, 32, 128),
     "cout1": cout1, "cout4": cout4, "cin1": cin1, "cin4": cin4,
     "up64": lambda: up(64, 128, True), "up128": lambda: up(128, 64, True), "up128s": lambda: up(128, 32, False),
     "upn64": lambda: up_new(64, 128, True), "upn128": lambda: up_new(128, 64, True), "upn128s": lambda: up_new(128, 32, False),
