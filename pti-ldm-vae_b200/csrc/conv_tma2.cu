@@ -70,15 +70,16 @@ struct Cfg {
   }
   static constexpr Pick pick() {
     // preference: double-buffered chunks > (fp32 input) a tile's worth of raw blocks in flight > weight-ring depth
-    const int nbufs[2] = {2 * NCH, NCH};
+    // (16-bit input: the chunk buffer is also the TMA landing zone, so more than two keep a load in flight)
+    const int nbufs[4] = {IN32 ? 0 : 4 * NCH, IN32 ? 0 : 3 * NCH, 2 * NCH, NCH};
     for (int pass = 0; pass < 2; ++pass) {          // pass 0 insists on a ring of >= 3 stages
       const int min_nst = pass == 0 ? 3 : 2;
-      for (int bi = 0; bi < 2; ++bi) {
+      for (int bi = 0; bi < 4; ++bi) {
         const int nbuf = nbufs[bi];
-        if (nbuf < 2) continue;
+        if (nbuf < 2 || nbuf > 4) continue;
         if (!IN32) {
           const Pick p = weights(nbuf, 32, 0, min_nst);
-          if (p.ok) return p;
+          if (p.ok && (p.resb || nbuf <= 2 * NCH)) return p;    // extra buffers only if the weights stay resident
         } else {
           const int per_tile32 = CIN / 32;
           for (int nxs = (per_tile32 < 4 ? per_tile32 * 2 : 4); nxs >= 2; --nxs) {
