@@ -158,14 +158,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
 
 using namespace ptivae;
 
-static int stats_chunks(int N, int HW, int C, int* ppb_out) {
-  int chunks = (148 * 8 + N - 1) / N;
+// The partition of an image into statistics chunks depends on the image only, never on the batch size: the
+// summation order -- and therefore every output bit -- of an image is the same whatever batch it arrives in.
+static int stats_chunks(int /*N*/, int HW, int C, int* ppb_out) {
   const int prows = 256 / (C / 8);
-  int ppb = (HW + chunks - 1) / chunks;
+  int ppb = 1024;                       // pixels per block
   if (ppb < prows * 4) ppb = prows * 4;
-  chunks = (HW + ppb - 1) / ppb;
   *ppb_out = ppb;
-  return chunks;
+  return (HW + ppb - 1) / ppb;
 }
 
 extern "C" int ptivae_gn_stats_parts(int N, int HW, int C) {

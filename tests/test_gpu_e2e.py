@@ -274,3 +274,21 @@ def test_pipelined_host_streaming_matches_serial(b200, oracle):
         assert torch.equal(w, o)
     with pytest.raises(ValueError):
         pipe.submit(torch.zeros(2, 1, 64, 64), outs[0])
+
+
+def test_large_batch_is_bitwise_the_concatenation_of_small_batches(b200, oracle):
+    """Size-independent property at more than the bench's full size: images are independent and every reduction has
+    a fixed order, so a 160-image 256^2 batch (2.7 GB fp32 stream tensors: > 2^31 bytes, 32-bit offsets would wrap)
+    must reproduce, bit for bit, what the same images give in batches of 64 + 64 + 32."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    _, vae = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(160, 256, 256, seed=23).to(DEV)
+    big = vae.reconstruct_deterministic(x)
+    mu_big = vae.encode_deterministic(x)
+    lo = 0
+    for n in (64, 64, 32):
+        part = vae.reconstruct_deterministic(x[lo:lo + n])
+        assert torch.equal(part, big[lo:lo + n]), f"batch slice {lo}:{lo + n} differs"
+        assert torch.equal(vae.encode_deterministic(x[lo:lo + n]), mu_big[lo:lo + n])
+        lo += n
+    assert torch.isfinite(big).all()
