@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
                                                                 const float* __restrict__ w,  // [Cout][Cin][3][3]
                                                                 const float* __restrict__ bias,
                                                                 void* __restrict__ out, int H, int W, int Cin,
-                                                                int Cout, int out_fmt) {
+                                                                int Cout, int out_fmt, int rows) {
   extern __shared__ float sw[];  // [9*Cin][Cout] then bias [Cout]
   float* sb = sw + 9 * Cin * Cout;
   for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
   const size_t plane = static_cast<size_t>(H) * W;
   // one block walks kSmallRows consecutive rows: the weight staging above and its global latency are paid
   // once per 16 rows, and two of the three input rows of every step are L1 hits
-  for (int py = blockIdx.y * kSmallRows; py < min(H, (blockIdx.y + 1) * kSmallRows); ++py) {
+  for (int py = blockIdx.y * rows; py < min(H, (static_cast<int>(blockIdx.y) + 1) * rows); ++py) {
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = sb[v * 8 + j];
@@ -308,7 +308,7 @@ template <int FMT>                    // 0 bf16 | 1 fp16 | 2 fp32 input
 __global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                                                      const float* __restrict__ bias,
                                                                      const float* __restrict__ ss, float* __restrict__ out,
-                                                                     int H, int W, int Cin, int Cout) {
+                                                                     int H, int W, int Cin, int Cout, int nvt) {
   extern __shared__ float fsm[];
   float* sp = fsm;                        // [9][kFcHalo] tap partials
   float* sw = sp + 9 * kFcHalo;           // [Cin/8][9][8] folded weights, octet-major
@@ -320,12 +320,17 @@ __global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void*
     const float sc = ss ? __ldg(ss + (static_cast<size_t>(n) * Cin + c) * 2) : 1.f;
     sw[i] = __ldg(w + (static_cast<size_t>(co) * Cin + c) * 9 + t) * sc;          // w is [Cout][Cin][3][3]
   }
-  if (threadIdx.x < 9) {
-    float k = 0.f;
-    if (ss)
-      for (int c = 0; c < Cin; ++c)
-        k = fmaf(__ldg(w + (static_cast<size_t>(co) * Cin + c) * 9 + threadIdx.x), __ldg(ss + (static_cast<size_t>(n) * Cin + c) * 2 + 1), k);
-    sk[threadIdx.x] = k;
+  {  // K[tap] = sum_c w[tap][c] * shift[c]: one warp per tap (5 warps, 2 rounds), lanes stride over c, fixed-order fold
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = wrp; t < 9; t += kFcThreads / 32) {
+      float k = 0.f;
+      if (ss)
+        for (int c = lane; c < Cin; c += 32)
+          k = fmaf(__ldg(w + (static_cast<size_t>(co) * Cin + c) * 9 + t), __ldg(ss + (static_cast<size_t>(n) * Cin + c) * 2 + 1), k);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+      if (lane == 0) sk[t] = k;
+    }
   }
   __syncthreads();
   constexpr int ESZ = FMT == 2 ? 4 : 2;
@@ -334,8 +339,8 @@ __global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void*
   float* oplane = out + (static_cast<size_t>(n) * Cout + co) * H * W;
   const int x0 = blockIdx.x * kFcTW - 1;
   const int noct = Cin / 8;
-  for (int vt = 0; vt < kFcVT; ++vt) {
-    const int ty0 = (blockIdx.y * kFcVT + vt) * kFcTH;
+  for (int vt = 0; vt < nvt; ++vt) {
+    const int ty0 = (blockIdx.y * nvt + vt) * kFcTH;
     if (ty0 >= H) break;
     const int y0 = ty0 - 1;
     for (int slot = threadIdx.x; slot < kFcQ; slot += blockDim.x) {
@@ -457,7 +462,9 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
     conv3x3_cin1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, out, H, W, Cout, out_fmt, gn_part, gn_groups);
     return static_cast<int>(cudaGetLastError());
   }
-  conv3x3_small_cin_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt);
+  const int rows = H <= 64 ? 4 : kSmallRows;     // small images: more, shorter blocks (the layer is latency bound)
+  grid.y = (H + rows - 1) / rows;
+  conv3x3_small_cin_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -482,14 +489,14 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
 
 template <int FMT>
 static int launch_fewcout(dim3 grid, size_t smem, const void* x, const float* w, const float* bias, const float* ss,
-                          float* out, int H, int W, int Cin, int Cout, cudaStream_t stream) {
+                          float* out, int H, int W, int Cin, int Cout, int nvt, cudaStream_t stream) {
   static bool attr_set = false;   // one flag per instantiation (the three kernels share a function-pointer type)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_fewcout_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  conv3x3_fewcout_kernel<FMT><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout);
+  conv3x3_fewcout_kernel<FMT><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout, nvt);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -500,13 +507,14 @@ extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const fl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (Cin % 8 == 0 && Cin <= 256 && in_fmt >= 0 && in_fmt <= 2) {   // tap-partial kernel (weights folded per image)
     const long long gz = static_cast<long long>(N) * Cout;
-    const int gy = (H + kFcTH * kFcVT - 1) / (kFcTH * kFcVT);
+    const int nvt = kFcVT;
+    const int gy = (H + kFcTH * nvt - 1) / (kFcTH * nvt);
     if (gz <= 65535 && gy <= 65535) {
       dim3 grid((W + kFcTW - 1) / kFcTW, gy, static_cast<unsigned>(gz));
       const size_t smem = (static_cast<size_t>(9) * kFcHalo + 9 * Cin + 16) * sizeof(float);
-      if (in_fmt == 2) return launch_fewcout<2>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, stream);
-      if (in_fmt == 1) return launch_fewcout<1>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, stream);
-      return launch_fewcout<0>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, stream);
+      if (in_fmt == 2) return launch_fewcout<2>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream);
+      if (in_fmt == 1) return launch_fewcout<1>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream);
+      return launch_fewcout<0>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream);
     }
   }
   switch (Cout) {
