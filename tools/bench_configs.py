@@ -1,0 +1,27 @@
+"""Forward throughput of the other BASELINE.json configurations (parity-test cases, not bench lines):
+config A at the regression sweep's extents and config B (AR-VAE model) -- CUDA-graph replay, device-resident input."""
+import sys, pathlib
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import torch
+import _pkg
+from oracle import aekl_ref
+b200 = _pkg.load()
+GFLOP = {("A", 256): 48.916, ("A", 384): 113.08, ("A", 512): 208.55, ("B", 256): 242.39}
+for name, cfg, hw, b, mode in (("A", b200.config.AUTOENCODER_DEF_A, 256, 64, "forward"), ("A", b200.config.AUTOENCODER_DEF_A, 384, 32, "reconstruct"),
+                               ("A", b200.config.AUTOENCODER_DEF_A, 512, 16, "reconstruct"), ("B", b200.config.AUTOENCODER_DEF_B, 256, 16, "forward"),
+                               ("A", b200.config.AUTOENCODER_DEF_A, 256, 64, "encode")):
+    vae = b200.VAEModel.from_config(cfg).cuda().eval()
+    vae.load_state_dict(aekl_ref.seeded_model(cfg, 1234).state_dict())
+    g = b200.GraphedVAE(vae, b, hw, hw, mode=mode)
+    g.x.copy_(aekl_ref.synthetic_images(b, hw, hw, seed=0).cuda())
+    for _ in range(3):
+        g()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        g()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gf = GFLOP[(name, hw)] * (17.46 / 48.916 if mode == "encode" else 1.0)
+    print(f"config {name} {hw}x{hw} batch {b:3d} {mode:11s}: {ms:8.3f} ms/step  {b / ms * 1e3:9.1f} img/s  {gf * b / ms:7.1f} TFLOP/s (nominal)", flush=True)
