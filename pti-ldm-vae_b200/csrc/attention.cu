@@ -10,6 +10,12 @@
 //               rescale the O accumulator in TMEM, write P (bf16) to smem in the UMMA K-major layout
 //               O += P V         UMMA M=128 N=D  K=BKV   (B = V used MN-major)    -> TMEM cols [BKV,BKV+D)
 //   Warps   : 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = softmax / epilogue.
+//   Pipeline: S is double buffered in TMEM, so S(j+1) = Q K(j+1)^T is issued BEFORE the MMA thread waits for P(j):
+//             the score GEMM runs under the softmax of the previous block.  The O accumulator is rescaled LAZILY:
+//             probabilities are taken relative to a reference maximum that is only moved (and O, l rescaled) when
+//             the running maximum exceeds it by more than 2^8 -- mathematically the same softmax (shift invariance),
+//             P <= 256 stays exact to 11 bits in the 16-bit operand, and the TMEM read-modify-write pass over O
+//             (the longest part of the first version's critical path) almost never runs.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -38,7 +44,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr uint32_t KV_TILE = uint32_t(BKV) * D * 2u;  // one K (or V) tile
   constexpr uint32_t KV_CHUNK = uint32_t(BKV) * 128u;   // one 64-channel chunk of a K/V tile
   constexpr uint32_t P_BYTES = 128u * BKV * 2u;
-  constexpr uint32_t TMEM_COLS = (BKV + D <= 256) ? 256u : 512u;
+  constexpr uint32_t TMEM_COLS = (2 * BKV + D <= 256) ? 256u : 512u;   // S0 | S1 | O
   constexpr uint32_t kIdescS = make_idesc_16(128, BKV, F16, 0);
   constexpr uint32_t kIdescO = make_idesc_16(128, D, F16, 1);  // B (=V) is MN-major
 
@@ -47,15 +53,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = smem_raw + pad;
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;          // 2 stages x (K tile, V tile)
-  uint8_t* sP = sKV + 4 * KV_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint8_t* sP = sKV + 4 * KV_TILE;      // 2 buffers: P(j) is written while P V(j-1) still reads the other one
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;    // [2]
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* pv_done = bars + 9;   // [2] P V(j) has finished reading P buffer j & 1 (and accumulating into O)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -72,8 +79,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
     mbar_init(p_full, 128);
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -82,8 +92,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + BKV;
+  const uint32_t tmem_S = tmem_base;             // S(j) lives at columns (j & 1) * BKV
+  const uint32_t tmem_O = tmem_base + 2 * BKV;
 
   if (warp == 0) {
     if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
@@ -105,25 +115,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == 1) {
     if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
+      const uint32_t qb = smem_u32(sQ);
+      auto issue_s = [&](int j) {      // S(j) = Q K(j)^T into S buffer j & 1
         const int s = j & 1;
         mbar_wait(&kv_full[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t kb = smem_u32(sKV + s * 2 * KV_TILE);
-        const uint32_t vb = kb + KV_TILE;
-        const uint32_t qb = smem_u32(sQ);
-        // S = Q K^T
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t ad = make_smem_desc(qb + (kk / 4) * (128 * 128) + (kk % 4) * 32, 16, 1024, kLayoutSW128);
           const uint64_t bd = make_smem_desc(kb + (kk / 4) * KV_CHUNK + (kk % 4) * 32, 16, 1024, kLayoutSW128);
-          umma_bf16(tmem_S, ad, bd, kIdescS, kk != 0 ? 1u : 0u);
+          umma_bf16(tmem_S + s * BKV, ad, bd, kIdescS, kk != 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
-        // wait for P (and the rescaled O)
+        umma_commit(&s_full[s]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        // the next block's scores run under this block's softmax (its S buffer was last read before P(j-1) was signalled)
+        if (j + 1 < nkv) issue_s(j + 1);
+        const uint32_t vb = smem_u32(sKV + s * 2 * KV_TILE) + KV_TILE;
+        // wait for P (and the possibly rescaled O)
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t pb = smem_u32(sP);
+        const uint32_t pb = smem_u32(sP + s * P_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t ad = make_smem_desc(pb + (kk / 4) * (128 * 128) + (kk % 4) * 32, 16, 1024, kLayoutSW128);
@@ -133,6 +148,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_bf16(tmem_O, ad, bd, kIdescO, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&kv_empty[s]);
+        umma_commit(&pv_done[s]);
       }
       umma_commit(o_full);
     }
@@ -141,17 +157,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int m = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float c2 = args.scale_log2e;
-    float m_run = -CUDART_INF_F, l_run = 0.f;
-    uint8_t* prow = sP + m * 128;
+    float m_ref = 0.f, l_run = 0.f;      // reference maximum (raw score units) the probabilities are relative to
+    constexpr float kLazy = 8.0f;         // move the reference only when the maximum exceeds it by 2^8
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);
+      uint8_t* prow = sP + (j & 1) * P_BYTES + m * 128;
+      const uint32_t tS = tmem_S + (j & 1) * BKV;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int kvalid = L - j * BKV;  // keys >= kvalid are out of range (zero-filled by TMA)
-      float mx = m_run;
+      float mx = -CUDART_INF_F;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, r);
+        tmem_ld32(tS + lane_addr + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -159,8 +177,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mx = fmaxf(mx, sv);
         }
       }
-      const float alpha = ex2_approx((m_run - mx) * c2);  // j == 0: exp2(-inf) = 0
-      if (j > 0) {
+      float alpha = 1.0f;
+      if (j == 0) {
+        m_ref = mx;                               // O and l are still empty: nothing to rescale
+      } else if ((mx - m_ref) * c2 > kLazy) {
+        alpha = ex2_approx((m_ref - mx) * c2);
+        m_ref = mx;
+      }
+      if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: TMEM read-modify-write of this warp's 32 O rows
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // P V(j-1) must have finished accumulating into O
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
           uint32_t r[32];
@@ -171,13 +197,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st32(tmem_O + lane_addr + c * 32, r);
         }
         tmem_st_wait();
+        l_run *= alpha;
       }
+      if (j >= 2) mbar_wait(&pv_done[j & 1], ((j >> 1) - 1) & 1);   // P V(j-2) has released this P buffer
       float rowsum = 0.f;
-      const float mxc = mx * c2;
+      const float mxc = m_ref * c2;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, r);
+        tmem_ld32(tS + lane_addr + c * 32, r);
         tmem_ld_wait();
         float p[32];
 #pragma unroll
@@ -198,8 +226,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           *reinterpret_cast<uint4*>(chunk + ((unit ^ (m & 7)) << 4)) = o;
         }
       }
-      l_run = l_run * alpha + rowsum;
-      m_run = mx;
+      l_run += rowsum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -247,7 +274,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   if (rc) return rc;
   rc = encode_tmap_16(&tmV, v, 3, dims, strides, boxkv, 128, F16);
   if (rc) return rc;
-  const size_t smem = 128 * D * 2 + 4 * size_t(BKV) * D * 2 + 128 * BKV * 2 + 1024 + 128;
+  const size_t smem = 128 * D * 2 + 4 * size_t(BKV) * D * 2 + 2 * 128 * BKV * 2 + 1024 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =

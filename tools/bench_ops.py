@@ -78,7 +78,15 @@ def fused_sc(c, sc, hw):
     return timeit(lambda: ops.conv3x3_fused_sc(h, ss, True, wp, bias, xr, wsc, gn_groups=min(32, c // 2))), by
 
 
+def attn(l, d, b=64):
+    q, k, v = (torch.randn(b, l, d, device="cuda").to(DT) for _ in range(3))
+    ms, _ = timeit(lambda: ops.attention(q, k, v)), 0
+    print(f"   attention L={l} d={d}: {4.0 * b * l * l * d / ms / 1e9:.0f} TFLOP/s")
+    return ms, 8 * b * l * d
+
+
 CASES = {
+    "attn1k": lambda: attn(1024, 128), "attn4k": lambda: attn(4096, 128, 16), "attn4k256": lambda: attn(4096, 256, 8),
     "f32c2sc": lambda: fused_sc(32, 64, 256), "f64c2sc": lambda: fused_sc(64, 32, 128),
     "cout1": cout1, "cout4": cout4, "cin1": cin1, "cin4": cin4,
     "up64": lambda: up(64, 128, True), "up128": lambda: up(128, 64, True), "up128s": lambda: up(128, 32, False),
