@@ -135,9 +135,10 @@ int ptivae_conv3x3_small_cout(const void* x, const float* w, const float* bias, 
 int ptivae_conv1x1_small(const float* x, const float* w, const float* bias, float* out, int N, int HW, int Cin,
                          int Cout, int act, void* stream);
 
-/* Single-head self-attention core: out = softmax(Q K^T * D^-0.5) V; q,k,v,out h16 [B][L][D], D in {64,128,256}
- * (monai SABlock with num_heads = 1, use_flash_attention=False semantics). */
-int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D, int f16,
+/* Single-head self-attention core: out = softmax(Q K^T * D^-0.5) V; q,k,v h16 [B][L][ld] views (row stride ld >= D
+ * elements, ld % 8 == 0: ld = 3*D for a fused q|k|v projection, ld = D for separate tensors), out h16 [B][L][D],
+ * D in {64,128,256} (monai SABlock with num_heads = 1, use_flash_attention=False semantics). */
+int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D, int ld, int f16,
                          void* stream);
 
 /* AutoencoderKL.sampling: z = mu + sigma*eps.  eps_in != NULL: use the injected noise; else draw

@@ -42,7 +42,7 @@ SIGNATURES = {
     "ptivae_conv3x3_small_cin_parts": [_c_int] * 3,
     "ptivae_conv3x3_small_cout": [_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p],
     "ptivae_conv1x1_small": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
-    "ptivae_attention_fwd": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
+    "ptivae_attention_fwd": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
     "ptivae_latent_sample": [_c_void_p] * 6 + [_c_ll, _c_ull, _c_ull, _c_void_p],
     "ptivae_rng_advance": [_c_void_p, _c_void_p],
     "ptivae_kl_loss": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],

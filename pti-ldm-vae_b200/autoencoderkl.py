@@ -166,6 +166,19 @@ class _Executor:
     def f32(p: torch.Tensor) -> torch.Tensor:
         return p.detach()
 
+    def qkv_packed(self, attn: nn.Module):
+        """Packed [1][3C][C] weight and [3C] bias of the fused q|k|v projection, cached until a master changes."""
+        ws = (attn.to_q.weight, attn.to_k.weight, attn.to_v.weight)
+        bs = (attn.to_q.bias, attn.to_k.bias, attn.to_v.bias)
+        key = (id(ws[0]), "qkv")
+        ver = tuple((t.data_ptr(), t._version) for t in ws + bs) + (self.op_dtype, ws[0].device)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            wcat = torch.cat([t.detach() for t in ws], dim=0)
+            hit = (ver, ops.pack_conv_weight(wcat, 0, self.op_dtype), torch.cat([t.detach() for t in bs]).contiguous())
+            self._packed[key] = hit
+        return hit[1], hit[2]
+
     def bias_sum(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         """a + b of two bias vectors, cached until either master changes (fused conv2 + shortcut)."""
         key = (id(a), id(b), "bias_sum")
@@ -241,11 +254,17 @@ class _Executor:
 
     def attention(self, blk: SpatialAttentionBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
         xn = ops.gn_apply(a.t, self.scale_shift(a, blk.norm), silu=False, dtype=self.op_dtype)
-        q = self.conv(xn, blk.attn.to_q, 3, stats=False).t
-        k = self.conv(xn, blk.attn.to_k, 3, stats=False).t
-        v = self.conv(xn, blk.attn.to_v, 3, stats=False).t
-        n, h, w, c = q.shape
-        o = ops.attention(q.view(n, h * w, c), k.view(n, h * w, c), v.view(n, h * w, c)).view(n, h, w, c)
+        n, h, w, c = xn.shape
+        if c % 128 == 0:
+            # one GEMM for q | k | v (N = 3C); the attention kernel reads the three channel slices in place
+            wq, bq = self.qkv_packed(blk.attn)
+            qkv = ops.conv_umma(xn, wq, bq, 3).view(n, h * w, 3 * c)
+            q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+        else:
+            q = self.conv(xn, blk.attn.to_q, 3, stats=False).t.view(n, h * w, c)
+            k = self.conv(xn, blk.attn.to_k, 3, stats=False).t.view(n, h * w, c)
+            v = self.conv(xn, blk.attn.to_v, 3, stats=False).t.view(n, h * w, c)
+        o = ops.attention(q, k, v).view(n, h, w, c)
         return self.conv(o, blk.attn.out_proj, 3, residual=a.t, stats=stats, out_f32=out_f32)
 
     def run_stack(self, blocks: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:

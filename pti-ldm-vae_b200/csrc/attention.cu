@@ -262,10 +262,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 template <int D, int BKV, bool F16>
-static int launch_attn(const void* q, const void* k, const void* v, void* out, int B, int L, cudaStream_t stream) {
+static int launch_attn(const void* q, const void* k, const void* v, void* out, int B, int L, int ld, cudaStream_t stream) {
   CUtensorMap tmQ, tmK, tmV;
   uint64_t dims[3] = {uint64_t(D), uint64_t(L), uint64_t(B)};
-  uint64_t strides[2] = {uint64_t(D) * 2, uint64_t(L) * D * 2};
+  uint64_t strides[2] = {uint64_t(ld) * 2, uint64_t(L) * ld * 2};   // ld = row stride of q/k/v in elements (>= D)
   uint32_t boxq[3] = {64, 128, 1};
   uint32_t boxkv[3] = {64, BKV, 1};
   int rc = encode_tmap_16(&tmQ, q, 3, dims, strides, boxq, 128, F16);
@@ -296,14 +296,14 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
 using namespace ptivae;
 
 extern "C" int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D,
-                                    int f16, void* stream_) {
-  if (!q || !k || !v || !out || B <= 0 || L <= 0) return PTIVAE_ERR_ARG;
+                                    int ld, int f16, void* stream_) {
+  if (!q || !k || !v || !out || B <= 0 || L <= 0 || ld < D || ld % 8 != 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (D == 128) return f16 ? launch_attn<128, 128, true>(q, k, v, out, B, L, stream)
-                           : launch_attn<128, 128, false>(q, k, v, out, B, L, stream);
-  if (D == 256) return f16 ? launch_attn<256, 64, true>(q, k, v, out, B, L, stream)
-                           : launch_attn<256, 64, false>(q, k, v, out, B, L, stream);
-  if (D == 64) return f16 ? launch_attn<64, 128, true>(q, k, v, out, B, L, stream)
-                          : launch_attn<64, 128, false>(q, k, v, out, B, L, stream);
+  if (D == 128) return f16 ? launch_attn<128, 128, true>(q, k, v, out, B, L, ld, stream)
+                           : launch_attn<128, 128, false>(q, k, v, out, B, L, ld, stream);
+  if (D == 256) return f16 ? launch_attn<256, 64, true>(q, k, v, out, B, L, ld, stream)
+                           : launch_attn<256, 64, false>(q, k, v, out, B, L, ld, stream);
+  if (D == 64) return f16 ? launch_attn<64, 128, true>(q, k, v, out, B, L, ld, stream)
+                          : launch_attn<64, 128, false>(q, k, v, out, B, L, ld, stream);
   return PTIVAE_ERR_UNSUPPORTED;
 }

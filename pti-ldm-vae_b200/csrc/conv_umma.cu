@@ -294,7 +294,7 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   if (N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
   if (mode < 0 || mode > 3) return PTIVAE_ERR_ARG;
   if (!(Cin == 32 || (Cin % 64 == 0 && Cin <= 1024))) return PTIVAE_ERR_UNSUPPORTED;
-  if (!(Cout == 32 || Cout == 64 || Cout == 128 || Cout % 256 == 0)) return PTIVAE_ERR_UNSUPPORTED;
+  if (!(Cout == 32 || Cout == 64 || Cout % 128 == 0)) return PTIVAE_ERR_UNSUPPORTED;
   if (mode == 1 && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;  // even extents only (F.pad(0,1,0,1) + s2)
   if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
     return PTIVAE_ERR_ARG;
@@ -360,7 +360,7 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   CUtensorMap tmA, tmB;
   int rc = encode_tmap_16(&tmA, in, 5, dims, strides, box, KCH * 2, f16 != 0);
   if (rc != PTIVAE_OK) return rc;
-  const int BN = Cout >= 256 ? 256 : Cout;
+  const int BN = Cout % 256 == 0 ? 256 : (Cout >= 128 ? 128 : Cout);   // (e.g. 384 = fused q|k|v projection: 3 x 128)
   uint64_t wd[3] = {uint64_t(Cin), uint64_t(Cout), uint64_t(T)};
   uint64_t ws[2] = {C2, uint64_t(Cout) * C2};
   uint32_t wb[3] = {static_cast<uint32_t>(KCH), static_cast<uint32_t>(BN), 1};

@@ -277,11 +277,16 @@ def conv1x1_small(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, act: int = 
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
-    """bf16 [B,L,D] x3 -> bf16 [B,L,D]; single head, scale D^-0.5."""
+    """16-bit [B,L,D] x3 -> [B,L,D]; single head, scale D^-0.5.  q, k, v may be channel slices of one fused
+    [B,L,3D] projection (any common row stride, unit channel stride)."""
     _need_cuda(q, k, v)
     b, l, d = q.shape
-    out = torch.empty_like(q)
-    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), b, l, d,
+    ld = q.stride(1)
+    for t in (q, k, v):
+        if t.shape != q.shape or t.stride(2) != 1 or t.stride(1) != ld or t.stride(0) != l * ld or t.dtype != q.dtype:
+            raise _lib.PtivaeError("q, k, v must share shape, dtype and a [B, L, D] layout with one common row stride")
+    out = torch.empty((b, l, d), device=q.device, dtype=q.dtype)
+    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), b, l, d, ld,
           _op16(q), _stream())
     return out
 

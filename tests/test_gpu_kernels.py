@@ -120,6 +120,8 @@ CONV_CASES = [
     (3, 1, 32, 32, 128, 64),
     (3, 2, 32, 32, 128, 128),
     (3, 1, 16, 16, 256, 256),
+    (3, 2, 16, 24, 128, 384),    # fused q|k|v projection: three 128-column tiles
+    (3, 1, 16, 16, 256, 768),
 ]
 
 
@@ -479,6 +481,18 @@ def test_attention(b200, b, l, d):
     ref = torch.einsum("bxy,byd->bxd", att, v.float())
     # P is rounded to 16 bit before PV: allow 2 ulps of the output scale
     _check_bf16(out, ref, f"attention L={l} d={d}", rel=6e-3, ulp=2.0 ** -6)
+
+
+def test_attention_reads_fused_qkv_slices(b200):
+    """q, k, v as channel slices of one [B, L, 3D] projection (row stride 3D) == separate contiguous tensors."""
+    b, l, d = 2, 320, 128
+    qkv = (torch.randn(b, l, 3 * d, device=DEV) * 0.7).to(DT)
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    fused = b200.ops.attention(q, k, v)
+    sep = b200.ops.attention(q.contiguous(), k.contiguous(), v.contiguous())
+    assert torch.equal(fused, sep)
+    with pytest.raises(b200._lib.PtivaeError):
+        b200.ops.attention(q, k.contiguous(), v)
 
 
 def test_attention_peaked(b200):
