@@ -16,3 +16,4 @@ cap tma32_conv2 conv3x3_tma_kernel f32c2
 cap tma2_128_conv2 conv3x3_tma2_kernel f128c2
 cap up64 up2x_conv3x3_kernel upn64
 cap tma2_sc32 conv3x3_tma2_kernel f32c2sc
+cap attn attn_fwd_kernel attn1k
