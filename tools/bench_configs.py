@@ -4,16 +4,15 @@ import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import torch
 import _pkg
-from oracle import aekl_ref
 b200 = _pkg.load()
 GFLOP = {("A", 256): 48.916, ("A", 384): 113.08, ("A", 512): 208.55, ("B", 256): 242.39}
 for name, cfg, hw, b, mode in (("A", b200.config.AUTOENCODER_DEF_A, 256, 64, "forward"), ("A", b200.config.AUTOENCODER_DEF_A, 384, 32, "reconstruct"),
                                ("A", b200.config.AUTOENCODER_DEF_A, 512, 16, "reconstruct"), ("B", b200.config.AUTOENCODER_DEF_B, 256, 16, "forward"),
                                ("A", b200.config.AUTOENCODER_DEF_A, 256, 64, "encode")):
-    vae = b200.VAEModel.from_config(cfg).cuda().eval()
-    vae.load_state_dict(aekl_ref.seeded_model(cfg, 1234).state_dict())
+    torch.manual_seed(1234)
+    vae = b200.VAEModel.from_config(cfg).cuda().eval()          # default-initialised weights (timing only)
     g = b200.GraphedVAE(vae, b, hw, hw, mode=mode)
-    g.x.copy_(aekl_ref.synthetic_images(b, hw, hw, seed=0).cuda())
+    g.x.copy_(torch.randn(b, 1, hw, hw, generator=torch.Generator().manual_seed(0)).cuda())
     for _ in range(3):
         g()
     torch.cuda.synchronize()
