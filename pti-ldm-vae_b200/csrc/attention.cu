@@ -9,7 +9,10 @@
 //               softmax warps: row max / exp2 / row sum in registers (one thread per query row),
 //               rescale the O accumulator in TMEM, write P (bf16) to smem in the UMMA K-major layout
 //               O += P V         UMMA M=128 N=D  K=BKV   (B = V used MN-major)    -> TMEM cols [BKV,BKV+D)
-//   Warps   : 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = softmax / epilogue.
+//   Warps   : 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..9 = softmax / epilogue: TWO threads per query row
+//             (warps w and w + 4 share a TMEM lane quarter and split the score / output columns in halves; they
+//             exchange the block maximum and, at the end, the row sum through shared memory) -- one softmax warp per
+//             scheduler was issue bound (ncu: "selected" 27 % with a single warp per SMSP).
 //   Pipeline: S is double buffered in TMEM, so S(j+1) = Q K(j+1)^T is issued BEFORE the MMA thread waits for P(j):
 //             the score GEMM runs under the softmax of the previous block.  The O accumulator is rescaled LAZILY:
 //             probabilities are taken relative to a reference maximum that is only moved (and O, l rescaled) when
@@ -36,7 +39,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int D, int BKV, bool F16>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs args) {
   constexpr int DCH = D / 64;                        // 64-channel chunks of the head dim
@@ -64,6 +67,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* pv_done = bars + 9;   // [2] P V(j) has finished reading P buffer j & 1 (and accumulating into O)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
+  __shared__ float xch[2][128];    // per-row exchange between the two column halves (block max, final row sum)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int q0 = blockIdx.x * 128;
@@ -81,7 +85,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(&pv_done[0], 1);
     mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
@@ -153,21 +157,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(o_full);
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                       // TMEM lane quarter (hardware: warp id % 4)
+    const int hsel = (warp - 2) >> 2;             // column half this thread owns
     const int m = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float c2 = args.scale_log2e;
+    constexpr int HB = BKV / 2, HD = D / 2;       // score / output columns per half
     float m_ref = 0.f, l_run = 0.f;      // reference maximum (raw score units) the probabilities are relative to
     constexpr float kLazy = 8.0f;         // move the reference only when the maximum exceeds it by 2^8
     for (int j = 0; j < nkv; ++j) {
       uint8_t* prow = sP + (j & 1) * P_BYTES + m * 128;
-      const uint32_t tS = tmem_S + (j & 1) * BKV;
+      const uint32_t tS = tmem_S + (j & 1) * BKV + hsel * HB;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const int kvalid = L - j * BKV;  // keys >= kvalid are out of range (zero-filled by TMA)
+      const int kvalid = L - j * BKV - hsel * HB;  // this half's keys >= kvalid are out of range (zero-filled by TMA)
       float mx = -CUDART_INF_F;
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
+      for (int c = 0; c < HB / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tS + lane_addr + c * 32, r);
         tmem_ld_wait();
@@ -177,6 +183,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mx = fmaxf(mx, sv);
         }
       }
+      // both halves of a row must agree on the reference maximum
+      xch[hsel][m] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      mx = fmaxf(mx, xch[hsel ^ 1][m]);
+      asm volatile("bar.sync 3, 256;" ::: "memory");    // exchange slots are rewritten next block
       float alpha = 1.0f;
       if (j == 0) {
         m_ref = mx;                               // O and l are still empty: nothing to rescale
@@ -184,17 +195,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         alpha = ex2_approx((m_ref - mx) * c2);
         m_ref = mx;
       }
-      if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: TMEM read-modify-write of this warp's 32 O rows
+      if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: TMEM read-modify-write of this warp's 32 O rows (its columns)
         mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // P V(j-1) must have finished accumulating into O
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < HD / 32; ++c) {
           uint32_t r[32];
-          tmem_ld32(tmem_O + lane_addr + c * 32, r);
+          tmem_ld32(tmem_O + hsel * HD + lane_addr + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st32(tmem_O + lane_addr + c * 32, r);
+          tmem_st32(tmem_O + hsel * HD + lane_addr + c * 32, r);
         }
         tmem_st_wait();
         l_run *= alpha;
@@ -203,7 +214,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float rowsum = 0.f;
       const float mxc = m_ref * c2;
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
+      for (int c = 0; c < HB / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tS + lane_addr + c * 32, r);
         tmem_ld_wait();
@@ -214,7 +225,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           p[i] = ex2_approx(fmaf(sv, c2, -mxc));
           rowsum += p[i];
         }
-        uint8_t* chunk = prow + (c / 2) * (128 * 128);
+        const int cg = hsel * (HB / 32) + c;          // 32-column group inside the full row of BKV probabilities
+        uint8_t* chunk = prow + (cg / 2) * (128 * 128);
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           uint4 o;
@@ -222,7 +234,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           o.y = pack2<F16>(p[u4 * 8 + 2], p[u4 * 8 + 3]);
           o.z = pack2<F16>(p[u4 * 8 + 4], p[u4 * 8 + 5]);
           o.w = pack2<F16>(p[u4 * 8 + 6], p[u4 * 8 + 7]);
-          const int unit = (c & 1) * 4 + u4;  // 16-byte unit inside the 128-byte row
+          const int unit = (cg & 1) * 4 + u4;  // 16-byte unit inside the 128-byte row
           *reinterpret_cast<uint4*>(chunk + ((unit ^ (m & 7)) << 4)) = o;
         }
       }
@@ -231,16 +243,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // ---- final: O / l -> bf16
+    // ---- final: O / l -> 16-bit (row sum = the two halves' sums)
+    xch[hsel][m] = l_run;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    l_run += xch[hsel ^ 1][m];
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const bool valid = (q0 + m) < L;
-    uint16_t* optr = args.out + (static_cast<size_t>(b) * L + q0 + m) * D;
+    uint16_t* optr = args.out + (static_cast<size_t>(b) * L + q0 + m) * D + hsel * HD;
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < HD / 32; ++c) {
       uint32_t r[32];
-      tmem_ld32(tmem_O + lane_addr + c * 32, r);
+      tmem_ld32(tmem_O + hsel * HD + lane_addr + c * 32, r);
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
@@ -287,7 +302,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   a.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   a.out = static_cast<uint16_t*>(out);
   dim3 grid((L + 127) / 128, B);
-  attn_fwd_kernel<D, BKV, F16><<<grid, 192, smem, stream>>>(tmQ, tmK, tmV, a);
+  attn_fwd_kernel<D, BKV, F16><<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, a);
   return static_cast<int>(cudaGetLastError());
 }
 
