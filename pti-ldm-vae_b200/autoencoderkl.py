@@ -164,7 +164,9 @@ class _Executor:
 
     @staticmethod
     def f32(p: torch.Tensor) -> torch.Tensor:
-        return p.detach()
+        """Bias / affine parameters as the kernels read them (fp32; a module cast with .half()/.bfloat16() still works)."""
+        p = p.detach()
+        return p if p.dtype == torch.float32 else p.float()
 
     def qkv_packed(self, attn: nn.Module):
         """Packed [1][3C][C] weight and [3C] bias of the fused q|k|v projection, cached until a master changes."""
@@ -175,7 +177,7 @@ class _Executor:
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
             wcat = torch.cat([t.detach() for t in ws], dim=0)
-            hit = (ver, ops.pack_conv_weight(wcat, 0, self.op_dtype), torch.cat([t.detach() for t in bs]).contiguous())
+            hit = (ver, ops.pack_conv_weight(wcat, 0, self.op_dtype), torch.cat([t.detach().float() for t in bs]).contiguous())
             self._packed[key] = hit
         return hit[1], hit[2]
 
@@ -185,7 +187,7 @@ class _Executor:
         ver = (a.data_ptr(), a._version, b.data_ptr(), b._version, a.device)
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
-            hit = (ver, (a.detach() + b.detach()).contiguous())
+            hit = (ver, (a.detach().float() + b.detach().float()).contiguous())
             self._packed[key] = hit
         return hit[1]
 
@@ -384,9 +386,9 @@ class AutoencoderKL(nn.Module):
     def _encode(self, x: torch.Tensor):
         x = self._prep(x)
         h = self._exec.run_stack(self.encoder.blocks, x)
-        mu = ops.conv1x1_small(h, self.quant_conv_mu.conv.weight.detach(), self.quant_conv_mu.conv.bias.detach(), 0)
-        sigma = ops.conv1x1_small(h, self.quant_conv_log_sigma.conv.weight.detach(),
-                                  self.quant_conv_log_sigma.conv.bias.detach(), 1)
+        mu = ops.conv1x1_small(h, self._exec.f32(self.quant_conv_mu.conv.weight), self._exec.f32(self.quant_conv_mu.conv.bias), 0)
+        sigma = ops.conv1x1_small(h, self._exec.f32(self.quant_conv_log_sigma.conv.weight),
+                                  self._exec.f32(self.quant_conv_log_sigma.conv.bias), 1)
         return mu, sigma
 
     @torch.no_grad()
@@ -409,7 +411,7 @@ class AutoencoderKL(nn.Module):
 
     def _decode(self, z: torch.Tensor) -> torch.Tensor:
         z = self._prep(z)
-        zq = ops.conv1x1_small(z, self.post_quant_conv.conv.weight.detach(), self.post_quant_conv.conv.bias.detach(), 0)
+        zq = ops.conv1x1_small(z, self._exec.f32(self.post_quant_conv.conv.weight), self._exec.f32(self.post_quant_conv.conv.bias), 0)
         return self._exec.run_stack(self.decoder.blocks, zq)
 
     def forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):

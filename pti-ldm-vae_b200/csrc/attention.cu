@@ -290,13 +290,8 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   rc = encode_tmap_16(&tmV, v, 3, dims, strides, boxkv, 128, F16);
   if (rc) return rc;
   const size_t smem = 128 * D * 2 + 4 * size_t(BKV) * D * 2 + 2 * 128 * BKV * 2 + 1024 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(attn_fwd_kernel<D, BKV, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(attn_fwd_kernel<D, BKV, F16>, int(smem), attr_set)) return rc_attr;
   AttnArgs a;
   a.L = L;
   a.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(D));

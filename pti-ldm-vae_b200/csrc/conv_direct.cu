@@ -490,12 +490,8 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
 template <int FMT>
 static int launch_fewcout(dim3 grid, size_t smem, const void* x, const float* w, const float* bias, const float* ss,
                           float* out, int H, int W, int Cin, int Cout, int nvt, cudaStream_t stream) {
-  static bool attr_set = false;   // one flag per instantiation (the three kernels share a function-pointer type)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_fewcout_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(conv3x3_fewcout_kernel<FMT>, 64 * 1024, attr_set)) return rc_attr;
   conv3x3_fewcout_kernel<FMT><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout, nvt);
   return static_cast<int>(cudaGetLastError());
 }

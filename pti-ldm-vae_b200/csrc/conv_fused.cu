@@ -433,13 +433,8 @@ static int launch_fused(const CUtensorMap& tmB, FusedArgs& a, cudaStream_t strea
     a.nstages = stages;
     smem = Cfg::FIXED + size_t(stages) * Cfg::SLAB;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_fused_kernel<CIN, COUT, F16, IN32>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(conv3x3_fused_kernel<CIN, COUT, F16, IN32>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
   int sms = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

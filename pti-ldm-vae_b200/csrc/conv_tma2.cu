@@ -672,13 +672,8 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
       tmXs = tmX;
       tmWs = tmW;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemMax));
-      if (e != cudaSuccess) return static_cast<int>(e);
-      attr_set = true;
-    }
+    static bool attr_set[64] = {};
+    if (int rc_attr = ensure_dyn_smem(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;

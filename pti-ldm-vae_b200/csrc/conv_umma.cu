@@ -264,13 +264,8 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs&
   if (stages < 1) stages = 1;
   a.nstages = stages;
   const size_t smem = size_t(stages) * STAGE + 1024 /*align*/ + (2 * kMaxStages + 1) * 8 + 16 + 4 * (BN / 2) * 2 * 4 + 4 * 512 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KCH, BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(conv_umma_kernel<KCH, BN, F16>, 200 * 1024, attr_set)) return rc_attr;
   dim3 grid(a.tiles_x * a.tiles_y * N, a.Cout / BN, nphase);
   conv_umma_kernel<KCH, BN, F16><<<grid, 192, smem, stream>>>(tmA, tmB, a);
   return static_cast<int>(cudaGetLastError());

@@ -372,13 +372,8 @@ static int launch(const void* x, const void* w_packed, const float* bias, float*
       maps.o16[p] = maps.o32[p];
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(up2x_conv3x3_kernel<C, EMIT16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kSmemMax));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(up2x_conv3x3_kernel<C, EMIT16>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;

@@ -201,12 +201,8 @@ extern "C" int ptivae_eval_metrics(const float* pred, const float* target, const
   if (planes > 65535 || ty > 65535) return PTIVAE_ERR_UNSUPPORTED;
   const int R = kMT + 2 * (win / 2);
   const size_t smem = (static_cast<size_t>(2) * R * (R + 1) + 5 * R * kMT + kMaxWin + 1) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(eval_metrics_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(eval_metrics_tile_kernel, 96 * 1024, attr_set)) return rc_attr;
   const float c1 = (k1 * data_range) * (k1 * data_range), c2 = (k2 * data_range) * (k2 * data_range);
   eval_metrics_tile_kernel<<<dim3(tx, ty, static_cast<unsigned>(planes)), 256, smem, stream>>>(
       pred, target, window, win, static_cast<float*>(workspace), H, W, do_clamp, lo, hi, c1, c2);

@@ -28,6 +28,20 @@ int conv3x3_tma_launch(const FusedCall& c, cudaStream_t stream);
 // chunk-pipelined TMA implementation (conv_tma2.cu): all widths in {32, 64, 128}; same contract
 int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a function: remember per device (a process
+// that drives several GPUs must opt in on each of them).  `flags` is a function-local static array of 64 bools.
+template <class F>
+inline int ensure_dyn_smem(F* func, int bytes, bool (&flags)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!flags[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    flags[dev] = true;
+  }
+  return 0;
+}
+
 inline int grid_for(size_t work_items, int block, int max_blocks = 148 * 16) {
   size_t g = (work_items + block - 1) / block;
   if (g > static_cast<size_t>(max_blocks)) g = max_blocks;

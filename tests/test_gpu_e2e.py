@@ -292,3 +292,15 @@ def test_large_batch_is_bitwise_the_concatenation_of_small_batches(b200, oracle)
         assert torch.equal(vae.encode_deterministic(x[lo:lo + n]), mu_big[lo:lo + n])
         lo += n
     assert torch.isfinite(big).all()
+
+
+def test_module_cast_to_half_still_runs(b200, oracle):
+    """A module cast with .half() (fp16 master parameters) still feeds the kernels correctly typed operands."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    ref, vae = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(2, 64, 64, seed=5)
+    with torch.no_grad():
+        mu_r = ref.encode(x)[0]
+    vae = vae.half()
+    mu = vae.encode_deterministic(x.to(DEV))
+    assert mu.dtype == torch.float32 and _rel_l2(mu, mu_r) <= 4 * TOL_LATENT      # masters themselves were rounded to fp16
