@@ -485,7 +485,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint8_t* xb = xs + s * C::XS_BYTES + u * (IN32 ? 32 : 16);
       uint8_t* ob = opbuf + b * OPBUF + dst_chunk;
       const bool interior = y0 >= 0 && x0 >= 0 && y0 + kHP <= args.H && x0 + kHP <= args.W;   // uniform per tile
-#pragma unroll 2
+#pragma unroll 4
       for (int k = 0; k < VPT; ++k) {
         const int L = Lbase + k * LS;
         if (L >= kHalo) break;
