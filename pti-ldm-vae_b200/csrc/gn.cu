@@ -100,10 +100,22 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
   const int n = wid / G, g = wid - n * G;
   const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * G + g;
   float s = 0.f, q = 0.f;
-  for (int p = lane; p < P; p += 32) {
-    const float2 t = __ldg(src + static_cast<size_t>(p) * G);
-    s += t.x;
-    q += t.y;
+  // batches of 8 independent loads per lane, then the adds in the same order as a plain loop: the kernel is pure
+  // load latency (44 launches per forward), the sums stay bit-identical
+  for (int p0 = lane; p0 < P; p0 += 256) {
+    float2 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = p0 + 32 * i;
+      t[i] = p < P ? __ldg(src + static_cast<size_t>(p) * G) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (p0 + 32 * i < P) {
+        s += t[i].x;
+        q += t[i].y;
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
