@@ -304,3 +304,19 @@ def test_module_cast_to_half_still_runs(b200, oracle):
     vae = vae.half()
     mu = vae.encode_deterministic(x.to(DEV))
     assert mu.dtype == torch.float32 and _rel_l2(mu, mu_r) <= 4 * TOL_LATENT      # masters themselves were rounded to fp16
+
+
+def test_eval_metrics_multichannel_and_ragged_vs_oracle(b200, oracle):
+    """The fused metrics kernel on shapes the reference's compute_ssim cannot take (C = 3; it is single-channel only),
+    checked against the oracle restatement, plus extents that are not multiples of the 32-pixel tile."""
+    from pti_ldm_vae_b200 import eval_metrics
+    g = torch.Generator().manual_seed(31)
+    for shape in ((2, 3, 45, 70), (1, 1, 31, 33), (3, 2, 64, 64)):
+        img = torch.rand(*shape, generator=g)
+        rec = (img + 0.07 * torch.randn(*shape, generator=g)).clamp(-0.2, 1.2)
+        want = oracle.eval_metrics_ref(rec, img)
+        got = eval_metrics.compute_eval_metrics(rec.to(DEV), img.to(DEV))
+        assert np.allclose(got["ssim"].cpu().numpy(), want["ssim"].numpy(), atol=1e-4), shape
+        assert np.allclose(got["psnr"].cpu().numpy(), want["psnr"].numpy(), atol=1e-3), shape
+        assert np.allclose(got["mse"].cpu().numpy(), want["mse"].numpy(), rtol=1e-4)
+        assert np.allclose(got["mae"].cpu().numpy(), want["mae"].numpy(), rtol=1e-4)
