@@ -179,6 +179,79 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
   }
 }
 
+// Few-input-channel 3x3 conv with register blocking over pixels (the decoder's first conv, 4|10 -> 128|256):
+// thread -> (4 consecutive pixels of one row, 8 output channels), so every pair of LDS.128 weight loads feeds 32 FMAs
+// (the one-pixel kernel above is LSU bound: 2 LDS.128 per 8 FMAs) and one thread per row gives H*W/4*Cout/8 threads.
+__global__ void __launch_bounds__(256) conv3x3_small_cin_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, void* __restrict__ out,
+                                                                    int H, int W, int Cin, int Cout, int out_fmt) {
+  extern __shared__ float sw[];  // [9*Cin][Cout] then bias [Cout]
+  float* sb = sw + 9 * Cin * Cout;
+  for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
+    const int co = i % Cout;
+    const int r = i / Cout;  // tap*Cin + ci
+    const int tap = r / Cin, ci = r % Cin;
+    sw[i] = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const int vecs = Cout / 8, xq = (W + 3) / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = i % vecs;
+  const int q = (i / vecs) % xq;
+  const int py = i / (vecs * xq);
+  if (py >= H) return;
+  const int n = blockIdx.z, x0 = q * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = sb[v * 8 + j];
+  const size_t plane = static_cast<size_t>(H) * W;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * plane;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      float xr[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int xx = x0 - 1 + k;
+        xr[k] = (xx >= 0 && xx < W) ? __ldg(xp + static_cast<size_t>(yy) * W + xx) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * Cin + ci) * Cout + v * 8);
+        const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float xv = xr[p + kx];
+          acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
+          acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
+          acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+          acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (x0 + p >= W) break;
+    const size_t o = ((static_cast<size_t>(n) * H + py) * W + x0 + p) * vecs + v;  // 8-channel vector index
+    if (out_fmt == 2) {
+      reinterpret_cast<float4*>(out)[2 * o] = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+      reinterpret_cast<float4*>(out)[2 * o + 1] = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+    } else if (out_fmt == 1) {
+      reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<true>(acc[p][0], acc[p][1]), pack2<true>(acc[p][2], acc[p][3]),
+                                                    pack2<true>(acc[p][4], acc[p][5]), pack2<true>(acc[p][6], acc[p][7]));
+    } else {
+      reinterpret_cast<uint4*>(out)[o] = make_uint4(pack2<false>(acc[p][0], acc[p][1]), pack2<false>(acc[p][2], acc[p][3]),
+                                                    pack2<false>(acc[p][4], acc[p][5]), pack2<false>(acc[p][6], acc[p][7]));
+    }
+  }
+}
+
 // Single-input-channel 3x3 conv (the encoder's first conv, 1 -> 32|64): thread -> (x, 8 consecutive output
 // channels) walking kSmallRows image rows.  The first version read its weights from shared memory inside the
 // tap loop (2 LDS.128 per 8 FMAs: the LSU pipe, not HBM, bounded it at 1.1 TB/s); here the thread's 72 weights
@@ -461,6 +534,19 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
   if (Cin == 1) {
     conv3x3_cin1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, out, H, W, Cout, out_fmt, gn_part, gn_groups);
     return static_cast<int>(cudaGetLastError());
+  }
+  if (Cin > 1) {   // register-blocked over 4 pixels: one thread per (row, pixel quad, channel octet)
+    const long long threads = static_cast<long long>(H) * ((W + 3) / 4) * (Cout / 8);
+    if (threads <= 0x7fffffffLL) {
+      dim3 g4(static_cast<unsigned>((threads + 255) / 256), 1, N);
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_small_cin_px4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+      }
+      conv3x3_small_cin_px4_kernel<<<g4, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt);
+      return static_cast<int>(cudaGetLastError());
+    }
   }
   const int rows = H <= 64 ? 4 : kSmallRows;     // small images: more, shorter blocks (the layer is latency bound)
   grid.y = (H + rows - 1) / rows;
