@@ -373,15 +373,17 @@ __global__ void __launch_bounds__(256, 2) conv3x3_cin1_kernel(const float* __res
 // History (ncu): weights re-read per pixel = LSU bound (0.32 ms at 32->1, 256^2 x 64); 4 lanes per pixel with
 // register weights and a shuffle fold = issue bound at 257 instructions per lane-pixel (0.26 ms); this form
 // issues ~90 per pixel-octet.
-constexpr int kFcTW = 64, kFcTH = 16, kFcHW = kFcTW + 2, kFcHH = kFcTH + 2, kFcHalo = kFcHW * kFcHH;   // 1188 = 4 * 297
-constexpr int kFcQ = kFcHalo / 4;     // halo pixels per thread-slot
+constexpr int kFcTH = 16, kFcHH = kFcTH + 2;
+// tile width: 64 (halo 66 x 18 = 1188 = 4 * 297 slots), or 32 for images at most 32 wide (34 x 18 = 612 = 4 * 153)
+template <int TW> struct FcTile { static constexpr int HW = TW + 2, Halo = HW * kFcHH, Q = Halo / 4; };
 constexpr int kFcThreads = 160;       // two rounds cover the 297 slots
 constexpr int kFcVT = 2;              // vertically stacked tiles per block (amortises the weight fold)
-template <int FMT>                    // 0 bf16 | 1 fp16 | 2 fp32 input
+template <int FMT, int kFcTW>         // FMT: 0 bf16 | 1 fp16 | 2 fp32 input
 __global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                                                      const float* __restrict__ bias,
                                                                      const float* __restrict__ ss, float* __restrict__ out,
                                                                      int H, int W, int Cin, int Cout, int nvt) {
+  constexpr int kFcHW = FcTile<kFcTW>::HW, kFcHalo = FcTile<kFcTW>::Halo, kFcQ = FcTile<kFcTW>::Q;
   extern __shared__ float fsm[];
   float* sp = fsm;                        // [9][kFcHalo] tap partials
   float* sw = sp + 9 * kFcHalo;           // [Cin/8][9][8] folded weights, octet-major
@@ -573,12 +575,12 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
   return static_cast<int>(cudaGetLastError());
 }
 
-template <int FMT>
+template <int FMT, int TW>
 static int launch_fewcout(dim3 grid, size_t smem, const void* x, const float* w, const float* bias, const float* ss,
                           float* out, int H, int W, int Cin, int Cout, int nvt, cudaStream_t stream) {
   static bool attr_set[64] = {};
-  if (int rc_attr = ensure_dyn_smem(conv3x3_fewcout_kernel<FMT>, 64 * 1024, attr_set)) return rc_attr;
-  conv3x3_fewcout_kernel<FMT><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout, nvt);
+  if (int rc_attr = ensure_dyn_smem(conv3x3_fewcout_kernel<FMT, TW>, 64 * 1024, attr_set)) return rc_attr;
+  conv3x3_fewcout_kernel<FMT, TW><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout, nvt);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -592,11 +594,17 @@ extern "C" int ptivae_conv3x3_small_cout(const void* x, const float* w, const fl
     const int nvt = kFcVT;
     const int gy = (H + kFcTH * nvt - 1) / (kFcTH * nvt);
     if (gz <= 65535 && gy <= 65535) {
-      dim3 grid((W + kFcTW - 1) / kFcTW, gy, static_cast<unsigned>(gz));
-      const size_t smem = (static_cast<size_t>(9) * kFcHalo + 9 * Cin + 16) * sizeof(float);
-      if (in_fmt == 2) return launch_fewcout<2>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream);
-      if (in_fmt == 1) return launch_fewcout<1>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream);
-      return launch_fewcout<0>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream);
+      const bool narrow = W <= 32;
+      const int tw = narrow ? 32 : 64;
+      dim3 grid((W + tw - 1) / tw, gy, static_cast<unsigned>(gz));
+      const size_t smem = (static_cast<size_t>(9) * (narrow ? FcTile<32>::Halo : FcTile<64>::Halo) + 9 * Cin + 16) * sizeof(float);
+#define PTIVAE_FC(F)                                                                                                   \
+  return narrow ? launch_fewcout<F, 32>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream)        \
+                : launch_fewcout<F, 64>(grid, smem, x, w, bias, scale_shift, out, H, W, Cin, Cout, nvt, stream)
+      if (in_fmt == 2) PTIVAE_FC(2);
+      if (in_fmt == 1) PTIVAE_FC(1);
+      PTIVAE_FC(0);
+#undef PTIVAE_FC
     }
   }
   switch (Cout) {
