@@ -47,7 +47,12 @@ int ptivae_abi_version(void);
  *             ptivae_conv_parts(H, W, mode); plain stores, fixed order (deterministic); ignored when
  *             gn_groups == 0.  Feed to ptivae_gn_finalize(..., P, ...).
  *   mode      0: 3x3 stride 1 pad 1 (Hout=H)      1: pad right/bottom + 3x3 stride 2 (Hout=H/2, H,W even)
- *             2: nearest x2 upsample + 3x3 pad 1 (Hout=2H)   3: 1x1 */
+ *             2: nearest x2 upsample + 3x3 pad 1 (Hout=2H)   3: 1x1
+ *             data gradients (autograd's conv backward-input under train_vae.py:444), `in` = dY with the extent
+ *             (H, W) of dY, Cin = channels of dY, w_packed = the TRANSPOSED pack [T][Cin_fwd][Cout_fwd]
+ *             (ptivae_pack_conv_weight mode | 4):
+ *             4: of mode 0 (Hout=H)   5: of mode 1 (Hout=2H)   6: of mode 2 (Hout=H/2, w_packed = transposed 16-slab pack)
+ *             (the data gradient of mode 3 is mode 3 with the transposed pack) */
 int ptivae_conv_umma(const void* in, const void* w_packed, const float* bias, const void* residual, void* out,
                      void* out16, float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int mode, int out_f32,
                      int res_f32, int f16, void* stream);
@@ -99,21 +104,23 @@ int ptivae_debug_set_trace(void* buf);
 
 /* fp32 master weights [Cout][Cin][k][k] -> h16 UMMA operand [T][Cout][Cin].
  *   mode 0: T = k*k (k in {1,3}); mode 2: T = 16, the 4-phase x (2x2)-tap decomposition of
- *   nearest-x2-upsample + 3x3 (weights of taps that hit the same low-res pixel are pre-summed). */
+ *   nearest-x2-upsample + 3x3 (weights of taps that hit the same low-res pixel are pre-summed).
+ *   mode 4 / 6: the same slabs transposed, [T][Cin][Cout] (operand of the data-gradient convolutions). */
 int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, int f16, void* stream);
 
 /* nn.GroupNorm statistics, deterministic two-stage form.
  *   gn_stats: partial[n][p][g] = (sum, sumsq) over pixel chunk p of x [N][HW][C] (storage in_fmt); P = ptivae_gn_stats_parts(N, HW, C) chunks per image.
  *   gn_finalize: partial [N][P][G][2] -> scale_shift fp32 [N][C][2], scale = gamma*rstd,
  *             shift = beta - mean*scale (biased variance, eps inside the sqrt:
- *             nn.GroupNorm(eps=norm_eps, affine=True)); partials are summed in index order.
+ *             nn.GroupNorm(eps=norm_eps, affine=True)); partials are summed in index order.  mean_rstd (NULL ok):
+ *             fp32 [N][G][2] = (mean, rstd) per group, saved for ptivae_gn_bwd.
  *   gn_apply: y(h16) = act(x*scale + shift); act = SiLU when silu != 0 (AEKLResBlock:
  *             F.silu(norm(x))), identity otherwise (SpatialAttentionBlock.norm).  raw16 (may be
  *             NULL) additionally receives x rounded to h16 (the nin_shortcut operand). */
 int ptivae_gn_stats(const void* x, float* partial, int N, int HW, int C, int G, int in_fmt, void* stream);
 int ptivae_gn_stats_parts(int N, int HW, int C);
-int ptivae_gn_finalize(const float* partial, const float* gamma, const float* beta, float* scale_shift, int N, int HW,
-                       int C, int G, int P, float eps, void* stream);
+int ptivae_gn_finalize(const float* partial, const float* gamma, const float* beta, float* scale_shift,
+                       float* mean_rstd, int N, int HW, int C, int G, int P, float eps, void* stream);
 int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, void* raw16, int N, int HW, int C, int silu,
                     int in_fmt, int out_f16, void* stream);
 
@@ -137,9 +144,10 @@ int ptivae_conv1x1_small(const float* x, const float* w, const float* bias, floa
 
 /* Single-head self-attention core: out = softmax(Q K^T * D^-0.5) V; q,k,v h16 [B][L][ld] views (row stride ld >= D
  * elements, ld % 8 == 0: ld = 3*D for a fused q|k|v projection, ld = D for separate tensors), out h16 [B][L][D],
- * D in {64,128,256} (monai SABlock with num_heads = 1, use_flash_attention=False semantics). */
-int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D, int ld, int f16,
-                         void* stream);
+ * D in {64,128,256} (monai SABlock with num_heads = 1, use_flash_attention=False semantics).
+ * lse (NULL ok): fp32 [B][L], log2-domain log-sum-exp of the scaled score rows, saved for the backward pass. */
+int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int L, int D, int ld,
+                         int f16, void* stream);
 
 /* AutoencoderKL.sampling: z = mu + sigma*eps.  eps_in != NULL: use the injected noise; else draw
  * eps from Philox4x32-10 (key = seed, counter = (element/4, offset)) + Box-Muller.  eps_out (may be
@@ -194,6 +202,73 @@ int ptivae_eval_metrics_workspace(int B, int C, int H, int W);
  *   ptivae_local_normalize_workspace(B) bytes (fp64 partial sums, fixed order) */
 int ptivae_local_normalize(const float* x, float* out, float* stats, void* workspace, int B, int per_img, void* stream);
 int ptivae_local_normalize_workspace(int B);
+
+/* ---- backward pass (`loss_g.backward()`, vae_scripts/train_vae.py:444) -----------------
+ * Gradient tensors are NHWC; 16-bit gradient operands are bf16 (range), activations keep the forward's operand format.
+ *
+ * Weight gradient of a convolution on tcgen05 (replaces cuDNN wgrad): dw[co][ci][ky][kx] = sum dY[p][co]*X[p+tap][ci].
+ *   dy   h16 NHWC gradient of the conv output, Ca channels;  x  h16 NHWC conv input (as the forward GEMM read it), Cb channels
+ *   mode 0: 3x3 s1 p1, H,W = extent of x (= of dy)     1: F.pad(0,1,0,1)+3x3 s2, H,W = extent of x (dy is H/2 x W/2)
+ *        2: nearest x2 upsample + 3x3, H,W = extent of x (dy is 2H x 2W)     3: 1x1
+ *   dw   fp32 [Ca][Cb][3][3] (modes 0-2) or [Ca][Cb] (mode 3): the master-weight layout, overwritten
+ *   workspace: ptivae_wgrad_workspace(...) bytes of split-K partial sums (plain stores, summed in index order)
+ *   halo != 0 (mode 0 only): the three kx taps of a kernel row read one 18-pixel-wide TMA box */
+int ptivae_wgrad(const void* dy, const void* x, float* workspace, float* dw, int N, int H, int W, int Ca, int Cb, int mode,
+                 int dy_f16, int x_f16, int halo, void* stream);
+long long ptivae_wgrad_workspace(int N, int H, int W, int Ca, int Cb, int mode);
+
+/* Batched GEMM on tcgen05 with operands consumed as they lie in memory (attention backward):
+ *   out[b][m][n] = epi( sum_k A[b](m,k) * B[b](n,k) ),  16-bit operands (formats may differ), fp32 accumulate, 16-bit out.
+ *   a_mn == 0: A(m,k) at a[b*bs_a + m*lda + k] (K-major);  a_mn != 0: at a[b*bs_a + k*lda + m] (MN-major); same for b.
+ *   epi 0: acc*alpha;  1: exp2(acc*alpha - rowv[b][m]);  2: aux[b][m][n]*(acc - rowv[b][m])*alpha
+ *   leading dimensions / batch strides in elements (multiples of 8); N % 8 == 0. */
+int ptivae_bgemm(const void* a, const void* b, void* out, int B, int M, int N, int K, long long lda, long long bs_a, int a_mn,
+                 int a_f16, long long ldb, long long bs_b, int b_mn, int b_f16, long long ldo, long long bs_out, int out_f16,
+                 int epi, float alpha, const float* rowv, const void* aux, long long ld_aux, long long bs_aux, int aux_f16,
+                 void* stream);
+/* out[row] = sum_d a[row][d]*b[row][d] (16-bit rows with strides lda/ldb, fp32 out): rowsum(dO o O) of the softmax backward */
+int ptivae_rowdot(const void* a, const void* b, float* out, long long rows, int D, long long lda, long long ldb, int a_f16,
+                  int b_f16, void* stream);
+
+/* Backward of y = act(GroupNorm(x)) (act = SiLU when silu != 0), given da = dL/dy:
+ *   dx = scale_c*du - e_g - x*f_g (+ residual), du = da*act'(x*scale+shift);  dgamma/dbeta fp32 [C] (overwritten)
+ *   x (x_fmt), da (da_fmt), residual (res_fmt, NULL ok): NHWC [N][HW][C];  dx32 (fp32) and/or dx16 (bf16): at least one
+ *   scale_shift [N][C][2], mean_rstd [N][G][2] from ptivae_gn_finalize;  coef: fp32 [N][C][2] scratch
+ *   workspace: (N*P*C*2 + N*C*2) floats, P = ptivae_gn_bwd_parts(HW).  Deterministic, batch-invariant chunking. */
+int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fmt, const float* scale_shift, const float* mean_rstd,
+                  const float* gamma, const void* residual, int res_fmt, float* dx32, void* dx16, float* dgamma,
+                  float* dbeta, float* coef, float* workspace, int N, int HW, int C, int G, int silu, void* stream);
+int ptivae_gn_bwd_parts(int HW);
+/* bias gradient: out[c] = sum over rows of x[row][c] (x NHWC storage fmt); workspace ptivae_colsum_blocks(rows)*C floats */
+int ptivae_colsum(const void* x, float* out, float* workspace, long long rows, int C, int fmt, void* stream);
+int ptivae_colsum_blocks(long long rows);
+
+/* Weight (and thin-side bias) gradient of the thin-end 3x3 convs (ptivae_conv3x3_small_cin / _small_cout):
+ *   wide_is_input != 0: thin = dOut fp32 NCHW [N][Ct][H][W], wide = the conv's NHWC input (optional fused GroupNorm
+ *       affine scale_shift, as the forward applied it);  dw [Ct][C][3][3], db [Ct] (NULL ok)
+ *   wide_is_input == 0: thin = the conv's fp32 NCHW input, wide = dOut NHWC;  dw [C][Ct][3][3], db must be NULL */
+int ptivae_thin_wgrad(const float* thin, const void* wide, const float* scale_shift, float* dw, float* db, float* workspace,
+                      int N, int H, int W, int C, int Ct, int wide_fmt, int wide_is_input, void* stream);
+long long ptivae_thin_wgrad_workspace(int N, int H, int C, int Ct);
+/* Gradient through the latent head (AutoencoderKL.encode tail + sampling + post_quant_conv), fp32 NCHW [N][L][HW]:
+ *   in: dzq = dL/d(post_quant_conv out), dmu_ext / dsig_ext = gradients arriving at the returned z_mu / z_sigma (NULL ok),
+ *       eps, h (encoder stack output), mu, sigma, the three [L][L] weights and quant_conv_log_sigma's bias
+ *   out: dh = dL/dh, dmu, dlv (gradients at the two quant conv outputs), z = mu + sigma*eps (for dW of post_quant) */
+int ptivae_latent_bwd(const float* dzq, const float* dmu_ext, const float* dsig_ext, const float* eps, const float* h,
+                      const float* mu, const float* sigma, const float* wp, const float* wm, const float* ws, const float* bs,
+                      float* dh, float* dmu, float* dlv, float* z, int N, int HW, int L, void* stream);
+/* dw[i][j] = sum_{n,p} a[n][i][p]*b[n][j][p], db[i] = sum_{n,p} a[n][i][p] (NULL ok): gradients of a 1x1 latent conv */
+int ptivae_outer_reduce(const float* a, const float* b, float* dw, float* db, int N, int I, int J, int HW, void* stream);
+
+/* Gradients of the loss terms; gout points to the upstream gradient scalar(s) in DEVICE memory.
+ *   l1l2_bwd: d = gout[0]*sign(a-b)/n + gout[1]*2(a-b)/n   (outputs of ptivae_l1l2);  kl_bwd: see ptivae_kl_loss */
+int ptivae_l1l2_bwd(const float* a, const float* b, const float* gout, float* d, long long n, void* stream);
+int ptivae_kl_bwd(const float* mu, const float* t, const float* gout, float* dmu, float* dt, int N, int per_img,
+                  int input_is_logvar, void* stream);
+/* torch.optim.Adam (defaults) over one flat fp32 buffer; step_dev: device float = 1-based step of this update,
+ * incremented afterwards when advance != 0; grad_scale multiplies g (1/world_size after a sum all-reduce). */
+int ptivae_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                float grad_scale, float* step_dev, int advance, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,13 +36,13 @@ SIGNATURES = {
     "ptivae_pack_conv_weight": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats_parts": [_c_int] * 3,
-    "ptivae_gn_finalize": [_c_void_p] * 4 + [_c_int] * 5 + [_c_float, _c_void_p],
+    "ptivae_gn_finalize": [_c_void_p] * 5 + [_c_int] * 5 + [_c_float, _c_void_p],
     "ptivae_gn_apply": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
     "ptivae_conv3x3_small_cin": [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p],
     "ptivae_conv3x3_small_cin_parts": [_c_int] * 3,
     "ptivae_conv3x3_small_cout": [_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p],
     "ptivae_conv1x1_small": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
-    "ptivae_attention_fwd": [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p],
+    "ptivae_attention_fwd": [_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p],
     "ptivae_latent_sample": [_c_void_p] * 6 + [_c_ll, _c_ull, _c_ull, _c_void_p],
     "ptivae_rng_advance": [_c_void_p, _c_void_p],
     "ptivae_kl_loss": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
@@ -50,7 +50,27 @@ SIGNATURES = {
     "ptivae_spatial_mean": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
     "ptivae_ar_vae_loss": [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p] * 4,
     "ptivae_linear_act": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
+    # backward pass
+    "ptivae_wgrad": [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p],
+    "ptivae_wgrad_workspace": [_c_int] * 6,
+    "ptivae_bgemm": [_c_void_p] * 3 + [_c_int] * 4 + [_c_ll, _c_ll, _c_int, _c_int, _c_ll, _c_ll, _c_int, _c_int, _c_ll, _c_ll,
+                                                      _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_ll, _c_ll, _c_int,
+                                                      _c_void_p],
+    "ptivae_rowdot": [_c_void_p] * 3 + [_c_ll, _c_int, _c_ll, _c_ll, _c_int, _c_int, _c_void_p],
+    "ptivae_gn_bwd": [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int] +
+                     [_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p],
+    "ptivae_gn_bwd_parts": [_c_int],
+    "ptivae_colsum": [_c_void_p] * 3 + [_c_ll, _c_int, _c_int, _c_void_p],
+    "ptivae_colsum_blocks": [_c_ll],
+    "ptivae_thin_wgrad": [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p],
+    "ptivae_thin_wgrad_workspace": [_c_int] * 4,
+    "ptivae_latent_bwd": [_c_void_p] * 15 + [_c_int] * 3 + [_c_void_p],
+    "ptivae_outer_reduce": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
+    "ptivae_l1l2_bwd": [_c_void_p] * 4 + [_c_ll, _c_void_p],
+    "ptivae_kl_bwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],
+    "ptivae_adam": [_c_void_p] * 4 + [_c_ll] + [_c_float] * 5 + [_c_void_p, _c_int, _c_void_p],
 }
+_RESTYPE_LL = {"ptivae_wgrad_workspace", "ptivae_thin_wgrad_workspace"}
 
 _lib = None
 
@@ -77,7 +97,7 @@ def lib() -> ctypes.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export it
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_longlong if name in _RESTYPE_LL else ctypes.c_int
         _lib = handle
     return _lib
 

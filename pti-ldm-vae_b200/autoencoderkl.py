@@ -350,18 +350,30 @@ class AutoencoderKL(nn.Module):
         self._rng_dev = None  # device-resident (seed, offset) when running under CUDA-graph capture
 
     # -- helpers ------------------------------------------------------------------------------
-    def _prep(self, x: torch.Tensor) -> torch.Tensor:
+    def _prep(self, x: torch.Tensor, channels: int | None = None) -> torch.Tensor:
         if isinstance(x, torch.Tensor) and type(x) is not torch.Tensor:
             x = x.as_subclass(torch.Tensor)  # MONAI MetaTensor batches
         if not x.is_cuda:
             raise RuntimeError("B200 AutoencoderKL runs on CUDA only; there is no CPU fallback "
                                "(the CPU restatement lives in oracle/ and is test-only)")
+        channels = self.in_channels if channels is None else channels
+        if x.dim() != 4 or x.shape[1] != channels or x.shape[0] == 0 or x.shape[2] == 0 or x.shape[3] == 0:
+            raise ValueError(f"expected a non-empty [N, {channels}, H, W] tensor, got {tuple(x.shape)}")
+        dev = next(self.parameters()).device
+        if x.device != dev:
+            raise ValueError(f"input on {x.device} but the model is on {dev}")
         return x.detach().contiguous().float()
 
     def _check_mode(self) -> None:
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("the backward kernels (SURVEY 8a row a20) are not built yet: call under "
-                                      "torch.no_grad() / model.eval() -- forward, encode, decode are inference-only")
+            raise NotImplementedError("encode()/decode() on their own are inference entry points: call them under "
+                                      "torch.no_grad() / model.eval(); gradients flow through forward() "
+                                      "(train_vae.py:385 only ever differentiates the full pass)")
+
+    def invalidate_packed(self) -> None:
+        """Drop the cached 16-bit weight packs.  Needed after an in-place update that does not bump the parameters'
+        version counters (``p.data.copy_(...)``, a fused optimizer step on the flat buffer)."""
+        self._exec._packed.clear()
 
     def set_operand_dtype(self, dtype: torch.dtype) -> None:
         """Storage format of the tensor-core operands: torch.float16 (default) or torch.bfloat16."""
@@ -410,11 +422,16 @@ class AutoencoderKL(nn.Module):
             return self._decode(z)
 
     def _decode(self, z: torch.Tensor) -> torch.Tensor:
-        z = self._prep(z)
+        z = self._prep(z, self.latent_channels)
         zq = ops.conv1x1_small(z, self._exec.f32(self.post_quant_conv.conv.weight), self._exec.f32(self.post_quant_conv.conv.bias), 0)
         return self._exec.run_stack(self.decoder.blocks, zq)
 
     def forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        if self.training and torch.is_grad_enabled():
+            # differentiable path: forward with a tape + the backward kernels behind one autograd node whose inputs
+            # are x and every parameter (so DDP's reducer and find_unused_parameters see all of them)
+            from .training import VAEFunction
+            return VAEFunction.apply(self, x, eps, *self.parameters())
         z_mu, z_sigma = self.encode(x)
         z = self.sampling(z_mu, z_sigma, eps)
         return self.decode(z), z_mu, z_sigma

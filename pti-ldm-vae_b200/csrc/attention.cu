@@ -30,6 +30,7 @@ struct AttnArgs {
   int L;
   float scale_log2e;  // D^-0.5 * log2(e)
   uint16_t* out;
+  float* lse;         // optional [B][L]: log2-domain log-sum-exp of the scaled scores (saved for the backward pass)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -251,6 +252,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const bool valid = (q0 + m) < L;
+    if (args.lse != nullptr && hsel == 0 && valid)
+      args.lse[static_cast<size_t>(b) * L + q0 + m] = fmaf(m_ref, c2, log2f(l_run));
     uint16_t* optr = args.out + (static_cast<size_t>(b) * L + q0 + m) * D + hsel * HD;
 #pragma unroll 1
     for (int c = 0; c < HD / 32; ++c) {
@@ -277,7 +280,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 template <int D, int BKV, bool F16>
-static int launch_attn(const void* q, const void* k, const void* v, void* out, int B, int L, int ld, cudaStream_t stream) {
+static int launch_attn(const void* q, const void* k, const void* v, void* out, float* lse, int B, int L, int ld,
+                       cudaStream_t stream) {
   CUtensorMap tmQ, tmK, tmV;
   uint64_t dims[3] = {uint64_t(D), uint64_t(L), uint64_t(B)};
   uint64_t strides[2] = {uint64_t(ld) * 2, uint64_t(L) * ld * 2};   // ld = row stride of q/k/v in elements (>= D)
@@ -296,6 +300,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
   a.L = L;
   a.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   a.out = static_cast<uint16_t*>(out);
+  a.lse = lse;
   dim3 grid((L + 127) / 128, B);
   attn_fwd_kernel<D, BKV, F16><<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, a);
   return static_cast<int>(cudaGetLastError());
@@ -305,15 +310,15 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, i
 
 using namespace ptivae;
 
-extern "C" int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, int B, int L, int D,
-                                    int ld, int f16, void* stream_) {
+extern "C" int ptivae_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int L,
+                                    int D, int ld, int f16, void* stream_) {
   if (!q || !k || !v || !out || B <= 0 || L <= 0 || ld < D || ld % 8 != 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (D == 128) return f16 ? launch_attn<128, 128, true>(q, k, v, out, B, L, ld, stream)
-                           : launch_attn<128, 128, false>(q, k, v, out, B, L, ld, stream);
-  if (D == 256) return f16 ? launch_attn<256, 64, true>(q, k, v, out, B, L, ld, stream)
-                           : launch_attn<256, 64, false>(q, k, v, out, B, L, ld, stream);
-  if (D == 64) return f16 ? launch_attn<64, 128, true>(q, k, v, out, B, L, ld, stream)
-                          : launch_attn<64, 128, false>(q, k, v, out, B, L, ld, stream);
+  if (D == 128) return f16 ? launch_attn<128, 128, true>(q, k, v, out, lse, B, L, ld, stream)
+                           : launch_attn<128, 128, false>(q, k, v, out, lse, B, L, ld, stream);
+  if (D == 256) return f16 ? launch_attn<256, 64, true>(q, k, v, out, lse, B, L, ld, stream)
+                           : launch_attn<256, 64, false>(q, k, v, out, lse, B, L, ld, stream);
+  if (D == 64) return f16 ? launch_attn<64, 128, true>(q, k, v, out, lse, B, L, ld, stream)
+                          : launch_attn<64, 128, false>(q, k, v, out, lse, B, L, ld, stream);
   return PTIVAE_ERR_UNSUPPORTED;
 }

@@ -28,7 +28,7 @@ namespace ptivae {
 constexpr int kTW = 16;  // tile width  (pixels)
 constexpr int kTH = 8;   // tile height (pixels)
 constexpr int kMaxStages = 8;
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 16;
 
 struct ConvTap {
   int16_t dx, dy;   // offset added to the tile origin, in tensor-map coordinates
@@ -42,7 +42,7 @@ struct ConvArgs {
   int Hout, Wout;    // spatial extent of the output tensor
   int Cin, Cout;
   int os;            // output coordinate scale (2 for the up-sampling phases)
-  int ntaps;         // taps per phase
+  int ntaps[4];      // taps of each output phase
   int tiles_x, tiles_y;
   int nstages;
   int gn_groups;     // >0: write per-(n, tile, group) sum/sumsq of the stored output into gn_part
@@ -90,7 +90,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n0 = blockIdx.y * BN;
   const int phase_id = blockIdx.z;
   const int KC = args.Cin / KCH;
-  const int iters = args.ntaps * KC;
+  const int ntaps = args.ntaps[phase_id];
+  const int iters = ntaps * KC;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -112,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < args.ntaps; ++t) {
+      for (int t = 0; t < ntaps; ++t) {
         const ConvTap tap = args.taps[phase_id][t];
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -254,7 +255,9 @@ template <int KCH, int BN, bool F16>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs& a, int N, int nphase,
                        cudaStream_t stream) {
   constexpr int STAGE = (128 + BN) * KCH * 2;
-  const int iters = a.ntaps * (a.Cin / KCH);
+  int maxt = 0;
+  for (int p = 0; p < nphase; ++p) maxt = a.ntaps[p] > maxt ? a.ntaps[p] : maxt;
+  const int iters = maxt * (a.Cin / KCH);
   // These launches are one tile per CTA and latency bound (TMA fill + epilogue drain), so co-residency is
   // what hides it: aim for 3 CTAs per SM (<= ~72 KB each) rather than a deep pipeline.
   int stages = (62 * 1024) / STAGE;
@@ -287,12 +290,13 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!in || !w_packed || !bias || !out) return PTIVAE_ERR_ARG;
   if (N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
-  if (mode < 0 || mode > 3) return PTIVAE_ERR_ARG;
+  if (mode < 0 || mode > 6) return PTIVAE_ERR_ARG;
   if (!(Cin == 32 || (Cin % 64 == 0 && Cin <= 1024))) return PTIVAE_ERR_UNSUPPORTED;
   if (!(Cout == 32 || Cout == 64 || Cout % 128 == 0)) return PTIVAE_ERR_UNSUPPORTED;
-  if (mode == 1 && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;  // even extents only (F.pad(0,1,0,1) + s2)
+  if ((mode == 1 || mode == 6) && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;  // even extents only
   if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
     return PTIVAE_ERR_ARG;
+  if (gn_groups > 0 && mode > 3) return PTIVAE_ERR_ARG;
 
   ConvArgs a{};
   a.Cin = Cin;
@@ -311,34 +315,56 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
   uint64_t dims[5], strides[4];
   uint32_t box[5] = {static_cast<uint32_t>(KCH), kTW, 1, kTH, 1};
   const uint64_t C2 = uint64_t(Cin) * 2;
-  if (mode == 1) {
-    a.Ho = H / 2; a.Wo = W / 2; a.Hout = a.Ho; a.Wout = a.Wo; a.ntaps = 9;
+  if (mode == 1 || mode == 6) {
+    // parity-split view of the input: (2*Cin [x-parity, c], W/2, 2 [y-parity], H/2, N)
+    a.Ho = H / 2; a.Wo = W / 2; a.Hout = a.Ho; a.Wout = a.Wo;
     dims[0] = 2 * Cin; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
     strides[0] = 2 * C2; strides[1] = uint64_t(W) * C2; strides[2] = 2 * uint64_t(W) * C2;
     strides[3] = uint64_t(H) * W * C2;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        ConvTap& t = a.taps[0][ky * 3 + kx];
-        t.dy = ky >> 1; t.pz = ky & 1; t.dx = kx >> 1; t.cmul = kx & 1; t.wtap = ky * 3 + kx;
-      }
+    if (mode == 1) {
+      a.ntaps[0] = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          ConvTap& t = a.taps[0][ky * 3 + kx];
+          t.dy = ky >> 1; t.pz = ky & 1; t.dx = kx >> 1; t.cmul = kx & 1; t.wtap = ky * 3 + kx;
+        }
+    } else {
+      // mode 6: data gradient of mode 2.  Forward: out[2y+py][2x+px] += Wp[py][px][ty][tx] * x[y+dyf][x+dxf],
+      // dyf = (py == 0 ? ty - 1 : ty); so dx[y][x] += Wp^T * dY[2(y-dyf)+py][2(x-dxf)+px]: 16 taps over the parity view.
+      a.ntaps[0] = 16; T = 16;
+      int i = 0;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          for (int ty = 0; ty < 2; ++ty)
+            for (int tx = 0; tx < 2; ++tx) {
+              ConvTap& t = a.taps[0][i++];
+              t.dy = -((py == 0) ? ty - 1 : ty);
+              t.dx = -((px == 0) ? tx - 1 : tx);
+              t.pz = py; t.cmul = px;
+              t.wtap = ((py * 2 + px) * 2 + ty) * 2 + tx;
+            }
+    }
   } else {
     dims[0] = Cin; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
     strides[0] = C2; strides[1] = uint64_t(W) * C2; strides[2] = uint64_t(W) * C2; strides[3] = uint64_t(H) * W * C2;
     a.Ho = H; a.Wo = W;
-    if (mode == 0) {
-      a.Hout = H; a.Wout = W; a.ntaps = 9;
+    if (mode == 0 || mode == 4) {
+      // mode 4: data gradient of mode 0 = the same conv with the taps mirrored (weights packed transposed)
+      a.Hout = H; a.Wout = W; a.ntaps[0] = 9;
       for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
           ConvTap& t = a.taps[0][ky * 3 + kx];
-          t.dy = ky - 1; t.dx = kx - 1; t.pz = 0; t.cmul = 0; t.wtap = ky * 3 + kx;
+          t.dy = mode == 0 ? ky - 1 : 1 - ky; t.dx = mode == 0 ? kx - 1 : 1 - kx; t.pz = 0; t.cmul = 0;
+          t.wtap = ky * 3 + kx;
         }
     } else if (mode == 3) {
-      a.Hout = H; a.Wout = W; a.ntaps = 1; T = 1;
+      a.Hout = H; a.Wout = W; a.ntaps[0] = 1; T = 1;
       a.taps[0][0] = ConvTap{0, 0, 0, 0, 0};
-    } else {  // mode 2: 4 phases x (2x2) taps, weight slab index ((py*2+px)*2+ty)*2+tx
-      a.Hout = 2 * H; a.Wout = 2 * W; a.ntaps = 4; a.os = 2; nphase = 4; T = 16;
+    } else if (mode == 2) {  // 4 phases x (2x2) taps, weight slab index ((py*2+px)*2+ty)*2+tx
+      a.Hout = 2 * H; a.Wout = 2 * W; a.os = 2; nphase = 4; T = 16;
       for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px)
+        for (int px = 0; px < 2; ++px) {
+          a.ntaps[py * 2 + px] = 4;
           for (int ty = 0; ty < 2; ++ty)
             for (int tx = 0; tx < 2; ++tx) {
               ConvTap& t = a.taps[py * 2 + px][ty * 2 + tx];
@@ -347,6 +373,26 @@ extern "C" int ptivae_conv_umma(const void* in, const void* w_packed, const floa
               t.pz = 0; t.cmul = 0;
               t.wtap = ((py * 2 + px) * 2 + ty) * 2 + tx;
             }
+        }
+    } else {
+      // mode 5: data gradient of mode 1 (F.pad(0,1,0,1) + 3x3 stride 2).  y[oy] = sum_ky w[ky] xpad[2oy+ky], so
+      // dx[2a]   += w[0]^T dy[a] + w[2]^T dy[a-1]     (output phase 0: two taps)
+      // dx[2a+1] += w[1]^T dy[a]                       (output phase 1: one tap);  same along x.
+      a.Hout = 2 * H; a.Wout = 2 * W; a.os = 2; nphase = 4;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          int i = 0;
+          for (int ky = 0; ky < 3; ++ky) {
+            if ((ky & 1) != py) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+              if ((kx & 1) != px) continue;
+              ConvTap& t = a.taps[py * 2 + px][i++];
+              t.dy = ky == 2 ? -1 : 0; t.dx = kx == 2 ? -1 : 0; t.pz = 0; t.cmul = 0;
+              t.wtap = ky * 3 + kx;
+            }
+          }
+          a.ntaps[py * 2 + px] = i;
+        }
     }
   }
   a.tiles_x = (a.Wo + kTW - 1) / kTW;

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta,
-                                                          float* __restrict__ scale_shift, int N, int C, int G, int P,
+                                                          float* __restrict__ scale_shift,
+                                                          float* __restrict__ mean_rstd, int N, int C, int G, int P,
                                                           float inv_count, float eps) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,6 +126,10 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
+  if (mean_rstd != nullptr && lane == 0) {   // saved for the backward pass: [N][G][2]
+    mean_rstd[static_cast<size_t>(wid) * 2] = mean;
+    mean_rstd[static_cast<size_t>(wid) * 2 + 1] = rstd;
+  }
   const int cpg = C / G;
   for (int j = lane; j < cpg; j += 32) {
     const int c = g * cpg + j;
@@ -200,11 +205,11 @@ extern "C" int ptivae_gn_stats(const void* x, float* partial, int N, int HW, int
 }
 
 extern "C" int ptivae_gn_finalize(const float* partial, const float* gamma, const float* beta, float* scale_shift,
-                                  int N, int HW, int C, int G, int P, float eps, void* stream_) {
+                                  float* mean_rstd, int N, int HW, int C, int G, int P, float eps, void* stream_) {
   if (!partial || !gamma || !beta || !scale_shift || N <= 0 || C % G != 0 || P <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
-  gn_finalize_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(partial, gamma, beta, scale_shift, N, C, G, P, inv,
+  gn_finalize_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(partial, gamma, beta, scale_shift, mean_rstd, N, C, G, P, inv,
                                                                    eps);
   return static_cast<int>(cudaGetLastError());
 }

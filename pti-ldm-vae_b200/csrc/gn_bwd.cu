@@ -1,0 +1,300 @@
+// Backward of GroupNorm (+ SiLU) and the bias gradients (SURVEY.md 8a row a20 for rows a4/a5/a6; autograd of
+// `F.silu(norm(x))` in MONAI AEKLResBlock / SpatialAttentionBlock under train_vae.py:444).  HBM-bound.
+//
+// Forward (per image n, group g):  xh = (x - mean)*rstd,  u = gamma*xh + beta = x*scale + shift,  a = act(u).
+// Given dA (gradient of a, 16-bit):
+//     du   = dA * act'(u)                      act = SiLU: s = sigmoid(u), act' = s*(1 + u*(1 - s));  identity: 1
+//     S1_c = sum_hw du        S2_c = sum_hw du*xh           (per image, per channel)
+//     dbeta_c = sum_n S1_c    dgamma_c = sum_n S2_c
+//     dx   = rstd*(gamma*du - mean_g(gamma*du) - xh*mean_g(gamma*du*xh))  =  scale_c*du - e_g - x*f_g
+// Three deterministic stages (no atomics, fixed summation order, batch-invariant chunking):
+//   gn_bwd_reduce   : per (image, pixel chunk, channel) partial (S1, S2)
+//   gn_bwd_finalize : partials -> per-(image, channel) totals and the (e, f) coefficients; gn_bwd_param sums the
+//                     totals over the batch into dgamma / dbeta
+//   gn_bwd_apply    : dx (+ the gradient arriving over the residual connection) as fp32 stream and/or bf16 operand
+// colsum: bias gradient = per-channel sum of a 16-bit NHWC gradient tensor (two stages).
+#include "common.cuh"
+#include "ptivae_internal.h"
+
+namespace ptivae {
+
+__device__ __forceinline__ void ld8(const void* base, size_t vec_index, int fmt, float (&v)[8]) {
+  if (fmt == 2) {
+    const float4* p = reinterpret_cast<const float4*>(base) + vec_index * 2;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base) + vec_index);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (fmt == 1) unpack2<true>(w[e], v[2 * e], v[2 * e + 1]);
+      else unpack2<false>(w[e], v[2 * e], v[2 * e + 1]);
+    }
+  }
+}
+
+// du for one element
+template <bool kSilu>
+__device__ __forceinline__ float act_grad(float x, float sc, float sh, float da) {
+  if (!kSilu) return da;
+  const float u = fmaf(x, sc, sh);
+  const float s = 1.0f / (1.0f + __expf(-u));
+  return da * s * fmaf(u, 1.0f - s, 1.0f);
+}
+
+constexpr int kGbPix = 1024;   // pixels per reduce chunk (depends on the image only: batch-invariant summation order)
+
+// grid (chunks, N); block 256.  Thread t owns one 8-channel vector column and walks the chunk's pixels.
+template <bool kSilu>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restrict__ x, const void* __restrict__ da,
+                                                            const float* __restrict__ ss,
+                                                            const float* __restrict__ mr, float* __restrict__ partial,
+                                                            int HW, int C, int G, int x_fmt, int da_fmt) {
+  __shared__ float sm[256][17];
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const int v = threadIdx.x % vecs;
+  const int prow = threadIdx.x / vecs;
+  const int prows = blockDim.x / vecs;
+  const int p_begin = blockIdx.x * kGbPix;
+  const int p_end = min(HW, p_begin + kGbPix);
+  float sc[8], sh[8], mean[8], rstd[8];
+  const int cpg = C / G;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e;
+    sc[e] = __ldg(ss + (static_cast<size_t>(n) * C + c) * 2);
+    sh[e] = __ldg(ss + (static_cast<size_t>(n) * C + c) * 2 + 1);
+    mean[e] = __ldg(mr + (static_cast<size_t>(n) * G + c / cpg) * 2);
+    rstd[e] = __ldg(mr + (static_cast<size_t>(n) * G + c / cpg) * 2 + 1);
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  const size_t img = static_cast<size_t>(n) * HW * vecs;
+  if (prow < prows) {
+    for (int p = p_begin + prow; p < p_end; p += prows) {
+      float f[8], d[8];
+      ld8(x, img + static_cast<size_t>(p) * vecs + v, x_fmt, f);
+      ld8(da, img + static_cast<size_t>(p) * vecs + v, da_fmt, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float du = act_grad<kSilu>(f[e], sc[e], sh[e], d[e]);
+        s1[e] += du;
+        s2[e] = fmaf(du, (f[e] - mean[e]) * rstd[e], s2[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sm[threadIdx.x][e] = s1[e]; sm[threadIdx.x][8 + e] = s2[e]; }
+  __syncthreads();
+  // fixed-order fold over the pixel rows: thread c sums rows 0..prows-1 of its channel
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cv = c / 8, ce = c % 8;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < prows; ++r) {
+      a += sm[r * vecs + cv][ce];
+      b += sm[r * vecs + cv][8 + ce];
+    }
+    float* dst = partial + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C + c) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+// grid N; block = C rounded up to a warp (<= 1024).  totals [N][C][2], coef [N][C][2] = (e, f).
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                       const float* __restrict__ mr, float* __restrict__ totals,
+                                       float* __restrict__ coef, int C, int G, int P, float inv_count) {
+  extern __shared__ float st[];   // [C][2] gamma-weighted totals
+  const int n = blockIdx.x;
+  const int c = threadIdx.x;
+  if (c < C) {
+    float a = 0.f, b = 0.f;
+    const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * C + c;
+    for (int p = 0; p < P; ++p) {
+      const float2 t = __ldg(src + static_cast<size_t>(p) * C);
+      a += t.x;
+      b += t.y;
+    }
+    totals[(static_cast<size_t>(n) * C + c) * 2] = a;
+    totals[(static_cast<size_t>(n) * C + c) * 2 + 1] = b;
+    const float g = gamma[c];
+    st[2 * c] = g * a;
+    st[2 * c + 1] = g * b;
+  }
+  __syncthreads();
+  if (c < C) {
+    const int cpg = C / G;
+    const int g0 = (c / cpg) * cpg;
+    float p1 = 0.f, p2 = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      p1 += st[2 * (g0 + j)];
+      p2 += st[2 * (g0 + j) + 1];
+    }
+    const float mean = mr[(static_cast<size_t>(n) * G + c / cpg) * 2];
+    const float rstd = mr[(static_cast<size_t>(n) * G + c / cpg) * 2 + 1];
+    const float k1 = rstd * p1 * inv_count, k2 = rstd * p2 * inv_count;
+    coef[(static_cast<size_t>(n) * C + c) * 2] = k1 - mean * rstd * k2;
+    coef[(static_cast<size_t>(n) * C + c) * 2 + 1] = rstd * k2;
+  }
+}
+
+// dgamma_c = sum_n totals[n][c][1], dbeta_c = sum_n totals[n][c][0]   (index order)
+__global__ void gn_bwd_param_kernel(const float* __restrict__ totals, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    a += totals[(static_cast<size_t>(n) * C + c) * 2];
+    b += totals[(static_cast<size_t>(n) * C + c) * 2 + 1];
+  }
+  dbeta[c] = a;
+  dgamma[c] = b;
+}
+
+template <bool kSilu>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restrict__ x, const void* __restrict__ da,
+                                                           const float* __restrict__ ss,
+                                                           const float* __restrict__ coef,
+                                                           const void* __restrict__ residual, float* __restrict__ out32,
+                                                           uint4* __restrict__ out16, size_t total_vecs, int HW, int C,
+                                                           int x_fmt, int da_fmt, int res_fmt) {
+  const int vecs = C / 8;
+  const size_t per_img = static_cast<size_t>(HW) * vecs;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vecs;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / per_img);
+    const int v = static_cast<int>(i % vecs);
+    const float4* sp = reinterpret_cast<const float4*>(ss + (static_cast<size_t>(n) * C + v * 8) * 2);
+    const float4* cp = reinterpret_cast<const float4*>(coef + (static_cast<size_t>(n) * C + v * 8) * 2);
+    float f[8], d[8], r[8];
+    ld8(x, i, x_fmt, f);
+    ld8(da, i, da_fmt, d);
+    if (residual != nullptr) {
+      ld8(residual, i, res_fmt, r);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = 0.f;
+    }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 s4 = __ldg(sp + e);   // (scale0, shift0, scale1, shift1)
+      const float4 c4 = __ldg(cp + e);   // (e0, f0, e1, f1)
+      const float du0 = act_grad<kSilu>(f[2 * e], s4.x, s4.y, d[2 * e]);
+      const float du1 = act_grad<kSilu>(f[2 * e + 1], s4.z, s4.w, d[2 * e + 1]);
+      o[2 * e] = fmaf(s4.x, du0, -c4.x) - f[2 * e] * c4.y + r[2 * e];
+      o[2 * e + 1] = fmaf(s4.z, du1, -c4.z) - f[2 * e + 1] * c4.w + r[2 * e + 1];
+    }
+    if (out32 != nullptr) {
+      float4* op = reinterpret_cast<float4*>(out32) + i * 2;
+      op[0] = make_float4(o[0], o[1], o[2], o[3]);
+      op[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (out16 != nullptr)
+      out16[i] = make_uint4(pack2<false>(o[0], o[1]), pack2<false>(o[2], o[3]), pack2<false>(o[4], o[5]),
+                            pack2<false>(o[6], o[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- column sums
+// stage 1: grid (blocks); block 256 = (vecs x prows); block b walks rows [b*rpb, (b+1)*rpb) -> partial[b][C]
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ x, float* __restrict__ partial,
+                                                             long long rows, int C, int rows_per_block, int fmt) {
+  __shared__ float sm[256][9];
+  const int vecs = C / 8;
+  const int v = threadIdx.x % vecs;
+  const int prow = threadIdx.x / vecs;
+  const int prows = blockDim.x / vecs;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  if (prow < prows) {
+    for (long long r = r0 + prow; r < r1; r += prows) {
+      float f[8];
+      ld8(x, static_cast<size_t>(r) * vecs + v, fmt, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm[threadIdx.x][e] = s[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < prows; ++r) a += sm[r * vecs + c / 8][c % 8];
+    partial[static_cast<size_t>(blockIdx.x) * C + c] = a;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += partial[static_cast<size_t>(b) * C + c];
+  out[c] = a;
+}
+
+}  // namespace ptivae
+
+using namespace ptivae;
+
+extern "C" int ptivae_gn_bwd_parts(int HW) { return HW <= 0 ? PTIVAE_ERR_ARG : (HW + kGbPix - 1) / kGbPix; }
+
+// workspace floats: partial N*P*C*2 + totals N*C*2  (P = ptivae_gn_bwd_parts(HW))
+extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fmt, const float* scale_shift,
+                             const float* mean_rstd, const float* gamma, const void* residual, int res_fmt,
+                             float* dx32, void* dx16, float* dgamma, float* dbeta, float* coef, float* workspace,
+                             int N, int HW, int C, int G, int silu, void* stream_) {
+  if (!x || !da || !scale_shift || !mean_rstd || !gamma || !dgamma || !dbeta || !coef || !workspace ||
+      (!dx32 && !dx16))
+    return PTIVAE_ERR_ARG;
+  if (N <= 0 || HW <= 0 || C % 8 != 0 || G <= 0 || C % G != 0 || C > 1024 || 256 % (C / 8) != 0 || x_fmt < 0 ||
+      x_fmt > 2 || da_fmt < 0 || da_fmt > 2 || res_fmt < 0 || res_fmt > 2)
+    return PTIVAE_ERR_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int P = (HW + kGbPix - 1) / kGbPix;
+  float* partial = workspace;
+  float* totals = workspace + static_cast<size_t>(N) * P * C * 2;
+  dim3 grid(P, N);
+  if (silu) gn_bwd_reduce_kernel<true><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, HW, C, G, x_fmt, da_fmt);
+  else gn_bwd_reduce_kernel<false><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, HW, C, G, x_fmt, da_fmt);
+  const int bt = ((C + 31) / 32) * 32;
+  const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
+  gn_bwd_finalize_kernel<<<N, bt, C * 2 * sizeof(float), stream>>>(partial, gamma, mean_rstd, totals, coef, C, G, P, inv);
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(totals, dgamma, dbeta, N, C);
+  const size_t total = static_cast<size_t>(N) * HW * (C / 8);
+  const int g2 = grid_for(total, 256, 148 * 32);
+  if (silu)
+    gn_bwd_apply_kernel<true><<<g2, 256, 0, stream>>>(x, da, scale_shift, coef, residual, dx32, static_cast<uint4*>(dx16),
+                                                      total, HW, C, x_fmt, da_fmt, res_fmt);
+  else
+    gn_bwd_apply_kernel<false><<<g2, 256, 0, stream>>>(x, da, scale_shift, coef, residual, dx32, static_cast<uint4*>(dx16),
+                                                       total, HW, C, x_fmt, da_fmt, res_fmt);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// out[c] = sum over rows of x[row][c]; workspace: ptivae_colsum_blocks(rows) * C floats
+extern "C" int ptivae_colsum_blocks(long long rows) {
+  if (rows <= 0) return PTIVAE_ERR_ARG;
+  long long b = (rows + 2047) / 2048;
+  if (b > 592) b = 592;
+  return static_cast<int>(b);
+}
+extern "C" int ptivae_colsum(const void* x, float* out, float* workspace, long long rows, int C, int fmt,
+                             void* stream_) {
+  if (!x || !out || !workspace || rows <= 0 || C % 8 != 0 || C > 2048 || 256 % (C / 8 > 256 ? 256 : C / 8) != 0 ||
+      fmt < 0 || fmt > 2)
+    return PTIVAE_ERR_ARG;
+  if (C / 8 > 256) return PTIVAE_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int blocks = ptivae_colsum_blocks(rows);
+  const int rpb = static_cast<int>((rows + blocks - 1) / blocks);
+  colsum_partial_kernel<<<blocks, 256, 0, stream>>>(x, workspace, rows, C, rpb, fmt);
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, out, blocks, C);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -153,14 +153,16 @@ __global__ void l1l2_final_kernel(const float* __restrict__ partial, float* __re
 // ----------------------------------------------------------------------------- weight packing
 // out[t][co][ci] = sum over source taps selected by mask[t] (bit ky*3+kx) of w[co][ci][ky][kx]
 struct PackMasks { uint32_t m[16]; };
+// transpose != 0: out[t][ci][co] instead (the operand of the data-gradient convolution, whose GEMM K is Cout)
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin,
-                                   int ksq, int T, PackMasks masks, int f16) {
+                                   int ksq, int T, PackMasks masks, int f16, int transpose) {
   const size_t total = static_cast<size_t>(T) * Cout * Cin;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % Cin);
-    const int co = static_cast<int>((i / Cin) % Cout);
     const int t = static_cast<int>(i / (static_cast<size_t>(Cin) * Cout));
+    const int r = static_cast<int>(i % (static_cast<size_t>(Cin) * Cout));
+    const int ci = transpose ? r / Cout : r % Cin;
+    const int co = transpose ? r % Cout : r / Cin;
     const float* src = w + (static_cast<size_t>(co) * Cin + ci) * ksq;
     float a = 0.f;
     const uint32_t m = masks.m[t];
@@ -217,10 +219,12 @@ extern "C" int ptivae_l1l2(const float* a, const float* b, float* workspace, flo
 }
 
 // mode 0: plain (T = k*k slabs, tap-major).  mode 2: the 4-phase nearest-x2-upsample decomposition
-// (T = 16 slabs ordered [py][px][ty][tx]; k must be 3).
+// (T = 16 slabs ordered [py][px][ty][tx]; k must be 3).  mode | 4: the same slabs transposed ([T][Cin][Cout]).
 extern "C" int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, int f16,
                                        void* stream_) {
-  if (!w || !out || Cout <= 0 || Cin <= 0 || !(k == 1 || k == 3) || !(mode == 0 || mode == 2)) return PTIVAE_ERR_ARG;
+  if (!w || !out || Cout <= 0 || Cin <= 0 || !(k == 1 || k == 3) || !(mode == 0 || mode == 2 || mode == 4 || mode == 6)) return PTIVAE_ERR_ARG;
+  const int transpose = mode >> 2;
+  mode &= 3;
   if (mode == 2 && k != 3) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PackMasks pm{};
@@ -249,6 +253,6 @@ extern "C" int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int 
   }
   const size_t total = static_cast<size_t>(T) * Cout * Cin;
   pack_conv_w_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, static_cast<uint16_t*>(out), Cout, Cin, k * k, T, pm,
-                                                               f16);
+                                                               f16, transpose);
   return static_cast<int>(cudaGetLastError());
 }

@@ -1,0 +1,386 @@
+// Weight gradient of the convolutions on the sm_100a tensor cores (the backward of rows
+// a3/a4/a7/a8/a12 that autograd runs for `loss_g.backward()`, /root/reference/vae_scripts/train_vae.py:444;
+// cuDNN's wgrad in the reference).
+//
+//   dW[tap][co][ci] = sum over images and pixels p of  dY[p][co] * X[p + tap][ci]
+//
+// GEMM view:  M = Cout (dY channels, padded to 128 lanes), N = Cin block (64 or 128 columns), K = pixels.
+// Both operands are NHWC, i.e. channel-contiguous = "MN-major" for this GEMM: a TMA box of (64 channels x 16 pixels x
+// 4 rows) lands in shared memory as 64 K-rows of 128 bytes (SWIZZLE_128B), which the MN-major UMMA descriptor reads
+// directly (LBO = stride between 64-channel atoms, SBO = 8 K-rows).  No transpose, no im2col: the tap shift is a
+// TMA coordinate offset and the zero padding is TMA out-of-bounds fill.  The two operands may use different 16-bit
+// formats in one MMA (kind::f16 has independent A/B format fields): gradients are bf16 (range), activations fp16.
+//
+//   CTA     : one (split-K range of pixel tiles) x (tap group: up to 4 taps that share the dY tile) x (Cout block,
+//             Cin block).  The taps of a group accumulate into separate TMEM column ranges [t*nb, (t+1)*nb).
+//   halo    : for the stride-1 3x3 conv a tap group is one kernel row ky; its three kx taps read ONE 18-pixel-wide
+//             box, shifted by kx lines (the swizzle is a function of the absolute shared-memory address, so a
+//             128-byte-aligned start is legal) -- B traffic 1.125x instead of 3x.
+//   output  : fp32 partial sums [split][slab][Cout][Cin] with plain stores; wgrad_reduce_kernel adds the splits in
+//             index order (deterministic) and writes the master layout [Cout][Cin][kh][kw] (for the up-sampling conv it
+//             also folds the 16 phase-tap slabs back onto the 9 taps).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include "common.cuh"
+#include "ptivae_internal.h"
+
+namespace ptivae {
+
+constexpr int kWTW = 16;        // tile width  (pixels) = one UMMA K step
+constexpr int kWTH = 4;         // tile height (rows)
+constexpr int kWMaxTaps = 4;
+constexpr int kWMaxGroups = 4;
+constexpr int kWMaxStages = 8;
+constexpr uint32_t kWAtom = 64u * 128u;                 // 64 pixels x 64 channels x 2 B
+constexpr uint32_t kWHaloAtom = kWTH * 18u * 128u;      // 4 rows x 18 pixels x 64 channels x 2 B  (9216 = 9 * 1024)
+
+struct WTap {
+  int16_t dx, dy;   // offset of the activation box relative to the dY tile origin (tensor-map coordinates)
+  int16_t pz;       // coordinate along the parity dim of the activation map
+  int16_t cmul;     // channel-dim base = cmul * Cb
+  int32_t slab;     // output slab index
+};
+struct WGroup {
+  int16_t a_pz, a_cmul;   // parity coordinates of the dY map (up-sampling conv), else 0
+  int16_t ntaps, halo;    // halo != 0: the taps are kx = 0..2 of one 18-wide box loaded at (dx, dy) of taps[0]
+  WTap taps[kWMaxTaps];
+};
+struct WgradArgs {
+  int tiles_x, tiles_y, total_tiles, tiles_per_split;
+  int Ca, Cb;        // channels of dY (GEMM M) and of the activation (GEMM N)
+  int nb;            // UMMA N: 64 or 128
+  int n_cb_blocks;
+  int nslabs, nstages;
+  uint32_t idesc;
+  uint32_t b_bytes, stage_bytes, tmem_cols;
+  WGroup groups[kWMaxGroups];
+  float* partial;    // [splits][nslabs][Ca][Cb]
+};
+
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmBh, const WgradArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const int nstages = args.nstages;
+  const uint32_t stage_bytes = args.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kWMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kWMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const WGroup& grp = args.groups[blockIdx.y];
+  const int ca_blk = blockIdx.z / args.n_cb_blocks;
+  const int cb_blk = blockIdx.z - ca_blk * args.n_cb_blocks;
+  const int ca0 = ca_blk * 128, cb0 = cb_blk * args.nb;
+  const int na_atoms = min(2, (args.Ca - ca0 + 63) / 64);
+  const int nb_atoms = args.nb / 64;
+  const int ntaps = grp.ntaps;
+  const bool halo = grp.halo != 0;
+  const int t_begin = split * args.tiles_per_split;
+  const int t_end = min(args.total_tiles, t_begin + args.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(halo ? &tmBh : &tmB);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_ptr_smem, args.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = na_atoms * kWAtom + (halo ? nb_atoms * kWHaloAtom : ntaps * nb_atoms * kWAtom);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int tix = t % args.tiles_x;
+        const int tiy = (t / args.tiles_x) % args.tiles_y;
+        const int n = t / (args.tiles_x * args.tiles_y);
+        const int x0 = tix * kWTW, y0 = tiy * kWTH;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        uint8_t* sa = smem + s * stage_bytes;
+        uint8_t* sb = sa + 2 * kWAtom;
+        for (int a = 0; a < na_atoms; ++a)
+          tma_load_5d(sa + a * kWAtom, &tmA, &full_bar[s], grp.a_cmul * args.Ca + ca0 + a * 64, x0, grp.a_pz, y0, n);
+        if (halo) {
+          const WTap tp = grp.taps[0];
+          for (int b = 0; b < nb_atoms; ++b)
+            tma_load_5d(sb + b * kWHaloAtom, &tmBh, &full_bar[s], cb0 + b * 64, x0 + tp.dx, 0, y0 + tp.dy, n);
+        } else {
+          for (int k = 0; k < ntaps; ++k) {
+            const WTap tp = grp.taps[k];
+            for (int b = 0; b < nb_atoms; ++b)
+              tma_load_5d(sb + (k * nb_atoms + b) * kWAtom, &tmB, &full_bar[s], tp.cmul * args.Cb + cb0 + b * 64,
+                          x0 + tp.dx, tp.pz, y0 + tp.dy, n);
+          }
+        }
+        if (++s == nstages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t a_hi = desc_hi(1024, kLayoutSW128);
+      const uint32_t b_hi = a_hi;
+      const uint32_t b_lbo = halo ? kWHaloAtom : kWAtom;
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * stage_bytes);
+        const uint32_t sb = sa + 2 * kWAtom;
+#pragma unroll
+        for (int r = 0; r < kWTH; ++r) {
+          const uint32_t a_lo = desc_lo(sa + r * 2048u, kWAtom);
+          for (int k = 0; k < ntaps; ++k) {
+            const uint32_t baddr = halo ? sb + (r * 18u + k) * 128u : sb + k * nb_atoms * kWAtom + r * 2048u;
+            umma_f16_lohi(tmem_base + k * args.nb, a_lo, a_hi, desc_lo(baddr, b_lbo), b_hi, args.idesc, accum);
+          }
+          accum = 1;
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == nstages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;                      // TMEM lane quarter
+    const int m = q * 32 + lane;
+    const int ca = ca0 + m;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __syncwarp();
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const bool empty = t_end <= t_begin;         // (host never launches an empty split; defensive)
+    for (int k = 0; k < ntaps; ++k) {
+      float* dst = args.partial + ((static_cast<size_t>(split) * args.nslabs + grp.taps[k].slab) * args.Ca + ca) * args.Cb + cb0;
+      for (int c = 0; c < args.nb / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_addr + k * args.nb + c * 32, r);
+        tmem_ld_wait();
+        if (ca < args.Ca && cb0 + c * 32 < args.Cb) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 v = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]),
+                                   __uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
+            if (empty) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + c * 32 + 4 * u) = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, args.tmem_cols);
+}
+
+// out[(ca*Cb + cb)*T + t] = sum over slabs in masks[t], then over splits (index order), of partial[split][slab][ca][cb]
+struct SlabMasks { uint32_t m[9]; };
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                           int splits, int nslabs, int Ca, int Cb, int T,
+                                                           SlabMasks masks) {
+  const size_t plane = static_cast<size_t>(Ca) * Cb;
+  const size_t total = plane * T;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / plane);
+    const size_t e = i - t * plane;   // ca * Cb + cb
+    const uint32_t m = masks.m[t];
+    float acc = 0.f;
+    for (int sl = 0; sl < nslabs; ++sl) {
+      if (!(m >> sl & 1u)) continue;
+      const float* src = partial + sl * plane + e;
+      float a = 0.f;
+      for (int sp = 0; sp < splits; ++sp) a += __ldg(src + static_cast<size_t>(sp) * nslabs * plane);
+      acc += a;
+    }
+    out[e * T + t] = acc;
+  }
+}
+
+struct WgradPlan {
+  int tiles_x, tiles_y, total_tiles, tiles_per_split, splits;
+  int nb, n_ca_blocks, n_cb_blocks, ngroups, nslabs, T;
+};
+
+// mode 0: 3x3 stride 1 pad 1 (H, W = extent of x and dY)      1: F.pad(0,1,0,1) + 3x3 stride 2 (H, W = extent of x)
+// mode 2: nearest x2 upsample + 3x3 (H, W = extent of x)      3: 1x1
+static int wgrad_plan(int N, int H, int W, int Ca, int Cb, int mode, WgradPlan* p) {
+  if (N <= 0 || H <= 0 || W <= 0 || Ca <= 0 || Cb <= 0 || mode < 0 || mode > 3) return PTIVAE_ERR_ARG;
+  if (Ca % 8 != 0 || Cb % 8 != 0) return PTIVAE_ERR_UNSUPPORTED;
+  if (mode == 1 && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;
+  const int Ho = mode == 1 ? H / 2 : H, Wo = mode == 1 ? W / 2 : W;   // grid the tiles walk (dY pixels; low-res for mode 2)
+  p->tiles_x = (Wo + kWTW - 1) / kWTW;
+  p->tiles_y = (Ho + kWTH - 1) / kWTH;
+  p->total_tiles = p->tiles_x * p->tiles_y * N;
+  p->nb = Cb > 64 ? 128 : 64;
+  p->n_ca_blocks = (Ca + 127) / 128;
+  p->n_cb_blocks = (Cb + p->nb - 1) / p->nb;
+  p->ngroups = mode == 3 ? 1 : (mode == 2 ? 4 : 3);
+  p->nslabs = mode == 3 ? 1 : (mode == 2 ? 16 : 9);
+  p->T = mode == 3 ? 1 : 9;
+  // split K so that the grid is about two waves of 148 CTAs, but keep >= 8 tiles (32 UMMA K steps) per CTA: the
+  // fp32 partials cost 4*taps*Ca*Cb bytes per split
+  const int per = p->ngroups * p->n_ca_blocks * p->n_cb_blocks;
+  int splits = (2 * 148 + per - 1) / per;
+  const int max_by_work = (p->total_tiles + 7) / 8;
+  if (splits > max_by_work) splits = max_by_work;
+  if (splits < 1) splits = 1;
+  p->tiles_per_split = (p->total_tiles + splits - 1) / splits;
+  p->splits = (p->total_tiles + p->tiles_per_split - 1) / p->tiles_per_split;   // every split is non-empty
+  return PTIVAE_OK;
+}
+
+}  // namespace ptivae
+
+using namespace ptivae;
+
+extern "C" long long ptivae_wgrad_workspace(int N, int H, int W, int Ca, int Cb, int mode) {
+  WgradPlan p;
+  const int rc = wgrad_plan(N, H, W, Ca, Cb, mode, &p);
+  if (rc != PTIVAE_OK) return rc;
+  return static_cast<long long>(p.splits) * p.nslabs * Ca * Cb * 4;
+}
+
+extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, float* dw, int N, int H, int W, int Ca,
+                            int Cb, int mode, int dy_f16, int x_f16, int halo, void* stream_) {
+  if (!dy || !x || !workspace || !dw) return PTIVAE_ERR_ARG;
+  WgradPlan p;
+  int rc = wgrad_plan(N, H, W, Ca, Cb, mode, &p);
+  if (rc != PTIVAE_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+  WgradArgs a{};
+  a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y; a.total_tiles = p.total_tiles; a.tiles_per_split = p.tiles_per_split;
+  a.Ca = Ca; a.Cb = Cb; a.nb = p.nb; a.n_cb_blocks = p.n_cb_blocks; a.nslabs = p.nslabs;
+  a.partial = workspace;
+  // instruction descriptor: fp32 accumulate, A = dY, B = activations, both MN-major, M = 128, N = nb
+  const uint32_t afmt = dy_f16 ? 0u : 1u, bfmt = x_f16 ? 0u : 1u;
+  a.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t(p.nb) >> 3) << 17) |
+            ((128u >> 4) << 24);
+
+  // tensor maps: both operands as 5-D (C, W, parity, H, N) views with a (64, 16, 1, 4, 1) box
+  uint64_t da[5], sa[4], db[5], sb[4];
+  uint32_t box[5] = {64, kWTW, 1, kWTH, 1};
+  uint32_t boxh[5] = {64, 18, 1, kWTH, 1};
+  const uint64_t A2 = uint64_t(Ca) * 2, B2 = uint64_t(Cb) * 2;
+  auto plain = [](uint64_t* d, uint64_t* s, uint64_t C2b, int C, int Hh, int Ww, int Nn) {
+    d[0] = C; d[1] = Ww; d[2] = 1; d[3] = Hh; d[4] = Nn;
+    s[0] = C2b; s[1] = uint64_t(Ww) * C2b; s[2] = uint64_t(Ww) * C2b; s[3] = uint64_t(Hh) * Ww * C2b;
+  };
+  auto parity = [](uint64_t* d, uint64_t* s, uint64_t C2b, int C, int Hh, int Ww, int Nn) {   // Hh, Ww even: full-res extent
+    d[0] = 2 * C; d[1] = Ww / 2; d[2] = 2; d[3] = Hh / 2; d[4] = Nn;
+    s[0] = 2 * C2b; s[1] = uint64_t(Ww) * C2b; s[2] = 2 * uint64_t(Ww) * C2b; s[3] = uint64_t(Hh) * Ww * C2b;
+  };
+  bool use_halo = false;
+  if (mode == 0) {
+    plain(da, sa, A2, Ca, H, W, N);
+    plain(db, sb, B2, Cb, H, W, N);
+    use_halo = halo != 0;
+    for (int ky = 0; ky < 3; ++ky) {
+      WGroup& g = a.groups[ky];
+      g.a_pz = 0; g.a_cmul = 0; g.ntaps = 3; g.halo = use_halo ? 1 : 0;
+      for (int kx = 0; kx < 3; ++kx) g.taps[kx] = WTap{int16_t(kx - 1), int16_t(ky - 1), 0, 0, ky * 3 + kx};
+    }
+  } else if (mode == 1) {
+    plain(da, sa, A2, Ca, H / 2, W / 2, N);
+    parity(db, sb, B2, Cb, H, W, N);
+    for (int ky = 0; ky < 3; ++ky) {
+      WGroup& g = a.groups[ky];
+      g.a_pz = 0; g.a_cmul = 0; g.ntaps = 3; g.halo = 0;
+      for (int kx = 0; kx < 3; ++kx)
+        g.taps[kx] = WTap{int16_t(kx >> 1), int16_t(ky >> 1), int16_t(ky & 1), int16_t(kx & 1), ky * 3 + kx};
+    }
+  } else if (mode == 2) {
+    parity(da, sa, A2, Ca, 2 * H, 2 * W, N);
+    plain(db, sb, B2, Cb, H, W, N);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        WGroup& g = a.groups[py * 2 + px];
+        g.a_pz = int16_t(py); g.a_cmul = int16_t(px); g.ntaps = 4; g.halo = 0;
+        for (int ty = 0; ty < 2; ++ty)
+          for (int tx = 0; tx < 2; ++tx)
+            g.taps[ty * 2 + tx] = WTap{int16_t(px == 0 ? tx - 1 : tx), int16_t(py == 0 ? ty - 1 : ty), 0, 0,
+                                       ((py * 2 + px) * 2 + ty) * 2 + tx};
+      }
+  } else {
+    plain(da, sa, A2, Ca, H, W, N);
+    plain(db, sb, B2, Cb, H, W, N);
+    WGroup& g = a.groups[0];
+    g.a_pz = 0; g.a_cmul = 0; g.ntaps = 1; g.halo = 0;
+    g.taps[0] = WTap{0, 0, 0, 0, 0};
+  }
+  CUtensorMap tmA, tmB, tmBh;
+  rc = encode_tmap_16(&tmA, dy, 5, da, sa, box, 128, dy_f16 != 0);
+  if (rc != PTIVAE_OK) return rc;
+  rc = encode_tmap_16(&tmB, x, 5, db, sb, box, 128, x_f16 != 0);
+  if (rc != PTIVAE_OK) return rc;
+  rc = encode_tmap_16(&tmBh, x, 5, db, sb, use_halo ? boxh : box, 128, x_f16 != 0);
+  if (rc != PTIVAE_OK) return rc;
+
+  const int max_taps = mode == 3 ? 1 : (mode == 2 ? 4 : 3);
+  const int nb_atoms = p.nb / 64;
+  a.b_bytes = use_halo ? nb_atoms * kWHaloAtom : max_taps * nb_atoms * kWAtom;
+  a.stage_bytes = 2 * kWAtom + a.b_bytes;
+  int stages = (200 * 1024) / static_cast<int>(a.stage_bytes);
+  if (stages > kWMaxStages) stages = kWMaxStages;
+  if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
+  if (stages < 2) stages = 2;
+  a.nstages = stages;
+  uint32_t cols = uint32_t(max_taps * p.nb);
+  uint32_t pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  a.tmem_cols = pow2;
+  if (pow2 > 512) return PTIVAE_ERR_UNSUPPORTED;
+  const size_t smem = size_t(stages) * a.stage_bytes + 1024 + (2 * kWMaxStages + 1) * 8 + 16;
+  if (smem > 227 * 1024) return PTIVAE_ERR_UNSUPPORTED;
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(wgrad_umma_kernel, 227 * 1024, attr_set)) return rc_attr;
+  dim3 grid(p.splits, p.ngroups, p.n_ca_blocks * p.n_cb_blocks);
+  wgrad_umma_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, tmBh, a);
+  rc = static_cast<int>(cudaGetLastError());
+  if (rc != 0) return rc;
+
+  SlabMasks sm{};
+  if (mode == 2) {
+    // adjoint of the pre-summed phase taps (ptivae_pack_conv_weight mode 2): tap (ky, kx) collects every phase slab
+    // whose mask contains it
+    auto tsel = [](int p_, int k) { return p_ == 0 ? (k == 0 ? 0 : 1) : (k == 2 ? 1 : 0); };
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        uint32_t m = 0;
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) m |= 1u << (((py * 2 + px) * 2 + tsel(py, ky)) * 2 + tsel(px, kx));
+        sm.m[ky * 3 + kx] = m;
+      }
+  } else {
+    for (int t = 0; t < p.T; ++t) sm.m[t] = 1u << t;
+  }
+  const size_t total = static_cast<size_t>(Ca) * Cb * p.T;
+  wgrad_reduce_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(workspace, dw, p.splits, p.nslabs, Ca, Cb, p.T, sm);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -8,23 +8,64 @@ import torch
 from . import ops
 
 
+class _KLFn(torch.autograd.Function):
+    """compute_kl_loss with its gradient kernel; the upstream gradient stays on the device (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, mu, t, input_is_logvar):
+        mu_c, t_c = mu.detach().contiguous().float(), t.detach().contiguous().float()
+        ctx.save_for_backward(mu_c, t_c)
+        ctx.is_logvar = bool(input_is_logvar)
+        return ops.kl_loss(mu_c, t_c, ctx.is_logvar)
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, t = ctx.saved_tensors
+        dmu, dt = ops.kl_bwd(mu, t, g.detach().reshape(1).float().contiguous(), ctx.is_logvar)
+        return dmu, dt, None
+
+
+class _L1L2Fn(torch.autograd.Function):
+    """(mean |a-b|, mean (a-b)^2) as one pass; gradient w.r.t. both arguments."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a_c, b_c = a.detach().contiguous().float(), b.detach().contiguous().float()
+        ctx.save_for_backward(a_c, b_c)
+        return ops.l1l2(a_c, b_c)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        d = ops.l1l2_bwd(a, b, g.detach().float().contiguous())
+        return (d if ctx.needs_input_grad[0] else None), (-d if ctx.needs_input_grad[1] else None)
+
+
+def _wants_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
+
+
 def compute_kl_loss(z_mu: torch.Tensor, z_logvar: torch.Tensor, *, input_is_logvar: bool = True) -> torch.Tensor:
     """KL of a diagonal Gaussian, batch mean.  As the reference calls it (train_vae.py:394) the second
-    argument is sigma interpreted as log-variance; that quirk is preserved bit-for-formula."""
+    argument is sigma interpreted as log-variance; that quirk is preserved bit-for-formula.  Differentiable."""
+    if _wants_grad(z_mu, z_logvar):
+        return _KLFn.apply(z_mu, z_logvar, input_is_logvar)
     return ops.kl_loss(z_mu, z_logvar, input_is_logvar)
 
 
+def l1_and_mse(a: torch.Tensor, b: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    r = _L1L2Fn.apply(a, b) if _wants_grad(a, b) else ops.l1l2(a, b)
+    return r[0], r[1]
+
+
 def l1_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    return ops.l1l2(a, b)[0]
+    """nn.L1Loss() (mean), differentiable."""
+    return l1_and_mse(a, b)[0]
 
 
 def mse_loss(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    return ops.l1l2(a, b)[1]
-
-
-def l1_and_mse(a: torch.Tensor, b: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-    r = ops.l1l2(a, b)
-    return r[0], r[1]
+    """nn.MSELoss() (mean), differentiable."""
+    return l1_and_mse(a, b)[1]
 
 
 def compute_total_loss(recons_loss, kl_loss, perceptual_loss, adv_gen_loss, ar_loss, *, kl_weight: float,

@@ -62,14 +62,15 @@ def _need_cuda(*ts):
 
 
 def pack_conv_weight(w: torch.Tensor, mode: int = 0, dtype: torch.dtype = F16) -> torch.Tensor:
-    """fp32 [Cout,Cin,k,k] (or Linear [out,in]) -> 16-bit [T,Cout,Cin]."""
+    """fp32 [Cout,Cin,k,k] (or Linear [out,in]) -> 16-bit [T,Cout,Cin]; mode | 4: transposed slabs [T,Cin,Cout]
+    (the operand of the data-gradient convolutions, conv_umma modes 4/5/6 and the transposed 1x1)."""
     _need_cuda(w)
     if w.dim() == 2:
         w = w[:, :, None, None]
     w = w.detach().contiguous().float()
     cout, cin, k, _ = w.shape
-    t = 16 if mode == 2 else k * k
-    out = torch.empty((t, cout, cin), device=w.device, dtype=dtype)
+    t = 16 if (mode & 3) == 2 else k * k
+    out = torch.empty((t, cin, cout) if mode & 4 else (t, cout, cin), device=w.device, dtype=dtype)
     _call("pack_conv_weight", None, 1, _lib.lib().ptivae_pack_conv_weight, _p(w), _p(out), cout, cin, k, mode,
           _op16(out), _stream())
     return out
@@ -90,7 +91,10 @@ def conv_umma(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, mode:
         raise _lib.PtivaeError("activation and packed-weight operand dtypes differ")
     n, h, w, cin = x.shape
     cout = w_packed.shape[1]
-    ho, wo = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+    if w_packed.shape[2] != cin or bias.numel() != cout or h <= 0 or w <= 0:
+        raise _lib.PtivaeError(f"conv_umma: activation {tuple(x.shape)} / packed weight {tuple(w_packed.shape)} / bias "
+                               f"{bias.numel()} mismatch")
+    ho, wo = (h // 2, w // 2) if mode in (1, 6) else ((2 * h, 2 * w) if mode in (2, 5) else (h, w))
     out = torch.empty((n, ho, wo, cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
     res_f32 = 0
     if residual is not None:
@@ -210,13 +214,16 @@ def gn_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
     return part
 
 
-def gn_finalize(part: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, eps: float) -> torch.Tensor:
+def gn_finalize(part: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, eps: float,
+                return_mean_rstd: bool = False):
+    """partials [N,P,G,2] -> scale/shift [N,C,2] (and, for the backward pass, (mean, rstd) [N,G,2])."""
     n, parts, g, _ = part.shape
     c = gamma.numel()
     ss = torch.empty((n, c, 2), device=part.device, dtype=torch.float32)
-    _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(part), _p(gamma), _p(beta), _p(ss), n, hw, c, g,
+    mr = torch.empty((n, g, 2), device=part.device, dtype=torch.float32) if return_mean_rstd else None
+    _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(part), _p(gamma), _p(beta), _p(ss), _p(mr), n, hw, c, g,
           parts, float(eps), _stream())
-    return ss
+    return (ss, mr) if return_mean_rstd else ss
 
 
 def gn_apply(x: torch.Tensor, scale_shift: torch.Tensor, silu: bool, emit_raw: bool = False,
@@ -276,9 +283,10 @@ def conv1x1_small(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, act: int = 
     return out
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, return_lse: bool = False):
     """16-bit [B,L,D] x3 -> [B,L,D]; single head, scale D^-0.5.  q, k, v may be channel slices of one fused
-    [B,L,3D] projection (any common row stride, unit channel stride)."""
+    [B,L,3D] projection (any common row stride, unit channel stride).  return_lse: also the fp32 [B,L] log2-domain
+    log-sum-exp of the scaled score rows (what attention_bwd needs)."""
     _need_cuda(q, k, v)
     b, l, d = q.shape
     ld = q.stride(1)
@@ -286,9 +294,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor
         if t.shape != q.shape or t.stride(2) != 1 or t.stride(1) != ld or t.stride(0) != l * ld or t.dtype != q.dtype:
             raise _lib.PtivaeError("q, k, v must share shape, dtype and a [B, L, D] layout with one common row stride")
     out = torch.empty((b, l, d), device=q.device, dtype=q.dtype)
-    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), b, l, d, ld,
+    lse = torch.empty((b, l), device=q.device, dtype=torch.float32) if return_lse else None
+    _call("attention_fwd", (b, l, d), 1, _lib.lib().ptivae_attention_fwd, _p(q), _p(k), _p(v), _p(out), _p(lse), b, l, d, ld,
           _op16(q), _stream())
-    return out
+    return (out, lse) if return_lse else out
 
 
 def latent_sample(mu, sigma, eps=None, seed: int = 0, offset: int = 0, rng_dev=None, return_eps: bool = False):
@@ -403,3 +412,166 @@ def local_normalize(x: torch.Tensor, return_stats: bool = False):
     _call("local_normalize", (b, per), 2, _lib.lib().ptivae_local_normalize, _p(x), _p(out), _p(stats), _p(ws), b, per,
           _stream())
     return (out, stats) if return_stats else out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward pass
+# ---------------------------------------------------------------------------------------------------------------
+WGRAD_HALO = 1   # 3x3 s1 weight gradient: one 18-wide halo box per kernel row (0: one box per tap; tests force both)
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Weight gradient of a conv on tensor cores.  dy: 16-bit NHWC gradient of the conv output, x: 16-bit NHWC conv input
+    (as the forward GEMM read it).  mode as conv_umma (0 3x3 | 1 pad+3x3 s2 | 2 up2x+3x3 | 3 1x1).
+    -> fp32 [Cout,Cin,3,3] (or [Cout,Cin,1,1]), written into `out` when given (a view of the flat gradient buffer)."""
+    _need_cuda(dy, x)
+    n, h, w, cb = x.shape
+    ca = dy.shape[-1]
+    exp = (n, h // 2, w // 2) if mode == 1 else ((n, 2 * h, 2 * w) if mode == 2 else (n, h, w))
+    if tuple(dy.shape[:3]) != exp:
+        raise _lib.PtivaeError(f"wgrad: dy {tuple(dy.shape)} does not match x {tuple(x.shape)} for mode {mode}")
+    k = 1 if mode == 3 else 3
+    if out is None:
+        out = torch.empty((ca, cb, k, k), device=x.device, dtype=torch.float32)
+    elif out.numel() != ca * cb * k * k or out.dtype != torch.float32 or not out.is_contiguous():
+        raise _lib.PtivaeError("wgrad: bad output buffer")
+    nbytes = _lib.lib().ptivae_wgrad_workspace(n, h, w, ca, cb, mode)
+    if nbytes < 0:
+        _lib.check(int(nbytes), "wgrad_workspace")
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+    _call("wgrad", (mode, n, h, w, ca, cb), 2, _lib.lib().ptivae_wgrad, _p(dy), _p(x), _p(ws), _p(out), n, h, w, ca, cb,
+          mode, _op16(dy), _op16(x), WGRAD_HALO if mode == 0 else 0, _stream())
+    return out
+
+
+def bgemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, a_mn: bool, b_mn: bool, epi: int = 0, alpha: float = 1.0,
+          rowv: torch.Tensor | None = None, aux: torch.Tensor | None = None, k: int | None = None) -> torch.Tensor:
+    """out[b,m,n] = epi(sum_k A(m,k)*B(n,k)) for 3-D 16-bit views with unit inner stride.  a is [B,M,K] (a_mn False) or
+    [B,K,M] (a_mn True); likewise b with N; `k` overrides the contraction length (padded row strides)."""
+    _need_cuda(a, b, out)
+    for t in (a, b, out) + ((aux,) if aux is not None else ()):
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise _lib.PtivaeError("bgemm operands must be 3-D with unit inner stride")
+    bsz, m, n = out.shape
+    kk = k if k is not None else (a.shape[1] if a_mn else a.shape[2])
+    _call("bgemm", (bsz, m, n, kk, int(a_mn), int(b_mn), epi), 1, _lib.lib().ptivae_bgemm, _p(a), _p(b), _p(out), bsz, m, n,
+          kk, a.stride(1), a.stride(0), int(a_mn), _op16(a), b.stride(1), b.stride(0), int(b_mn), _op16(b), out.stride(1),
+          out.stride(0), _op16(out), epi, float(alpha), _p(rowv), _p(aux), 0 if aux is None else aux.stride(1),
+          0 if aux is None else aux.stride(0), 0 if aux is None else _op16(aux), _stream())
+    return out
+
+
+def rowdot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """16-bit [B,L,D] x2 (unit inner stride, dense rows) -> fp32 [B,L] row dot products."""
+    _need_cuda(a, b)
+    bsz, l, d = a.shape
+    for t in (a, b):
+        if t.stride(2) != 1 or t.stride(0) != l * t.stride(1):
+            raise _lib.PtivaeError("rowdot needs [B,L,D] views with one row stride")
+    out = torch.empty((bsz, l), device=a.device, dtype=torch.float32)
+    _call("rowdot", (bsz, l, d), 1, _lib.lib().ptivae_rowdot, _p(a), _p(b), _p(out), bsz * l, d, a.stride(1), b.stride(1),
+          _op16(a), _op16(b), _stream())
+    return out
+
+
+def attention_bwd(q, k, v, o, lse, d_o, dqkv: torch.Tensor) -> None:
+    """Backward of ops.attention.  q,k,v: fp16/bf16 [B,L,D] views (row stride ld); o: forward output; lse: from the
+    forward; d_o: bf16 [B,L,D] gradient of o.  Writes dq|dk|dv into the three channel slices of dqkv bf16 [B,L,3D]."""
+    bsz, l, d = q.shape
+    lp = (l + 7) // 8 * 8
+    scale = float(d) ** -0.5
+    drow = rowdot(d_o, o)
+    p = torch.empty((bsz, l, lp), device=q.device, dtype=q.dtype)[:, :, :l]
+    ds = torch.empty((bsz, l, lp), device=q.device, dtype=torch.bfloat16)[:, :, :l]
+    bgemm(q, k, p, False, False, epi=1, alpha=scale * 1.4426950408889634, rowv=lse)           # P = exp2(QK^T c - lse)
+    bgemm(p, d_o, dqkv[:, :, 2 * d:], True, True)                                            # dV = P^T dO
+    bgemm(d_o, v, ds, False, False, epi=2, alpha=scale, rowv=drow, aux=p)                    # dS = P o (dO V^T - D) * scale
+    bgemm(ds, k, dqkv[:, :, :d], False, True)                                                # dQ = dS K
+    bgemm(ds, q, dqkv[:, :, d:2 * d], True, True)                                            # dK = dS^T Q
+
+
+def gn_bwd(x: torch.Tensor, da: torch.Tensor, ss: torch.Tensor, mr: torch.Tensor, gamma: torch.Tensor, silu: bool,
+           dgamma: torch.Tensor, dbeta: torch.Tensor, residual=None, want32: bool = True, want16: bool = True):
+    """Backward of act(GroupNorm(x)).  -> (dx fp32 | None, dx bf16 | None); dgamma/dbeta (fp32 [C]) are overwritten."""
+    _need_cuda(x, da, ss, mr, gamma)
+    n, hw, c = _nhwc_dims(x)
+    g = mr.shape[1]
+    if da.shape != x.shape or (residual is not None and residual.shape != x.shape):
+        raise _lib.PtivaeError("gn_bwd shape mismatch")
+    parts = _lib.lib().ptivae_gn_bwd_parts(hw)
+    ws = torch.empty(n * parts * c * 2 + n * c * 2, device=x.device, dtype=torch.float32)
+    coef = torch.empty((n, c, 2), device=x.device, dtype=torch.float32)
+    dx32 = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want32 else None
+    dx16 = torch.empty(x.shape, device=x.device, dtype=BF16) if want16 else None
+    _call("gn_bwd", (n, hw, c, x.element_size(), int(silu)), 4, _lib.lib().ptivae_gn_bwd, _p(x), _fmt(x), _p(da), _fmt(da),
+          _p(ss), _p(mr), _p(gamma), _p(residual), 0 if residual is None else _fmt(residual), _p(dx32), _p(dx16),
+          _p(dgamma), _p(dbeta), _p(coef), _p(ws), n, hw, c, g, int(silu), _stream())
+    return dx32, dx16
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-channel sum of an NHWC tensor (bias gradient) -> fp32 [C]."""
+    _need_cuda(x)
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if out is None:
+        out = torch.empty(c, device=x.device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib().ptivae_colsum_blocks(rows) * c, device=x.device, dtype=torch.float32)
+    _call("colsum", (rows, c), 2, _lib.lib().ptivae_colsum, _p(x), _p(out), _p(ws), rows, c, _fmt(x), _stream())
+    return out
+
+
+def thin_wgrad(thin: torch.Tensor, wide: torch.Tensor, wide_is_input: bool, dw: torch.Tensor, db=None, scale_shift=None):
+    """Weight gradient of a thin-end 3x3 conv (see include/ptivae.h).  thin fp32 NCHW, wide NHWC."""
+    _need_cuda(thin, wide, dw)
+    n, ct, h, w = thin.shape
+    c = wide.shape[-1]
+    if tuple(wide.shape[:3]) != (n, h, w) or dw.numel() != ct * c * 9:
+        raise _lib.PtivaeError("thin_wgrad shape mismatch")
+    ws = torch.empty(_lib.lib().ptivae_thin_wgrad_workspace(n, h, c, ct) // 4, device=thin.device, dtype=torch.float32)
+    _call("thin_wgrad", (n, h, w, c, ct), 2, _lib.lib().ptivae_thin_wgrad, _p(thin), _p(wide), _p(scale_shift), _p(dw),
+          _p(db), _p(ws), n, h, w, c, ct, _fmt(wide), int(wide_is_input), _stream())
+    return dw
+
+
+def latent_bwd(dzq, dmu_ext, dsig_ext, eps, h, mu, sigma, wp, wm, ws_, bs):
+    """-> (dh, dmu, dlv, z): see include/ptivae.h ptivae_latent_bwd.  All fp32 NCHW [N,L,h,w]."""
+    _need_cuda(dzq, eps, h, mu, sigma)
+    n, l = h.shape[:2]
+    hw = h.numel() // (n * l)
+    dh, dmu, dlv, z = (torch.empty_like(h) for _ in range(4))
+    _call("latent_bwd", None, 1, _lib.lib().ptivae_latent_bwd, _p(dzq), _p(dmu_ext), _p(dsig_ext), _p(eps), _p(h), _p(mu),
+          _p(sigma), _p(wp), _p(wm), _p(ws_), _p(bs), _p(dh), _p(dmu), _p(dlv), _p(z), n, hw, l, _stream())
+    return dh, dmu, dlv, z
+
+
+def outer_reduce(a: torch.Tensor, b: torch.Tensor, dw: torch.Tensor, db=None):
+    """dw[i,j] = sum_{n,p} a[n,i,p] b[n,j,p]; db[i] = sum a[n,i,p] (gradients of a 1x1 latent conv)."""
+    n, i = a.shape[:2]
+    j = b.shape[1]
+    hw = a.numel() // (n * i)
+    _call("outer_reduce", None, 1, _lib.lib().ptivae_outer_reduce, _p(a), _p(b), _p(dw), _p(db), n, i, j, hw, _stream())
+    return dw
+
+
+def l1l2_bwd(a: torch.Tensor, b: torch.Tensor, gout: torch.Tensor) -> torch.Tensor:
+    """gout: fp32 device 2-vector (dL/d l1, dL/d l2) -> dL/da."""
+    d = torch.empty_like(a)
+    _call("l1l2_bwd", None, 1, _lib.lib().ptivae_l1l2_bwd, _p(a), _p(b), _p(gout), _p(d), a.numel(), _stream())
+    return d
+
+
+def kl_bwd(mu: torch.Tensor, t: torch.Tensor, gout: torch.Tensor, input_is_logvar: bool = True):
+    n = mu.shape[0]
+    dmu, dt = torch.empty_like(mu), torch.empty_like(t)
+    _call("kl_bwd", None, 1, _lib.lib().ptivae_kl_bwd, _p(mu), _p(t), _p(gout), _p(dmu), _p(dt), n, mu.numel() // n,
+          int(input_is_logvar), _stream())
+    return dmu, dt
+
+
+def adam(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step_dev: torch.Tensor, lr: float,
+         betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0, advance: bool = True) -> None:
+    """torch.optim.Adam (defaults) over flat fp32 buffers, in place; step_dev = device float with the 1-based step."""
+    _need_cuda(p, g, m, v, step_dev)
+    _call("adam", None, 2 if advance else 1, _lib.lib().ptivae_adam, _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr),
+          float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _p(step_dev), int(advance), _stream())

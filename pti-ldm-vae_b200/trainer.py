@@ -1,0 +1,153 @@
+"""The VAE part of one training step of vae_scripts/train_vae.py (:380-445) as a fused, graph-capturable unit:
+
+    recon, z_mu, z_sigma = autoencoder(images)            train_vae.py:385
+    loss = L1|L2(recon, images) + kl_weight * compute_kl_loss(z_mu, z_sigma)      :393-394,419
+    loss.backward()                                       :444   (+ DDP gradient all-reduce, :282)
+    optimizer_g.step()                                    :445   (torch.optim.Adam, lr * world_size, :301)
+
+``TrainStep`` owns ONE flat fp32 buffer each for parameters, gradients and the two Adam moments.  The backward
+kernels write straight into the flat gradient buffer; the data-parallel reduction is one NCCL all-reduce per segment
+of that buffer -- the decoder segment is issued on a side stream as soon as the decoder backward has finished, so
+it travels over NVLink while the encoder backward runs; Adam is one kernel over the flat buffers.
+The reference does the same work as 218 per-tensor autograd accumulations, DDP's bucketed reducer with a
+``find_unused_parameters`` graph walk, and a per-tensor optimizer loop.
+
+The perceptual / adversarial terms of the reference step (LPIPS-SqueezeNet, PatchDiscriminator) are outside the hot
+path: a caller that needs them uses the autograd path (``AutoencoderKL.forward`` in train mode
+returns differentiable tensors) and adds those losses with stock PyTorch.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .training import FlatGrads, TrainRun
+
+
+def flatten_parameters(module: torch.nn.Module) -> torch.Tensor:
+    """Re-points every parameter of ``module`` at a slice of one flat fp32 buffer (values preserved) and returns it.
+    ``state_dict()`` / ``load_state_dict()`` keep working: the parameters are ordinary views."""
+    params = list(module.parameters())
+    total = sum(p.numel() for p in params)
+    flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
+    off = 0
+    for p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.detach().reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        off += n
+    return flat
+
+
+class TrainStep:
+    """step(images) -> dict of device scalars (loss terms); parameters are updated in place."""
+
+    def __init__(self, model, lr: float = 2.5e-5, kl_weight: float = 1e-3, recon_loss: str = "l1",
+                 betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, overlap: bool = True,
+                 scale_lr_by_world: bool = True):
+        ae = getattr(model, "autoencoder", model)
+        self.ae = ae
+        dev = next(ae.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainStep needs the model on a CUDA device (there is no CPU path)")
+        if recon_loss not in ("l1", "l2"):
+            raise ValueError("recon_loss must be 'l1' or 'l2'")
+        self.dev = dev
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.lr = lr * (self.world if scale_lr_by_world else 1)       # train_vae.py:301
+        self.kl_weight, self.betas, self.eps = float(kl_weight), betas, eps
+        self.overlap = overlap and self.world > 1
+        self.params = flatten_parameters(ae)
+        ae.invalidate_packed()
+        self.grads = torch.zeros_like(self.params)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.step_dev = torch.ones(1, device=dev, dtype=torch.float32)
+        self.G = FlatGrads(ae, self.grads)
+        # gradient-buffer split: parameters() order is encoder | decoder | quant_mu | quant_log_sigma | post_quant
+        n_enc = sum(p.numel() for p in ae.encoder.parameters())
+        n_dec = sum(p.numel() for p in ae.decoder.parameters())
+        n_q = sum(p.numel() for p in ae.quant_conv_mu.parameters()) + sum(p.numel() for p in ae.quant_conv_log_sigma.parameters())
+        self.seg_dec = (n_enc, n_enc + n_dec)                       # final after the decoder backward
+        self.seg_pq = (n_enc + n_dec + n_q, self.params.numel())    # post_quant_conv: also final at that point
+        self.seg_enc = [(0, n_enc), (n_enc + n_dec, n_enc + n_dec + n_q)]
+        self.comm = torch.cuda.Stream(device=dev) if self.overlap else None
+        self.gout_rec = torch.tensor([1.0, 0.0] if recon_loss == "l1" else [0.0, 1.0], device=dev)
+        self.gout_kl = torch.tensor([self.kl_weight], device=dev)
+        self.recon_idx = 0 if recon_loss == "l1" else 1
+        if ae._rng_dev is None:
+            ae._rng_dev = torch.tensor([torch.initial_seed() & (2**63 - 1), 1], device=dev, dtype=torch.int64)
+        if self.world > 1:
+            # same starting point on every rank (DDP broadcasts at wrap time, train_vae.py:282)
+            dist.broadcast(self.params, src=0, group=self.pg)
+        self.graph = None
+        self._static_x = None
+        self._static_out = None
+
+    # -- communication ------------------------------------------------------------------------------
+    def _allreduce(self, lo: int, hi: int) -> None:
+        dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _after_decoder(self) -> None:
+        if self.world == 1:
+            return
+        if self.comm is None:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            self._allreduce(*self.seg_dec)
+            self._allreduce(*self.seg_pq)
+
+    # -- one step -----------------------------------------------------------------------------------
+    def _step_impl(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        ae = self.ae
+        with torch.no_grad():
+            run = TrainRun(ae)
+            recon, mu, sigma = run.forward(x, eps)
+            xf = x.detach().contiguous().float()
+            rec_terms = ops.l1l2(recon, xf)                     # (l1, l2)
+            kl = ops.kl_loss(mu, sigma, True)
+            d_recon = ops.l1l2_bwd(recon, xf, self.gout_rec)
+            d_mu, d_sigma = ops.kl_bwd(mu, sigma, self.gout_kl, True)
+            run.backward(d_recon, d_mu, d_sigma, self.G, need_dx=False, after_decoder=self._after_decoder)
+            if self.world > 1:
+                if self.comm is not None:
+                    for lo, hi in self.seg_enc:
+                        self._allreduce(lo, hi)
+                    torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+                else:
+                    self._allreduce(0, self.params.numel())
+            ops.adam(self.params, self.grads, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps,
+                     grad_scale=1.0 / self.world, advance=True)
+            ae.invalidate_packed()
+        return {"recon_loss": rec_terms[self.recon_idx], "kl_loss": kl, "recon": recon, "z_mu": mu, "z_sigma": sigma}
+
+    def step(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        return self._step_impl(x, eps)
+
+    # -- CUDA graph ---------------------------------------------------------------------------------
+    def capture(self, batch: int, height: int, width: int, warmup: int = 2):
+        """Captures the whole step (forward, losses, backward, all-reduce, Adam, weight re-pack) for a fixed shape.
+        Afterwards ``replay(x)`` copies x into the static input and launches the graph."""
+        ae = self.ae
+        self._static_x = torch.zeros((batch, ae.in_channels, height, width), device=self.dev, dtype=torch.float32)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(self._static_x)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._static_out = self._step_impl(self._static_x)
+        return self
+
+    def replay(self, x: torch.Tensor | None = None):
+        if x is not None:
+            self._static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self._static_out

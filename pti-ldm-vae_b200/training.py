@@ -1,0 +1,392 @@
+"""Training-mode execution of the AutoencoderKL hot path: the forward pass with a tape of what the backward
+needs, and the backward pass itself (the reference gets both from autograd under
+``loss_g.backward()``, /root/reference/vae_scripts/train_vae.py:385,444).
+
+Everything that touches an activation is a kernel of libptivae.so:
+  conv data gradients   -> ops.conv_umma modes 3/4/5/6 (the forward implicit-GEMM kernel with transposed weights and
+                           mirrored / phase-split tap tables)
+  conv weight gradients -> ops.wgrad (tcgen05, both operands consumed MN-major straight from NHWC, split-K)
+  GroupNorm+SiLU        -> ops.gn_bwd (reduce / finalize / apply, deterministic)
+  attention             -> ops.attention_bwd (five batched tcgen05 GEMMs around the saved log-sum-exp)
+  thin ends, latent head-> ops.thin_wgrad / conv3x3_small_* with mirrored weights / ops.latent_bwd / ops.outer_reduce
+PyTorch only owns memory and the autograd edge (``VAEFunction``): gradients of all parameters are written into ONE
+flat fp32 buffer (the views are what autograd / DDP see), which is also what the NCCL all-reduce moves.
+
+Precision: gradient GEMM operands are bf16 (fp16 underflows for mean-reduced losses: dL/drecon ~ 1/(B*H*W)),
+activations keep the forward's fp16 operands (the two formats are mixed inside one MMA), accumulation and the
+gradient of the residual stream are fp32.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .autoencoderkl import (AEKLDownsample, AEKLResBlock, Convolution, SpatialAttentionBlock, UpSample, _Act)
+
+BF16 = torch.bfloat16
+
+
+class _G:
+    """Gradient of an NHWC activation: fp32 (residual-stream precision) and/or bf16 (GEMM operand)."""
+    __slots__ = ("t32", "t16")
+
+    def __init__(self, t32=None, t16=None):
+        self.t32, self.t16 = t32, t16
+
+    @property
+    def any(self):
+        return self.t32 if self.t32 is not None else self.t16
+
+
+class FlatGrads:
+    """One flat fp32 buffer holding the gradient of every parameter, in ``named_parameters()`` order."""
+
+    def __init__(self, module: nn.Module, buffer: torch.Tensor | None = None):
+        params = list(module.parameters())
+        self.total = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat = buffer if buffer is not None else torch.zeros(self.total, device=dev, dtype=torch.float32)
+        self.views: dict[int, torch.Tensor] = {}
+        self.order = []
+        off = 0
+        for p in params:
+            v = self.flat[off:off + p.numel()].view(p.shape)
+            self.views[id(p)] = v
+            self.order.append(v)
+            off += p.numel()
+
+    def __getitem__(self, p: torch.Tensor) -> torch.Tensor:
+        return self.views[id(p)]
+
+
+class TrainRun:
+    """One forward (with tape) + backward of an ``AutoencoderKL`` on the kernels."""
+
+    def __init__(self, ae):
+        self.ae = ae
+        self.ex = ae._exec
+        self.tape: list = []
+        self.latent = None
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _ss_mr(self, a: _Act, norm: nn.GroupNorm):
+        ex = self.ex
+        part = a.part if a.part is not None else ops.gn_stats(a.t, norm.num_groups)
+        n, c = a.t.shape[0], a.t.shape[-1]
+        return ops.gn_finalize(part, ex.f32(norm.weight), ex.f32(norm.bias), a.t.numel() // (n * c), norm.eps,
+                               return_mean_rstd=True)
+
+    def _zero_bias(self, c: int, dev) -> torch.Tensor:
+        zeros = self.ex.__dict__.setdefault("_zeros", {})     # survives invalidate_packed(): never stale
+        key = (c, str(dev))
+        hit = zeros.get(key)
+        if hit is None:
+            hit = torch.zeros(c, device=dev, dtype=torch.float32)
+            zeros[key] = hit
+        return hit
+
+    def _packT(self, w: torch.Tensor, mode: int = 0) -> torch.Tensor:
+        """bf16 transposed pack [T][Cin][Cout] of a master weight (operand of the data-gradient conv)."""
+        key = (id(w), "T", mode)
+        ver = (w.data_ptr(), w._version, w.device)
+        hit = self.ex._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.pack_conv_weight(w, mode | 4, BF16))
+            self.ex._packed[key] = hit
+        return hit[1]
+
+    def _mirrored(self, w: torch.Tensor) -> torch.Tensor:
+        """fp32 [Cin][Cout][3][3] with the taps mirrored: the data gradient of a thin 3x3 conv is the opposite thin conv."""
+        key = (id(w), "mirror")
+        ver = (w.data_ptr(), w._version, w.device)
+        hit = self.ex._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, w.detach().float().flip(2, 3).transpose(0, 1).contiguous())
+            self.ex._packed[key] = hit
+        return hit[1]
+
+    def _fconv(self, x, ss, conv, residual, stats: bool, out_f32: bool) -> _Act:
+        """conv3x3(silu(x*scale+shift)) + bias (+ residual) with the forward's kernels."""
+        ex = self.ex
+        w = conv.weight
+        cout, cin = w.shape[0], w.shape[1]
+        g = ex._want_stats(cout, stats)
+        if ex.fused_conv and cin in (32, 64, 128) and cout in (32, 64, 128):
+            r = ops.conv3x3_fused(x, ss, True, ex.packed(w), ex.f32(conv.bias), residual=residual, gn_groups=g,
+                                  out_f32=out_f32)
+        else:
+            y = ops.gn_apply(x, ss, silu=True, dtype=ex.op_dtype)
+            r = ops.conv_umma(y, ex.packed(w), ex.f32(conv.bias), 0, residual=residual, gn_groups=g, out_f32=out_f32)
+        return _Act(*r) if g else _Act(r)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _resblock(self, blk: AEKLResBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
+        ex = self.ex
+        x = a.t
+        ss1, mr1 = self._ss_mr(a, blk.norm1)
+        has_sc = isinstance(blk.nin_shortcut, Convolution)
+        raw = None
+        if has_sc:
+            raw = a.raw16
+            if raw is None:
+                _, raw = ops.gn_apply(x, ss1, silu=True, emit_raw=True, dtype=ex.op_dtype)
+        h = self._fconv(x, ss1, blk.conv1.conv, None, True, False)
+        ss2, mr2 = self._ss_mr(h, blk.norm2)
+        if has_sc:
+            w2, wsc = blk.conv2.conv.weight, blk.nin_shortcut.conv.weight
+            if ex.fused_conv and out_f32 and ops.fused_sc_supported(raw.dtype, w2.shape[1], w2.shape[0], wsc.shape[1]):
+                g = ex._want_stats(w2.shape[0], stats)
+                r = ops.conv3x3_fused_sc(h.t, ss2, True, ex.packed(w2),
+                                         ex.bias_sum(blk.conv2.conv.bias, blk.nin_shortcut.conv.bias), raw,
+                                         ex.packed(wsc), gn_groups=g)
+                out = _Act(*r) if g else _Act(r)
+            else:
+                sc = ex.conv(raw, blk.nin_shortcut.conv, 3, stats=False, out_f32=True).t
+                out = self._fconv(h.t, ss2, blk.conv2.conv, sc, stats, out_f32)
+        else:
+            out = self._fconv(h.t, ss2, blk.conv2.conv, x, stats, out_f32)
+        self.tape.append(("res", blk, x, ss1, mr1, h.t, ss2, mr2, raw))
+        return out
+
+    def _attention(self, blk: SpatialAttentionBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
+        ex = self.ex
+        x = a.t
+        ss, mr = self._ss_mr(a, blk.norm)
+        xn = ops.gn_apply(x, ss, silu=False, dtype=ex.op_dtype)
+        n, h, w, c = xn.shape
+        if c % 128 != 0:
+            raise NotImplementedError("training-mode attention needs a channel width that is a multiple of 128")
+        wq, bq = ex.qkv_packed(blk.attn)
+        qkv = ops.conv_umma(xn, wq, bq, 3).view(n, h * w, 3 * c)
+        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+        o, lse = ops.attention(q, k, v, return_lse=True)
+        out = ex.conv(o.view(n, h, w, c), blk.attn.out_proj, 3, residual=x, stats=stats, out_f32=out_f32)
+        self.tape.append(("attn", blk, x, ss, mr, xn, qkv, o, lse))
+        return out
+
+    def _stack_fwd(self, blocks: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:
+        ex = self.ex
+        first, last_norm, last = blocks[0], blocks[-2], blocks[-1]
+        body = list(blocks)[1:-2]
+
+        def operand_only(i):
+            return i < len(body) and isinstance(body[i], (AEKLDownsample, UpSample))
+
+        def needs_raw16(i):
+            return i < len(body) and isinstance(body[i], AEKLResBlock) and isinstance(body[i].nin_shortcut, Convolution)
+
+        cw = first.conv.weight
+        g0 = ex.groups if (ex.fused_stats and not operand_only(0) and
+                           ops.small_cin_stats_supported(cw.shape[1], cw.shape[0], ex.groups)) else 0
+        r0 = ops.conv3x3_small_cin(x, ex.f32(cw), ex.f32(first.conv.bias),
+                                   dtype=ex.op_dtype if operand_only(0) else torch.float32, gn_groups=g0)
+        a = _Act(*r0) if g0 else _Act(r0)
+        self.tape.append(("first", first, x))
+        for i, blk in enumerate(body):
+            nxt_operand = operand_only(i + 1)
+            to_stream = not (nxt_operand or i + 1 == len(body))
+            if isinstance(blk, AEKLResBlock):
+                a = self._resblock(blk, a, out_f32=to_stream, stats=not nxt_operand)
+            elif isinstance(blk, SpatialAttentionBlock):
+                a = self._attention(blk, a, out_f32=to_stream, stats=not nxt_operand)
+            else:
+                xin = a.t
+                down = isinstance(blk, AEKLDownsample)
+                conv = blk.conv.conv if down else blk.postconv.conv
+                a = ex.conv(xin, conv, 1 if down else 2, out_f32=not nxt_operand, stats=not nxt_operand,
+                            emit16=(not nxt_operand) and needs_raw16(i + 1))
+                self.tape.append(("resample", conv, xin, 1 if down else 2))
+        ss, mr = self._ss_mr(a, last_norm)
+        out = ops.conv3x3_small_cout(a.t, ex.f32(last.conv.weight), ex.f32(last.conv.bias), ss)
+        self.tape.append(("last", last_norm, last, a.t, ss, mr))
+        return out
+
+    def forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        ae, ex = self.ae, self.ex
+        x = ae._prep(x)
+        self.tape.append(("mark", "encoder"))
+        h = self._stack_fwd(ae.encoder.blocks, x)
+        wm, bm = ex.f32(ae.quant_conv_mu.conv.weight), ex.f32(ae.quant_conv_mu.conv.bias)
+        ws, bs = ex.f32(ae.quant_conv_log_sigma.conv.weight), ex.f32(ae.quant_conv_log_sigma.conv.bias)
+        wp, bp = ex.f32(ae.post_quant_conv.conv.weight), ex.f32(ae.post_quant_conv.conv.bias)
+        mu = ops.conv1x1_small(h, wm, bm, 0)
+        sigma = ops.conv1x1_small(h, ws, bs, 1)
+        if eps is not None:
+            eps = eps.detach().contiguous().float()
+            z = ops.latent_sample(mu, sigma, eps=eps)
+        elif ae._rng_dev is not None:
+            z, eps = ops.latent_sample(mu, sigma, rng_dev=ae._rng_dev, return_eps=True)
+            ops.rng_advance(ae._rng_dev)
+        else:
+            ae._rng_offset += 1
+            z, eps = ops.latent_sample(mu, sigma, seed=torch.initial_seed(), offset=ae._rng_offset, return_eps=True)
+        zq = ops.conv1x1_small(z, wp, bp, 0)
+        self.latent = (h, mu, sigma, eps)
+        self.tape.append(("mark", "decoder"))
+        recon = self._stack_fwd(ae.decoder.blocks, zq)
+        return recon, mu, sigma
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _res_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
+        _, blk, x, ss1, mr1, h, ss2, mr2, raw = rec
+        ex = self.ex
+        dev = x.device
+        c1, c2 = blk.conv1.conv, blk.conv2.conv
+        d16 = g.t16
+        a2 = ops.gn_apply(h, ss2, silu=True, dtype=ex.op_dtype)
+        ops.wgrad(d16, a2, 0, out=G[c2.weight])
+        ops.colsum(d16, out=G[c2.bias])
+        da2 = ops.conv_umma(d16, self._packT(c2.weight), self._zero_bias(c2.weight.shape[1], dev), 4)
+        _, dh16 = ops.gn_bwd(h, da2, ss2, mr2, ex.f32(blk.norm2.weight), True, G[blk.norm2.weight], G[blk.norm2.bias],
+                             want32=False)
+        a1 = ops.gn_apply(x, ss1, silu=True, dtype=ex.op_dtype)
+        ops.wgrad(dh16, a1, 0, out=G[c1.weight])
+        ops.colsum(dh16, out=G[c1.bias])
+        da1 = ops.conv_umma(dh16, self._packT(c1.weight), self._zero_bias(c1.weight.shape[1], dev), 4)
+        if raw is not None:
+            sc = blk.nin_shortcut.conv
+            ops.wgrad(d16, raw, 3, out=G[sc.weight])
+            G[sc.bias].copy_(G[c2.bias])
+            res = ops.conv_umma(d16, self._packT(sc.weight), self._zero_bias(sc.weight.shape[1], dev), 3, out_f32=True)
+        else:
+            res = g.any
+        dx32, dx16 = ops.gn_bwd(x, da1, ss1, mr1, ex.f32(blk.norm1.weight), True, G[blk.norm1.weight],
+                                G[blk.norm1.bias], residual=res)
+        return _G(dx32, dx16)
+
+    def _attn_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
+        _, blk, x, ss, mr, xn, qkv, o, lse = rec
+        ex = self.ex
+        dev = x.device
+        n, h, w, c = xn.shape
+        at = blk.attn
+        d16 = g.t16
+        ops.wgrad(d16, o.view(n, h, w, c), 3, out=G[at.out_proj.weight])
+        ops.colsum(d16, out=G[at.out_proj.bias])
+        d_o = ops.conv_umma(d16, self._packT(at.out_proj.weight), self._zero_bias(c, dev), 3).view(n, h * w, c)
+        dqkv = torch.empty((n, h * w, 3 * c), device=dev, dtype=BF16)
+        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+        ops.attention_bwd(q, k, v, o, lse, d_o, dqkv)
+        dq4 = dqkv.view(n, h, w, 3 * c)
+        dwqkv = ops.wgrad(dq4, xn, 3)                       # [3C, C, 1, 1]
+        dbqkv = ops.colsum(dq4)
+        for i, lin in enumerate((at.to_q, at.to_k, at.to_v)):
+            G[lin.weight].copy_(dwqkv[i * c:(i + 1) * c].view(c, c))
+            G[lin.bias].copy_(dbqkv[i * c:(i + 1) * c])
+        key = (id(at.to_q.weight), "qkvT")
+        ws = (at.to_q.weight, at.to_k.weight, at.to_v.weight)
+        ver = tuple((t.data_ptr(), t._version) for t in ws)
+        hit = ex._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.pack_conv_weight(torch.cat([t.detach() for t in ws], dim=0), 4, BF16))
+            ex._packed[key] = hit
+        dxn = ops.conv_umma(dq4, hit[1], self._zero_bias(c, dev), 3)
+        dx32, dx16 = ops.gn_bwd(x, dxn, ss, mr, ex.f32(blk.norm.weight), False, G[blk.norm.weight], G[blk.norm.bias],
+                                residual=g.any)
+        return _G(dx32, dx16)
+
+    def _resample_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
+        _, conv, xin, mode = rec
+        d16 = g.t16
+        ops.wgrad(d16, xin, mode, out=G[conv.weight])
+        ops.colsum(d16, out=G[conv.bias])
+        c = conv.weight.shape[1]
+        dx16 = ops.conv_umma(d16, self._packT(conv.weight, 2 if mode == 2 else 0), self._zero_bias(c, xin.device),
+                             5 if mode == 1 else 6)
+        return _G(None, dx16)
+
+    def _last_bwd(self, rec, d_out: torch.Tensor, G: FlatGrads) -> _G:
+        _, norm, last, x, ss, mr = rec
+        ex = self.ex
+        conv = last.conv
+        d_out = d_out.detach().contiguous().float()
+        ops.thin_wgrad(d_out, x, True, G[conv.weight], db=G[conv.bias], scale_shift=ss)
+        c = conv.weight.shape[1]
+        da = ops.conv3x3_small_cin(d_out, self._mirrored(conv.weight), self._zero_bias(c, x.device), dtype=BF16)
+        dx32, dx16 = ops.gn_bwd(x, da, ss, mr, ex.f32(norm.weight), False, G[norm.weight], G[norm.bias])
+        return _G(dx32, dx16)
+
+    def _first_bwd(self, rec, g: _G, G: FlatGrads, need_dx: bool):
+        _, first, x = rec
+        conv = first.conv
+        ops.thin_wgrad(x, g.any, False, G[conv.weight])
+        ops.colsum(g.any, out=G[conv.bias])
+        if not need_dx:
+            return None
+        ct = conv.weight.shape[1]
+        return ops.conv3x3_small_cout(g.t16 if g.t16 is not None else g.t32, self._mirrored(conv.weight),
+                                      self._zero_bias(ct, x.device))
+
+    def _stack_bwd(self, d_out: torch.Tensor, G: FlatGrads, need_dx: bool):
+        g = None
+        while self.tape:
+            rec = self.tape.pop()
+            kind = rec[0]
+            if kind == "last":
+                g = self._last_bwd(rec, d_out, G)
+            elif kind == "res":
+                g = self._res_bwd(rec, g, G)
+            elif kind == "attn":
+                g = self._attn_bwd(rec, g, G)
+            elif kind == "resample":
+                g = self._resample_bwd(rec, g, G)
+            elif kind == "first":
+                return self._first_bwd(rec, g, G, need_dx)
+            else:  # pragma: no cover
+                raise RuntimeError(f"unexpected tape record {kind}")
+        raise RuntimeError("tape underflow")  # pragma: no cover
+
+    def backward(self, d_recon, d_mu, d_sigma, G: FlatGrads, need_dx: bool = False, after_decoder=None):
+        """Walks the tape backwards.  ``after_decoder`` (callable) fires when the decoder-side gradients are final
+        (the flat buffer's decoder + post_quant segment can be all-reduced while the encoder backward runs)."""
+        ae, ex = self.ae, self.ex
+        h, mu, sigma, eps = self.latent
+        if d_recon is None:
+            raise RuntimeError("TrainRun.backward needs a reconstruction gradient (VAEFunction supplies zeros)")
+        dzq = self._stack_bwd(d_recon, G, True)
+        mark = self.tape.pop()
+        assert mark == ("mark", "decoder")
+        wm, ws = ex.f32(ae.quant_conv_mu.conv.weight), ex.f32(ae.quant_conv_log_sigma.conv.weight)
+        wp, bs = ex.f32(ae.post_quant_conv.conv.weight), ex.f32(ae.quant_conv_log_sigma.conv.bias)
+        f = lambda t: None if t is None else t.detach().contiguous().float()   # noqa: E731
+        dh, dmu, dlv, z = ops.latent_bwd(dzq, f(d_mu), f(d_sigma), eps, h, mu, sigma, wp, wm, ws, bs)
+        ops.outer_reduce(dzq, z, G[ae.post_quant_conv.conv.weight], G[ae.post_quant_conv.conv.bias])
+        if after_decoder is not None:
+            after_decoder()
+        ops.outer_reduce(dmu, h, G[ae.quant_conv_mu.conv.weight], G[ae.quant_conv_mu.conv.bias])
+        ops.outer_reduce(dlv, h, G[ae.quant_conv_log_sigma.conv.weight], G[ae.quant_conv_log_sigma.conv.bias])
+        dx = self._stack_bwd(dh, G, need_dx)
+        mark = self.tape.pop()
+        assert mark == ("mark", "encoder")
+        self.latent = None
+        return dx
+
+
+class VAEFunction(torch.autograd.Function):
+    """The autograd edge: ``recon, z_mu, z_sigma = VAEFunction.apply(ae, x, eps, *ae.parameters())``."""
+
+    @staticmethod
+    def forward(ctx, ae, x, eps, *params):
+        run = TrainRun(ae)
+        with torch.no_grad():
+            recon, mu, sigma = run.forward(x, eps)
+        ctx.run = run
+        ctx.ae = ae
+        ctx.set_materialize_grads(False)
+        return recon, mu, sigma
+
+    @staticmethod
+    def backward(ctx, d_recon, d_mu, d_sigma):
+        run, ae = ctx.run, ctx.ae
+        if run is None:
+            raise RuntimeError("the B200 AutoencoderKL backward can run only once per forward (no retain_graph)")
+        ctx.run = None
+        G = FlatGrads(ae)
+        with torch.no_grad():
+            if d_recon is None:   # loss does not depend on the reconstruction: the decoder still needs a gradient tensor
+                d_recon = torch.zeros((run.latent[0].shape[0], ae.out_channels) + tuple(run.tape[-1][3].shape[1:3]),
+                                      device=run.latent[0].device, dtype=torch.float32)
+            dx = run.backward(d_recon, d_mu, d_sigma, G, need_dx=ctx.needs_input_grad[1])
+        ae._last_flat_grads = G
+        return (None, dx, None) + tuple(G.order)

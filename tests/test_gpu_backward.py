@@ -1,0 +1,418 @@
+"""Parity of the backward kernels on the GPU.
+
+Per-kernel: every backward C-ABI entry point against torch autograd of the same fp32 operator on identical
+(16-bit-rounded) inputs.  End to end: dX and EVERY dW of configs A and B against ``.backward()`` of the CPU oracle
+(fp32, same weights / inputs / eps).
+
+Tolerances (written next to each check): a GEMM whose operands are exact in their 16-bit formats must reproduce the
+fp32 result to accumulation-order noise (rel-L2 <= 2e-3 incl. the bf16 rounding of a 16-bit output); end-to-end
+gradients go through ~60 bf16 roundings of gradient operands, held to rel-L2 <= 3e-2 per tensor and 1.5e-2 for dX.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16, F16 = torch.bfloat16, torch.float16
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.cuda.synchronize()
+
+
+def _randn(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _conv_fwd(x_nchw, w, mode):
+    if mode == 0:
+        return F.conv2d(x_nchw, w, None, padding=1)
+    if mode == 1:
+        return F.conv2d(F.pad(x_nchw, (0, 1, 0, 1)), w, None, stride=2)
+    if mode == 2:
+        return F.conv2d(F.interpolate(x_nchw, scale_factor=2.0, mode="nearest"), w, None, padding=1)
+    return F.conv2d(x_nchw, w, None)
+
+
+def _conv_grads(x_nhwc16, w, dy_nhwc16, mode):
+    """fp32 autograd reference: (dx NHWC, dw) for 16-bit-rounded x / dy and fp32 w."""
+    x = x_nhwc16.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y = _conv_fwd(x, wr, mode)
+    y.backward(dy_nhwc16.float().permute(0, 3, 1, 2))
+    return x.grad.permute(0, 2, 3, 1).contiguous(), wr.grad
+
+
+BWD_CASES = [
+    # (mode, N, H, W (of x), Cin, Cout)
+    (0, 2, 32, 32, 128, 128),
+    (0, 1, 64, 64, 32, 32),
+    (0, 2, 24, 40, 64, 64),
+    (0, 1, 32, 32, 64, 32),
+    (0, 1, 32, 32, 32, 64),
+    (0, 1, 32, 32, 128, 64),
+    (0, 1, 16, 16, 256, 256),
+    (0, 3, 9, 9, 128, 128),
+    (1, 2, 32, 32, 32, 32),
+    (1, 1, 64, 64, 64, 64),
+    (1, 2, 16, 16, 128, 128),
+    (1, 1, 24, 40, 64, 64),
+    (2, 2, 16, 16, 128, 128),
+    (2, 1, 32, 32, 64, 64),
+    (2, 1, 8, 24, 256, 256),
+    (3, 2, 32, 32, 64, 32),
+    (3, 1, 32, 32, 128, 64),
+    (3, 2, 16, 24, 128, 384),
+    (3, 2, 16, 24, 384, 128),
+]
+
+
+@pytest.mark.parametrize("mode,n,h,w,cin,cout", BWD_CASES)
+def test_conv_dgrad(b200, mode, n, h, w, cin, cout):
+    """conv_umma modes 4/5/6 (and 3 with the transposed pack) == autograd's grad_input of the forward modes."""
+    k = 1 if mode == 3 else 3
+    wt = (_randn((cout, cin, k, k), 3) / math.sqrt(cin * k * k)).to(BF16).float()
+    x = _randn((n, h, w, cin), 1).to(F16)
+    ho, wo = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+    dy = _randn((n, ho, wo, cout), 2).to(BF16)
+    dx_ref, _ = _conv_grads(x, wt, dy, mode)
+    wp = b200.ops.pack_conv_weight(wt, (2 if mode == 2 else 0) | 4, BF16)
+    zero = torch.zeros(cin, device=DEV)
+    dmode = {0: 4, 1: 5, 2: 6, 3: 3}[mode]
+    dx = b200.ops.conv_umma(dy, wp, zero, dmode)
+    assert dx.shape == dx_ref.shape and dx.dtype == BF16
+    r = _rel(dx, dx_ref)
+    # operands exact in bf16, fp32 accumulate, one bf16 rounding of the result (2^-9 rms ~ 1.1e-3); the up-sampling
+    # gradient uses pre-summed bf16 weights (one more rounding)
+    assert r <= (4e-3 if mode == 2 else 2.5e-3), f"dgrad mode {mode}: rel-L2 {r:.3e}"
+    dx32 = b200.ops.conv_umma(dy, wp, zero, dmode, out_f32=True)
+    r32 = _rel(dx32, dx_ref)
+    assert r32 <= (3e-3 if mode == 2 else 2e-5), f"dgrad mode {mode} fp32 out: rel-L2 {r32:.3e}"
+
+
+@pytest.mark.parametrize("halo", [0, 1])
+@pytest.mark.parametrize("mode,n,h,w,cin,cout", BWD_CASES)
+def test_conv_wgrad(b200, mode, n, h, w, cin, cout, halo):
+    """ops.wgrad (tcgen05, mixed bf16 x fp16 operands, split-K) == autograd's grad_weight."""
+    if halo and mode != 0:
+        pytest.skip("halo boxes exist for the stride-1 3x3 conv only")
+    k = 1 if mode == 3 else 3
+    wt = _randn((cout, cin, k, k), 3) / math.sqrt(cin * k * k)
+    x = _randn((n, h, w, cin), 1).to(F16)
+    ho, wo = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+    dy = _randn((n, ho, wo, cout), 2).to(BF16)
+    _, dw_ref = _conv_grads(x, wt, dy, mode)
+    b200.ops.WGRAD_HALO = halo
+    try:
+        dw = b200.ops.wgrad(dy, x, mode)
+        dw2 = b200.ops.wgrad(dy, x, mode)
+    finally:
+        b200.ops.WGRAD_HALO = 1
+    assert dw.shape == dw_ref.shape and dw.dtype == torch.float32
+    assert torch.equal(dw, dw2), "wgrad is not run-to-run deterministic"
+    r = _rel(dw, dw_ref)
+    assert r <= 2e-5, f"wgrad mode {mode} halo {halo}: rel-L2 {r:.3e}"   # exact operands, fp32 accumulate
+
+
+def test_wgrad_same_format_operands(b200):
+    """bf16 x bf16 and fp16 x fp16 operand pairs (the mixed pair is the default above)."""
+    n, h, w, c = 2, 16, 16, 64
+    wt = _randn((c, c, 3, 3), 3)
+    for dt_y, dt_x in ((BF16, BF16), (F16, F16)):
+        x = _randn((n, h, w, c), 1).to(dt_x)
+        dy = _randn((n, h, w, c), 2).to(dt_y)
+        _, dw_ref = _conv_grads(x, wt, dy, 0)
+        assert _rel(b200.ops.wgrad(dy, x, 0), dw_ref) <= 2e-5
+
+
+@pytest.mark.parametrize("b,m,n,k", [(2, 256, 128, 128), (1, 128, 256, 192), (3, 81, 128, 81), (2, 200, 64, 72)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_bgemm(b200, b, m, n, k, a_mn, b_mn):
+    """out[b,m,n] = sum_k A(m,k) B(n,k) with each operand K-major or MN-major, mixed formats, ragged extents."""
+    kp, mp, np_ = (k + 7) // 8 * 8, (m + 7) // 8 * 8, (n + 7) // 8 * 8
+    a_full = _randn((b, kp, mp) if a_mn else (b, m, kp), 1).to(F16)
+    b_full = _randn((b, kp, np_) if b_mn else (b, n, kp), 2).to(BF16)
+    a = a_full[:, :k, :m] if a_mn else a_full[:, :, :k]
+    bb = b_full[:, :k, :n] if b_mn else b_full[:, :, :k]
+    a_mk = a.float().transpose(1, 2) if a_mn else a.float()
+    b_nk = bb.float().transpose(1, 2) if b_mn else bb.float()
+    ref = torch.einsum("bmk,bnk->bmn", a_mk, b_nk)
+    out = torch.zeros((b, m, np_), device=DEV, dtype=BF16)[:, :, :n]
+    b200.ops.bgemm(a, bb, out, a_mn, b_mn, k=k)
+    r = _rel(out, ref)
+    assert r <= 2.5e-3, f"bgemm a_mn={a_mn} b_mn={b_mn}: rel-L2 {r:.3e}"
+
+
+@pytest.mark.parametrize("b,l,d", [(2, 256, 128), (1, 1024, 128), (2, 81, 128), (1, 256, 256), (1, 200, 64)])
+def test_attention_bwd(b200, b, l, d):
+    qkv = (_randn((b, l, 3 * d), 5) * 0.7).to(F16)
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    o, lse = b200.ops.attention(q, k, v, return_lse=True)
+    d_o = _randn((b, l, d), 6).to(BF16)
+    dqkv = torch.zeros((b, l, 3 * d), device=DEV, dtype=BF16)
+    b200.ops.attention_bwd(q, k, v, o, lse, d_o, dqkv)
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bxd,byd->bxy", qf, kf) * (d ** -0.5)
+    lse_ref = torch.logsumexp(s, dim=-1) * 1.4426950408889634
+    assert float((lse - lse_ref).abs().max()) <= 2e-3, "forward log-sum-exp"
+    oref = torch.softmax(s, dim=-1) @ vf
+    oref.backward(d_o.float())
+    for name, got, ref in (("dq", dqkv[..., :d], qf.grad), ("dk", dqkv[..., d:2 * d], kf.grad),
+                           ("dv", dqkv[..., 2 * d:], vf.grad)):
+        r = _rel(got, ref)
+        # P and dS are rounded to 16 bits (fp16 / bf16) between the GEMMs: ~3e-3 rms each
+        assert r <= 1e-2, f"attention_bwd {name} L={l} D={d}: rel-L2 {r:.3e}"
+
+
+@pytest.mark.parametrize("n,h,w,c,g", [(2, 32, 32, 32, 16), (1, 64, 64, 64, 16), (3, 24, 40, 128, 16), (2, 16, 16, 256, 32),
+                                       (2, 9, 9, 128, 16)])
+@pytest.mark.parametrize("silu", [True, False])
+@pytest.mark.parametrize("xdt", [torch.float32, F16])
+def test_gn_bwd(b200, n, h, w, c, g, silu, xdt):
+    eps = 1e-6
+    x = (_randn((n, h, w, c), 1) * 1.5 + 0.3).to(xdt)
+    da = _randn((n, h, w, c), 2).to(BF16)
+    gamma = _randn((c,), 3) * 0.5 + 1.0
+    beta = _randn((c,), 4) * 0.2
+    res = _randn((n, h, w, c), 5)
+    part = b200.ops.gn_stats(x, g)
+    ss, mr = b200.ops.gn_finalize(part, gamma, beta, h * w, eps, return_mean_rstd=True)
+    dg, db = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    dx32, dx16 = b200.ops.gn_bwd(x, da, ss, mr, gamma, silu, dg, db, residual=res)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr, g, gr, br, eps)
+    if silu:
+        y = F.silu(y)
+    y.backward(da.float().permute(0, 3, 1, 2))
+    dx_ref = xr.grad.permute(0, 2, 3, 1) + res
+    assert _rel(dx32, dx_ref) <= 2e-5, _rel(dx32, dx_ref)            # fp32 math end to end
+    assert _rel(dx16, dx_ref) <= 2.5e-3                              # + one bf16 rounding
+    assert _rel(dg, gr.grad) <= 2e-5 and _rel(db, br.grad) <= 2e-5, (_rel(dg, gr.grad), _rel(db, br.grad))
+    dg2, db2 = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    dx32b, _ = b200.ops.gn_bwd(x, da, ss, mr, gamma, silu, dg2, db2, residual=res)
+    assert torch.equal(dx32, dx32b) and torch.equal(dg, dg2) and torch.equal(db, db2), "gn_bwd not deterministic"
+
+
+@pytest.mark.parametrize("rows,c,dt", [(4096, 32, BF16), (1000, 128, BF16), (70000, 64, F16), (33, 384, torch.float32)])
+def test_colsum(b200, rows, c, dt):
+    x = _randn((1, rows, 1, c), 1).to(dt)
+    out = b200.ops.colsum(x)
+    ref = x.float().sum(dim=(0, 1, 2))
+    assert float((out - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())) + 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,c,ct", [(2, 32, 32, 32, 1), (1, 24, 40, 128, 4), (2, 16, 16, 64, 10)])
+def test_thin_wgrad(b200, n, h, w, c, ct):
+    # wide -> thin conv (small_cout, with the fused GroupNorm affine): dW, db
+    x = _randn((n, h, w, c), 1).to(F16)
+    ss = torch.stack([_randn((n, c), 2) * 0.3 + 1.0, _randn((n, c), 3) * 0.2], dim=-1).contiguous()
+    d_out = _randn((n, ct, h, w), 4)
+    wt = _randn((ct, c, 3, 3), 5).requires_grad_(True)
+    bt = torch.zeros(ct, device=DEV, requires_grad=True)
+    xa = (x.float() * ss[:, None, None, :, 0] + ss[:, None, None, :, 1]).permute(0, 3, 1, 2)
+    F.conv2d(xa, wt, bt, padding=1).backward(d_out)
+    dw, db = torch.empty_like(wt), torch.empty(ct, device=DEV)
+    b200.ops.thin_wgrad(d_out, x, True, dw, db=db, scale_shift=ss)
+    assert _rel(dw, wt.grad) <= 2e-5 and _rel(db, bt.grad) <= 2e-5, (_rel(dw, wt.grad), _rel(db, bt.grad))
+    # thin -> wide conv (small_cin): dW from the thin fp32 input and the wide gradient
+    xin = _randn((n, ct, h, w), 6)
+    dy = _randn((n, h, w, c), 7).to(BF16)
+    w2 = _randn((c, ct, 3, 3), 8).requires_grad_(True)
+    F.conv2d(xin, w2, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    dw2 = torch.empty_like(w2)
+    b200.ops.thin_wgrad(xin, dy, False, dw2)
+    assert _rel(dw2, w2.grad) <= 2e-5, _rel(dw2, w2.grad)
+
+
+def test_thin_dgrad_via_mirrored_weights(b200):
+    """Data gradients of the thin convs are the opposite thin conv with mirrored, transposed weights."""
+    n, h, w, c, ct = 2, 24, 40, 32, 4
+    wt = _randn((ct, c, 3, 3), 1)                                    # wide -> thin conv weight
+    d_out = _randn((n, ct, h, w), 2)
+    x = _randn((n, c, h, w), 3).requires_grad_(True)
+    F.conv2d(x, wt, None, padding=1).backward(d_out)
+    mir = wt.flip(2, 3).transpose(0, 1).contiguous()                 # [c][ct][3][3]
+    da = b200.ops.conv3x3_small_cin(d_out, mir, torch.zeros(c, device=DEV), dtype=torch.float32)
+    assert _rel(da, x.grad.permute(0, 2, 3, 1)) <= 2e-5
+    w2 = _randn((c, ct, 3, 3), 4)                                    # thin -> wide conv weight
+    dy = _randn((n, h, w, c), 5).to(BF16)
+    xin = _randn((n, ct, h, w), 6).requires_grad_(True)
+    F.conv2d(xin, w2, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    mir2 = w2.flip(2, 3).transpose(0, 1).contiguous()                # [ct][c][3][3]
+    dxin = b200.ops.conv3x3_small_cout(dy, mir2, torch.zeros(ct, device=DEV))
+    assert _rel(dxin, xin.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("n,l,h,w", [(2, 4, 8, 8), (3, 10, 16, 16)])
+def test_latent_bwd(b200, n, l, h, w):
+    hh = _randn((n, l, h, w), 1)
+    eps = _randn((n, l, h, w), 2)
+    ws_ = [(_randn((l, l, 1, 1), 10 + i) * 0.5).requires_grad_(True) for i in range(3)]
+    bs_ = [(_randn((l,), 20 + i) * 0.1).requires_grad_(True) for i in range(3)]
+    # push some log-variances outside the clamp range so the mask is exercised
+    hh[:, 0] *= 40.0
+    hr = hh.clone().requires_grad_(True)
+    mu = F.conv2d(hr, ws_[0], bs_[0])
+    lv = torch.clamp(F.conv2d(hr, ws_[1], bs_[1]), -30.0, 20.0)
+    sigma = torch.exp(lv / 2)
+    z = mu + sigma * eps
+    zq = F.conv2d(z, ws_[2], bs_[2])
+    dzq, dmu_e, dsg_e = _randn((n, l, h, w), 3), _randn((n, l, h, w), 4), _randn((n, l, h, w), 5) * 1e-3
+    (zq * dzq).sum().backward(retain_graph=True)
+    (mu * dmu_e).sum().backward(retain_graph=True)
+    (sigma * dsg_e).sum().backward()
+    w2 = [t.detach().reshape(l, l).contiguous() for t in ws_]
+    dh, dmu, dlv, zz = b200.ops.latent_bwd(dzq, dmu_e, dsg_e, eps, hh, mu.detach(), sigma.detach(), w2[2], w2[0], w2[1],
+                                           bs_[1].detach())
+    assert _rel(zz, z.detach()) <= 1e-6
+    assert _rel(dh, hr.grad) <= 1e-4, _rel(dh, hr.grad)
+    for (a, b, wi, bi) in ((dzq, zz, ws_[2], bs_[2]), (dmu, hh, ws_[0], bs_[0]), (dlv, hh, ws_[1], bs_[1])):
+        dw, db = torch.empty((l, l), device=DEV), torch.empty(l, device=DEV)
+        b200.ops.outer_reduce(a, b, dw, db)
+        assert _rel(dw, wi.grad.reshape(l, l)) <= 1e-4 and _rel(db, bi.grad) <= 1e-4
+
+
+def test_loss_gradients_and_adam(b200):
+    a, b = _randn((4, 1, 32, 32), 1), _randn((4, 1, 32, 32), 2)
+    ar = a.clone().requires_grad_(True)
+    (0.7 * F.l1_loss(ar, b) + 0.3 * F.mse_loss(ar, b)).backward()
+    d = b200.ops.l1l2_bwd(a, b, torch.tensor([0.7, 0.3], device=DEV))
+    assert _rel(d, ar.grad) <= 1e-6
+    mu, sg = _randn((4, 4, 8, 8), 3), _randn((4, 4, 8, 8), 4).abs() + 0.1
+    for is_lv in (True, False):
+        mr, sr = mu.clone().requires_grad_(True), sg.clone().requires_grad_(True)
+        t = sr if is_lv else torch.log(sr.pow(2) + 1e-8)
+        kl = (-0.5 * torch.sum(1 + t - mr.pow(2) - t.exp(), dim=[1, 2, 3])).mean()
+        (2.5 * kl).backward()
+        dmu, dt = b200.ops.kl_bwd(mu, sg, torch.tensor([2.5], device=DEV), is_lv)
+        assert _rel(dmu, mr.grad) <= 1e-6 and _rel(dt, sr.grad) <= 1e-5
+    # differentiable wrappers
+    ar2 = a.clone().requires_grad_(True)
+    mr, sr = mu.clone().requires_grad_(True), sg.clone().requires_grad_(True)
+    loss = b200.l1_loss(ar2, b) + 1e-3 * b200.compute_kl_loss(mr, sr)
+    loss.backward()
+    ar3 = a.clone().requires_grad_(True)
+    F.l1_loss(ar3, b).backward()
+    assert _rel(ar2.grad, ar3.grad) <= 1e-6 and mr.grad is not None and sr.grad is not None
+    # Adam on a flat buffer == torch.optim.Adam, three steps
+    p = _randn((1000,), 5)
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.ones(1, device=DEV)
+    for i in range(3):
+        g = _randn((1000,), 10 + i)
+        pt.grad = g.clone()
+        opt.step()
+        b200.ops.adam(p, g, m, v, step, 1e-3)
+    assert float(step) == 4.0
+    assert float((p - pt.detach()).abs().max()) <= 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------- end to end
+def _models(b200, oracle, cfg):
+    ref = oracle.seeded_model(cfg, 1234)
+    vae = b200.VAEModel.from_config(cfg)
+    vae.load_state_dict(ref.state_dict(), strict=True)
+    return ref, vae.to(DEV).train()
+
+
+E2E_TOL_W, E2E_TOL_X = 3e-2, 1.5e-2
+
+
+@pytest.mark.parametrize("cfgname,b,h,w", [("AUTOENCODER_DEF_A", 2, 64, 64), ("AUTOENCODER_DEF_B", 1, 64, 64),
+                                           ("AUTOENCODER_DEF_A", 1, 72, 72)])
+def test_backward_matches_oracle(b200, oracle, cfgname, b, h, w):
+    """loss = L1(recon, x) + 1e-3 * KL(z_mu, z_sigma) + a probe on z_mu / z_sigma; gradients of x and of every
+    parameter vs. the oracle's fp32 CPU autograd on the same weights, input and eps (train_vae.py:385-444)."""
+    cfg = getattr(b200.config, cfgname)
+    ref, vae = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(b, h, w, seed=0)
+    with torch.no_grad():
+        mu0, _ = ref.encode(x)
+    eps = torch.randn(mu0.shape, generator=torch.Generator().manual_seed(7))
+
+    def loss_fn(recon, mu, sigma, xin, kl):
+        return F.l1_loss(recon, xin) + 1e-3 * kl(mu, sigma) + 1e-2 * mu.mean() + 1e-2 * sigma.pow(2).mean()
+
+    xr = x.clone().requires_grad_(True)
+    loss_r = loss_fn(*ref(xr, eps), xr, oracle.kl_loss_ref)
+    loss_r.backward()
+    xg = x.to(DEV).requires_grad_(True)
+    with torch.autograd.set_detect_anomaly(True):          # the reference trainer keeps anomaly mode on (train_vae.py:95)
+        recon, mu, sigma = vae.autoencoder(xg, eps.to(DEV))
+        loss_g = loss_fn(recon, mu, sigma, xg, b200.compute_kl_loss)
+        loss_g.backward()
+    assert abs(float(loss_g) - float(loss_r)) <= 2e-3 * abs(float(loss_r))
+    ex = _rel(xg.grad, xr.grad)
+    worst, bad = 0.0, []
+    ref_params = dict(ref.named_parameters())
+    for name, p in vae.autoencoder.named_parameters():
+        assert p.grad is not None, f"no gradient for {name}"
+        assert torch.isfinite(p.grad).all(), name
+        r = _rel(p.grad, ref_params[name].grad)
+        worst = max(worst, r)
+        if r > E2E_TOL_W:
+            bad.append((name, r))
+    print(f"{cfgname} {b}x{h}x{w}: dX rel-L2 {ex:.2e}, worst dW rel-L2 {worst:.2e}")
+    assert not bad, bad[:10]
+    assert ex <= E2E_TOL_X, ex
+
+
+def test_train_step_matches_autograd_path(b200, oracle):
+    """The fused TrainStep (flat buffers, own Adam) takes the same step as autograd + torch.optim.Adam."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    ref, vae_a = _models(b200, oracle, cfg)
+    _, vae_b = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(2, 64, 64, seed=0).to(DEV)
+    with torch.no_grad():
+        mu0, _ = ref.encode(x.cpu())
+    eps = torch.randn(mu0.shape, generator=torch.Generator().manual_seed(7)).to(DEV)
+    opt = torch.optim.Adam(vae_a.autoencoder.parameters(), lr=1e-4)
+    recon, mu, sigma = vae_a.autoencoder(x, eps)
+    (b200.l1_loss(recon, x) + 1e-3 * b200.compute_kl_loss(mu, sigma)).backward()
+    ga = torch.cat([p.grad.reshape(-1) for p in vae_a.autoencoder.parameters()])
+    p_before = torch.cat([p.detach().reshape(-1) for p in vae_b.autoencoder.parameters()]).clone()
+    ts = b200.TrainStep(vae_b, lr=1e-4, kl_weight=1e-3, recon_loss="l1")
+    assert torch.equal(ts.params, p_before), "flattening must preserve the parameter values"
+    out = ts.step(x, eps)
+    assert abs(float(out["recon_loss"]) - float(F.l1_loss(recon.detach(), x))) <= 1e-5
+    assert _rel(ts.grads, ga) <= 1e-5, _rel(ts.grads, ga)          # same kernels, same order: the same gradients
+    # Adam's first step moves a weight by ~lr*sign(g); where |g| is not tiny the two optimizers agree
+    opt.step()
+    pa = torch.cat([p.detach().reshape(-1) for p in vae_a.autoencoder.parameters()])
+    big = ga.abs() > 1e-6
+    assert float(((pa - ts.params)[big]).abs().max()) <= 2e-6, float(((pa - ts.params)[big]).abs().max())
+    assert float((ts.params - p_before).abs().max()) <= 1.001e-4
+    # state_dict still exposes the (updated) parameters under the reference's keys
+    sd = vae_b.state_dict()
+    assert len(sd) == len(ref.state_dict()) and all(torch.isfinite(v).all() for v in sd.values())
+    # and the model keeps working after the in-place update (packed weights were invalidated)
+    out2 = ts.step(x, eps)
+    assert torch.isfinite(out2["recon_loss"]) and float(out2["recon_loss"]) < float(out["recon_loss"]) + 1e-3
+
+
+def test_train_step_graph_replay(b200, oracle):
+    cfg = b200.config.AUTOENCODER_DEF_A
+    _, vae = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(2, 64, 64, seed=0).to(DEV)
+    ts = b200.TrainStep(vae, lr=1e-4).capture(2, 64, 64)
+    losses = []
+    for _ in range(5):
+        out = ts.replay(x)
+        losses.append(float(out["recon_loss"]))
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
