@@ -204,7 +204,8 @@ int ptivae_local_normalize(const float* x, float* out, float* stats, void* works
 int ptivae_local_normalize_workspace(int B);
 
 /* ---- backward pass (`loss_g.backward()`, vae_scripts/train_vae.py:444) -----------------
- * Gradient tensors are NHWC; 16-bit gradient operands are bf16 (range), activations keep the forward's operand format.
+ * Gradient tensors are NHWC; every 16-bit operand of a backward GEMM is bf16 (the gradients' range; both operands of
+ * one MMA must share a format).
  *
  * Weight gradient of a convolution on tcgen05 (replaces cuDNN wgrad): dw[co][ci][ky][kx] = sum dY[p][co]*X[p+tap][ci].
  *   dy   h16 NHWC gradient of the conv output, Ca channels;  x  h16 NHWC conv input (as the forward GEMM read it), Cb channels
@@ -212,16 +213,20 @@ int ptivae_local_normalize_workspace(int B);
  *        2: nearest x2 upsample + 3x3, H,W = extent of x (dy is 2H x 2W)     3: 1x1
  *   dw   fp32 [Ca][Cb][3][3] (modes 0-2) or [Ca][Cb] (mode 3): the master-weight layout, overwritten
  *   workspace: ptivae_wgrad_workspace(...) bytes of split-K partial sums (plain stores, summed in index order)
- *   halo != 0 (mode 0 only): the three kx taps of a kernel row read one 18-pixel-wide TMA box */
+ *   f16: 16-bit format of BOTH operands (one tcgen05 MMA cannot mix fp16 and bf16) */
 int ptivae_wgrad(const void* dy, const void* x, float* workspace, float* dw, int N, int H, int W, int Ca, int Cb, int mode,
-                 int dy_f16, int x_f16, int halo, void* stream);
+                 int f16, void* stream);
 long long ptivae_wgrad_workspace(int N, int H, int W, int Ca, int Cb, int mode);
+/* debug only: 6 ints of host-mapped memory that receive (role, tile, stage, block x, y, z) of the first barrier wait that
+ * timed out in subsequent ptivae_wgrad launches (the kernel then exits instead of trapping); NULL switches it off */
+int ptivae_debug_set_wgrad_status(void* status);
 
 /* Batched GEMM on tcgen05 with operands consumed as they lie in memory (attention backward):
- *   out[b][m][n] = epi( sum_k A[b](m,k) * B[b](n,k) ),  16-bit operands (formats may differ), fp32 accumulate, 16-bit out.
+ *   out[b][m][n] = epi( sum_k A[b](m,k) * B[b](n,k) ),  16-bit operands of ONE format, fp32 accumulate, 16-bit out.
  *   a_mn == 0: A(m,k) at a[b*bs_a + m*lda + k] (K-major);  a_mn != 0: at a[b*bs_a + k*lda + m] (MN-major); same for b.
  *   epi 0: acc*alpha;  1: exp2(acc*alpha - rowv[b][m]);  2: aux[b][m][n]*(acc - rowv[b][m])*alpha
- *   leading dimensions / batch strides in elements (multiples of 8); N % 8 == 0. */
+ *   leading dimensions / batch strides in elements (multiples of 8); stores are 8 columns wide, so with N % 8 != 0 the
+ *   last group spills into the row padding of out (ldo >= round_up(N, 8)). */
 int ptivae_bgemm(const void* a, const void* b, void* out, int B, int M, int N, int K, long long lda, long long bs_a, int a_mn,
                  int a_f16, long long ldb, long long bs_b, int b_mn, int b_f16, long long ldo, long long bs_out, int out_f16,
                  int epi, float alpha, const float* rowv, const void* aux, long long ld_aux, long long bs_aux, int aux_f16,
@@ -265,6 +270,10 @@ int ptivae_outer_reduce(const float* a, const float* b, float* dw, float* db, in
 int ptivae_l1l2_bwd(const float* a, const float* b, const float* gout, float* d, long long n, void* stream);
 int ptivae_kl_bwd(const float* mu, const float* t, const float* gout, float* dmu, float* dt, int N, int per_img,
                   int input_is_logvar, void* stream);
+/* dst (h16: fp16 when dst_f16 != 0, else bf16) = src (storage src_fmt); n % 8 == 0.  One tcgen05 MMA needs both
+ * operands in the same 16-bit format (measured: mixing raises an illegal-instruction fault), the backward GEMMs run in
+ * bf16, so the saved fp16 forward operands they read are converted once. */
+int ptivae_cast16(const void* src, void* dst, long long n, int src_fmt, int dst_f16, void* stream);
 /* torch.optim.Adam (defaults) over one flat fp32 buffer; step_dev: device float = 1-based step of this update,
  * incremented afterwards when advance != 0; grad_scale multiplies g (1/world_size after a sum all-reduce). */
 int ptivae_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,

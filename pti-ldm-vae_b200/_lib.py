@@ -51,8 +51,9 @@ SIGNATURES = {
     "ptivae_ar_vae_loss": [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p] * 4,
     "ptivae_linear_act": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
     # backward pass
-    "ptivae_wgrad": [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p],
+    "ptivae_wgrad": [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p],
     "ptivae_wgrad_workspace": [_c_int] * 6,
+    "ptivae_debug_set_wgrad_status": [_c_void_p],
     "ptivae_bgemm": [_c_void_p] * 3 + [_c_int] * 4 + [_c_ll, _c_ll, _c_int, _c_int, _c_ll, _c_ll, _c_int, _c_int, _c_ll, _c_ll,
                                                       _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_ll, _c_ll, _c_int,
                                                       _c_void_p],
@@ -68,6 +69,7 @@ SIGNATURES = {
     "ptivae_outer_reduce": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
     "ptivae_l1l2_bwd": [_c_void_p] * 4 + [_c_ll, _c_void_p],
     "ptivae_kl_bwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],
+    "ptivae_cast16": [_c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_void_p],
     "ptivae_adam": [_c_void_p] * 4 + [_c_ll] + [_c_float] * 5 + [_c_void_p, _c_int, _c_void_p],
 }
 _RESTYPE_LL = {"ptivae_wgrad_workspace", "ptivae_thin_wgrad_workspace"}

@@ -151,7 +151,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int nn = n0 + c * 32 + u * 8;
-        if (nn >= args.N) continue;     // N % 8 == 0
+        if (nn >= args.N) continue;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[u * 8 + e]);
@@ -229,7 +229,9 @@ extern "C" int ptivae_bgemm(const void* a, const void* b, void* out, int B, int 
                             long long ldo, long long bs_out, int out_f16, int epi, float alpha, const float* rowv,
                             const void* aux, long long ld_aux, long long bs_aux, int aux_f16, void* stream_) {
   if (!a || !b || !out || B <= 0 || M <= 0 || N <= 0 || K <= 0) return PTIVAE_ERR_ARG;
-  if (N % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldo % 8 != 0) return PTIVAE_ERR_ARG;
+  // stores are 8 columns wide: with N % 8 != 0 the last group spills into the row padding (ldo >= N and ldo % 8 == 0
+  // make that padding exist); the spilled values are never read back (tensor maps use the true extents)
+  if (lda % 8 != 0 || ldb % 8 != 0 || ldo % 8 != 0 || ldo < N) return PTIVAE_ERR_ARG;
   if (epi < 0 || epi > 2 || (epi != 0 && !rowv) || (epi == 2 && (!aux || ld_aux % 8 != 0))) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int bn = N > 64 ? 128 : 64;

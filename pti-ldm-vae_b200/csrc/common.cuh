@@ -74,6 +74,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// Acquire fence of the tensormap proxy on one descriptor: drops any stale copy of the 128 bytes at this address from the
+// TMA unit's descriptor cache.  Needed in practice even for __grid_constant__ descriptors: kernel parameter buffers are
+// recycled between launches, and after cuDNN's TF32 (TMA-based) convolution kernels had run in the same process the
+// loads of the SECOND descriptor parameter of wgrad_umma_kernel never completed (measured: tools/stress_wgrad.py).
+__device__ __forceinline__ void tma_acquire_desc(const CUtensorMap* m) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ x, float* __restrict__ partial,
                                                              long long rows, int C, int rows_per_block, int fmt) {
   __shared__ float sm[256][9];
-  const int vecs = C / 8;
+  const int vecs = C / 8;                      // any vecs <= 256: threads beyond vecs * prows stay idle
   const int v = threadIdx.x % vecs;
   const int prow = threadIdx.x / vecs;
   const int prows = blockDim.x / vecs;
@@ -287,9 +287,7 @@ extern "C" int ptivae_colsum_blocks(long long rows) {
 }
 extern "C" int ptivae_colsum(const void* x, float* out, float* workspace, long long rows, int C, int fmt,
                              void* stream_) {
-  if (!x || !out || !workspace || rows <= 0 || C % 8 != 0 || C > 2048 || 256 % (C / 8 > 256 ? 256 : C / 8) != 0 ||
-      fmt < 0 || fmt > 2)
-    return PTIVAE_ERR_ARG;
+  if (!x || !out || !workspace || rows <= 0 || C % 8 != 0 || fmt < 0 || fmt > 2) return PTIVAE_ERR_ARG;
   if (C / 8 > 256) return PTIVAE_ERR_UNSUPPORTED;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int blocks = ptivae_colsum_blocks(rows);

@@ -64,6 +64,30 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 __global__ void adam_step_kernel(float* step_dev) { step_dev[0] += 1.0f; }
 
+// 8 elements per thread: any of {bf16, fp16, fp32} -> {bf16, fp16}
+__global__ void __launch_bounds__(256) cast16_kernel(const void* __restrict__ src, uint4* __restrict__ dst, size_t nvec,
+                                                     int src_fmt, int dst_f16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float v[8];
+    if (src_fmt == 2) {
+      const float4* p = reinterpret_cast<const float4*>(src) + i * 2;
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (src_fmt == 1) unpack2<true>(w[e], v[2 * e], v[2 * e + 1]);
+        else unpack2<false>(w[e], v[2 * e], v[2 * e + 1]);
+      }
+    }
+    dst[i] = dst_f16 ? make_uint4(pack2<true>(v[0], v[1]), pack2<true>(v[2], v[3]), pack2<true>(v[4], v[5]), pack2<true>(v[6], v[7]))
+                     : make_uint4(pack2<false>(v[0], v[1]), pack2<false>(v[2], v[3]), pack2<false>(v[4], v[5]), pack2<false>(v[6], v[7]));
+  }
+}
+
 }  // namespace ptivae
 
 using namespace ptivae;
@@ -94,5 +118,16 @@ extern "C" int ptivae_adam(float* p, const float* g, float* m, float* v, long lo
   adam_kernel<<<grid_for(static_cast<size_t>(n), 256, 148 * 8), 256, 0, stream>>>(p, g, m, v, static_cast<size_t>(n), lr,
                                                                                   beta1, beta2, eps, grad_scale, step_dev);
   if (advance) adam_step_kernel<<<1, 1, 0, stream>>>(step_dev);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// dst (16-bit: fp16 when dst_f16 != 0, else bf16) = src (storage src_fmt: 0 bf16, 1 fp16, 2 fp32); n % 8 == 0.
+// tcgen05 kind::f16 needs both operands of one MMA in the same 16-bit format: the backward GEMMs run in bf16 (the
+// gradients' range), so the few saved fp16 forward operands they read are converted once.
+extern "C" int ptivae_cast16(const void* src, void* dst, long long n, int src_fmt, int dst_f16, void* stream_) {
+  if (!src || !dst || n <= 0 || n % 8 != 0 || src_fmt < 0 || src_fmt > 2) return PTIVAE_ERR_ARG;
+  const size_t nvec = static_cast<size_t>(n) / 8;
+  cast16_kernel<<<grid_for(nvec, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      src, static_cast<uint4*>(dst), nvec, src_fmt, dst_f16);
   return static_cast<int>(cudaGetLastError());
 }

@@ -8,14 +8,16 @@
 // Both operands are NHWC, i.e. channel-contiguous = "MN-major" for this GEMM: a TMA box of (64 channels x 16 pixels x
 // 4 rows) lands in shared memory as 64 K-rows of 128 bytes (SWIZZLE_128B), which the MN-major UMMA descriptor reads
 // directly (LBO = stride between 64-channel atoms, SBO = 8 K-rows).  No transpose, no im2col: the tap shift is a
-// TMA coordinate offset and the zero padding is TMA out-of-bounds fill.  The two operands may use different 16-bit
-// formats in one MMA (kind::f16 has independent A/B format fields): gradients are bf16 (range), activations fp16.
+// TMA coordinate offset and the zero padding is TMA out-of-bounds fill.
+// (Both operands of one MMA must use the same 16-bit format: mixing fp16 and bf16 raises an illegal-instruction
+// fault although the instruction descriptor has separate A/B format fields -- measured.  The backward runs in bf16.)
 //
 //   CTA     : one (split-K range of pixel tiles) x (tap group: up to 4 taps that share the dY tile) x (Cout block,
 //             Cin block).  The taps of a group accumulate into separate TMEM column ranges [t*nb, (t+1)*nb).
-//   halo    : for the stride-1 3x3 conv a tap group is one kernel row ky; its three kx taps read ONE 18-pixel-wide
-//             box, shifted by kx lines (the swizzle is a function of the absolute shared-memory address, so a
-//             128-byte-aligned start is legal) -- B traffic 1.125x instead of 3x.
+//   (measured and not kept: one 18-pixel-wide halo box per kernel row with the three kx taps as descriptors shifted
+//    by kx lines -- an MN-major operand whose start address is not swizzle-atom (1024 B) aligned raises
+//    cudaErrorIllegalAddress, with and without the descriptor's base-offset field; the K-major forward kernels do
+//    use such shifted starts.)
 //   output  : fp32 partial sums [split][slab][Cout][Cin] with plain stores; wgrad_reduce_kernel adds the splits in
 //             index order (deterministic) and writes the master layout [Cout][Cin][kh][kw] (for the up-sampling conv it
 //             also folds the 16 phase-tap slabs back onto the 9 taps).
@@ -30,8 +32,8 @@ constexpr int kWTH = 4;         // tile height (rows)
 constexpr int kWMaxTaps = 4;
 constexpr int kWMaxGroups = 4;
 constexpr int kWMaxStages = 8;
+constexpr int kWBarsPerStage = 1 + kWMaxTaps;
 constexpr uint32_t kWAtom = 64u * 128u;                 // 64 pixels x 64 channels x 2 B
-constexpr uint32_t kWHaloAtom = kWTH * 18u * 128u;      // 4 rows x 18 pixels x 64 channels x 2 B  (9216 = 9 * 1024)
 
 struct WTap {
   int16_t dx, dy;   // offset of the activation box relative to the dY tile origin (tensor-map coordinates)
@@ -41,7 +43,7 @@ struct WTap {
 };
 struct WGroup {
   int16_t a_pz, a_cmul;   // parity coordinates of the dY map (up-sampling conv), else 0
-  int16_t ntaps, halo;    // halo != 0: the taps are kx = 0..2 of one 18-wide box loaded at (dx, dy) of taps[0]
+  int16_t ntaps, pad_;
   WTap taps[kWMaxTaps];
 };
 struct WgradArgs {
@@ -51,9 +53,10 @@ struct WgradArgs {
   int n_cb_blocks;
   int nslabs, nstages;
   uint32_t idesc;
-  uint32_t b_bytes, stage_bytes, tmem_cols;
+  uint32_t stage_bytes, tmem_cols;
   WGroup groups[kWMaxGroups];
   float* partial;    // [splits][nslabs][Ca][Cb]
+  int* status;       // optional debug word block (mapped host memory): see report_timeout
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t cols) {
@@ -65,16 +68,45 @@ __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t cols) 
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
+// Bounded wait that REPORTS instead of trapping: returns false after the same budget as mbar_wait.
+__device__ __forceinline__ bool mbar_wait_soft(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < 4096u; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+// status[0] = role code (1 producer / 2 MMA / 3 epilogue) of the FIRST wait that timed out, then (tile, stage, block x, y, z)
+__device__ __forceinline__ void report_timeout(int* status, int role, int t, int s) {
+  if (status == nullptr) __trap();                   // a protocol failure must be loud: the result would be garbage
+  int* st = status + role * 8;                       // one record per role: the first CTA that timed out in that role
+  if (atomicCAS(st, 0, role) == 0) {
+    st[1] = t; st[2] = s; st[3] = blockIdx.x; st[4] = blockIdx.y; st[5] = blockIdx.z;
+    __threadfence_system();
+  }
+}
+
 __global__ void __launch_bounds__(192, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmBh, const WgradArgs args) {
+                  const WgradArgs args) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const int nstages = args.nstages;
   const uint32_t stage_bytes = args.stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
-  uint64_t* empty_bar = full_bar + kWMaxStages;
+  // barriers: per stage one "full" barrier for the dY tile and one per tap (at most two TMA loads signal one barrier:
+  // with all of a stage's 4..8 loads on a single barrier the kernel dead-locked on some SMs once cuDNN's TF32
+  // convolution kernels had run in the process -- measured with tools/stress_wgrad.py, cause not understood)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);   // [stage][1 + kWMaxTaps]
+  uint64_t* empty_bar = full_bar + kWMaxStages * kWBarsPerStage;
   uint64_t* tmem_full_bar = empty_bar + kWMaxStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
@@ -88,15 +120,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int na_atoms = min(2, (args.Ca - ca0 + 63) / 64);
   const int nb_atoms = args.nb / 64;
   const int ntaps = grp.ntaps;
-  const bool halo = grp.halo != 0;
   const int t_begin = split * args.tiles_per_split;
   const int t_end = min(args.total_tiles, t_begin + args.tiles_per_split);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(halo ? &tmBh : &tmB);
+    tma_prefetch_desc(&tmB);
     for (int s = 0; s < nstages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      for (int j = 0; j <= ntaps; ++j) mbar_init(&full_bar[s * kWBarsPerStage + j], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -112,53 +143,47 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx_bytes = na_atoms * kWAtom + (halo ? nb_atoms * kWHaloAtom : ntaps * nb_atoms * kWAtom);
       for (int t = t_begin; t < t_end; ++t) {
         const int tix = t % args.tiles_x;
         const int tiy = (t / args.tiles_x) % args.tiles_y;
         const int n = t / (args.tiles_x * args.tiles_y);
         const int x0 = tix * kWTW, y0 = tiy * kWTH;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], tx_bytes);
+        if (!mbar_wait_soft(&empty_bar[s], ph ^ 1u)) { report_timeout(args.status, 1, t, s); break; }
+        uint64_t* fb = &full_bar[s * kWBarsPerStage];
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + 2 * kWAtom;
+        mbar_expect_tx(&fb[0], na_atoms * kWAtom);
         for (int a = 0; a < na_atoms; ++a)
-          tma_load_5d(sa + a * kWAtom, &tmA, &full_bar[s], grp.a_cmul * args.Ca + ca0 + a * 64, x0, grp.a_pz, y0, n);
-        if (halo) {
-          const WTap tp = grp.taps[0];
+          tma_load_5d(sa + a * kWAtom, &tmA, &fb[0], grp.a_cmul * args.Ca + ca0 + a * 64, x0, grp.a_pz, y0, n);
+        for (int k = 0; k < ntaps; ++k) {
+          const WTap tp = grp.taps[k];
+          mbar_expect_tx(&fb[1 + k], nb_atoms * kWAtom);
           for (int b = 0; b < nb_atoms; ++b)
-            tma_load_5d(sb + b * kWHaloAtom, &tmBh, &full_bar[s], cb0 + b * 64, x0 + tp.dx, 0, y0 + tp.dy, n);
-        } else {
-          for (int k = 0; k < ntaps; ++k) {
-            const WTap tp = grp.taps[k];
-            for (int b = 0; b < nb_atoms; ++b)
-              tma_load_5d(sb + (k * nb_atoms + b) * kWAtom, &tmB, &full_bar[s], tp.cmul * args.Cb + cb0 + b * 64,
-                          x0 + tp.dx, tp.pz, y0 + tp.dy, n);
-          }
+            tma_load_5d(sb + (k * nb_atoms + b) * kWAtom, &tmB, &fb[1 + k], tp.cmul * args.Cb + cb0 + b * 64,
+                        x0 + tp.dx, tp.pz, y0 + tp.dy, n);
         }
         if (++s == nstages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t a_hi = desc_hi(1024, kLayoutSW128);
-      const uint32_t b_hi = a_hi;
-      const uint32_t b_lbo = halo ? kWHaloAtom : kWAtom;
+      const uint32_t hi = desc_hi(1024, kLayoutSW128);
       int s = 0;
-      uint32_t ph = 0, accum = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int t = t_begin; t < t_end && ok; ++t) {
+        uint64_t* fb = &full_bar[s * kWBarsPerStage];
+        if (!mbar_wait_soft(&fb[0], ph)) { report_timeout(args.status, 2, t, s); break; }
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
         const uint32_t sb = sa + 2 * kWAtom;
+        for (int k = 0; k < ntaps; ++k) {
+          if (!mbar_wait_soft(&fb[1 + k], ph)) { report_timeout(args.status, 2, t, 100 + k); ok = false; break; }
+          tc_fence_after();
 #pragma unroll
-        for (int r = 0; r < kWTH; ++r) {
-          const uint32_t a_lo = desc_lo(sa + r * 2048u, kWAtom);
-          for (int k = 0; k < ntaps; ++k) {
-            const uint32_t baddr = halo ? sb + (r * 18u + k) * 128u : sb + k * nb_atoms * kWAtom + r * 2048u;
-            umma_f16_lohi(tmem_base + k * args.nb, a_lo, a_hi, desc_lo(baddr, b_lbo), b_hi, args.idesc, accum);
-          }
-          accum = 1;
+          for (int r = 0; r < kWTH; ++r)     // one UMMA K step = the 16 pixels of tile row r
+            umma_f16_lohi(tmem_base + k * args.nb, desc_lo(sa + r * 2048u, kWAtom), hi,
+                          desc_lo(sb + k * nb_atoms * kWAtom + r * 2048u, kWAtom), hi, args.idesc,
+                          (t != t_begin || r != 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
         if (++s == nstages) { s = 0; ph ^= 1u; }
@@ -169,7 +194,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;                      // TMEM lane quarter
     const int m = q * 32 + lane;
     const int ca = ca0 + m;
-    mbar_wait(tmem_full_bar, 0);
+    bool timed_out = true;
+    for (int rep = 0; rep < 3 && timed_out; ++rep) timed_out = !mbar_wait_soft(tmem_full_bar, 0);   // outlasts the other roles
+    if (timed_out) report_timeout(args.status, 3, -1, -1);
     tc_fence_after();
     __syncwarp();
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -259,6 +286,14 @@ static int wgrad_plan(int N, int H, int W, int Ca, int Cb, int mode, WgradPlan* 
 
 using namespace ptivae;
 
+static int* g_wgrad_status = nullptr;
+// debug only: 32 ints of host-mapped memory (device-accessible pointer) that receive (role, tile, stage, block x, y, z) of
+// the first barrier wait that timed out in subsequent ptivae_wgrad launches; NULL switches reporting off.
+extern "C" int ptivae_debug_set_wgrad_status(void* p) {
+  g_wgrad_status = static_cast<int*>(p);
+  return 0;
+}
+
 extern "C" long long ptivae_wgrad_workspace(int N, int H, int W, int Ca, int Cb, int mode) {
   WgradPlan p;
   const int rc = wgrad_plan(N, H, W, Ca, Cb, mode, &p);
@@ -267,7 +302,7 @@ extern "C" long long ptivae_wgrad_workspace(int N, int H, int W, int Ca, int Cb,
 }
 
 extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, float* dw, int N, int H, int W, int Ca,
-                            int Cb, int mode, int dy_f16, int x_f16, int halo, void* stream_) {
+                            int Cb, int mode, int f16, void* stream_) {
   if (!dy || !x || !workspace || !dw) return PTIVAE_ERR_ARG;
   WgradPlan p;
   int rc = wgrad_plan(N, H, W, Ca, Cb, mode, &p);
@@ -278,15 +313,15 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
   a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y; a.total_tiles = p.total_tiles; a.tiles_per_split = p.tiles_per_split;
   a.Ca = Ca; a.Cb = Cb; a.nb = p.nb; a.n_cb_blocks = p.n_cb_blocks; a.nslabs = p.nslabs;
   a.partial = workspace;
+  a.status = g_wgrad_status;
   // instruction descriptor: fp32 accumulate, A = dY, B = activations, both MN-major, M = 128, N = nb
-  const uint32_t afmt = dy_f16 ? 0u : 1u, bfmt = x_f16 ? 0u : 1u;
+  const uint32_t afmt = f16 ? 0u : 1u, bfmt = afmt;
   a.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t(p.nb) >> 3) << 17) |
             ((128u >> 4) << 24);
 
   // tensor maps: both operands as 5-D (C, W, parity, H, N) views with a (64, 16, 1, 4, 1) box
   uint64_t da[5], sa[4], db[5], sb[4];
   uint32_t box[5] = {64, kWTW, 1, kWTH, 1};
-  uint32_t boxh[5] = {64, 18, 1, kWTH, 1};
   const uint64_t A2 = uint64_t(Ca) * 2, B2 = uint64_t(Cb) * 2;
   auto plain = [](uint64_t* d, uint64_t* s, uint64_t C2b, int C, int Hh, int Ww, int Nn) {
     d[0] = C; d[1] = Ww; d[2] = 1; d[3] = Hh; d[4] = Nn;
@@ -296,14 +331,12 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
     d[0] = 2 * C; d[1] = Ww / 2; d[2] = 2; d[3] = Hh / 2; d[4] = Nn;
     s[0] = 2 * C2b; s[1] = uint64_t(Ww) * C2b; s[2] = 2 * uint64_t(Ww) * C2b; s[3] = uint64_t(Hh) * Ww * C2b;
   };
-  bool use_halo = false;
   if (mode == 0) {
     plain(da, sa, A2, Ca, H, W, N);
     plain(db, sb, B2, Cb, H, W, N);
-    use_halo = halo != 0;
     for (int ky = 0; ky < 3; ++ky) {
       WGroup& g = a.groups[ky];
-      g.a_pz = 0; g.a_cmul = 0; g.ntaps = 3; g.halo = use_halo ? 1 : 0;
+      g.a_pz = 0; g.a_cmul = 0; g.ntaps = 3;
       for (int kx = 0; kx < 3; ++kx) g.taps[kx] = WTap{int16_t(kx - 1), int16_t(ky - 1), 0, 0, ky * 3 + kx};
     }
   } else if (mode == 1) {
@@ -311,7 +344,7 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
     parity(db, sb, B2, Cb, H, W, N);
     for (int ky = 0; ky < 3; ++ky) {
       WGroup& g = a.groups[ky];
-      g.a_pz = 0; g.a_cmul = 0; g.ntaps = 3; g.halo = 0;
+      g.a_pz = 0; g.a_cmul = 0; g.ntaps = 3;
       for (int kx = 0; kx < 3; ++kx)
         g.taps[kx] = WTap{int16_t(kx >> 1), int16_t(ky >> 1), int16_t(ky & 1), int16_t(kx & 1), ky * 3 + kx};
     }
@@ -321,7 +354,7 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         WGroup& g = a.groups[py * 2 + px];
-        g.a_pz = int16_t(py); g.a_cmul = int16_t(px); g.ntaps = 4; g.halo = 0;
+        g.a_pz = int16_t(py); g.a_cmul = int16_t(px); g.ntaps = 4;
         for (int ty = 0; ty < 2; ++ty)
           for (int tx = 0; tx < 2; ++tx)
             g.taps[ty * 2 + tx] = WTap{int16_t(px == 0 ? tx - 1 : tx), int16_t(py == 0 ? ty - 1 : ty), 0, 0,
@@ -331,21 +364,18 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
     plain(da, sa, A2, Ca, H, W, N);
     plain(db, sb, B2, Cb, H, W, N);
     WGroup& g = a.groups[0];
-    g.a_pz = 0; g.a_cmul = 0; g.ntaps = 1; g.halo = 0;
+    g.a_pz = 0; g.a_cmul = 0; g.ntaps = 1;
     g.taps[0] = WTap{0, 0, 0, 0, 0};
   }
-  CUtensorMap tmA, tmB, tmBh;
-  rc = encode_tmap_16(&tmA, dy, 5, da, sa, box, 128, dy_f16 != 0);
+  CUtensorMap tmA, tmB;
+  rc = encode_tmap_16(&tmA, dy, 5, da, sa, box, 128, f16 != 0);
   if (rc != PTIVAE_OK) return rc;
-  rc = encode_tmap_16(&tmB, x, 5, db, sb, box, 128, x_f16 != 0);
-  if (rc != PTIVAE_OK) return rc;
-  rc = encode_tmap_16(&tmBh, x, 5, db, sb, use_halo ? boxh : box, 128, x_f16 != 0);
+  rc = encode_tmap_16(&tmB, x, 5, db, sb, box, 128, f16 != 0);
   if (rc != PTIVAE_OK) return rc;
 
   const int max_taps = mode == 3 ? 1 : (mode == 2 ? 4 : 3);
   const int nb_atoms = p.nb / 64;
-  a.b_bytes = use_halo ? nb_atoms * kWHaloAtom : max_taps * nb_atoms * kWAtom;
-  a.stage_bytes = 2 * kWAtom + a.b_bytes;
+  a.stage_bytes = 2 * kWAtom + max_taps * nb_atoms * kWAtom;
   int stages = (200 * 1024) / static_cast<int>(a.stage_bytes);
   if (stages > kWMaxStages) stages = kWMaxStages;
   if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
@@ -356,12 +386,12 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
   while (pow2 < cols) pow2 <<= 1;
   a.tmem_cols = pow2;
   if (pow2 > 512) return PTIVAE_ERR_UNSUPPORTED;
-  const size_t smem = size_t(stages) * a.stage_bytes + 1024 + (2 * kWMaxStages + 1) * 8 + 16;
+  const size_t smem = size_t(stages) * a.stage_bytes + 1024 + (kWMaxStages * (kWBarsPerStage + 1) + 1) * 8 + 16;
   if (smem > 227 * 1024) return PTIVAE_ERR_UNSUPPORTED;
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(wgrad_umma_kernel, 227 * 1024, attr_set)) return rc_attr;
   dim3 grid(p.splits, p.ngroups, p.n_ca_blocks * p.n_cb_blocks);
-  wgrad_umma_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, tmBh, a);
+  wgrad_umma_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, a);
   rc = static_cast<int>(cudaGetLastError());
   if (rc != 0) return rc;
 

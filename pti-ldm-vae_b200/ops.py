@@ -417,9 +417,6 @@ def local_normalize(x: torch.Tensor, return_stats: bool = False):
 # ---------------------------------------------------------------------------------------------------------------
 # backward pass
 # ---------------------------------------------------------------------------------------------------------------
-WGRAD_HALO = 1   # 3x3 s1 weight gradient: one 18-wide halo box per kernel row (0: one box per tap; tests force both)
-
-
 def wgrad(dy: torch.Tensor, x: torch.Tensor, mode: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """Weight gradient of a conv on tensor cores.  dy: 16-bit NHWC gradient of the conv output, x: 16-bit NHWC conv input
     (as the forward GEMM read it).  mode as conv_umma (0 3x3 | 1 pad+3x3 s2 | 2 up2x+3x3 | 3 1x1).
@@ -439,8 +436,10 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, mode: int, out: torch.Tensor | None
     if nbytes < 0:
         _lib.check(int(nbytes), "wgrad_workspace")
     ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+    if dy.dtype != x.dtype:
+        raise _lib.PtivaeError("wgrad: both operands of one tcgen05 MMA must share a 16-bit format")
     _call("wgrad", (mode, n, h, w, ca, cb), 2, _lib.lib().ptivae_wgrad, _p(dy), _p(x), _p(ws), _p(out), n, h, w, ca, cb,
-          mode, _op16(dy), _op16(x), WGRAD_HALO if mode == 0 else 0, _stream())
+          mode, _op16(dy), _stream())
     return out
 
 
@@ -453,6 +452,8 @@ def bgemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, a_mn: bool, b_mn:
         if t.dim() != 3 or t.stride(2) != 1:
             raise _lib.PtivaeError("bgemm operands must be 3-D with unit inner stride")
     bsz, m, n = out.shape
+    if a.dtype != b.dtype:
+        raise _lib.PtivaeError("bgemm: both operands of one tcgen05 MMA must share a 16-bit format")
     kk = k if k is not None else (a.shape[1] if a_mn else a.shape[2])
     _call("bgemm", (bsz, m, n, kk, int(a_mn), int(b_mn), epi), 1, _lib.lib().ptivae_bgemm, _p(a), _p(b), _p(out), bsz, m, n,
           kk, a.stride(1), a.stride(0), int(a_mn), _op16(a), b.stride(1), b.stride(0), int(b_mn), _op16(b), out.stride(1),
@@ -474,14 +475,27 @@ def rowdot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cast16(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Storage conversion to a 16-bit operand format (contiguous input, numel % 8 == 0)."""
+    _need_cuda(x)
+    if x.dtype == dtype:
+        return x
+    if not x.is_contiguous():
+        raise _lib.PtivaeError("cast16 needs a contiguous tensor")
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    _call("cast16", (x.numel(),), 1, _lib.lib().ptivae_cast16, _p(x), _p(out), x.numel(), _fmt(x), _op16(out), _stream())
+    return out
+
+
 def attention_bwd(q, k, v, o, lse, d_o, dqkv: torch.Tensor) -> None:
-    """Backward of ops.attention.  q,k,v: fp16/bf16 [B,L,D] views (row stride ld); o: forward output; lse: from the
-    forward; d_o: bf16 [B,L,D] gradient of o.  Writes dq|dk|dv into the three channel slices of dqkv bf16 [B,L,3D]."""
+    """Backward of ops.attention.  q,k,v: bf16 [B,L,D] views (row stride ld) of the forward's projections; o: forward
+    output (any 16-bit format); lse: from the forward; d_o: bf16 [B,L,D] gradient of o.  Writes dq|dk|dv into the three
+    channel slices of dqkv bf16 [B,L,3D]."""
     bsz, l, d = q.shape
     lp = (l + 7) // 8 * 8
     scale = float(d) ** -0.5
     drow = rowdot(d_o, o)
-    p = torch.empty((bsz, l, lp), device=q.device, dtype=q.dtype)[:, :, :l]
+    p = torch.empty((bsz, l, lp), device=q.device, dtype=torch.bfloat16)[:, :, :l]
     ds = torch.empty((bsz, l, lp), device=q.device, dtype=torch.bfloat16)[:, :, :l]
     bgemm(q, k, p, False, False, epi=1, alpha=scale * 1.4426950408889634, rowv=lse)           # P = exp2(QK^T c - lse)
     bgemm(p, d_o, dqkv[:, :, 2 * d:], True, True)                                            # dV = P^T dO

@@ -12,9 +12,10 @@ Everything that touches an activation is a kernel of libptivae.so:
 PyTorch only owns memory and the autograd edge (``VAEFunction``): gradients of all parameters are written into ONE
 flat fp32 buffer (the views are what autograd / DDP see), which is also what the NCCL all-reduce moves.
 
-Precision: gradient GEMM operands are bf16 (fp16 underflows for mean-reduced losses: dL/drecon ~ 1/(B*H*W)),
-activations keep the forward's fp16 operands (the two formats are mixed inside one MMA), accumulation and the
-gradient of the residual stream are fp32.
+Precision: every operand of a backward GEMM is bf16 -- gradients need the range (fp16 underflows for mean-reduced
+losses: dL/drecon ~ 1/(B*H*W)) and one tcgen05 MMA cannot mix fp16 and bf16 (measured: illegal instruction), so the
+normalised activations are re-materialised in bf16 and the few saved fp16 operands are converted once; accumulation
+and the gradient of the residual stream are fp32.
 """
 from __future__ import annotations
 
@@ -234,19 +235,19 @@ class TrainRun:
         dev = x.device
         c1, c2 = blk.conv1.conv, blk.conv2.conv
         d16 = g.t16
-        a2 = ops.gn_apply(h, ss2, silu=True, dtype=ex.op_dtype)
+        a2 = ops.gn_apply(h, ss2, silu=True, dtype=BF16)
         ops.wgrad(d16, a2, 0, out=G[c2.weight])
         ops.colsum(d16, out=G[c2.bias])
         da2 = ops.conv_umma(d16, self._packT(c2.weight), self._zero_bias(c2.weight.shape[1], dev), 4)
         _, dh16 = ops.gn_bwd(h, da2, ss2, mr2, ex.f32(blk.norm2.weight), True, G[blk.norm2.weight], G[blk.norm2.bias],
                              want32=False)
-        a1 = ops.gn_apply(x, ss1, silu=True, dtype=ex.op_dtype)
+        a1 = ops.gn_apply(x, ss1, silu=True, dtype=BF16)
         ops.wgrad(dh16, a1, 0, out=G[c1.weight])
         ops.colsum(dh16, out=G[c1.bias])
         da1 = ops.conv_umma(dh16, self._packT(c1.weight), self._zero_bias(c1.weight.shape[1], dev), 4)
         if raw is not None:
             sc = blk.nin_shortcut.conv
-            ops.wgrad(d16, raw, 3, out=G[sc.weight])
+            ops.wgrad(d16, ops.cast16(raw, BF16), 3, out=G[sc.weight])
             G[sc.bias].copy_(G[c2.bias])
             res = ops.conv_umma(d16, self._packT(sc.weight), self._zero_bias(sc.weight.shape[1], dev), 3, out_f32=True)
         else:
@@ -262,14 +263,15 @@ class TrainRun:
         n, h, w, c = xn.shape
         at = blk.attn
         d16 = g.t16
-        ops.wgrad(d16, o.view(n, h, w, c), 3, out=G[at.out_proj.weight])
+        ops.wgrad(d16, ops.cast16(o, BF16).view(n, h, w, c), 3, out=G[at.out_proj.weight])
         ops.colsum(d16, out=G[at.out_proj.bias])
         d_o = ops.conv_umma(d16, self._packT(at.out_proj.weight), self._zero_bias(c, dev), 3).view(n, h * w, c)
         dqkv = torch.empty((n, h * w, 3 * c), device=dev, dtype=BF16)
-        q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+        qkv16 = ops.cast16(qkv, BF16)
+        q, k, v = qkv16[..., :c], qkv16[..., c:2 * c], qkv16[..., 2 * c:]
         ops.attention_bwd(q, k, v, o, lse, d_o, dqkv)
         dq4 = dqkv.view(n, h, w, 3 * c)
-        dwqkv = ops.wgrad(dq4, xn, 3)                       # [3C, C, 1, 1]
+        dwqkv = ops.wgrad(dq4, ops.cast16(xn, BF16), 3)     # [3C, C, 1, 1]
         dbqkv = ops.colsum(dq4)
         for i, lin in enumerate((at.to_q, at.to_k, at.to_v)):
             G[lin.weight].copy_(dwqkv[i * c:(i + 1) * c].view(c, c))
@@ -289,7 +291,7 @@ class TrainRun:
     def _resample_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
         _, conv, xin, mode = rec
         d16 = g.t16
-        ops.wgrad(d16, xin, mode, out=G[conv.weight])
+        ops.wgrad(d16, ops.cast16(xin, BF16), mode, out=G[conv.weight])
         ops.colsum(d16, out=G[conv.bias])
         c = conv.weight.shape[1]
         dx16 = ops.conv_umma(d16, self._packT(conv.weight, 2 if mode == 2 else 0), self._zero_bias(c, xin.device),

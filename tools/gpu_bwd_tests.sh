@@ -5,6 +5,6 @@ out=gpurun_out/bwd_tests.log
 : > $out
 for t in "$@"; do
   echo "=== $t" >> $out
-  timeout 600 python -m pytest tests/test_gpu_backward.py -q -k "$t" --timeout 180 -p no:cacheprovider 2>&1 | tail -60 >> $out
+  timeout 900 python -m pytest tests/test_gpu_backward.py -q -k "$t" --timeout 300 -p no:cacheprovider --tb=short -rP 2>&1 | grep -v "^\s*$" | tail -${TAILN:-80} >> $out
 done
-tail -c 6000 $out
+tail -c ${TAILC:-9000} $out
