@@ -108,6 +108,14 @@ int ptivae_debug_set_trace(void* buf);
  *   mode 4 / 6: the same slabs transposed, [T][Cin][Cout] (operand of the data-gradient convolutions). */
 int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int Cin, int k, int mode, int f16, void* stream);
 
+/* Many weight packs in ONE launch (after an optimizer step every conv / linear weight needs its forward pack and its
+ * transposed backward pack again).  descs: DEVICE array of n records of ptivae_pack_desc_bytes() bytes:
+ *   { const float* src [Cout][Cin][ksq]; uint16* dst; int64 start (prefix sum of T*Cout*Cin); int32 Cout, Cin, ksq, T;
+ *     int64 st_t; int32 st_r, f16, transpose, up2x; }   element (t, r, c) -> dst[t*st_t + r*st_r + c],
+ *   (r, c) = (co, ci), or (ci, co) when transpose; up2x selects the 16-slab pre-summed decomposition. */
+int ptivae_pack_many(const void* descs, int n, long long total, void* stream);
+int ptivae_pack_desc_bytes(void);
+
 /* nn.GroupNorm statistics, deterministic two-stage form.
  *   gn_stats: partial[n][p][g] = (sum, sumsq) over pixel chunk p of x [N][HW][C] (storage in_fmt); P = ptivae_gn_stats_parts(N, HW, C) chunks per image.
  *   gn_finalize: partial [N][P][G][2] -> scale_shift fp32 [N][C][2], scale = gamma*rstd,
@@ -254,7 +262,7 @@ int ptivae_colsum_blocks(long long rows);
  *   wide_is_input == 0: thin = the conv's fp32 NCHW input, wide = dOut NHWC;  dw [C][Ct][3][3], db must be NULL */
 int ptivae_thin_wgrad(const float* thin, const void* wide, const float* scale_shift, float* dw, float* db, float* workspace,
                       int N, int H, int W, int C, int Ct, int wide_fmt, int wide_is_input, void* stream);
-long long ptivae_thin_wgrad_workspace(int N, int H, int C, int Ct);
+long long ptivae_thin_wgrad_workspace(int N, int H, int W, int C, int Ct);
 /* Gradient through the latent head (AutoencoderKL.encode tail + sampling + post_quant_conv), fp32 NCHW [N][L][HW]:
  *   in: dzq = dL/d(post_quant_conv out), dmu_ext / dsig_ext = gradients arriving at the returned z_mu / z_sigma (NULL ok),
  *       eps, h (encoder stack output), mu, sigma, the three [L][L] weights and quant_conv_log_sigma's bias

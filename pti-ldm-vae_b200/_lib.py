@@ -64,11 +64,13 @@ SIGNATURES = {
     "ptivae_colsum": [_c_void_p] * 3 + [_c_ll, _c_int, _c_int, _c_void_p],
     "ptivae_colsum_blocks": [_c_ll],
     "ptivae_thin_wgrad": [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p],
-    "ptivae_thin_wgrad_workspace": [_c_int] * 4,
+    "ptivae_thin_wgrad_workspace": [_c_int] * 5,
     "ptivae_latent_bwd": [_c_void_p] * 15 + [_c_int] * 3 + [_c_void_p],
     "ptivae_outer_reduce": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
     "ptivae_l1l2_bwd": [_c_void_p] * 4 + [_c_ll, _c_void_p],
     "ptivae_kl_bwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],
+    "ptivae_pack_many": [_c_void_p, _c_int, _c_ll, _c_void_p],
+    "ptivae_pack_desc_bytes": [],
     "ptivae_cast16": [_c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_void_p],
     "ptivae_adam": [_c_void_p] * 4 + [_c_ll] + [_c_float] * 5 + [_c_void_p, _c_int, _c_void_p],
 }

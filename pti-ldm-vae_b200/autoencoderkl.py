@@ -151,6 +151,11 @@ class _Executor:
         self.op_dtype = operand_dtype
         self.fused_conv = True
         self._packed: dict = {}
+        # how each cached pack is produced: key -> list of (src fp32 weight, dst 16-bit tensor, dst element offset,
+        # st_r, pack mode); and derived fp32 tensors (bias sums, mirrored thin weights): key -> refresh closure.
+        # TrainStep re-runs all of them in ONE launch after a fused optimizer step (refresh_packed).
+        self._recipes: dict = {}
+        self._derived: dict = {}
 
     # -- weights: 16-bit UMMA operands cached until the fp32 master changes (optimizer step, load_state_dict, .to())
     def packed(self, w: torch.Tensor, mode: int = 0) -> torch.Tensor:
@@ -160,6 +165,7 @@ class _Executor:
         if hit is None or hit[0] != ver:
             hit = (ver, ops.pack_conv_weight(w, mode, self.op_dtype))
             self._packed[key] = hit
+            self._recipes[key] = [(w, hit[1], 0, hit[1].shape[2], mode)]
         return hit[1]
 
     @staticmethod
@@ -179,6 +185,10 @@ class _Executor:
             wcat = torch.cat([t.detach() for t in ws], dim=0)
             hit = (ver, ops.pack_conv_weight(wcat, 0, self.op_dtype), torch.cat([t.detach().float() for t in bs]).contiguous())
             self._packed[key] = hit
+            c = ws[0].shape[0]
+            self._recipes[key] = [(t, hit[1], i * c * c, c, 0) for i, t in enumerate(ws)]
+            bcat = hit[2]
+            self._derived[key] = lambda: torch.cat([t.detach().float() for t in bs], out=bcat)
         return hit[1], hit[2]
 
     def bias_sum(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -189,6 +199,8 @@ class _Executor:
         if hit is None or hit[0] != ver:
             hit = (ver, (a.detach().float() + b.detach().float()).contiguous())
             self._packed[key] = hit
+            out = hit[1]
+            self._derived[key] = lambda: torch.add(a.detach().float(), b.detach().float(), out=out)
         return hit[1]
 
     def _want_stats(self, cout: int, stats: bool) -> int:
@@ -374,6 +386,24 @@ class AutoencoderKL(nn.Module):
         """Drop the cached 16-bit weight packs.  Needed after an in-place update that does not bump the parameters'
         version counters (``p.data.copy_(...)``, a fused optimizer step on the flat buffer)."""
         self._exec._packed.clear()
+        self._exec._recipes.clear()
+        self._exec._derived.clear()
+
+    def refresh_packed(self) -> None:
+        """Recompute every cached weight pack IN PLACE from the current fp32 masters: one pack_many launch for all conv /
+        linear packs (forward and transposed backward packs) plus the few derived bias / mirrored tensors.  For callers
+        that update parameters in place without bumping their version counters (TrainStep's fused Adam)."""
+        ex = self._exec
+        if not ex._recipes and not ex._derived:
+            return
+        sig = tuple((k, rs[0][1].data_ptr()) for k, rs in ex._recipes.items())
+        tab = ex.__dict__.get("_pack_table")
+        if tab is None or tab[0] != sig:
+            tab = (sig,) + ops.build_pack_table([r for rs in ex._recipes.values() for r in rs])
+            ex._pack_table = tab
+        ops.pack_many(tab[1], tab[2], tab[3])
+        for fn in ex._derived.values():
+            fn()
 
     def set_operand_dtype(self, dtype: torch.dtype) -> None:
         """Storage format of the tensor-core operands: torch.float16 (default) or torch.bfloat16."""

@@ -231,12 +231,17 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restr
     partial[static_cast<size_t>(blockIdx.x) * C + c] = a;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the block partials (fixed assignment), xor-shuffle tree -> deterministic
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                           int blocks, int C) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += partial[static_cast<size_t>(b) * C + c];
-  out[c] = a;
+  for (int b = lane; b < blocks; b += 32) a += __ldg(partial + static_cast<size_t>(b) * C + c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[c] = a;
 }
 
 }  // namespace ptivae
@@ -281,7 +286,7 @@ extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fm
 // out[c] = sum over rows of x[row][c]; workspace: ptivae_colsum_blocks(rows) * C floats
 extern "C" int ptivae_colsum_blocks(long long rows) {
   if (rows <= 0) return PTIVAE_ERR_ARG;
-  long long b = (rows + 2047) / 2048;
+  long long b = (rows + 1023) / 1024;
   if (b > 592) b = 592;
   return static_cast<int>(b);
 }
@@ -293,6 +298,6 @@ extern "C" int ptivae_colsum(const void* x, float* out, float* workspace, long l
   const int blocks = ptivae_colsum_blocks(rows);
   const int rpb = static_cast<int>((rows + blocks - 1) / blocks);
   colsum_partial_kernel<<<blocks, 256, 0, stream>>>(x, workspace, rows, C, rpb, fmt);
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, out, blocks, C);
+  colsum_final_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(workspace, out, blocks, C);
   return static_cast<int>(cudaGetLastError());
 }

@@ -173,9 +173,80 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, uint16_t* __rest
   }
 }
 
+// Re-pack MANY weights in one launch (after an optimizer step every conv / linear weight needs its forward pack and
+// its transposed backward pack again: ~110 launches of pack_conv_w_kernel per step otherwise).
+struct PackDesc {
+  const float* src;     // fp32 [Cout][Cin][ksq]
+  uint16_t* dst;        // 16-bit, element (t, r, c) at dst[t*st_t + r*st_r + c]; (r, c) = (co, ci), or (ci, co) if transpose
+  long long start;      // first global element index of this descriptor (prefix sum of T*Cout*Cin)
+  int Cout, Cin, ksq, T;
+  long long st_t;
+  int st_r;
+  int f16, transpose, up2x;
+};
+__global__ void __launch_bounds__(256) pack_many_kernel(const PackDesc* __restrict__ descs, int n, long long total,
+                                                        PackMasks plain, PackMasks up2x) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int lo = 0, hi = n - 1;                       // last descriptor with start <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (descs[mid].start <= i) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = descs[lo];
+    const long long e = i - d.start;
+    const int plane = d.Cout * d.Cin;
+    const int t = static_cast<int>(e / plane);
+    const int rr = static_cast<int>(e % plane);
+    const int ci = d.transpose ? rr / d.Cout : rr % d.Cin;
+    const int co = d.transpose ? rr % d.Cout : rr / d.Cin;
+    const float* src = d.src + (static_cast<size_t>(co) * d.Cin + ci) * d.ksq;
+    const uint32_t m = d.up2x ? up2x.m[t] : plain.m[t];
+    float a = 0.f;
+    for (int s = 0; s < d.ksq; ++s)
+      if (m & (1u << s)) a += src[s];
+    const int r = d.transpose ? ci : co, c = d.transpose ? co : ci;
+    uint16_t* out = d.dst + t * d.st_t + static_cast<long long>(r) * d.st_r + c;
+    if (d.f16) *out = __half_as_ushort(__float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)));
+    else *out = __bfloat16_as_ushort(__float2bfloat16_rn(a));
+  }
+}
+
+static PackMasks up2x_masks() {
+  PackMasks pm{};
+  // rows/cols of the 3x3 kernel that collapse onto low-res offset index t (0 or 1) for output parity p
+  auto sel = [](int p, int t) -> uint32_t {  // bitmask over k in {0,1,2}
+    if (p == 0) return t == 0 ? 0b001u : 0b110u;  // parity 0: k=0 -> y-1 ; k=1,2 -> y
+    return t == 0 ? 0b011u : 0b100u;              // parity 1: k=0,1 -> y ; k=2 -> y+1
+  };
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          uint32_t m = 0;
+          const uint32_t ry = sel(py, ty), rx = sel(px, tx);
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+              if ((ry >> ky & 1u) && (rx >> kx & 1u)) m |= 1u << (ky * 3 + kx);
+          pm.m[((py * 2 + px) * 2 + ty) * 2 + tx] = m;
+        }
+  return pm;
+}
+
 }  // namespace ptivae
 
 using namespace ptivae;
+
+// descs: DEVICE array of n PackDesc (layout: see ptivae_pack_desc_bytes); total = sum of T*Cout*Cin.
+extern "C" int ptivae_pack_desc_bytes(void) { return static_cast<int>(sizeof(PackDesc)); }
+extern "C" int ptivae_pack_many(const void* descs, int n, long long total, void* stream_) {
+  if (!descs || n <= 0 || total <= 0) return PTIVAE_ERR_ARG;
+  PackMasks plain{};
+  for (int t = 0; t < 16; ++t) plain.m[t] = 1u << t;
+  pack_many_kernel<<<grid_for(static_cast<size_t>(total), 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const PackDesc*>(descs), n, total, plain, up2x_masks());
+  return static_cast<int>(cudaGetLastError());
+}
 
 __global__ void rng_advance_kernel(unsigned long long* rng_dev) { rng_dev[1] += 1ull; }
 
@@ -234,22 +305,7 @@ extern "C" int ptivae_pack_conv_weight(const float* w, void* out, int Cout, int 
     for (int t = 0; t < T; ++t) pm.m[t] = 1u << t;
   } else {
     T = 16;
-    // rows/cols of the 3x3 kernel that collapse onto low-res offset index t (0 or 1) for output parity p
-    auto sel = [](int p, int t) -> uint32_t {  // bitmask over k in {0,1,2}
-      if (p == 0) return t == 0 ? 0b001u : 0b110u;  // parity 0: k=0 -> y-1 ; k=1,2 -> y
-      return t == 0 ? 0b011u : 0b100u;              // parity 1: k=0,1 -> y ; k=2 -> y+1
-    };
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px)
-        for (int ty = 0; ty < 2; ++ty)
-          for (int tx = 0; tx < 2; ++tx) {
-            uint32_t m = 0;
-            const uint32_t ry = sel(py, ty), rx = sel(px, tx);
-            for (int ky = 0; ky < 3; ++ky)
-              for (int kx = 0; kx < 3; ++kx)
-                if ((ry >> ky & 1u) && (rx >> kx & 1u)) m |= 1u << (ky * 3 + kx);
-            pm.m[((py * 2 + px) * 2 + ty) * 2 + tx] = m;
-          }
+    pm = up2x_masks();
   }
   const size_t total = static_cast<size_t>(T) * Cout * Cin;
   pack_conv_w_kernel<<<grid_for(total, 256), 256, 0, stream>>>(w, static_cast<uint16_t*>(out), Cout, Cin, k * k, T, pm,

@@ -19,16 +19,20 @@ __device__ __forceinline__ float ld_wide(const void* base, size_t idx, int fmt) 
   return __uint_as_float(static_cast<uint32_t>(h) << 16);
 }
 
-// G[t][c][tap] = sum_{y,x} thin[n][t][y][x] * wide'[n][y+ky-1][x+kx-1][c]  over this block's rows;
+// G[t][c][tap] = sum_{y,x} thin[n][t][y][x] * wide'[n][y+ky-1][x+kx-1][c]  over this block's rows and x segment;
 // wide' = wide*scale + shift inside the image (ss may be NULL: identity), 0 outside.  slot 9 = sum of thin.
-// grid (row blocks, N); thread -> (t, c) pairs, c fastest (coalesced NHWC reads), sliding 3x3 window along x.
+// grid (x segments, row blocks, N); thread -> (t, c) pair, c fastest (coalesced NHWC reads), sliding 3x3 window along x.
+constexpr int kTwSeg = 32;   // pixels per x segment
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict__ thin, const void* __restrict__ wide,
                                                          const float* __restrict__ ss, float* __restrict__ partial,
                                                          int H, int W, int C, int Ct, int wide_fmt) {
-  const int n = blockIdx.y;
-  const int y_begin = blockIdx.x * kTwRows;
+  const int n = blockIdx.z;
+  const int y_begin = blockIdx.y * kTwRows;
   const int y_end = min(H, y_begin + kTwRows);
+  const int x_begin = blockIdx.x * kTwSeg;
+  const int x_end = min(W, x_begin + kTwSeg);
   const size_t plane = static_cast<size_t>(H) * W;
+  const size_t part = (static_cast<size_t>(n) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   for (int idx = threadIdx.x; idx < Ct * C; idx += blockDim.x) {
     const int t = idx / C, c = idx - t * C;
     float sc = 1.f, sh = 0.f;
@@ -41,7 +45,6 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict
 #pragma unroll
     for (int k = 0; k < 10; ++k) acc[k] = 0.f;
     for (int y = y_begin; y < y_end; ++y) {
-      float win[3][3];
       auto col = [&](int xx, float (&v)[3]) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -52,40 +55,45 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict
         }
       };
       float c0[3], c1[3], c2[3];
-      c0[0] = c0[1] = c0[2] = 0.f;
-      col(0, c1);
-      for (int x = 0; x < W; ++x) {
+      col(x_begin - 1, c0);
+      col(x_begin, c1);
+      for (int x = x_begin; x < x_end; ++x) {
         col(x + 1, c2);
         const float tv = __ldg(tp + static_cast<size_t>(y) * W + x);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          win[ky][0] = c0[ky]; win[ky][1] = c1[ky]; win[ky][2] = c2[ky];
-          acc[ky * 3 + 0] = fmaf(tv, win[ky][0], acc[ky * 3 + 0]);
-          acc[ky * 3 + 1] = fmaf(tv, win[ky][1], acc[ky * 3 + 1]);
-          acc[ky * 3 + 2] = fmaf(tv, win[ky][2], acc[ky * 3 + 2]);
+          acc[ky * 3 + 0] = fmaf(tv, c0[ky], acc[ky * 3 + 0]);
+          acc[ky * 3 + 1] = fmaf(tv, c1[ky], acc[ky * 3 + 1]);
+          acc[ky * 3 + 2] = fmaf(tv, c2[ky], acc[ky * 3 + 2]);
           c0[ky] = c1[ky]; c1[ky] = c2[ky];
         }
         acc[9] += tv;
       }
     }
-    float* dst = partial + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * Ct * C + idx) * 10;
+    float* dst = partial + (part * Ct * C + idx) * 10;
 #pragma unroll
     for (int k = 0; k < 10; ++k) dst[k] = acc[k];
   }
 }
 
-// dw[t*st_t + c*st_c + (flip ? 8 - tap : tap)] = sum over (n, row block) partials in index order; db[t] likewise.
-__global__ void thin_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                         float* __restrict__ db, int parts, int C, int Ct, int st_t, int st_c,
-                                         int flip) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (t*C + c)*10 + k
+// dw[t*st_t + c*st_c + (flip ? 8 - tap : tap)] = sum over the partials (one warp per output element, fixed lane
+// assignment + xor-shuffle tree: deterministic); db[t] likewise.
+__global__ void __launch_bounds__(256) thin_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                float* __restrict__ db, int parts, int C, int Ct,
+                                                                int st_t, int st_c, int flip) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (t*C + c)*10 + k
+  const int lane = threadIdx.x & 31;
   if (i >= Ct * C * 10) return;
   const int k = i % 10, idx = i / 10;
   const int t = idx / C, c = idx - t * C;
+  if (k == 9 && (db == nullptr || c != 0)) return;
   float a = 0.f;
-  for (int p = 0; p < parts; ++p) a += partial[static_cast<size_t>(p) * Ct * C * 10 + i];
+  for (int p = lane; p < parts; p += 32) a += __ldg(partial + static_cast<size_t>(p) * Ct * C * 10 + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane != 0) return;
   if (k < 9) dw[static_cast<size_t>(t) * st_t + static_cast<size_t>(c) * st_c + (flip ? 8 - k : k)] = a;
-  else if (db != nullptr && c == 0) db[t] = a;
+  else db[t] = a;
 }
 
 // ------------------------------------------------------------------------------------------------ latent head
@@ -166,9 +174,9 @@ __global__ void __launch_bounds__(256) outer_reduce_kernel(const float* __restri
 
 using namespace ptivae;
 
-extern "C" long long ptivae_thin_wgrad_workspace(int N, int H, int C, int Ct) {
-  if (N <= 0 || H <= 0 || C <= 0 || Ct <= 0) return PTIVAE_ERR_ARG;
-  return static_cast<long long>(N) * ((H + kTwRows - 1) / kTwRows) * Ct * C * 10 * 4;
+extern "C" long long ptivae_thin_wgrad_workspace(int N, int H, int W, int C, int Ct) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Ct <= 0) return PTIVAE_ERR_ARG;
+  return static_cast<long long>(N) * ((H + kTwRows - 1) / kTwRows) * ((W + kTwSeg - 1) / kTwSeg) * Ct * C * 10 * 4;
 }
 
 // Weight gradient of a thin 3x3 s1 p1 conv.
@@ -184,15 +192,15 @@ extern "C" int ptivae_thin_wgrad(const float* thin, const void* wide, const floa
     return PTIVAE_ERR_ARG;
   if (!wide_is_input && db) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int rb = (H + kTwRows - 1) / kTwRows;
+  const int rb = (H + kTwRows - 1) / kTwRows, xs = (W + kTwSeg - 1) / kTwSeg;
   int bt = ((Ct * C + 31) / 32) * 32;
   if (bt > 256) bt = 256;
-  dim3 grid(rb, N);
+  dim3 grid(xs, rb, N);
   thin_wgrad_kernel<<<grid, bt, 0, stream>>>(thin, wide, scale_shift, workspace, H, W, C, Ct, wide_fmt);
   const int tot = Ct * C * 10;
   const int st_t = wide_is_input ? C * 9 : 9, st_c = wide_is_input ? 9 : Ct * 9;
-  thin_wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(workspace, dw, db, N * rb, C, Ct, st_t, st_c,
-                                                                  wide_is_input ? 0 : 1);
+  thin_wgrad_reduce_kernel<<<(tot * 32 + 255) / 256, 256, 0, stream>>>(workspace, dw, db, N * rb * xs, C, Ct, st_t, st_c,
+                                                                       wide_is_input ? 0 : 1);
   return static_cast<int>(cudaGetLastError());
 }
 

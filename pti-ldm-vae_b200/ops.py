@@ -542,7 +542,7 @@ def thin_wgrad(thin: torch.Tensor, wide: torch.Tensor, wide_is_input: bool, dw: 
     c = wide.shape[-1]
     if tuple(wide.shape[:3]) != (n, h, w) or dw.numel() != ct * c * 9:
         raise _lib.PtivaeError("thin_wgrad shape mismatch")
-    ws = torch.empty(_lib.lib().ptivae_thin_wgrad_workspace(n, h, c, ct) // 4, device=thin.device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib().ptivae_thin_wgrad_workspace(n, h, w, c, ct) // 4, device=thin.device, dtype=torch.float32)
     _call("thin_wgrad", (n, h, w, c, ct), 2, _lib.lib().ptivae_thin_wgrad, _p(thin), _p(wide), _p(scale_shift), _p(dw),
           _p(db), _p(ws), n, h, w, c, ct, _fmt(wide), int(wide_is_input), _stream())
     return dw
@@ -589,3 +589,33 @@ def adam(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, ste
     _need_cuda(p, g, m, v, step_dev)
     _call("adam", None, 2 if advance else 1, _lib.lib().ptivae_adam, _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr),
           float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _p(step_dev), int(advance), _stream())
+
+
+def build_pack_table(recipes):
+    """recipes: list of (src fp32 weight [Cout,Cin,k,k] | [out,in], dst 16-bit tensor, dst element offset, st_r, mode)
+    -> (device table, n, total) for pack_many.  mode as pack_conv_weight (0 plain | 2 up2x 16-slab | +4 transposed)."""
+    import numpy as np
+    dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("start", "<i8"), ("Cout", "<i4"), ("Cin", "<i4"), ("ksq", "<i4"),
+                   ("T", "<i4"), ("st_t", "<i8"), ("st_r", "<i4"), ("f16", "<i4"), ("transpose", "<i4"), ("up2x", "<i4")])
+    if dt.itemsize != _lib.lib().ptivae_pack_desc_bytes():
+        raise _lib.PtivaeError("pack descriptor layout mismatch between ops.py and latent_loss.cu")
+    tab = np.zeros(len(recipes), dtype=dt)
+    start = 0
+    dev = None
+    for i, (w, dst, off, st_r, mode) in enumerate(recipes):
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            raise _lib.PtivaeError("pack_many sources must be contiguous fp32 master weights")
+        cout, cin = w.shape[0], w.shape[1]
+        ksq = w.numel() // (cout * cin)
+        up = (mode & 3) == 2
+        t = 16 if up else ksq
+        tab[i] = (w.data_ptr(), dst.data_ptr() + off * 2, start, cout, cin, ksq, t, dst.shape[1] * dst.shape[2], st_r,
+                  int(dst.dtype == F16), int(bool(mode & 4)), int(up))
+        start += t * cout * cin
+        dev = w.device
+    table = torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(dev)
+    return table, len(recipes), start
+
+
+def pack_many(table: torch.Tensor, n: int, total: int) -> None:
+    _call("pack_many", None, 1, _lib.lib().ptivae_pack_many, _p(table), n, total, _stream())

@@ -122,7 +122,7 @@ class TrainStep:
                     self._allreduce(0, self.params.numel())
             ops.adam(self.params, self.grads, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps,
                      grad_scale=1.0 / self.world, advance=True)
-            ae.invalidate_packed()
+            ae.refresh_packed()            # every weight pack from the updated masters: one launch
         return {"recon_loss": rec_terms[self.recon_idx], "kl_loss": kl, "recon": recon, "z_mu": mu, "z_sigma": sigma}
 
     def step(self, x: torch.Tensor, eps: torch.Tensor | None = None):

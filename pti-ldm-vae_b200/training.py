@@ -95,6 +95,7 @@ class TrainRun:
         if hit is None or hit[0] != ver:
             hit = (ver, ops.pack_conv_weight(w, mode | 4, BF16))
             self.ex._packed[key] = hit
+            self.ex._recipes[key] = [(w, hit[1], 0, hit[1].shape[2], mode | 4)]
         return hit[1]
 
     def _mirrored(self, w: torch.Tensor) -> torch.Tensor:
@@ -105,6 +106,8 @@ class TrainRun:
         if hit is None or hit[0] != ver:
             hit = (ver, w.detach().float().flip(2, 3).transpose(0, 1).contiguous())
             self.ex._packed[key] = hit
+            out = hit[1]
+            self.ex._derived[key] = lambda: out.copy_(w.detach().float().flip(2, 3).transpose(0, 1))
         return hit[1]
 
     def _fconv(self, x, ss, conv, residual, stats: bool, out_f32: bool) -> _Act:
@@ -283,6 +286,7 @@ class TrainRun:
         if hit is None or hit[0] != ver:
             hit = (ver, ops.pack_conv_weight(torch.cat([t.detach() for t in ws], dim=0), 4, BF16))
             ex._packed[key] = hit
+            ex._recipes[key] = [(t, hit[1], i * c, 3 * c, 4) for i, t in enumerate(ws)]    # [1][C][3C]: column blocks
         dxn = ops.conv_umma(dq4, hit[1], self._zero_bias(c, dev), 3)
         dx32, dx16 = ops.gn_bwd(x, dxn, ss, mr, ex.f32(blk.norm.weight), False, G[blk.norm.weight], G[blk.norm.bias],
                                 residual=g.any)

@@ -423,6 +423,13 @@ def test_train_step_matches_autograd_path(b200, oracle):
     # and the model keeps working after the in-place update (packed weights were invalidated)
     out2 = ts.step(x, eps)
     assert torch.isfinite(out2["recon_loss"]) and float(out2["recon_loss"]) < float(out["recon_loss"]) + 1e-3
+    # the one-launch refresh of all weight packs == packing each weight from scratch
+    vae_b.eval()
+    with torch.no_grad():
+        r1 = vae_b.autoencoder(x, eps)[0].clone()
+        vae_b.autoencoder.invalidate_packed()
+        r2 = vae_b.autoencoder(x, eps)[0]
+    assert torch.equal(r1, r2), "refresh_packed left a stale or different weight pack"
 
 
 def test_train_step_graph_replay(b200, oracle):

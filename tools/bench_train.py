@@ -95,7 +95,7 @@ def main():
         run.backward(d_recon, d_mu, d_sigma, ts.G, need_dx=False)
         ev[3].record()
         b200.ops.adam(ts.params, ts.grads, ts.m, ts.v, ts.step_dev, ts.lr, grad_scale=1.0 / world)
-        ts.ae.invalidate_packed()
+        ts.ae.refresh_packed()
         ev[4].record()
     torch.cuda.synchronize()
     launches_eager = b200.ops.LAUNCHES - launches0
