@@ -43,7 +43,8 @@ __device__ __forceinline__ float act_grad(float x, float sc, float sh, float da)
   return da * s * fmaf(u, 1.0f - s, 1.0f);
 }
 
-constexpr int kGbPix = 1024;   // pixels per reduce chunk (depends on the image only: batch-invariant summation order)
+constexpr int kGbPix = 256;    // pixels per reduce chunk (depends on the image only: batch-invariant summation order);
+                               // small chunks = many CTAs = enough loads in flight (1024-pixel chunks ran at 15 % of HBM peak)
 
 // grid (chunks, N); block 256.  Thread t owns one 8-channel vector column and walks the chunk's pixels.
 template <bool kSilu>
@@ -74,7 +75,28 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
   for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
   const size_t img = static_cast<size_t>(n) * HW * vecs;
   if (prow < prows) {
-    for (int p = p_begin + prow; p < p_end; p += prows) {
+    // two pixels per iteration: four independent 16/32-byte loads in flight per thread
+    int p = p_begin + prow;
+    for (; p + prows < p_end; p += 2 * prows) {
+      float f0[8], d0[8], f1[8], d1[8];
+      ld8(x, img + static_cast<size_t>(p) * vecs + v, x_fmt, f0);
+      ld8(da, img + static_cast<size_t>(p) * vecs + v, da_fmt, d0);
+      ld8(x, img + static_cast<size_t>(p + prows) * vecs + v, x_fmt, f1);
+      ld8(da, img + static_cast<size_t>(p + prows) * vecs + v, da_fmt, d1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float du0 = act_grad<kSilu>(f0[e], sc[e], sh[e], d0[e]);
+        s1[e] += du0;
+        s2[e] = fmaf(du0, (f0[e] - mean[e]) * rstd[e], s2[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float du1 = act_grad<kSilu>(f1[e], sc[e], sh[e], d1[e]);
+        s1[e] += du1;
+        s2[e] = fmaf(du1, (f1[e] - mean[e]) * rstd[e], s2[e]);
+      }
+    }
+    if (p < p_end) {
       float f[8], d[8];
       ld8(x, img + static_cast<size_t>(p) * vecs + v, x_fmt, f);
       ld8(da, img + static_cast<size_t>(p) * vecs + v, da_fmt, d);
@@ -103,29 +125,39 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
   }
 }
 
-// grid N; block = C rounded up to a warp (<= 1024).  totals [N][C][2], coef [N][C][2] = (e, f).
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                       const float* __restrict__ mr, float* __restrict__ totals,
-                                       float* __restrict__ coef, int C, int G, int P, float inv_count) {
+// grid N; block 256.  totals [N][C][2], coef [N][C][2] = (e, f).  One warp per channel sums the P chunk partials
+// (fixed lane assignment + xor-shuffle tree: deterministic), then one thread per channel folds its group.
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ partial,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ mr, float* __restrict__ totals,
+                                                              float* __restrict__ coef, int C, int G, int P,
+                                                              float inv_count) {
   extern __shared__ float st[];   // [C][2] gamma-weighted totals
   const int n = blockIdx.x;
-  const int c = threadIdx.x;
-  if (c < C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < C; c += 8) {
     float a = 0.f, b = 0.f;
     const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * C + c;
-    for (int p = 0; p < P; ++p) {
+    for (int p = lane; p < P; p += 32) {
       const float2 t = __ldg(src + static_cast<size_t>(p) * C);
       a += t.x;
       b += t.y;
     }
-    totals[(static_cast<size_t>(n) * C + c) * 2] = a;
-    totals[(static_cast<size_t>(n) * C + c) * 2 + 1] = b;
-    const float g = gamma[c];
-    st[2 * c] = g * a;
-    st[2 * c + 1] = g * b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      totals[(static_cast<size_t>(n) * C + c) * 2] = a;
+      totals[(static_cast<size_t>(n) * C + c) * 2 + 1] = b;
+      const float g = gamma[c];
+      st[2 * c] = g * a;
+      st[2 * c + 1] = g * b;
+    }
   }
   __syncthreads();
-  if (c < C) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int cpg = C / G;
     const int g0 = (c / cpg) * cpg;
     float p1 = 0.f, p2 = 0.f;
@@ -268,9 +300,8 @@ extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fm
   dim3 grid(P, N);
   if (silu) gn_bwd_reduce_kernel<true><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, HW, C, G, x_fmt, da_fmt);
   else gn_bwd_reduce_kernel<false><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, HW, C, G, x_fmt, da_fmt);
-  const int bt = ((C + 31) / 32) * 32;
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
-  gn_bwd_finalize_kernel<<<N, bt, C * 2 * sizeof(float), stream>>>(partial, gamma, mean_rstd, totals, coef, C, G, P, inv);
+  gn_bwd_finalize_kernel<<<N, 256, C * 2 * sizeof(float), stream>>>(partial, gamma, mean_rstd, totals, coef, C, G, P, inv);
   gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(totals, dgamma, dbeta, N, C);
   const size_t total = static_cast<size_t>(N) * HW * (C / 8);
   const int g2 = grid_for(total, 256, 148 * 32);
@@ -286,8 +317,8 @@ extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fm
 // out[c] = sum over rows of x[row][c]; workspace: ptivae_colsum_blocks(rows) * C floats
 extern "C" int ptivae_colsum_blocks(long long rows) {
   if (rows <= 0) return PTIVAE_ERR_ARG;
-  long long b = (rows + 1023) / 1024;
-  if (b > 592) b = 592;
+  long long b = (rows + 255) / 256;
+  if (b > 2368) b = 2368;
   return static_cast<int>(b);
 }
 extern "C" int ptivae_colsum(const void* x, float* out, float* workspace, long long rows, int C, int fmt,

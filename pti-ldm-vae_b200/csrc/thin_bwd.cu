@@ -23,56 +23,79 @@ __device__ __forceinline__ float ld_wide(const void* base, size_t idx, int fmt) 
 // wide' = wide*scale + shift inside the image (ss may be NULL: identity), 0 outside.  slot 9 = sum of thin.
 // grid (x segments, row blocks, N); thread -> (t, c) pair, c fastest (coalesced NHWC reads), sliding 3x3 window along x.
 constexpr int kTwSeg = 32;   // pixels per x segment
+// When there are fewer (t, c) pairs than threads (the 1<->32 layers at 256^2: 32 pairs), the block splits its x segment
+// into XP sub-segments handled by different threads and folds them through shared memory in a fixed order: 8x less
+// serial work per thread (the one-thread-per-pair version was pure load latency, 150 us per launch).
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict__ thin, const void* __restrict__ wide,
                                                          const float* __restrict__ ss, float* __restrict__ partial,
-                                                         int H, int W, int C, int Ct, int wide_fmt) {
+                                                         int H, int W, int C, int Ct, int wide_fmt, int PP, int XP) {
+  __shared__ float red[256][10];
   const int n = blockIdx.z;
   const int y_begin = blockIdx.y * kTwRows;
   const int y_end = min(H, y_begin + kTwRows);
-  const int x_begin = blockIdx.x * kTwSeg;
-  const int x_end = min(W, x_begin + kTwSeg);
+  const int sub = threadIdx.x / PP, lp = threadIdx.x - sub * PP;
+  const int sw = kTwSeg / XP;                                     // pixels per sub-segment
+  const int x_begin = blockIdx.x * kTwSeg + sub * sw;
+  const int x_end = min(W, x_begin + sw);
   const size_t plane = static_cast<size_t>(H) * W;
   const size_t part = (static_cast<size_t>(n) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  for (int idx = threadIdx.x; idx < Ct * C; idx += blockDim.x) {
-    const int t = idx / C, c = idx - t * C;
-    float sc = 1.f, sh = 0.f;
-    if (ss != nullptr) {
-      sc = __ldg(ss + (static_cast<size_t>(n) * C + c) * 2);
-      sh = __ldg(ss + (static_cast<size_t>(n) * C + c) * 2 + 1);
-    }
-    const float* tp = thin + (static_cast<size_t>(n) * Ct + t) * plane;
+  const int pairs = Ct * C;
+  for (int base = 0; base < pairs; base += PP) {
+    const int idx = base + lp;
     float acc[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) acc[k] = 0.f;
-    for (int y = y_begin; y < y_end; ++y) {
-      auto col = [&](int xx, float (&v)[3]) {
+    if (idx < pairs && sub < XP) {
+      const int t = idx / C, c = idx - t * C;
+      float sc = 1.f, sh = 0.f;
+      if (ss != nullptr) {
+        sc = __ldg(ss + (static_cast<size_t>(n) * C + c) * 2);
+        sh = __ldg(ss + (static_cast<size_t>(n) * C + c) * 2 + 1);
+      }
+      const float* tp = thin + (static_cast<size_t>(n) * Ct + t) * plane;
+      for (int y = y_begin; y < y_end; ++y) {
+        auto col = [&](int xx, float (&v)[3]) {
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int yy = y + ky - 1;
-          v[ky] = 0.f;
-          if (xx >= 0 && xx < W && yy >= 0 && yy < H)
-            v[ky] = fmaf(ld_wide(wide, ((static_cast<size_t>(n) * H + yy) * W + xx) * C + c, wide_fmt), sc, sh);
-        }
-      };
-      float c0[3], c1[3], c2[3];
-      col(x_begin - 1, c0);
-      col(x_begin, c1);
-      for (int x = x_begin; x < x_end; ++x) {
-        col(x + 1, c2);
-        const float tv = __ldg(tp + static_cast<size_t>(y) * W + x);
+          for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            v[ky] = 0.f;
+            if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+              v[ky] = fmaf(ld_wide(wide, ((static_cast<size_t>(n) * H + yy) * W + xx) * C + c, wide_fmt), sc, sh);
+          }
+        };
+        float c0[3], c1[3], c2[3];
+        col(x_begin - 1, c0);
+        col(x_begin, c1);
+        for (int x = x_begin; x < x_end; ++x) {
+          col(x + 1, c2);
+          const float tv = __ldg(tp + static_cast<size_t>(y) * W + x);
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          acc[ky * 3 + 0] = fmaf(tv, c0[ky], acc[ky * 3 + 0]);
-          acc[ky * 3 + 1] = fmaf(tv, c1[ky], acc[ky * 3 + 1]);
-          acc[ky * 3 + 2] = fmaf(tv, c2[ky], acc[ky * 3 + 2]);
-          c0[ky] = c1[ky]; c1[ky] = c2[ky];
+          for (int ky = 0; ky < 3; ++ky) {
+            acc[ky * 3 + 0] = fmaf(tv, c0[ky], acc[ky * 3 + 0]);
+            acc[ky * 3 + 1] = fmaf(tv, c1[ky], acc[ky * 3 + 1]);
+            acc[ky * 3 + 2] = fmaf(tv, c2[ky], acc[ky * 3 + 2]);
+            c0[ky] = c1[ky]; c1[ky] = c2[ky];
+          }
+          acc[9] += tv;
         }
-        acc[9] += tv;
       }
     }
-    float* dst = partial + (part * Ct * C + idx) * 10;
+    if (XP > 1) {
+      __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 10; ++k) dst[k] = acc[k];
+      for (int k = 0; k < 10; ++k) red[threadIdx.x][k] = acc[k];
+      __syncthreads();
+      if (sub == 0) {
+        for (int j = 1; j < XP; ++j)
+#pragma unroll
+          for (int k = 0; k < 10; ++k) acc[k] += red[j * PP + lp][k];
+      }
+    }
+    if (sub == 0 && idx < pairs) {
+      float* dst = partial + (part * pairs + idx) * 10;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) dst[k] = acc[k];
+    }
   }
 }
 
@@ -193,10 +216,12 @@ extern "C" int ptivae_thin_wgrad(const float* thin, const void* wide, const floa
   if (!wide_is_input && db) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int rb = (H + kTwRows - 1) / kTwRows, xs = (W + kTwSeg - 1) / kTwSeg;
-  int bt = ((Ct * C + 31) / 32) * 32;
-  if (bt > 256) bt = 256;
+  int pp = ((Ct * C + 31) / 32) * 32;           // (t, c) pairs handled concurrently (a multiple of the warp size)
+  if (pp > 256) pp = 256;
+  int xp = 1;                                   // sub-segments per block: a power of two, pp * xp <= 256, <= 8
+  while (xp < 8 && pp * xp * 2 <= 256) xp *= 2;
   dim3 grid(xs, rb, N);
-  thin_wgrad_kernel<<<grid, bt, 0, stream>>>(thin, wide, scale_shift, workspace, H, W, C, Ct, wide_fmt);
+  thin_wgrad_kernel<<<grid, pp * xp, 0, stream>>>(thin, wide, scale_shift, workspace, H, W, C, Ct, wide_fmt, pp, xp);
   const int tot = Ct * C * 10;
   const int st_t = wide_is_input ? C * 9 : 9, st_c = wide_is_input ? 9 : Ct * 9;
   thin_wgrad_reduce_kernel<<<(tot * 32 + 255) / 256, 256, 0, stream>>>(workspace, dw, db, N * rb * xs, C, Ct, st_t, st_c,

@@ -227,11 +227,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // out[(ca*Cb + cb)*T + t] = sum over slabs in masks[t], then over splits (index order), of partial[split][slab][ca][cb]
 struct SlabMasks { uint32_t m[9]; };
+// grid: one warp per 32 consecutive (ca, cb) elements of one tap; lanes = elements (coalesced), the split / slab loop is
+// unrolled four deep so that several loads are in flight (the plain serial loop was pure load latency: 24 us per launch).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                            int splits, int nslabs, int Ca, int Cb, int T,
                                                            SlabMasks masks) {
   const size_t plane = static_cast<size_t>(Ca) * Cb;
   const size_t total = plane * T;
+  const size_t stride = static_cast<size_t>(nslabs) * plane;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int t = static_cast<int>(i / plane);
@@ -242,7 +245,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
       if (!(m >> sl & 1u)) continue;
       const float* src = partial + sl * plane + e;
       float a = 0.f;
-      for (int sp = 0; sp < splits; ++sp) a += __ldg(src + static_cast<size_t>(sp) * nslabs * plane);
+      int sp = 0;
+      for (; sp + 4 <= splits; sp += 4) {
+        const float v0 = __ldg(src + (sp + 0) * stride), v1 = __ldg(src + (sp + 1) * stride);
+        const float v2 = __ldg(src + (sp + 2) * stride), v3 = __ldg(src + (sp + 3) * stride);
+        a += v0; a += v1; a += v2; a += v3;           // index order: same bits as the serial loop
+      }
+      for (; sp < splits; ++sp) a += __ldg(src + sp * stride);
       acc += a;
     }
     out[e * T + t] = acc;
@@ -270,11 +279,11 @@ static int wgrad_plan(int N, int H, int W, int Ca, int Cb, int mode, WgradPlan* 
   p->ngroups = mode == 3 ? 1 : (mode == 2 ? 4 : 3);
   p->nslabs = mode == 3 ? 1 : (mode == 2 ? 16 : 9);
   p->T = mode == 3 ? 1 : 9;
-  // split K so that the grid is about two waves of 148 CTAs, but keep >= 8 tiles (32 UMMA K steps) per CTA: the
-  // fp32 partials cost 4*taps*Ca*Cb bytes per split
+  // split K so that the grid is about one wave of 148 CTAs, but keep >= 16 tiles (64 UMMA K steps) per CTA: the
+  // fp32 partials cost 4*taps*Ca*Cb bytes per split and the reduction kernel reads all of them
   const int per = p->ngroups * p->n_ca_blocks * p->n_cb_blocks;
-  int splits = (2 * 148 + per - 1) / per;
-  const int max_by_work = (p->total_tiles + 7) / 8;
+  int splits = (148 + per - 1) / per;
+  const int max_by_work = (p->total_tiles + 15) / 16;
   if (splits > max_by_work) splits = max_by_work;
   if (splits < 1) splits = 1;
   p->tiles_per_split = (p->total_tiles + splits - 1) / splits;
@@ -411,6 +420,6 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
     for (int t = 0; t < p.T; ++t) sm.m[t] = 1u << t;
   }
   const size_t total = static_cast<size_t>(Ca) * Cb * p.T;
-  wgrad_reduce_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(workspace, dw, p.splits, p.nslabs, Ca, Cb, p.T, sm);
+  wgrad_reduce_kernel<<<grid_for(total, 128, 148 * 8), 128, 0, stream>>>(workspace, dw, p.splits, p.nslabs, Ca, Cb, p.T, sm);
   return static_cast<int>(cudaGetLastError());
 }
