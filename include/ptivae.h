@@ -247,11 +247,15 @@ int ptivae_rowdot(const void* a, const void* b, float* out, long long rows, int 
  *   dx = scale_c*du - e_g - x*f_g (+ residual), du = da*act'(x*scale+shift);  dgamma/dbeta fp32 [C] (overwritten)
  *   x (x_fmt), da (da_fmt), residual (res_fmt, NULL ok): NHWC [N][HW][C];  dx32 (fp32) and/or dx16 (bf16): at least one
  *   scale_shift [N][C][2], mean_rstd [N][G][2] from ptivae_gn_finalize;  coef: fp32 [N][C][2] scratch
- *   workspace: (N*P*C*2 + N*C*2) floats, P = ptivae_gn_bwd_parts(HW).  Deterministic, batch-invariant chunking. */
+ *   act_out (NULL ok): bf16 [N][HW][C] = act(x*scale+shift), the re-materialised forward operand (what the weight
+ *             gradient of the conv that consumed y reads), written by the reduction pass that has x in registers anyway
+ *   colsum_out (NULL ok): fp32 [C] = per-channel sum of dx = the bias gradient of the conv that produced x
+ *   workspace: ptivae_gn_bwd_workspace(N, HW, C) floats.  Deterministic, batch-invariant chunking. */
 int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fmt, const float* scale_shift, const float* mean_rstd,
                   const float* gamma, const void* residual, int res_fmt, float* dx32, void* dx16, float* dgamma,
-                  float* dbeta, float* coef, float* workspace, int N, int HW, int C, int G, int silu, void* stream);
-int ptivae_gn_bwd_parts(int HW);
+                  float* dbeta, void* act_out, float* colsum_out, float* coef, float* workspace, int N, int HW, int C, int G,
+                  int silu, void* stream);
+long long ptivae_gn_bwd_workspace(int N, int HW, int C);
 /* bias gradient: out[c] = sum over rows of x[row][c] (x NHWC storage fmt); workspace ptivae_colsum_blocks(rows)*C floats */
 int ptivae_colsum(const void* x, float* out, float* workspace, long long rows, int C, int fmt, void* stream);
 int ptivae_colsum_blocks(long long rows);

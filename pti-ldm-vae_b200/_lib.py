@@ -59,8 +59,8 @@ SIGNATURES = {
                                                       _c_void_p],
     "ptivae_rowdot": [_c_void_p] * 3 + [_c_ll, _c_int, _c_ll, _c_ll, _c_int, _c_int, _c_void_p],
     "ptivae_gn_bwd": [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int] +
-                     [_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p],
-    "ptivae_gn_bwd_parts": [_c_int],
+                     [_c_void_p] * 8 + [_c_int] * 5 + [_c_void_p],
+    "ptivae_gn_bwd_workspace": [_c_int] * 3,
     "ptivae_colsum": [_c_void_p] * 3 + [_c_ll, _c_int, _c_int, _c_void_p],
     "ptivae_colsum_blocks": [_c_ll],
     "ptivae_thin_wgrad": [_c_void_p] * 6 + [_c_int] * 7 + [_c_void_p],
@@ -74,7 +74,7 @@ SIGNATURES = {
     "ptivae_cast16": [_c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_void_p],
     "ptivae_adam": [_c_void_p] * 4 + [_c_ll] + [_c_float] * 5 + [_c_void_p, _c_int, _c_void_p],
 }
-_RESTYPE_LL = {"ptivae_wgrad_workspace", "ptivae_thin_wgrad_workspace"}
+_RESTYPE_LL = {"ptivae_wgrad_workspace", "ptivae_thin_wgrad_workspace", "ptivae_gn_bwd_workspace"}
 
 _lib = None
 

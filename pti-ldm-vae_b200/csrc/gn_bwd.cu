@@ -43,6 +43,19 @@ __device__ __forceinline__ float act_grad(float x, float sc, float sh, float da)
   return da * s * fmaf(u, 1.0f - s, 1.0f);
 }
 
+// a = act(x*scale + shift) of 8 channels as one bf16 vector: the operand the weight-gradient GEMM of the FOLLOWING conv
+// reads (re-materialised here, where x is in registers anyway, instead of by a separate gn_apply pass)
+template <bool kSilu>
+__device__ __forceinline__ uint4 act8_bf16(const float (&f)[8], const float (&sc)[8], const float (&sh)[8]) {
+  float a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float u = fmaf(f[e], sc[e], sh[e]);
+    a[e] = kSilu ? silu_f(u) : u;
+  }
+  return make_uint4(pack2<false>(a[0], a[1]), pack2<false>(a[2], a[3]), pack2<false>(a[4], a[5]), pack2<false>(a[6], a[7]));
+}
+
 constexpr int kGbPix = 256;    // pixels per reduce chunk (depends on the image only: batch-invariant summation order);
                                // small chunks = many CTAs = enough loads in flight (1024-pixel chunks ran at 15 % of HBM peak)
 
@@ -51,7 +64,8 @@ template <bool kSilu>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restrict__ x, const void* __restrict__ da,
                                                             const float* __restrict__ ss,
                                                             const float* __restrict__ mr, float* __restrict__ partial,
-                                                            int HW, int C, int G, int x_fmt, int da_fmt) {
+                                                            uint4* __restrict__ act_out, int HW, int C, int G,
+                                                            int x_fmt, int da_fmt) {
   __shared__ float sm[256][17];
   const int n = blockIdx.y;
   const int vecs = C / 8;
@@ -83,6 +97,10 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
       ld8(da, img + static_cast<size_t>(p) * vecs + v, da_fmt, d0);
       ld8(x, img + static_cast<size_t>(p + prows) * vecs + v, x_fmt, f1);
       ld8(da, img + static_cast<size_t>(p + prows) * vecs + v, da_fmt, d1);
+      if (act_out != nullptr) {
+        act_out[img + static_cast<size_t>(p) * vecs + v] = act8_bf16<kSilu>(f0, sc, sh);
+        act_out[img + static_cast<size_t>(p + prows) * vecs + v] = act8_bf16<kSilu>(f1, sc, sh);
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float du0 = act_grad<kSilu>(f0[e], sc[e], sh[e], d0[e]);
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
       float f[8], d[8];
       ld8(x, img + static_cast<size_t>(p) * vecs + v, x_fmt, f);
       ld8(da, img + static_cast<size_t>(p) * vecs + v, da_fmt, d);
+      if (act_out != nullptr) act_out[img + static_cast<size_t>(p) * vecs + v] = act8_bf16<kSilu>(f, sc, sh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float du = act_grad<kSilu>(f[e], sc[e], sh[e], d[e]);
@@ -135,6 +154,23 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __res
   extern __shared__ float st[];   // [C][2] gamma-weighted totals
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P <= 16) {   // few chunks: one thread per channel, plain index-order loop (the warp-per-channel path below would
+                   // serialise C/8 dependent shuffle chains per warp: 14 us for C = 128)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * C + c;
+      for (int p = 0; p < P; ++p) {
+        const float2 t = __ldg(src + static_cast<size_t>(p) * C);
+        a += t.x;
+        b += t.y;
+      }
+      totals[(static_cast<size_t>(n) * C + c) * 2] = a;
+      totals[(static_cast<size_t>(n) * C + c) * 2 + 1] = b;
+      const float g = gamma[c];
+      st[2 * c] = g * a;
+      st[2 * c + 1] = g * b;
+    }
+  } else
   for (int c = warp; c < C; c += 8) {
     float a = 0.f, b = 0.f;
     const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * C + c;
@@ -192,10 +228,15 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
                                                            const float* __restrict__ ss,
                                                            const float* __restrict__ coef,
                                                            const void* __restrict__ residual, float* __restrict__ out32,
-                                                           uint4* __restrict__ out16, size_t total_vecs, int HW, int C,
-                                                           int x_fmt, int da_fmt, int res_fmt) {
+                                                           uint4* __restrict__ out16, float* __restrict__ colpart,
+                                                           size_t total_vecs, int HW, int C, int x_fmt, int da_fmt,
+                                                           int res_fmt) {
+  __shared__ float csm[256][9];
   const int vecs = C / 8;
   const size_t per_img = static_cast<size_t>(HW) * vecs;
+  float cs[8];     // column sums of this thread's outputs: its channel vector is fixed (grid stride % vecs == 0)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cs[e] = 0.f;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vecs;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / per_img);
@@ -229,6 +270,19 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
     if (out16 != nullptr)
       out16[i] = make_uint4(pack2<false>(o[0], o[1]), pack2<false>(o[2], o[3]), pack2<false>(o[4], o[5]),
                             pack2<false>(o[6], o[7]));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] += o[e];
+  }
+  if (colpart != nullptr) {   // bias gradient of the conv that produced x: per-block column sums, fixed fold order
+#pragma unroll
+    for (int e = 0; e < 8; ++e) csm[threadIdx.x][e] = cs[e];
+    __syncthreads();
+    const int per = blockDim.x / vecs;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f;
+      for (int r = 0; r < per; ++r) a += csm[r * vecs + c / 8][c % 8];
+      colpart[static_cast<size_t>(blockIdx.x) * C + c] = a;
+    }
   }
 }
 
@@ -280,13 +334,21 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 
 using namespace ptivae;
 
-extern "C" int ptivae_gn_bwd_parts(int HW) { return HW <= 0 ? PTIVAE_ERR_ARG : (HW + kGbPix - 1) / kGbPix; }
+static int gn_bwd_apply_blocks(int N, int HW, int C) {
+  return grid_for(static_cast<size_t>(N) * HW * (C / 8), 256, 148 * 16);
+}
+// workspace floats: ptivae_gn_bwd_workspace(N, HW, C) = partial N*P*C*2 + totals N*C*2 + column-sum partials blocks*C
+extern "C" long long ptivae_gn_bwd_workspace(int N, int HW, int C) {
+  if (N <= 0 || HW <= 0 || C <= 0 || C % 8 != 0) return PTIVAE_ERR_ARG;
+  const long long P = (HW + kGbPix - 1) / kGbPix;
+  return static_cast<long long>(N) * P * C * 2 + static_cast<long long>(N) * C * 2 +
+         static_cast<long long>(gn_bwd_apply_blocks(N, HW, C)) * C;
+}
 
-// workspace floats: partial N*P*C*2 + totals N*C*2  (P = ptivae_gn_bwd_parts(HW))
 extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fmt, const float* scale_shift,
                              const float* mean_rstd, const float* gamma, const void* residual, int res_fmt,
-                             float* dx32, void* dx16, float* dgamma, float* dbeta, float* coef, float* workspace,
-                             int N, int HW, int C, int G, int silu, void* stream_) {
+                             float* dx32, void* dx16, float* dgamma, float* dbeta, void* act_out, float* colsum_out,
+                             float* coef, float* workspace, int N, int HW, int C, int G, int silu, void* stream_) {
   if (!x || !da || !scale_shift || !mean_rstd || !gamma || !dgamma || !dbeta || !coef || !workspace ||
       (!dx32 && !dx16))
     return PTIVAE_ERR_ARG;
@@ -297,20 +359,23 @@ extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fm
   const int P = (HW + kGbPix - 1) / kGbPix;
   float* partial = workspace;
   float* totals = workspace + static_cast<size_t>(N) * P * C * 2;
+  float* colpart = colsum_out ? totals + static_cast<size_t>(N) * C * 2 : nullptr;
+  uint4* act = static_cast<uint4*>(act_out);
   dim3 grid(P, N);
-  if (silu) gn_bwd_reduce_kernel<true><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, HW, C, G, x_fmt, da_fmt);
-  else gn_bwd_reduce_kernel<false><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, HW, C, G, x_fmt, da_fmt);
+  if (silu) gn_bwd_reduce_kernel<true><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, act, HW, C, G, x_fmt, da_fmt);
+  else gn_bwd_reduce_kernel<false><<<grid, 256, 0, stream>>>(x, da, scale_shift, mean_rstd, partial, act, HW, C, G, x_fmt, da_fmt);
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
   gn_bwd_finalize_kernel<<<N, 256, C * 2 * sizeof(float), stream>>>(partial, gamma, mean_rstd, totals, coef, C, G, P, inv);
   gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, stream>>>(totals, dgamma, dbeta, N, C);
   const size_t total = static_cast<size_t>(N) * HW * (C / 8);
-  const int g2 = grid_for(total, 256, 148 * 32);
+  const int g2 = gn_bwd_apply_blocks(N, HW, C);
   if (silu)
     gn_bwd_apply_kernel<true><<<g2, 256, 0, stream>>>(x, da, scale_shift, coef, residual, dx32, static_cast<uint4*>(dx16),
-                                                      total, HW, C, x_fmt, da_fmt, res_fmt);
+                                                      colpart, total, HW, C, x_fmt, da_fmt, res_fmt);
   else
     gn_bwd_apply_kernel<false><<<g2, 256, 0, stream>>>(x, da, scale_shift, coef, residual, dx32, static_cast<uint4*>(dx16),
-                                                       total, HW, C, x_fmt, da_fmt, res_fmt);
+                                                       colpart, total, HW, C, x_fmt, da_fmt, res_fmt);
+  if (colsum_out) colsum_final_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(colpart, colsum_out, g2, C);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -10,7 +10,6 @@
 
 namespace ptivae {
 
-constexpr int kTwRows = 4;   // image rows per block
 
 __device__ __forceinline__ float ld_wide(const void* base, size_t idx, int fmt) {
   if (fmt == 2) return __ldg(reinterpret_cast<const float*>(base) + idx);
@@ -22,13 +21,13 @@ __device__ __forceinline__ float ld_wide(const void* base, size_t idx, int fmt) 
 // G[t][c][tap] = sum_{y,x} thin[n][t][y][x] * wide'[n][y+ky-1][x+kx-1][c]  over this block's rows and x segment;
 // wide' = wide*scale + shift inside the image (ss may be NULL: identity), 0 outside.  slot 9 = sum of thin.
 // grid (x segments, row blocks, N); thread -> (t, c) pair, c fastest (coalesced NHWC reads), sliding 3x3 window along x.
-constexpr int kTwSeg = 32;   // pixels per x segment
 // When there are fewer (t, c) pairs than threads (the 1<->32 layers at 256^2: 32 pairs), the block splits its x segment
 // into XP sub-segments handled by different threads and folds them through shared memory in a fixed order: 8x less
 // serial work per thread (the one-thread-per-pair version was pure load latency, 150 us per launch).
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict__ thin, const void* __restrict__ wide,
                                                          const float* __restrict__ ss, float* __restrict__ partial,
-                                                         int H, int W, int C, int Ct, int wide_fmt, int PP, int XP) {
+                                                         int H, int W, int C, int Ct, int wide_fmt, int PP, int XP,
+                                                         int kTwRows, int kTwSeg) {
   __shared__ float red[256][10];
   const int n = blockIdx.z;
   const int y_begin = blockIdx.y * kTwRows;
@@ -197,9 +196,17 @@ __global__ void __launch_bounds__(256) outer_reduce_kernel(const float* __restri
 
 using namespace ptivae;
 
+// block tiling: (rows, x segment) per block; small images get small tiles so that the grid still fills the GPU
+static void thin_tiling(int N, int H, int W, int* rows, int* seg) {
+  const bool small = static_cast<long long>(N) * H * W <= 65536;
+  *rows = small ? 2 : 4;
+  *seg = small ? 16 : 32;
+}
 extern "C" long long ptivae_thin_wgrad_workspace(int N, int H, int W, int C, int Ct) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Ct <= 0) return PTIVAE_ERR_ARG;
-  return static_cast<long long>(N) * ((H + kTwRows - 1) / kTwRows) * ((W + kTwSeg - 1) / kTwSeg) * Ct * C * 10 * 4;
+  int rows, seg;
+  thin_tiling(N, H, W, &rows, &seg);
+  return static_cast<long long>(N) * ((H + rows - 1) / rows) * ((W + seg - 1) / seg) * Ct * C * 10 * 4;
 }
 
 // Weight gradient of a thin 3x3 s1 p1 conv.
@@ -215,13 +222,15 @@ extern "C" int ptivae_thin_wgrad(const float* thin, const void* wide, const floa
     return PTIVAE_ERR_ARG;
   if (!wide_is_input && db) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int rb = (H + kTwRows - 1) / kTwRows, xs = (W + kTwSeg - 1) / kTwSeg;
+  int rows, seg;
+  thin_tiling(N, H, W, &rows, &seg);
+  const int rb = (H + rows - 1) / rows, xs = (W + seg - 1) / seg;
   int pp = ((Ct * C + 31) / 32) * 32;           // (t, c) pairs handled concurrently (a multiple of the warp size)
   if (pp > 256) pp = 256;
   int xp = 1;                                   // sub-segments per block: a power of two, pp * xp <= 256, <= 8
-  while (xp < 8 && pp * xp * 2 <= 256) xp *= 2;
+  while (xp < 8 && pp * xp * 2 <= 256 && seg / (xp * 2) >= 2) xp *= 2;
   dim3 grid(xs, rb, N);
-  thin_wgrad_kernel<<<grid, pp * xp, 0, stream>>>(thin, wide, scale_shift, workspace, H, W, C, Ct, wide_fmt, pp, xp);
+  thin_wgrad_kernel<<<grid, pp * xp, 0, stream>>>(thin, wide, scale_shift, workspace, H, W, C, Ct, wide_fmt, pp, xp, rows, seg);
   const int tot = Ct * C * 10;
   const int st_t = wide_is_input ? C * 9 : 9, st_c = wide_is_input ? 9 : Ct * 9;
   thin_wgrad_reduce_kernel<<<(tot * 32 + 255) / 256, 256, 0, stream>>>(workspace, dw, db, N * rb * xs, C, Ct, st_t, st_c,

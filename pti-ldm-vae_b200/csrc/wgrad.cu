@@ -279,11 +279,11 @@ static int wgrad_plan(int N, int H, int W, int Ca, int Cb, int mode, WgradPlan* 
   p->ngroups = mode == 3 ? 1 : (mode == 2 ? 4 : 3);
   p->nslabs = mode == 3 ? 1 : (mode == 2 ? 16 : 9);
   p->T = mode == 3 ? 1 : 9;
-  // split K so that the grid is about one wave of 148 CTAs, but keep >= 16 tiles (64 UMMA K steps) per CTA: the
+  // split K so that the grid is about one wave of 148 CTAs, but keep >= 4 tiles (16 UMMA K steps) per CTA: the
   // fp32 partials cost 4*taps*Ca*Cb bytes per split and the reduction kernel reads all of them
   const int per = p->ngroups * p->n_ca_blocks * p->n_cb_blocks;
   int splits = (148 + per - 1) / per;
-  const int max_by_work = (p->total_tiles + 15) / 16;
+  const int max_by_work = (p->total_tiles + 3) / 4;
   if (splits > max_by_work) splits = max_by_work;
   if (splits < 1) splits = 1;
   p->tiles_per_split = (p->total_tiles + splits - 1) / splits;

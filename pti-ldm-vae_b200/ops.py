@@ -505,22 +505,26 @@ def attention_bwd(q, k, v, o, lse, d_o, dqkv: torch.Tensor) -> None:
 
 
 def gn_bwd(x: torch.Tensor, da: torch.Tensor, ss: torch.Tensor, mr: torch.Tensor, gamma: torch.Tensor, silu: bool,
-           dgamma: torch.Tensor, dbeta: torch.Tensor, residual=None, want32: bool = True, want16: bool = True):
-    """Backward of act(GroupNorm(x)).  -> (dx fp32 | None, dx bf16 | None); dgamma/dbeta (fp32 [C]) are overwritten."""
+           dgamma: torch.Tensor, dbeta: torch.Tensor, residual=None, want32: bool = True, want16: bool = True,
+           want_act: bool = False, colsum_out: torch.Tensor | None = None):
+    """Backward of act(GroupNorm(x)).  -> (dx fp32 | None, dx bf16 | None[, act bf16]); dgamma/dbeta (fp32 [C]) are
+    overwritten.  want_act: also return act(GroupNorm(x)) in bf16 (the weight-gradient operand); colsum_out: fp32 [C]
+    that receives the per-channel sum of dx (the bias gradient of the conv that produced x)."""
     _need_cuda(x, da, ss, mr, gamma)
     n, hw, c = _nhwc_dims(x)
     g = mr.shape[1]
     if da.shape != x.shape or (residual is not None and residual.shape != x.shape):
         raise _lib.PtivaeError("gn_bwd shape mismatch")
-    parts = _lib.lib().ptivae_gn_bwd_parts(hw)
-    ws = torch.empty(n * parts * c * 2 + n * c * 2, device=x.device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib().ptivae_gn_bwd_workspace(n, hw, c), device=x.device, dtype=torch.float32)
     coef = torch.empty((n, c, 2), device=x.device, dtype=torch.float32)
     dx32 = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want32 else None
     dx16 = torch.empty(x.shape, device=x.device, dtype=BF16) if want16 else None
-    _call("gn_bwd", (n, hw, c, x.element_size(), int(silu)), 4, _lib.lib().ptivae_gn_bwd, _p(x), _fmt(x), _p(da), _fmt(da),
-          _p(ss), _p(mr), _p(gamma), _p(residual), 0 if residual is None else _fmt(residual), _p(dx32), _p(dx16),
-          _p(dgamma), _p(dbeta), _p(coef), _p(ws), n, hw, c, g, int(silu), _stream())
-    return dx32, dx16
+    act = torch.empty(x.shape, device=x.device, dtype=BF16) if want_act else None
+    _call("gn_bwd", (n, hw, c, x.element_size(), int(silu)), 4 + int(colsum_out is not None), _lib.lib().ptivae_gn_bwd, _p(x),
+          _fmt(x), _p(da), _fmt(da), _p(ss), _p(mr), _p(gamma), _p(residual), 0 if residual is None else _fmt(residual),
+          _p(dx32), _p(dx16), _p(dgamma), _p(dbeta), _p(act), _p(colsum_out), _p(coef), _p(ws), n, hw, c, g, int(silu),
+          _stream())
+    return (dx32, dx16, act) if want_act else (dx32, dx16)
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

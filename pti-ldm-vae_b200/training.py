@@ -125,7 +125,7 @@ class TrainRun:
         return _Act(*r) if g else _Act(r)
 
     # ------------------------------------------------------------------------------------------ forward
-    def _resblock(self, blk: AEKLResBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
+    def _resblock(self, blk: AEKLResBlock, a: _Act, out_f32: bool, stats: bool, in_bias) -> _Act:
         ex = self.ex
         x = a.t
         ss1, mr1 = self._ss_mr(a, blk.norm1)
@@ -150,10 +150,10 @@ class TrainRun:
                 out = self._fconv(h.t, ss2, blk.conv2.conv, sc, stats, out_f32)
         else:
             out = self._fconv(h.t, ss2, blk.conv2.conv, x, stats, out_f32)
-        self.tape.append(("res", blk, x, ss1, mr1, h.t, ss2, mr2, raw))
+        self.tape.append(("res", blk, x, ss1, mr1, h.t, ss2, mr2, raw, in_bias))
         return out
 
-    def _attention(self, blk: SpatialAttentionBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
+    def _attention(self, blk: SpatialAttentionBlock, a: _Act, out_f32: bool, stats: bool, in_bias) -> _Act:
         ex = self.ex
         x = a.t
         ss, mr = self._ss_mr(a, blk.norm)
@@ -166,7 +166,7 @@ class TrainRun:
         q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
         o, lse = ops.attention(q, k, v, return_lse=True)
         out = ex.conv(o.view(n, h, w, c), blk.attn.out_proj, 3, residual=x, stats=stats, out_f32=out_f32)
-        self.tape.append(("attn", blk, x, ss, mr, xn, qkv, o, lse))
+        self.tape.append(("attn", blk, x, ss, mr, qkv, o, lse, in_bias))
         return out
 
     def _stack_fwd(self, blocks: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:
@@ -187,23 +187,29 @@ class TrainRun:
                                    dtype=ex.op_dtype if operand_only(0) else torch.float32, gn_groups=g0)
         a = _Act(*r0) if g0 else _Act(r0)
         self.tape.append(("first", first, x))
+        # in_bias: bias parameters of the op that produced the current activation; their gradient is the per-channel sum of
+        # the gradient of that activation, which the CONSUMER's backward produces (and sums on the way out)
+        in_bias = [first.conv.bias]
         for i, blk in enumerate(body):
             nxt_operand = operand_only(i + 1)
             to_stream = not (nxt_operand or i + 1 == len(body))
             if isinstance(blk, AEKLResBlock):
-                a = self._resblock(blk, a, out_f32=to_stream, stats=not nxt_operand)
+                a = self._resblock(blk, a, out_f32=to_stream, stats=not nxt_operand, in_bias=in_bias)
+                in_bias = [blk.conv2.conv.bias] + ([blk.nin_shortcut.conv.bias] if isinstance(blk.nin_shortcut, Convolution) else [])
             elif isinstance(blk, SpatialAttentionBlock):
-                a = self._attention(blk, a, out_f32=to_stream, stats=not nxt_operand)
+                a = self._attention(blk, a, out_f32=to_stream, stats=not nxt_operand, in_bias=in_bias)
+                in_bias = [blk.attn.out_proj.bias]
             else:
                 xin = a.t
                 down = isinstance(blk, AEKLDownsample)
                 conv = blk.conv.conv if down else blk.postconv.conv
                 a = ex.conv(xin, conv, 1 if down else 2, out_f32=not nxt_operand, stats=not nxt_operand,
                             emit16=(not nxt_operand) and needs_raw16(i + 1))
-                self.tape.append(("resample", conv, xin, 1 if down else 2))
+                self.tape.append(("resample", conv, xin, 1 if down else 2, in_bias))
+                in_bias = [conv.bias]
         ss, mr = self._ss_mr(a, last_norm)
         out = ops.conv3x3_small_cout(a.t, ex.f32(last.conv.weight), ex.f32(last.conv.bias), ss)
-        self.tape.append(("last", last_norm, last, a.t, ss, mr))
+        self.tape.append(("last", last_norm, last, a.t, ss, mr, in_bias))
         return out
 
     def forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):
@@ -232,53 +238,56 @@ class TrainRun:
         return recon, mu, sigma
 
     # ------------------------------------------------------------------------------------------ backward
+    @staticmethod
+    def _bias_dst(G: FlatGrads, in_bias):
+        """Destination of the fused column sum (first bias) and a closure that mirrors it into the others."""
+        dst = G[in_bias[0]]
+
+        def mirror():
+            for b in in_bias[1:]:
+                G[b].copy_(dst)
+        return dst, mirror
+
     def _res_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
-        _, blk, x, ss1, mr1, h, ss2, mr2, raw = rec
+        _, blk, x, ss1, mr1, h, ss2, mr2, raw, in_bias = rec
         ex = self.ex
         dev = x.device
         c1, c2 = blk.conv1.conv, blk.conv2.conv
-        d16 = g.t16
-        a2 = ops.gn_apply(h, ss2, silu=True, dtype=BF16)
-        ops.wgrad(d16, a2, 0, out=G[c2.weight])
-        ops.colsum(d16, out=G[c2.bias])
+        d16 = g.t16                       # gradient of the block output (its column sum = conv2.bias gradient: already stored)
         da2 = ops.conv_umma(d16, self._packT(c2.weight), self._zero_bias(c2.weight.shape[1], dev), 4)
-        _, dh16 = ops.gn_bwd(h, da2, ss2, mr2, ex.f32(blk.norm2.weight), True, G[blk.norm2.weight], G[blk.norm2.bias],
-                             want32=False)
-        a1 = ops.gn_apply(x, ss1, silu=True, dtype=BF16)
-        ops.wgrad(dh16, a1, 0, out=G[c1.weight])
-        ops.colsum(dh16, out=G[c1.bias])
+        # GroupNorm+SiLU backward of norm2; the same pass re-materialises conv2's operand a2 = silu(norm2(h)) in bf16
+        # and sums dh over the pixels (= conv1.bias gradient)
+        _, dh16, a2 = ops.gn_bwd(h, da2, ss2, mr2, ex.f32(blk.norm2.weight), True, G[blk.norm2.weight], G[blk.norm2.bias],
+                                 want32=False, want_act=True, colsum_out=G[c1.bias])
+        ops.wgrad(d16, a2, 0, out=G[c2.weight])
         da1 = ops.conv_umma(dh16, self._packT(c1.weight), self._zero_bias(c1.weight.shape[1], dev), 4)
         if raw is not None:
             sc = blk.nin_shortcut.conv
             ops.wgrad(d16, ops.cast16(raw, BF16), 3, out=G[sc.weight])
-            G[sc.bias].copy_(G[c2.bias])
             res = ops.conv_umma(d16, self._packT(sc.weight), self._zero_bias(sc.weight.shape[1], dev), 3, out_f32=True)
         else:
             res = g.any
-        dx32, dx16 = ops.gn_bwd(x, da1, ss1, mr1, ex.f32(blk.norm1.weight), True, G[blk.norm1.weight],
-                                G[blk.norm1.bias], residual=res)
+        dst, mirror = self._bias_dst(G, in_bias)
+        dx32, dx16, a1 = ops.gn_bwd(x, da1, ss1, mr1, ex.f32(blk.norm1.weight), True, G[blk.norm1.weight],
+                                    G[blk.norm1.bias], residual=res, want_act=True, colsum_out=dst)
+        mirror()
+        ops.wgrad(dh16, a1, 0, out=G[c1.weight])
         return _G(dx32, dx16)
 
     def _attn_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
-        _, blk, x, ss, mr, xn, qkv, o, lse = rec
+        _, blk, x, ss, mr, qkv, o, lse, in_bias = rec
         ex = self.ex
         dev = x.device
-        n, h, w, c = xn.shape
+        n, h, w, c = x.shape
         at = blk.attn
         d16 = g.t16
         ops.wgrad(d16, ops.cast16(o, BF16).view(n, h, w, c), 3, out=G[at.out_proj.weight])
-        ops.colsum(d16, out=G[at.out_proj.bias])
         d_o = ops.conv_umma(d16, self._packT(at.out_proj.weight), self._zero_bias(c, dev), 3).view(n, h * w, c)
         dqkv = torch.empty((n, h * w, 3 * c), device=dev, dtype=BF16)
         qkv16 = ops.cast16(qkv, BF16)
         q, k, v = qkv16[..., :c], qkv16[..., c:2 * c], qkv16[..., 2 * c:]
         ops.attention_bwd(q, k, v, o, lse, d_o, dqkv)
         dq4 = dqkv.view(n, h, w, 3 * c)
-        dwqkv = ops.wgrad(dq4, ops.cast16(xn, BF16), 3)     # [3C, C, 1, 1]
-        dbqkv = ops.colsum(dq4)
-        for i, lin in enumerate((at.to_q, at.to_k, at.to_v)):
-            G[lin.weight].copy_(dwqkv[i * c:(i + 1) * c].view(c, c))
-            G[lin.bias].copy_(dbqkv[i * c:(i + 1) * c])
         key = (id(at.to_q.weight), "qkvT")
         ws = (at.to_q.weight, at.to_k.weight, at.to_v.weight)
         ver = tuple((t.data_ptr(), t._version) for t in ws)
@@ -288,36 +297,47 @@ class TrainRun:
             ex._packed[key] = hit
             ex._recipes[key] = [(t, hit[1], i * c, 3 * c, 4) for i, t in enumerate(ws)]    # [1][C][3C]: column blocks
         dxn = ops.conv_umma(dq4, hit[1], self._zero_bias(c, dev), 3)
-        dx32, dx16 = ops.gn_bwd(x, dxn, ss, mr, ex.f32(blk.norm.weight), False, G[blk.norm.weight], G[blk.norm.bias],
-                                residual=g.any)
+        dst, mirror = self._bias_dst(G, in_bias)
+        # norm backward (no activation); the pass also re-materialises xn = norm(x) in bf16 for the q|k|v weight gradient
+        dx32, dx16, xn16 = ops.gn_bwd(x, dxn, ss, mr, ex.f32(blk.norm.weight), False, G[blk.norm.weight], G[blk.norm.bias],
+                                      residual=g.any, want_act=True, colsum_out=dst)
+        mirror()
+        dwqkv = ops.wgrad(dq4, xn16, 3)                     # [3C, C, 1, 1]
+        dbqkv = ops.colsum(dq4)
+        for i, lin in enumerate((at.to_q, at.to_k, at.to_v)):
+            G[lin.weight].copy_(dwqkv[i * c:(i + 1) * c].view(c, c))
+            G[lin.bias].copy_(dbqkv[i * c:(i + 1) * c])
         return _G(dx32, dx16)
 
     def _resample_bwd(self, rec, g: _G, G: FlatGrads) -> _G:
-        _, conv, xin, mode = rec
+        _, conv, xin, mode, in_bias = rec
         d16 = g.t16
         ops.wgrad(d16, ops.cast16(xin, BF16), mode, out=G[conv.weight])
-        ops.colsum(d16, out=G[conv.bias])
         c = conv.weight.shape[1]
         dx16 = ops.conv_umma(d16, self._packT(conv.weight, 2 if mode == 2 else 0), self._zero_bias(c, xin.device),
                              5 if mode == 1 else 6)
+        dst, mirror = self._bias_dst(G, in_bias)
+        ops.colsum(dx16, out=dst)
+        mirror()
         return _G(None, dx16)
 
     def _last_bwd(self, rec, d_out: torch.Tensor, G: FlatGrads) -> _G:
-        _, norm, last, x, ss, mr = rec
+        _, norm, last, x, ss, mr, in_bias = rec
         ex = self.ex
         conv = last.conv
         d_out = d_out.detach().contiguous().float()
         ops.thin_wgrad(d_out, x, True, G[conv.weight], db=G[conv.bias], scale_shift=ss)
         c = conv.weight.shape[1]
         da = ops.conv3x3_small_cin(d_out, self._mirrored(conv.weight), self._zero_bias(c, x.device), dtype=BF16)
-        dx32, dx16 = ops.gn_bwd(x, da, ss, mr, ex.f32(norm.weight), False, G[norm.weight], G[norm.bias])
+        dst, mirror = self._bias_dst(G, in_bias)
+        dx32, dx16 = ops.gn_bwd(x, da, ss, mr, ex.f32(norm.weight), False, G[norm.weight], G[norm.bias], colsum_out=dst)
+        mirror()
         return _G(dx32, dx16)
 
     def _first_bwd(self, rec, g: _G, G: FlatGrads, need_dx: bool):
         _, first, x = rec
         conv = first.conv
-        ops.thin_wgrad(x, g.any, False, G[conv.weight])
-        ops.colsum(g.any, out=G[conv.bias])
+        ops.thin_wgrad(x, g.any, False, G[conv.weight])    # (conv.bias: summed by the backward of the block that follows)
         if not need_dx:
             return None
         ct = conv.weight.shape[1]

@@ -199,14 +199,17 @@ def test_gn_bwd(b200, n, h, w, c, g, silu, xdt):
     part = b200.ops.gn_stats(x, g)
     ss, mr = b200.ops.gn_finalize(part, gamma, beta, h * w, eps, return_mean_rstd=True)
     dg, db = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
-    dx32, dx16 = b200.ops.gn_bwd(x, da, ss, mr, gamma, silu, dg, db, residual=res)
+    csum = torch.empty(c, device=DEV)
+    dx32, dx16, act = b200.ops.gn_bwd(x, da, ss, mr, gamma, silu, dg, db, residual=res, want_act=True, colsum_out=csum)
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     y = F.group_norm(xr, g, gr, br, eps)
     if silu:
         y = F.silu(y)
+    assert _rel(act, y.detach().permute(0, 2, 3, 1)) <= 2.5e-3          # the re-materialised operand, bf16
     y.backward(da.float().permute(0, 3, 1, 2))
     dx_ref = xr.grad.permute(0, 2, 3, 1) + res
+    assert _rel(csum, dx_ref.sum(dim=(0, 1, 2))) <= 1e-4, _rel(csum, dx_ref.sum(dim=(0, 1, 2)))   # fused bias gradient
     assert _rel(dx32, dx_ref) <= 2e-5, _rel(dx32, dx_ref)            # fp32 math end to end
     assert _rel(dx16, dx_ref) <= 2.5e-3                              # + one bf16 rounding
     assert _rel(dg, gr.grad) <= 2e-5 and _rel(db, br.grad) <= 2e-5, (_rel(dg, gr.grad), _rel(db, br.grad))
