@@ -1,4 +1,4 @@
-"""Batch sharding for multi-GPU inference: images are independent (GroupNorm and attention
+"""Batch sharding for multi-GPU inference and the gradient all-reduce of data-parallel training: images are independent (GroupNorm and attention
 are per-sample), so every rank owns a contiguous shard of the batch, weights are replicated and there is
 NO data-path collective.  The only communication is host-side plumbing: a barrier and a max-reduce of the
 per-rank elapsed time for benchmarking, and an optional gather of results.  Works with the ``nccl`` backend
@@ -49,3 +49,34 @@ def max_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# data-parallel training (the reference: DistributedDataParallel around the autoencoder, train_vae.py:282; gradients are
+# averaged over ranks by bucketed NCCL all-reduces).  Here the gradients of all parameters live in ONE flat fp32 buffer
+# in ``parameters()`` order, so the reduction is a handful of contiguous segments.
+# ---------------------------------------------------------------------------------------------------------------------
+def gradient_segments(ae) -> dict:
+    """[lo, hi) element ranges of the flat gradient buffer, grouped by when they become final during the backward:
+    ``decoder`` (decoder stack + post_quant_conv: final once the decoder backward has finished, i.e. while the encoder
+    backward still runs) and ``encoder`` (encoder stack + the two quant convs: final at the end)."""
+    names = ["encoder", "decoder", "quant_conv_mu", "quant_conv_log_sigma", "post_quant_conv"]
+    have = [n for n, _ in ae.named_children() if n in names]
+    if have != names:
+        raise RuntimeError(f"unexpected child order {have}: the flat-buffer segments assume {names}")
+    order = [(n, getattr(ae, n)) for n in names]
+    sizes = [sum(p.numel() for p in m.parameters()) for _, m in order]
+    offs = [0]
+    for sz in sizes:
+        offs.append(offs[-1] + sz)
+    return {"decoder": [(offs[1], offs[2]), (offs[4], offs[5])], "encoder": [(offs[0], offs[1]), (offs[2], offs[4])],
+            "total": offs[5]}
+
+
+def allreduce_segments(flat: torch.Tensor, segments, group=None) -> None:
+    """Sum-all-reduce of the given [lo, hi) ranges of a flat buffer, in place (NCCL on GPUs, gloo in the CPU tests)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for lo, hi in segments:
+        if hi > lo:
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)

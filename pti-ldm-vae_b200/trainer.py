@@ -21,7 +21,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, parallel
 from .training import FlatGrads, TrainRun
 
 
@@ -66,13 +66,9 @@ class TrainStep:
         self.v = torch.zeros_like(self.params)
         self.step_dev = torch.ones(1, device=dev, dtype=torch.float32)
         self.G = FlatGrads(ae, self.grads)
-        # gradient-buffer split: parameters() order is encoder | decoder | quant_mu | quant_log_sigma | post_quant
-        n_enc = sum(p.numel() for p in ae.encoder.parameters())
-        n_dec = sum(p.numel() for p in ae.decoder.parameters())
-        n_q = sum(p.numel() for p in ae.quant_conv_mu.parameters()) + sum(p.numel() for p in ae.quant_conv_log_sigma.parameters())
-        self.seg_dec = (n_enc, n_enc + n_dec)                       # final after the decoder backward
-        self.seg_pq = (n_enc + n_dec + n_q, self.params.numel())    # post_quant_conv: also final at that point
-        self.seg_enc = [(0, n_enc), (n_enc + n_dec, n_enc + n_dec + n_q)]
+        # gradient-buffer split by the time the segments become final during the backward
+        self.segments = parallel.gradient_segments(ae)
+        assert self.segments["total"] == self.params.numel()
         self.comm = torch.cuda.Stream(device=dev) if self.overlap else None
         self.gout_rec = torch.tensor([1.0, 0.0] if recon_loss == "l1" else [0.0, 1.0], device=dev)
         self.gout_kl = torch.tensor([self.kl_weight], device=dev)
@@ -87,19 +83,14 @@ class TrainStep:
         self._static_out = None
 
     # -- communication ------------------------------------------------------------------------------
-    def _allreduce(self, lo: int, hi: int) -> None:
-        dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-
     def _after_decoder(self) -> None:
-        if self.world == 1:
+        """Called by the backward once the decoder-side gradients are final: their all-reduce goes out on the
+        communication stream and travels over NVLink while the encoder backward keeps the SMs busy."""
+        if self.world == 1 or self.comm is None:
             return
-        if self.comm is None:
-            return
-        cur = torch.cuda.current_stream(self.dev)
-        self.comm.wait_stream(cur)
+        self.comm.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(self.comm):
-            self._allreduce(*self.seg_dec)
-            self._allreduce(*self.seg_pq)
+            parallel.allreduce_segments(self.grads, self.segments["decoder"], self.pg)
 
     # -- one step -----------------------------------------------------------------------------------
     def _step_impl(self, x: torch.Tensor, eps: torch.Tensor | None = None):
@@ -115,11 +106,10 @@ class TrainStep:
             run.backward(d_recon, d_mu, d_sigma, self.G, need_dx=False, after_decoder=self._after_decoder)
             if self.world > 1:
                 if self.comm is not None:
-                    for lo, hi in self.seg_enc:
-                        self._allreduce(lo, hi)
+                    parallel.allreduce_segments(self.grads, self.segments["encoder"], self.pg)
                     torch.cuda.current_stream(self.dev).wait_stream(self.comm)
                 else:
-                    self._allreduce(0, self.params.numel())
+                    parallel.allreduce_segments(self.grads, [(0, self.params.numel())], self.pg)
             ops.adam(self.params, self.grads, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps,
                      grad_scale=1.0 / self.world, advance=True)
             ae.refresh_packed()            # every weight pack from the updated masters: one launch
