@@ -93,35 +93,49 @@ class TrainStep:
             parallel.allreduce_segments(self.grads, self.segments["decoder"], self.pg)
 
     # -- one step -----------------------------------------------------------------------------------
-    def _step_impl(self, x: torch.Tensor, eps: torch.Tensor | None = None):
-        ae = self.ae
-        with torch.no_grad():
-            run = TrainRun(ae)
-            recon, mu, sigma = run.forward(x, eps)
-            xf = x.detach().contiguous().float()
-            rec_terms = ops.l1l2(recon, xf)                     # (l1, l2)
-            kl = ops.kl_loss(mu, sigma, True)
-            d_recon = ops.l1l2_bwd(recon, xf, self.gout_rec)
-            d_mu, d_sigma = ops.kl_bwd(mu, sigma, self.gout_kl, True)
-            run.backward(d_recon, d_mu, d_sigma, self.G, need_dx=False, after_decoder=self._after_decoder)
-            if self.world > 1:
-                if self.comm is not None:
-                    parallel.allreduce_segments(self.grads, self.segments["encoder"], self.pg)
-                    torch.cuda.current_stream(self.dev).wait_stream(self.comm)
-                else:
-                    parallel.allreduce_segments(self.grads, [(0, self.params.numel())], self.pg)
-            ops.adam(self.params, self.grads, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps,
-                     grad_scale=1.0 / self.world, advance=True)
-            ae.refresh_packed()            # every weight pack from the updated masters: one launch
+    def _forward_backward(self, x: torch.Tensor, eps, after_decoder):
+        """forward, loss terms, loss gradients, backward into the flat gradient buffer."""
+        run = TrainRun(self.ae)
+        recon, mu, sigma = run.forward(x, eps)
+        xf = x.detach().contiguous().float()
+        rec_terms = ops.l1l2(recon, xf)                     # (l1, l2)
+        kl = ops.kl_loss(mu, sigma, True)
+        d_recon = ops.l1l2_bwd(recon, xf, self.gout_rec)
+        d_mu, d_sigma = ops.kl_bwd(mu, sigma, self.gout_kl, True)
+        run.backward(d_recon, d_mu, d_sigma, self.G, need_dx=False, after_decoder=after_decoder)
         return {"recon_loss": rec_terms[self.recon_idx], "kl_loss": kl, "recon": recon, "z_mu": mu, "z_sigma": sigma}
+
+    def _update(self) -> None:
+        ops.adam(self.params, self.grads, self.m, self.v, self.step_dev, self.lr, self.betas, self.eps,
+                 grad_scale=1.0 / self.world, advance=True)
+        self.ae.refresh_packed()            # every weight pack from the updated masters: one launch
+
+    def _reduce_encoder_and_join(self) -> None:
+        if self.world == 1:
+            return
+        if self.comm is not None:
+            parallel.allreduce_segments(self.grads, self.segments["encoder"], self.pg)
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+        else:
+            parallel.allreduce_segments(self.grads, [(0, self.params.numel())], self.pg)
+
+    def _step_impl(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        with torch.no_grad():
+            out = self._forward_backward(x, eps, self._after_decoder)
+            self._reduce_encoder_and_join()
+            self._update()
+        return out
 
     def step(self, x: torch.Tensor, eps: torch.Tensor | None = None):
         return self._step_impl(x, eps)
 
     # -- CUDA graph ---------------------------------------------------------------------------------
     def capture(self, batch: int, height: int, width: int, warmup: int = 2):
-        """Captures the whole step (forward, losses, backward, all-reduce, Adam, weight re-pack) for a fixed shape.
-        Afterwards ``replay(x)`` copies x into the static input and launches the graph."""
+        """Captures the step for a fixed shape; afterwards ``replay(x)`` copies x into the static input and replays.
+        One GPU: ONE graph (forward, losses, backward, Adam, weight re-pack).  Several GPUs: THREE graphs -- forward +
+        decoder backward | encoder backward | Adam + re-pack -- with the two NCCL all-reduces issued eagerly between
+        them (the decoder segment on the communication stream, overlapping the second graph): NCCL calls stay outside
+        the captures (capturing them dead-locked), at the price of two extra graph launches per step."""
         ae = self.ae
         self._static_x = torch.zeros((batch, ae.in_channels, height, width), device=self.dev, dtype=torch.float32)
         side = torch.cuda.Stream(device=self.dev)
@@ -131,13 +145,43 @@ class TrainStep:
                 self._step_impl(self._static_x)
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._static_out = self._step_impl(self._static_x)
+        if self.world == 1:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._static_out = self._step_impl(self._static_x)
+            self._graphs = None
+            return self
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=self.dev)
+        cap.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(cap), torch.no_grad():
+            g1.capture_begin()
+
+            def split():                    # decoder-side gradients are final: close graph 1, open graph 2 (same pool)
+                g1.capture_end()
+                g2.capture_begin(pool=g1.pool())
+
+            self._static_out = self._forward_backward(self._static_x, None, split)
+            g2.capture_end()
+            g3.capture_begin(pool=g1.pool())
+            self._update()
+            g3.capture_end()
+        torch.cuda.current_stream(self.dev).wait_stream(cap)
+        torch.cuda.synchronize(self.dev)
+        self._graphs = (g1, g2, g3)
+        self.graph = g1
         return self
 
     def replay(self, x: torch.Tensor | None = None):
         if x is not None:
             self._static_x.copy_(x, non_blocking=True)
-        self.graph.replay()
+        if getattr(self, "_graphs", None) is None:
+            self.graph.replay()
+            return self._static_out
+        g1, g2, g3 = self._graphs
+        g1.replay()
+        self._after_decoder()               # all-reduce of the decoder segment on the communication stream
+        g2.replay()                         # ... overlapped with the encoder backward
+        self._reduce_encoder_and_join()
+        g3.replay()
         return self._static_out

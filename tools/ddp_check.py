@@ -18,6 +18,10 @@ import _pkg  # noqa: E402
 from oracle import aekl_ref  # noqa: E402  (seeded weights / synthetic inputs only)
 
 
+def say(msg):
+    print(f"[ddp_check rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     b200 = _pkg.load()
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
@@ -25,6 +29,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
+    say("process group up")
     cfg = b200.config.AUTOENCODER_DEF_A
     ref = aekl_ref.seeded_model(cfg, 1234)
     per, S = 2, 64
@@ -42,11 +47,15 @@ def main():
     recon, mu, sigma = vae_ref.autoencoder(x_all, eps_all)
     (b200.l1_loss(recon, x_all) + 1e-3 * b200.compute_kl_loss(mu, sigma)).backward()
     g_full = torch.cat([p.grad.reshape(-1) for p in vae_ref.autoencoder.parameters()])
+    torch.cuda.synchronize()
+    say("full-batch reference gradients done")
 
     ts = b200.TrainStep(fresh(), lr=1e-4, kl_weight=1e-3, overlap=True)
     p0 = ts.params.clone()
+    say("TrainStep constructed (parameters broadcast)")
     ts.step(x_all[lo:hi], eps_all[lo:hi])
     torch.cuda.synchronize()
+    say("eager step done")
     g = ts.grads / world
     err = float((g - g_full).norm() / g_full.norm())
     # shards are summed in a different order than the full batch: fp32 noise + bf16 re-rounding of per-shard partials
@@ -56,12 +65,21 @@ def main():
     assert all(torch.equal(gathered[0], t) for t in gathered), "parameters diverged across ranks after one step"
     assert not torch.equal(ts.params, p0)
 
+    if os.environ.get("DDP_CHECK_GRAPH", "1") == "0":
+        if rank == 0:
+            print(f"DDP_CHECK OK world={world} grad rel-L2 vs full batch {err:.2e} (graph part skipped)", flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # graph replay with the all-reduce captured inside
+    say("capturing the step")
     ts2 = b200.TrainStep(fresh(), lr=1e-4, kl_weight=1e-3, overlap=True)
     ts2.ae._rng_dev = None
     ts2.capture(per, S, S, warmup=1)      # warm-up + capture advance the parameters: compare ranks, not values
+    say("captured; replaying")
     ts2.replay(x_all[lo:hi])
     torch.cuda.synchronize()
+    say("replay done")
     gathered = [torch.empty_like(ts2.params) for _ in range(world)]
     dist.all_gather(gathered, ts2.params)
     assert all(torch.isfinite(t).all() for t in gathered)
