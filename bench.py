@@ -355,6 +355,16 @@ def run_b200(args) -> None:
             times = cpu_oracle_throughput(4, S, threads, repeats=3, warmup=1)
             cpu = {"value": 4 / min(times), "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"B=4 forward (configs[0]) best of 3 after 1 warm-up, oracle/aekl_ref.py fp32, torch CPU {threads} threads"}
+        # ---- what a user would otherwise run on this GPU: the same op sequence in stock PyTorch (cuDNN / cuBLAS) --
+        # own process, after every measurement of this one
+        gpu_eager = None
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                r = subprocess.run([sys.executable, str(ROOT / "tools" / "gpu_eager_baseline.py"), "--mode", "infer",
+                                    "--batch", str(B), "--size", str(S)], capture_output=True, text=True, timeout=600)
+                gpu_eager = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as ex:  # noqa: BLE001
+                gpu_eager = {"error": str(ex)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -373,6 +383,7 @@ def run_b200(args) -> None:
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": gpu_eager,
             "model_tflops_per_gpu": model_tflops,
             "parity": parity,
         }
@@ -388,9 +399,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default, BASELINE.json configs[1]: the contract line) | train (configs[2] core: forward + L1 + "
+                         "KL + backward + gradient all-reduce + Adam, see tools/bench_train.py)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 64 infer / 8 train)")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the stock-PyTorch-on-the-same-GPU arm (a subprocess after the timed runs, N = 1 only)")
     args = ap.parse_args()
+    if args.mode == "train" and args.impl == "b200":
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_train
+        bench_train.main(["--batch", str(args.batch or 8), "--size", str(args.size), "--steps", str(args.steps),
+                          "--warmup", str(args.warmup)])
+        return
+    if args.batch is None:
+        args.batch = 64
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -23,7 +23,7 @@ sys.path.insert(0, str(ROOT))
 GFLOP_FWD = {"A": 48.916, "B": 242.39}   # per image @256^2; training = 3x (row a20)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (vae_dente_2.json: 8)")
     ap.add_argument("--size", type=int, default=256)
@@ -33,7 +33,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="per-op CUDA-event breakdown of one eager step")
-    args = ap.parse_args()
+    ap.add_argument("--eager-baseline", action="store_true",
+                    help="also time the stock-PyTorch (cuDNN) training step on this GPU in a subprocess (rank 0, 1 GPU)")
+    args = ap.parse_args(argv)
 
     import torch
     import torch.distributed as dist
@@ -161,6 +163,14 @@ def main():
                 "model_tflops_per_gpu": gf * 1e9 * value / world / 1e12,
                 "phases_eager": phases, "launches_per_step_eager": launches_eager,
                 "recon_loss_first_last": [first_loss, last_loss], "breakdown": breakdown}
+        if args.eager_baseline and world == 1:
+            import subprocess
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "gpu_eager_baseline.py"), "--mode", "train", "--batch", str(B),
+                                "--size", str(S), "--config", args.config], capture_output=True, text=True, timeout=900)
+            try:
+                line["gpu_eager_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception:  # noqa: BLE001
+                line["gpu_eager_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
