@@ -6,7 +6,7 @@ from .autoencoderkl import AutoencoderKL, B200AutoencoderKL  # noqa: F401
 from .graph import GraphedVAE, PipelinedVAE  # noqa: F401
 from .loader import load_vae_model  # noqa: F401
 from .losses import compute_ar_vae_loss, compute_kl_loss, compute_total_loss, l1_loss, mse_loss  # noqa: F401
-from .regression_head import LatentRegressor, VAELatentRegressor  # noqa: F401
+from .regression_head import LatentRegressor, regress_from_images  # noqa: F401
 from .trainer import TrainStep, flatten_parameters  # noqa: F401
 from .training import FlatGrads, TrainRun, VAEFunction  # noqa: F401
 from .vae_model import VAEModel  # noqa: F401

@@ -347,6 +347,18 @@ class AutoencoderKL(nn.Module):
                 raise ValueError(f"channel width {c} has no sm_100a kernel instantiation (supported: 32,64,128,256,512)")
         if in_channels > 16 or out_channels > 16 or latent_channels > 16:
             raise ValueError("in/out/latent channels must be <= 16 (thin-end direct kernels)")
+        for c in channels:
+            cpg = c // norm_num_groups
+            if cpg < 2 or cpg % 2 != 0:
+                raise ValueError(f"channel width {c} with norm_num_groups={norm_num_groups} gives {cpg} channel(s) per group: "
+                                 "the GroupNorm statistics kernels need an even number >= 2 (e.g. 32 channels -> at most 16 groups)")
+        attn_widths = [c for c, a in zip(channels, attention_levels) if a]
+        if with_encoder_nonlocal_attn or with_decoder_nonlocal_attn:
+            attn_widths.append(channels[-1])
+        for c in attn_widths:
+            if c not in (64, 128, 256):
+                raise ValueError(f"spatial self-attention at width {c}: the flash-attention kernel is instantiated for head "
+                                 "dimensions 64, 128 and 256 only")
         self.encoder = _encoder(in_channels, channels, latent_channels, num_res_blocks, norm_num_groups, norm_eps,
                                 attention_levels, with_encoder_nonlocal_attn)
         self.decoder = _decoder(channels, latent_channels, out_channels, num_res_blocks, norm_num_groups, norm_eps,
@@ -365,12 +377,12 @@ class AutoencoderKL(nn.Module):
     def _prep(self, x: torch.Tensor, channels: int | None = None) -> torch.Tensor:
         if isinstance(x, torch.Tensor) and type(x) is not torch.Tensor:
             x = x.as_subclass(torch.Tensor)  # MONAI MetaTensor batches
-        if not x.is_cuda:
-            raise RuntimeError("B200 AutoencoderKL runs on CUDA only; there is no CPU fallback "
-                               "(the CPU restatement lives in oracle/ and is test-only)")
         channels = self.in_channels if channels is None else channels
         if x.dim() != 4 or x.shape[1] != channels or x.shape[0] == 0 or x.shape[2] == 0 or x.shape[3] == 0:
             raise ValueError(f"expected a non-empty [N, {channels}, H, W] tensor, got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("B200 AutoencoderKL runs on CUDA only; there is no CPU fallback "
+                               "(the CPU restatement lives in oracle/ and is test-only)")
         dev = next(self.parameters()).device
         if x.device != dev:
             raise ValueError(f"input on {x.device} but the model is on {dev}")
@@ -420,9 +432,17 @@ class AutoencoderKL(nn.Module):
         self._exec.fused_stats = bool(enabled)
 
     # -- reference API ------------------------------------------------------------------------
+    def _dev(self):
+        """Context that makes the model's device current (kernels launch on the current device's stream)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("B200 AutoencoderKL runs on CUDA only; there is no CPU fallback "
+                               "(the CPU restatement lives in oracle/ and is test-only)")
+        return torch.cuda.device(dev)
+
     def encode(self, x: torch.Tensor):
         self._check_mode()
-        with torch.no_grad():
+        with torch.no_grad(), self._dev():
             return self._encode(x)
 
     def _encode(self, x: torch.Tensor):
@@ -448,7 +468,7 @@ class AutoencoderKL(nn.Module):
 
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         self._check_mode()
-        with torch.no_grad():
+        with torch.no_grad(), self._dev():
             return self._decode(z)
 
     def _decode(self, z: torch.Tensor) -> torch.Tensor:
@@ -461,9 +481,11 @@ class AutoencoderKL(nn.Module):
             # differentiable path: forward with a tape + the backward kernels behind one autograd node whose inputs
             # are x and every parameter (so DDP's reducer and find_unused_parameters see all of them)
             from .training import VAEFunction
-            return VAEFunction.apply(self, x, eps, *self.parameters())
+            with self._dev():
+                return VAEFunction.apply(self, x, eps, *self.parameters())
         z_mu, z_sigma = self.encode(x)
-        z = self.sampling(z_mu, z_sigma, eps)
+        with self._dev():
+            z = self.sampling(z_mu, z_sigma, eps)
         return self.decode(z), z_mu, z_sigma
 
     def reconstruct(self, x: torch.Tensor) -> torch.Tensor:

@@ -19,17 +19,25 @@ class GraphedVAE:
             raise ValueError(mode)
         self.ae, self.mode = ae, mode
         self.x = torch.zeros((batch, ae.in_channels, height, width), device=dev, dtype=torch.float32)
-        ae._rng_dev = torch.tensor([torch.initial_seed() & (2**63 - 1), 1], device=dev, dtype=torch.int64)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):  # packs weights, sets func attributes, warms the allocator
-                self._run()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self._run()
+        # ONE device-resident Philox (seed, offset) pair per model: every graph captured for this model bakes its address
+        # into latent_sample / rng_advance, so it must never be replaced (a second GraphedVAE used to overwrite it and the
+        # first graph then read / incremented freed memory); each graph also holds a reference.
+        if ae._rng_dev is None or ae._rng_dev.device != dev:
+            ae._rng_dev = torch.tensor([torch.initial_seed() & (2**63 - 1), 1], device=dev, dtype=torch.int64)
+        self._rng = ae._rng_dev
+        # packed weights are baked into the graph: remember the parameter versions to detect later in-place updates
+        self._versions = tuple(p._version for p in ae.parameters())
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):  # packs weights, sets func attributes, warms the allocator
+                    self._run()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
 
     def _run(self):
         if self.mode == "forward":
@@ -40,6 +48,9 @@ class GraphedVAE:
 
     def __call__(self, x: torch.Tensor | None = None):
         """Copies x into the static input (if given), replays, returns the static outputs."""
+        if tuple(p._version for p in self.ae.parameters()) != self._versions:
+            raise RuntimeError("the model's parameters changed after this graph was captured (load_state_dict / optimizer "
+                               "step): the graph replays the OLD packed weights -- capture a new GraphedVAE")
         if x is not None:
             self.x.copy_(x, non_blocking=True)
         self.graph.replay()

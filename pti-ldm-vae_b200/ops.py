@@ -56,9 +56,20 @@ def _call(name: str, meta, kernels: int, fn, *args) -> None:
 
 
 def _need_cuda(*ts):
+    """Every tensor handed to the C ABI must live on the CURRENT CUDA device: the kernels are launched on
+    torch.cuda.current_stream() of that device with raw pointers (the model-level entry points switch the current
+    device to the model's device for the duration of a call, so a model on cuda:1 works with cuda:0 current)."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.PtivaeError("ptivae ops need CUDA tensors (there is no CPU path)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.PtivaeError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: wrap the call in "
+                                   "torch.cuda.device(tensor.device) (kernels launch on the current device's stream)")
 
 
 def pack_conv_weight(w: torch.Tensor, mode: int = 0, dtype: torch.dtype = F16) -> torch.Tensor:
@@ -152,6 +163,9 @@ def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tens
     n, h, w, cin = x.shape
     cout = w_packed.shape[1]
     f16 = _op16(w_packed)
+    if w_packed.shape[2] != cin or bias.numel() != cout or h <= 0 or w <= 0:
+        raise _lib.PtivaeError(f"conv3x3_fused: activation {tuple(x.shape)} / packed weight {tuple(w_packed.shape)} / bias "
+                               f"{bias.numel()} mismatch")
     if x.dtype != torch.float32 and x.dtype != w_packed.dtype:
         raise _lib.PtivaeError("16-bit input must use the packed-weight dtype")
     out = torch.empty((n, h, w, cout), device=x.device, dtype=torch.float32 if out_f32 else w_packed.dtype)
@@ -252,6 +266,8 @@ def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: 
     _need_cuda(x, w, b)
     n, cin, h, wd = x.shape
     cout = w.shape[0]
+    if tuple(w.shape[1:]) != (cin, 3, 3) or b.numel() != cout or h <= 0 or wd <= 0:
+        raise _lib.PtivaeError(f"conv3x3_small_cin: input {tuple(x.shape)} does not match weight {tuple(w.shape)} / bias {b.numel()}")
     out = torch.empty((n, h, wd, cout), device=x.device, dtype=dtype)
     part = None
     if gn_groups > 0:
@@ -267,6 +283,8 @@ def conv3x3_small_cout(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, scale_
     _need_cuda(x, w, b)
     n, h, wd, cin = x.shape
     cout = w.shape[0]
+    if tuple(w.shape[1:]) != (cin, 3, 3) or b.numel() != cout or (scale_shift is not None and tuple(scale_shift.shape) != (n, cin, 2)):
+        raise _lib.PtivaeError(f"conv3x3_small_cout: input {tuple(x.shape)} does not match weight {tuple(w.shape)} / bias {b.numel()}")
     out = torch.empty((n, cout, h, wd), device=x.device, dtype=torch.float32)
     _call("conv3x3_small_cout", (n, h, wd, cin, cout, x.element_size()), 1, _lib.lib().ptivae_conv3x3_small_cout, _p(x), _p(w), _p(b),
           _p(scale_shift), _p(out), n, h, wd, cin, cout, _fmt(x), _stream())
@@ -278,6 +296,8 @@ def conv1x1_small(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, act: int = 
     n, cin = x.shape[:2]
     hw = x.numel() // (n * cin)
     cout = w.shape[0]
+    if w.numel() != cout * cin or b.numel() != cout:
+        raise _lib.PtivaeError(f"conv1x1_small: input {tuple(x.shape)} does not match weight {tuple(w.shape)} / bias {b.numel()}")
     out = torch.empty((n, cout) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
     _call("conv1x1_small", None, 1, _lib.lib().ptivae_conv1x1_small, _p(x), _p(w), _p(b), _p(out), n, hw, cin, cout, act, _stream())
     return out
@@ -332,9 +352,21 @@ def l1l2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     b = b.contiguous().float()
     if a.shape != b.shape:
         raise _lib.PtivaeError("l1l2 shape mismatch")
+    n = a.numel()
+    if n == 0:
+        raise _lib.PtivaeError("l1l2 of empty tensors")
     ws = torch.empty(2 * 1184, device=a.device, dtype=torch.float32)
     out = torch.empty(2, device=a.device, dtype=torch.float32)
-    _call("l1l2", None, 2, _lib.lib().ptivae_l1l2, _p(a), _p(b), _p(ws), _p(out), a.numel(), _stream())
+    if n % 4 != 0 or a.data_ptr() % 16 != 0 or b.data_ptr() % 16 != 0:
+        # the kernel reads float4: any other shape / alignment (nn.L1Loss accepts all) goes through zero-padded copies
+        # (|0 - 0| adds nothing to either sum) and the means are rescaled to the true element count
+        m = (n + 3) // 4 * 4
+        ap, bp = torch.zeros(m, device=a.device, dtype=torch.float32), torch.zeros(m, device=a.device, dtype=torch.float32)
+        ap[:n].copy_(a.reshape(-1))
+        bp[:n].copy_(b.reshape(-1))
+        _call("l1l2", None, 2, _lib.lib().ptivae_l1l2, _p(ap), _p(bp), _p(ws), _p(out), m, _stream())
+        return out * (m / n)
+    _call("l1l2", None, 2, _lib.lib().ptivae_l1l2, _p(a), _p(b), _p(ws), _p(out), n, _stream())
     return out
 
 
@@ -372,7 +404,10 @@ def linear_act(x: torch.Tensor, w: torch.Tensor, b, act: str | None = None) -> t
     bsz, i = x.shape
     o = w.shape[0]
     y = torch.empty((bsz, o), device=x.device, dtype=torch.float32)
-    _call("linear_act", None, 1, _lib.lib().ptivae_linear_act, _p(x), _p(w), _p(None if b is None else b.detach()), _p(y),
+    bias = None if b is None else b.detach().contiguous().float()
+    if w.shape[1] != i or (bias is not None and bias.numel() != o):
+        raise _lib.PtivaeError(f"linear_act: input {tuple(x.shape)} does not match weight {tuple(w.shape)}")
+    _call("linear_act", None, 1, _lib.lib().ptivae_linear_act, _p(x), _p(w), _p(bias), _p(y),
           bsz, i, o, _ACTS[act], _stream())
     return y
 

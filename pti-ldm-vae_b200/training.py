@@ -409,7 +409,7 @@ class VAEFunction(torch.autograd.Function):
             raise RuntimeError("the B200 AutoencoderKL backward can run only once per forward (no retain_graph)")
         ctx.run = None
         G = FlatGrads(ae)
-        with torch.no_grad():
+        with torch.no_grad(), ae._dev():
             if d_recon is None:   # loss does not depend on the reconstruction: the decoder still needs a gradient tensor
                 d_recon = torch.zeros((run.latent[0].shape[0], ae.out_channels) + tuple(run.tape[-1][3].shape[1:3]),
                                       device=run.latent[0].device, dtype=torch.float32)

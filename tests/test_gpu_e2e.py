@@ -161,7 +161,7 @@ def test_ar_vae_loss_matches_reference_golden(b200, oracle):
 
 
 def test_regressor_matches_reference_golden(b200, oracle):
-    """LatentRegressor (row a18) vs outputs of the reference's own class; VAELatentRegressor end to end vs the oracle."""
+    """LatentRegressor (row a18) vs outputs of the reference's own class; encode -> flatten -> head end to end vs the oracle."""
     g = np.load(GOLD / "regressor_ref.npz")
     x = torch.from_numpy(g["x"]).to(DEV)
     for tag, act, drop in (("relu", "relu", 0.1), ("gelu", "gelu", 0.0), ("lrelu", "leaky_relu", 0.0), ("elu", "elu", 0.0)):
@@ -176,12 +176,13 @@ def test_regressor_matches_reference_golden(b200, oracle):
     head = b200.LatentRegressor(4 * 8 * 8, [64, 16], 6, dropout=0.1).to(DEV).eval()
     head_ref = oracle.LatentRegressorRef(4 * 8 * 8, [64, 16], 6, dropout=0.1).eval()
     head_ref.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
-    assert b200.VAELatentRegressor.infer_flat_dim_from_patch(vae, (64, 64), torch.device(DEV)) == 256
-    model = b200.VAELatentRegressor(vae, head, latent_dim=256)
+    assert vae.encode_deterministic(torch.zeros(1, 1, 64, 64, device=DEV)).flatten(1).shape[1] == 256
     imgs = oracle.synthetic_images(3, 64, 64, seed=9)
     with torch.no_grad():
         want = head_ref(torch.flatten(ref_vae.encode(imgs)[0], 1))
-    got = model(imgs.to(DEV)).cpu()
+    got = b200.regress_from_images(vae, head, imgs.to(DEV)).cpu()
+    with pytest.raises(ValueError):
+        b200.regress_from_images(vae, head, oracle.synthetic_images(1, 32, 32).to(DEV))
     assert float((got - want).norm() / want.norm()) <= TOL_LATENT
 
 
@@ -196,13 +197,12 @@ def test_regression_sweep_extents(b200, oracle, hw):
     head = b200.LatentRegressor(lat, [256, 32], 6, dropout=0.1).to(DEV).eval()
     head_ref = oracle.LatentRegressorRef(lat, [256, 32], 6, dropout=0.1).eval()
     head_ref.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
-    model = b200.VAELatentRegressor(vae, head, latent_dim=lat)
     x = oracle.synthetic_images(1, hw, hw, seed=13)
     with torch.no_grad():
         mu_r, _ = ref_vae.encode(x)
         want = head_ref(torch.flatten(mu_r, 1))
         rec_r = ref_vae.decode(mu_r)
-    got = model(x.to(DEV)).cpu()
+    got = b200.regress_from_images(vae, head, x.to(DEV)).cpu()
     assert float((got - want).norm() / want.norm()) <= TOL_LATENT
     assert _rel_l2(vae.encode_deterministic(x.to(DEV)), mu_r) <= TOL_LATENT
     assert _rel_l2(vae.reconstruct_deterministic(x.to(DEV)), rec_r) <= TOL_RECON
