@@ -219,6 +219,8 @@ int ptivae_local_normalize_workspace(int B);
  *   dy   h16 NHWC gradient of the conv output, Ca channels;  x  h16 NHWC conv input (as the forward GEMM read it), Cb channels
  *   mode 0: 3x3 s1 p1, H,W = extent of x (= of dy)     1: F.pad(0,1,0,1)+3x3 s2, H,W = extent of x (dy is H/2 x W/2)
  *        2: nearest x2 upsample + 3x3, H,W = extent of x (dy is 2H x 2W)     3: 1x1
+ *        4: same result as mode 0 through the generic one-box-per-tap kernel (mode 0 shares one activation box
+ *           between the three kx taps of a kernel row; the tests compare the two)
  *   dw   fp32 [Ca][Cb][3][3] (modes 0-2) or [Ca][Cb] (mode 3): the master-weight layout, overwritten
  *   workspace: ptivae_wgrad_workspace(...) bytes of split-K partial sums (plain stores, summed in index order)
  *   f16: 16-bit format of BOTH operands (one tcgen05 MMA cannot mix fp16 and bf16) */

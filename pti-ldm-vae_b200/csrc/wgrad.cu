@@ -225,6 +225,142 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc_dyn(tmem_base, args.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Stride-1 3x3 weight gradient with the kx taps served from ONE activation box.
+//
+// The generic kernel above loads the activation tile once per tap: 9x the tensor through L2 (12x with dY), which is what
+// bounds it (6.6 TB/s of L2->SM traffic measured on the 64-channel 128^2 layers).  Sharing a halo box between taps needs
+// descriptor starts shifted by whole pixels; for an MN-major operand a start that is not swizzle-atom aligned faults
+// (see the note at the top).  So the K steps run DOWN THE COLUMNS instead: the tensor map lists (C, H, W, N), a box of
+// (64 channels, 16 rows, TX + 2 columns) lands as [column][row][channel], one UMMA K step = the 16 rows of one column =
+// 2048 bytes, and the kx tap is a start offset of kx columns = kx * 2048 bytes: always atom aligned.  The ky taps stay
+// separate CTAs (grid.y), i.e. activation traffic 3 x (TX+2)/TX instead of 9 x.
+struct Wgrad3Args {
+  int tiles_x, tiles_y, total_tiles, tiles_per_split;
+  int Ca, Cb, nb, n_cb_blocks, nstages, TX;
+  uint32_t idesc, stage_bytes, tmem_cols;
+  float* partial;    // [splits][9][Ca][Cb]
+  int* status;
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad3x3_col_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const Wgrad3Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const int nstages = args.nstages;
+  const uint32_t stage_bytes = args.stage_bytes;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
+  uint64_t* full_b = full_a + kWMaxStages;
+  uint64_t* empty_bar = full_b + kWMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kWMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int ky = blockIdx.y;
+  const int ca_blk = blockIdx.z / args.n_cb_blocks;
+  const int cb_blk = blockIdx.z - ca_blk * args.n_cb_blocks;
+  const int ca0 = ca_blk * 128, cb0 = cb_blk * args.nb;
+  const int na_atoms = min(2, (args.Ca - ca0 + 63) / 64);
+  const int nb_atoms = args.nb / 64;
+  const int TX = args.TX;
+  const uint32_t a_atom = uint32_t(TX) * 2048u, b_atom = uint32_t(TX + 2) * 2048u;
+  const int t_begin = split * args.tiles_per_split;
+  const int t_end = min(args.total_tiles, t_begin + args.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_ptr_smem, args.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int tix = t % args.tiles_x;
+        const int tiy = (t / args.tiles_x) % args.tiles_y;
+        const int n = t / (args.tiles_x * args.tiles_y);
+        const int x0 = tix * TX, y0 = tiy * 16;
+        if (!mbar_wait_soft(&empty_bar[s], ph ^ 1u)) { report_timeout(args.status, 1, t, s); break; }
+        uint8_t* sa = smem + s * stage_bytes;
+        uint8_t* sb = sa + 2 * a_atom;
+        mbar_expect_tx(&full_a[s], na_atoms * a_atom);
+        for (int a = 0; a < na_atoms; ++a) tma_load_4d(sa + a * a_atom, &tmA, &full_a[s], ca0 + a * 64, y0, x0, n);
+        mbar_expect_tx(&full_b[s], nb_atoms * b_atom);
+        for (int b = 0; b < nb_atoms; ++b)
+          tma_load_4d(sb + b * b_atom, &tmB, &full_b[s], cb0 + b * 64, y0 + ky - 1, x0 - 1, n);
+        if (++s == nstages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t hi = desc_hi(1024, kLayoutSW128);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        if (!mbar_wait_soft(&full_a[s], ph)) { report_timeout(args.status, 2, t, s); break; }
+        if (!mbar_wait_soft(&full_b[s], ph)) { report_timeout(args.status, 2, t, 100 + s); break; }
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * stage_bytes);
+        const uint32_t sb = sa + 2 * a_atom;
+        for (int xx = 0; xx < TX; ++xx) {            // one K step = the 16 rows of tile column xx
+          const uint32_t a_lo = desc_lo(sa + xx * 2048u, a_atom);
+          const uint32_t acc = (t != t_begin || xx != 0) ? 1u : 0u;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)             // dW[ky][kx] += dY[p] x[p + (ky-1, kx-1)]: box column xx + kx
+            umma_f16_lohi(tmem_base + kx * args.nb, a_lo, hi, desc_lo(sb + (xx + kx) * 2048u, b_atom), hi, args.idesc, acc);
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == nstages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ca = ca0 + m;
+    bool timed_out = true;
+    for (int rep = 0; rep < 3 && timed_out; ++rep) timed_out = !mbar_wait_soft(tmem_full_bar, 0);
+    if (timed_out) report_timeout(args.status, 3, -1, -1);
+    tc_fence_after();
+    __syncwarp();
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    for (int kx = 0; kx < 3; ++kx) {
+      float* dst = args.partial + ((static_cast<size_t>(split) * 9 + ky * 3 + kx) * args.Ca + ca) * args.Cb + cb0;
+      for (int c = 0; c < args.nb / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_addr + kx * args.nb + c * 32, r);
+        tmem_ld_wait();
+        if (ca < args.Ca && cb0 + c * 32 < args.Cb) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(dst + c * 32 + 4 * u) =
+                make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 2]),
+                            __uint_as_float(r[4 * u + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, args.tmem_cols);
+}
+
 // out[(ca*Cb + cb)*T + t] = sum over slabs in masks[t], then over splits (index order), of partial[split][slab][ca][cb]
 struct SlabMasks { uint32_t m[9]; };
 // grid: one warp per 32 consecutive (ca, cb) elements of one tap; lanes = elements (coalesced), the split / slab loop is
@@ -261,17 +397,27 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 struct WgradPlan {
   int tiles_x, tiles_y, total_tiles, tiles_per_split, splits;
   int nb, n_ca_blocks, n_cb_blocks, ngroups, nslabs, T;
+  int col, TX;     // column-major 3x3 kernel: tile = 16 rows x TX columns
 };
 
 // mode 0: 3x3 stride 1 pad 1 (H, W = extent of x and dY)      1: F.pad(0,1,0,1) + 3x3 stride 2 (H, W = extent of x)
 // mode 2: nearest x2 upsample + 3x3 (H, W = extent of x)      3: 1x1
 static int wgrad_plan(int N, int H, int W, int Ca, int Cb, int mode, WgradPlan* p) {
-  if (N <= 0 || H <= 0 || W <= 0 || Ca <= 0 || Cb <= 0 || mode < 0 || mode > 3) return PTIVAE_ERR_ARG;
+  const bool generic3x3 = mode == 4;
+  if (N <= 0 || H <= 0 || W <= 0 || Ca <= 0 || Cb <= 0 || mode < 0 || mode > 4) return PTIVAE_ERR_ARG;
+  if (mode == 4) mode = 0;   // (same plan; the caller picks the generic per-tap kernel)
   if (Ca % 8 != 0 || Cb % 8 != 0) return PTIVAE_ERR_UNSUPPORTED;
   if (mode == 1 && ((H | W) & 1)) return PTIVAE_ERR_UNSUPPORTED;
   const int Ho = mode == 1 ? H / 2 : H, Wo = mode == 1 ? W / 2 : W;   // grid the tiles walk (dY pixels; low-res for mode 2)
-  p->tiles_x = (Wo + kWTW - 1) / kWTW;
-  p->tiles_y = (Ho + kWTH - 1) / kWTH;
+  p->col = (mode == 0 && !generic3x3) ? 1 : 0;
+  p->TX = W >= 64 ? 8 : 4;
+  if (p->col) {
+    p->tiles_x = (Wo + p->TX - 1) / p->TX;
+    p->tiles_y = (Ho + 15) / 16;
+  } else {
+    p->tiles_x = (Wo + kWTW - 1) / kWTW;
+    p->tiles_y = (Ho + kWTH - 1) / kWTH;
+  }
   p->total_tiles = p->tiles_x * p->tiles_y * N;
   p->nb = Cb > 64 ? 128 : 64;
   p->n_ca_blocks = (Ca + 127) / 128;
@@ -318,6 +464,45 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
   if (rc != PTIVAE_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
+  SlabMasks sm{};
+  if (p.col) {
+    Wgrad3Args c{};
+    c.tiles_x = p.tiles_x; c.tiles_y = p.tiles_y; c.total_tiles = p.total_tiles; c.tiles_per_split = p.tiles_per_split;
+    c.Ca = Ca; c.Cb = Cb; c.nb = p.nb; c.n_cb_blocks = p.n_cb_blocks; c.TX = p.TX;
+    c.partial = workspace;
+    c.status = g_wgrad_status;
+    const uint32_t fmt = f16 ? 0u : 1u;
+    c.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t(p.nb) >> 3) << 17) | ((128u >> 4) << 24);
+    // (C, H, W, N) views: a box lands in shared memory as [column][row][channel]
+    uint64_t d[4] = {uint64_t(Ca), uint64_t(H), uint64_t(W), uint64_t(N)};
+    uint64_t st[3] = {uint64_t(W) * Ca * 2, uint64_t(Ca) * 2, uint64_t(H) * W * Ca * 2};
+    uint32_t bxa[4] = {64, 16, uint32_t(p.TX), 1}, bxb[4] = {64, 16, uint32_t(p.TX + 2), 1};
+    CUtensorMap tmA, tmB;
+    rc = encode_tmap_16(&tmA, dy, 4, d, st, bxa, 128, f16 != 0);
+    if (rc != PTIVAE_OK) return rc;
+    d[0] = Cb; st[0] = uint64_t(W) * Cb * 2; st[1] = uint64_t(Cb) * 2; st[2] = uint64_t(H) * W * Cb * 2;
+    rc = encode_tmap_16(&tmB, x, 4, d, st, bxb, 128, f16 != 0);
+    if (rc != PTIVAE_OK) return rc;
+    const int nb_atoms = p.nb / 64;
+    c.stage_bytes = 2u * p.TX * 2048u + uint32_t(nb_atoms) * (p.TX + 2) * 2048u;
+    int stages = (200 * 1024) / static_cast<int>(c.stage_bytes);
+    if (stages > kWMaxStages) stages = kWMaxStages;
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;
+    c.nstages = stages;
+    c.tmem_cols = 3 * p.nb > 256 ? 512 : 256;
+    const size_t smem = size_t(stages) * c.stage_bytes + 1024 + (3 * kWMaxStages + 1) * 8 + 16;
+    static bool attr3[64] = {};
+    if (int rc_attr = ensure_dyn_smem(wgrad3x3_col_kernel, 227 * 1024, attr3)) return rc_attr;
+    dim3 grid(p.splits, 3, p.n_ca_blocks * p.n_cb_blocks);
+    wgrad3x3_col_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, c);
+    rc = static_cast<int>(cudaGetLastError());
+    if (rc != 0) return rc;
+    for (int t = 0; t < 9; ++t) sm.m[t] = 1u << t;
+    const size_t total = static_cast<size_t>(Ca) * Cb * 9;
+    wgrad_reduce_kernel<<<grid_for(total, 128, 148 * 8), 128, 0, stream>>>(workspace, dw, p.splits, 9, Ca, Cb, 9, sm);
+    return static_cast<int>(cudaGetLastError());
+  }
+  if (mode == 4) mode = 0;
   WgradArgs a{};
   a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y; a.total_tiles = p.total_tiles; a.tiles_per_split = p.tiles_per_split;
   a.Ca = Ca; a.Cb = Cb; a.nb = p.nb; a.n_cb_blocks = p.n_cb_blocks; a.nslabs = p.nslabs;
@@ -404,7 +589,6 @@ extern "C" int ptivae_wgrad(const void* dy, const void* x, float* workspace, flo
   rc = static_cast<int>(cudaGetLastError());
   if (rc != 0) return rc;
 
-  SlabMasks sm{};
   if (mode == 2) {
     // adjoint of the pre-summed phase taps (ptivae_pack_conv_weight mode 2): tap (ky, kx) collects every phase slab
     // whose mask contains it

@@ -462,7 +462,7 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, mode: int, out: torch.Tensor | None
     exp = (n, h // 2, w // 2) if mode == 1 else ((n, 2 * h, 2 * w) if mode == 2 else (n, h, w))
     if tuple(dy.shape[:3]) != exp:
         raise _lib.PtivaeError(f"wgrad: dy {tuple(dy.shape)} does not match x {tuple(x.shape)} for mode {mode}")
-    k = 1 if mode == 3 else 3
+    k = 1 if mode == 3 else 3      # (mode 4: the 3x3 s1 gradient through the generic per-tap kernel)
     if out is None:
         out = torch.empty((ca, cb, k, k), device=x.device, dtype=torch.float32)
     elif out.numel() != ca * cb * k * k or out.dtype != torch.float32 or not out.is_contiguous():

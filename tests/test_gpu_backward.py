@@ -78,6 +78,8 @@ BWD_CASES = [
     (0, 1, 32, 32, 128, 64),
     (0, 1, 16, 16, 256, 256),
     (0, 3, 9, 9, 128, 128),
+    (0, 1, 72, 72, 32, 32),
+    (0, 2, 128, 128, 64, 64),
     (1, 2, 32, 32, 32, 32),
     (1, 1, 64, 64, 64, 64),
     (1, 2, 16, 16, 128, 128),
@@ -130,6 +132,9 @@ def test_conv_wgrad(b200, mode, n, h, w, cin, cout):
     assert torch.equal(dw, dw2), "wgrad is not run-to-run deterministic"
     r = _rel(dw, dw_ref)
     assert r <= _tol(2e-5), f"wgrad mode {mode}: rel-L2 {r:.3e}"   # exact operands, fp32 accumulate
+    if mode == 0:   # mode 0 = one activation box per kernel row (column-major K steps); mode 4 = generic one box per tap
+        r4 = _rel(b200.ops.wgrad(dy, x, 4), dw_ref)
+        assert r4 <= _tol(2e-5), f"wgrad mode 4 (generic 3x3): rel-L2 {r4:.3e}"
 
 
 def test_wgrad_operand_formats(b200):
