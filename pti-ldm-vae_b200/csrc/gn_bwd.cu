@@ -56,8 +56,9 @@ __device__ __forceinline__ uint4 act8_bf16(const float (&f)[8], const float (&sc
   return make_uint4(pack2<false>(a[0], a[1]), pack2<false>(a[2], a[3]), pack2<false>(a[4], a[5]), pack2<false>(a[6], a[7]));
 }
 
-constexpr int kGbPix = 256;    // pixels per reduce chunk (depends on the image only: batch-invariant summation order);
-                               // small chunks = many CTAs = enough loads in flight (1024-pixel chunks ran at 15 % of HBM peak)
+// pixels per reduce chunk: a function of the image size only (batch-invariant summation order); small chunks = many CTAs =
+// enough loads in flight (1024-pixel chunks ran at 15 % of HBM peak, and a 32x32 image gave 4 CTAs per image)
+__host__ __device__ constexpr int gb_pix(int HW) { return HW <= 4096 ? 64 : 256; }
 
 // grid (chunks, N); block 256.  Thread t owns one 8-channel vector column and walks the chunk's pixels.
 template <bool kSilu>
@@ -72,8 +73,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
   const int v = threadIdx.x % vecs;
   const int prow = threadIdx.x / vecs;
   const int prows = blockDim.x / vecs;
-  const int p_begin = blockIdx.x * kGbPix;
-  const int p_end = min(HW, p_begin + kGbPix);
+  const int p_begin = blockIdx.x * gb_pix(HW);
+  const int p_end = min(HW, p_begin + gb_pix(HW));
   float sc[8], sh[8], mean[8], rstd[8];
   const int cpg = C / G;
 #pragma unroll
@@ -127,16 +128,38 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const void* __restri
       }
     }
   }
+  // fold, fixed order: (1) xor-shuffles over the lanes of a warp that own the same channel vector (lane stride = vecs),
+  // (2) the 8 warps through shared memory.  (The first version let C threads walk all 256/vecs rows serially in
+  // shared memory: 2 us per CTA, as long as the loads themselves.)
+  if (vecs < 32) {
+    for (int o = vecs; o < 32; o <<= 1) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { sm[threadIdx.x][e] = s1[e]; sm[threadIdx.x][8 + e] = s2[e]; }
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vw = vecs < 32 ? vecs : 32;                 // distinct channel vectors per warp
+  if (lane < vw) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sm[warp * 32 + lane][e] = s1[e]; sm[warp * 32 + lane][8 + e] = s2[e]; }
+  }
   __syncthreads();
-  // fixed-order fold over the pixel rows: thread c sums rows 0..prows-1 of its channel
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int cv = c / 8, ce = c % 8;
     float a = 0.f, b = 0.f;
-    for (int r = 0; r < prows; ++r) {
-      a += sm[r * vecs + cv][ce];
-      b += sm[r * vecs + cv][8 + ce];
+    if (vecs <= 32) {                                   // every warp holds every vector: lane = cv
+      for (int w = 0; w < 8; ++w) {
+        a += sm[w * 32 + cv][ce];
+        b += sm[w * 32 + cv][8 + ce];
+      }
+    } else {                                            // vecs = 64: vector cv lives in the warps w with (w*32 + lane) % 64 == cv
+      for (int w = (cv >> 5); w < 8; w += 2) {
+        a += sm[w * 32 + (cv & 31)][ce];
+        b += sm[w * 32 + (cv & 31)][8 + ce];
+      }
     }
     float* dst = partial + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C + c) * 2;
     dst[0] = a;
@@ -345,7 +368,7 @@ static int gn_bwd_apply_blocks(int N, int HW, int C) {
 // workspace floats: ptivae_gn_bwd_workspace(N, HW, C) = partial N*P*C*2 + totals N*C*2 + column-sum partials blocks*C
 extern "C" long long ptivae_gn_bwd_workspace(int N, int HW, int C) {
   if (N <= 0 || HW <= 0 || C <= 0 || C % 8 != 0) return PTIVAE_ERR_ARG;
-  const long long P = (HW + kGbPix - 1) / kGbPix;
+  const long long P = (HW + gb_pix(HW) - 1) / gb_pix(HW);
   return static_cast<long long>(N) * P * C * 2 + static_cast<long long>(N) * C * 2 +
          static_cast<long long>(gn_bwd_apply_blocks(N, HW, C)) * C;
 }
@@ -361,7 +384,7 @@ extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fm
       x_fmt > 2 || da_fmt < 0 || da_fmt > 2 || res_fmt < 0 || res_fmt > 2)
     return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int P = (HW + kGbPix - 1) / kGbPix;
+  const int P = (HW + gb_pix(HW) - 1) / gb_pix(HW);
   float* partial = workspace;
   float* totals = workspace + static_cast<size_t>(N) * P * C * 2;
   float* colpart = colsum_out ? totals + static_cast<size_t>(N) * C * 2 : nullptr;
