@@ -528,7 +528,7 @@ extern "C" int ptivae_conv3x3_fused_sc(const void* h, const float* scale_shift, 
   if (!h || !w_packed || !bias || !out || !sc_x || !sc_w_packed || N <= 0 || H <= 0 || W <= 0 || sc_cin <= 0) return PTIVAE_ERR_ARG;
   if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
     return PTIVAE_ERR_ARG;
-  if (!f16 || !out_f32) return PTIVAE_ERR_UNSUPPORTED;
+  if (!f16) return PTIVAE_ERR_UNSUPPORTED;
   FusedCall c{h, 1, scale_shift, silu, w_packed, bias, nullptr, 0, out, out_f32, gn_part, gn_groups,
               N, H, W, Cin, Cout, f16, g_fused_trace, false};
   c.sc_x = sc_x; c.sc_w = sc_w_packed; c.sc_cin = sc_cin;

@@ -28,8 +28,10 @@ constexpr uint32_t kSmemMax = 232448;
 
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+// RES: 0 = no residual, 1 = fp32 residual, 2 = 16-bit residual (16-bit residual stream: needs a 16-bit output)
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32>
 struct Cfg {
+  static_assert(RES != 2 || !OUT32, "a 16-bit residual is added in place in a 16-bit output tile");
   static constexpr int KCH = CIN >= 64 ? 64 : 32;
   static constexpr int NCH = CIN / KCH;
   static constexpr uint32_t LB = KCH * 2;
@@ -45,7 +47,7 @@ struct Cfg {
   static constexpr uint32_t OLB = CBLK * OESZ;                // bytes per output line (64 or 128) = its swizzle span
   static constexpr int NOB = COUT / CBLK;
   static constexpr uint32_t OS_BYTES = uint32_t(kPix) * COUT * OESZ;
-  static constexpr bool SEP_RS = RES && !OUT32;               // fp32 residual staged separately from a 16-bit output
+  static constexpr bool SEP_RS = RES == 1 && !OUT32;          // fp32 residual staged separately from a 16-bit output
   static constexpr uint32_t RS_BYTES = SEP_RS ? uint32_t(kPix) * COUT * 4u : 0u;
   static constexpr uint32_t MISC = 1024 /*align*/ + NEW * COUT * 2 * 4 /*column sums*/ + COUT * 4 /*bias*/ + 40 * 8 + 64;
   static constexpr uint32_t BASE = MISC + 2 * OPBUF + RS_BYTES;
@@ -54,7 +56,7 @@ struct Cfg {
   }
   // preference: resident weights, then (for a residual) a double-buffered output tile, then a double-buffered halo
   static constexpr bool RESB = fits(1, 1, true) <= kSmemMax;
-  static constexpr int RO = (fits(1, 2, RESB) <= kSmemMax && (RES || fits(2, 2, RESB) <= kSmemMax)) ? 2 : 1;
+  static constexpr int RO = (fits(1, 2, RESB) <= kSmemMax && (RES != 0 || fits(2, 2, RESB) <= kSmemMax)) ? 2 : 1;
   static constexpr int XS = fits(2, RO, RESB) <= kSmemMax ? 2 : 1;
   static constexpr int NSTAGES = RESB ? 1 : 3;
   static constexpr uint32_t SMEM = fits(XS, RO, RESB);
@@ -77,7 +79,7 @@ struct Args {
     if (args.trace != nullptr && blockIdx.x == 0 && it < 64) args.trace[it * 32 + (slot)] = clock64(); \
   } while (0)
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
@@ -125,7 +127,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmO);
-    if (RES) tma_prefetch_desc(&tmR);
+    if (RES != 0) tma_prefetch_desc(&tmR);
     for (int s = 0; s < 4; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
@@ -207,7 +209,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         int n, x0, y0;
         tile_xy(k, n, x0, y0);
         const int r = k % RO;
-        if constexpr (RES && OUT32) {
+        if constexpr ((RES == 1 && OUT32) || RES == 2) {   // residual in the output tile's own format: added in place
           mbar_expect_tx(&os_full[r], C::OS_BYTES);
           for (int ob = 0; ob < NOB; ++ob)
             tma_load_4d(os + r * C::OS_BYTES + ob * (kPix * OLB), &tmR, &os_full[r], ob * CBLK, x0, y0, n);
@@ -333,7 +335,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + bb.w;
           }
           const int rb = cc >> 1, rj = (cc & 1) * 4;   // fp32 tiles: block of 32 channels, 16-byte chunk offset
-          if constexpr (RES) {
+          if constexpr (RES == 1) {
             // fp32 residual line of this pixel (32 channels = 128 B per block), 128B-swizzled by TMA
             const uint8_t* rl = (SEP_RS ? rs : ob_base) + rb * (kPix * 128) + p * 128;
 #pragma unroll
@@ -355,10 +357,19 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             uint8_t* ol = ob_base + ob * (kPix * OLB) + p * OLB;
             const int sw = (OLB == 128) ? (p & 7) : ((p >> 1) & 3);
 #pragma unroll
-            for (int j8 = 0; j8 < 2; ++j8)
-              *reinterpret_cast<uint4*>(ol + (((ch0 + j8) ^ sw) << 4)) =
-                  make_uint4(pack2<F16>(v[8 * j8 + 0], v[8 * j8 + 1]), pack2<F16>(v[8 * j8 + 2], v[8 * j8 + 3]),
-                             pack2<F16>(v[8 * j8 + 4], v[8 * j8 + 5]), pack2<F16>(v[8 * j8 + 6], v[8 * j8 + 7]));
+            for (int j8 = 0; j8 < 2; ++j8) {
+              uint4* o16 = reinterpret_cast<uint4*>(ol + (((ch0 + j8) ^ sw) << 4));
+              if constexpr (RES == 2) {   // 16-bit residual: TMA put it where the result goes
+                const uint4 rv = *o16;
+                float r[8];
+                unpack2<F16>(rv.x, r[0], r[1]); unpack2<F16>(rv.y, r[2], r[3]);
+                unpack2<F16>(rv.z, r[4], r[5]); unpack2<F16>(rv.w, r[6], r[7]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[8 * j8 + e] += r[e];
+              }
+              *o16 = make_uint4(pack2<F16>(v[8 * j8 + 0], v[8 * j8 + 1]), pack2<F16>(v[8 * j8 + 2], v[8 * j8 + 3]),
+                                pack2<F16>(v[8 * j8 + 4], v[8 * j8 + 5]), pack2<F16>(v[8 * j8 + 6], v[8 * j8 + 7]));
+            }
           }
         }
       }
@@ -549,7 +560,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32>
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32>
 static int launch(const FusedCall& c, cudaStream_t stream) {
   using C = Cfg<CIN, COUT, IN32, RES, OUT32>;
   if constexpr (!C::FITS) {
@@ -586,11 +597,17 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     int rc = encode_tmap(&tmO, c.out, OUT32 ? 2 : 1, 4, d, s, b, C::OLB);
     if (rc) return rc;
   }
-  if (RES) {  // fp32 residual: box (32, 16, 16, 1), 128B swizzle
+  if (RES == 1) {  // fp32 residual: box (32, 16, 16, 1), 128B swizzle
     uint64_t d[4] = {uint64_t(COUT), W, H, N};
     uint64_t s[3] = {uint64_t(COUT) * 4, W * COUT * 4, H * W * COUT * 4};
     uint32_t b[4] = {32, kT, kT, 1};
     int rc = encode_tmap(&tmR, c.residual, 2, 4, d, s, b, 128);
+    if (rc) return rc;
+  } else if (RES == 2) {  // 16-bit residual: the output tile's geometry
+    uint64_t d[4] = {uint64_t(COUT), W, H, N};
+    uint64_t s[3] = {uint64_t(COUT) * 2, W * COUT * 2, H * W * COUT * 2};
+    uint32_t b[4] = {uint32_t(C::CBLK), kT, kT, 1};
+    int rc = encode_tmap(&tmR, c.residual, 1, 4, d, s, b, C::OLB);
     if (rc) return rc;
   } else {
     tmR = tmO;
@@ -607,10 +624,13 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
 
 template <int CIN, int COUT>
 static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
-  const bool in32 = c.in_fmt == 2, res = c.residual != nullptr, out32 = c.out_f32 != 0;
-  if (in32 && !res && !out32) return launch<CIN, COUT, true, false, false>(c, stream);   // ResBlock conv1
-  if (!in32 && res && out32) return launch<CIN, COUT, false, true, true>(c, stream);     // ResBlock conv2 -> stream
-  if (!in32 && res && !out32) return launch<CIN, COUT, false, true, false>(c, stream);   // conv2 -> 16-bit operand
+  const bool in32 = c.in_fmt == 2, out32 = c.out_f32 != 0;
+  const int res = c.residual == nullptr ? 0 : (c.res_f32 ? 1 : 2);
+  if (in32 && res == 0 && !out32) return launch<CIN, COUT, true, 0, false>(c, stream);    // ResBlock conv1
+  if (!in32 && res == 1 && out32) return launch<CIN, COUT, false, 1, true>(c, stream);    // ResBlock conv2 -> fp32 stream
+  if (!in32 && res == 1 && !out32) return launch<CIN, COUT, false, 1, false>(c, stream);  // conv2 -> 16-bit operand
+  if (!in32 && res == 0 && !out32) return launch<CIN, COUT, false, 0, false>(c, stream);  // conv1 on a 16-bit stream
+  if (!in32 && res == 2 && !out32) return launch<CIN, COUT, false, 2, false>(c, stream);  // conv2 on a 16-bit stream
   return PTIVAE_ERR_UNSUPPORTED;
 }
 
@@ -618,7 +638,6 @@ static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
 
 int conv3x3_tma_launch(const FusedCall& c, cudaStream_t stream) {
   if (!c.f16) return PTIVAE_ERR_UNSUPPORTED;                           // fp16 operands only
-  if (c.residual != nullptr && !c.res_f32) return PTIVAE_ERR_UNSUPPORTED;
   if (c.gn_groups > 128 / 2) return PTIVAE_ERR_UNSUPPORTED;
   if (c.Cin == 32 && c.Cout == 32) return tma3::dispatch_mode<32, 32>(c, stream);
   if (c.Cin == 32 && c.Cout == 64) return tma3::dispatch_mode<32, 64>(c, stream);

@@ -33,15 +33,18 @@ constexpr int ntw() { return (IN32 && CIN >= 64) ? 12 : 8; }
 constexpr uint32_t kSmemMax = 232448;
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32, int SC = 0>
+// RES: 0 = no residual, 1 = fp32 residual, 2 = 16-bit residual (16-bit residual stream: needs a 16-bit output, the
+// residual unit lands in the output slot and is added in place)
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32, int SC = 0>
 struct Cfg {
+  static_assert(RES != 2 || !OUT32, "a 16-bit residual is added in place in a 16-bit output unit");
   static constexpr int KCH = CIN >= 64 ? 64 : 32;
   static constexpr int NCH = CIN / KCH;
   static constexpr uint32_t LB = KCH * 2;
   static constexpr uint32_t CHUNK = r1k(kHalo * LB);
   static constexpr uint32_t SLAB = uint32_t(COUT) * LB;
   static constexpr uint32_t WBYTES = 9u * NCH * SLAB;
-  static constexpr bool SEP_RS = RES && !OUT32;               // fp32 residual staged beside a 16-bit output unit
+  static constexpr bool SEP_RS = RES == 1 && !OUT32;          // fp32 residual staged beside a 16-bit output unit
   static constexpr uint32_t OLB = OUT32 ? 128 : 64;           // bytes per output line (32 channels)
   static constexpr uint32_t OSLOT = 128 * OLB;
   static constexpr uint32_t RSLOT = SEP_RS ? 128 * 128 : 0;
@@ -121,13 +124,13 @@ struct Args {
     if (args.trace != nullptr && blockIdx.x == 0 && (it) < 64) args.trace[(it) * 32 + (slot)] = clock64(); \
   } while (0)
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32, int SC>
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32, int SC>
 __global__ void __launch_bounds__((NEW + ntw<CIN, COUT, IN32>() + 3) * 32, 1)
 conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmXs, const __grid_constant__ CUtensorMap tmWs, const Args args) {
   using C = Cfg<CIN, COUT, IN32, RES, OUT32, SC>;
-  static_assert(SC == 0 || (!RES && !IN32), "the fused shortcut replaces the residual of a 16-bit-input conv2");
+  static_assert(SC == 0 || (RES == 0 && !IN32), "the fused shortcut replaces the residual of a 16-bit-input conv2");
   constexpr bool F16 = true;
   constexpr int NTW = ntw<CIN, COUT, IN32>(), NT = NTW * 32;
   constexpr int W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
@@ -174,7 +177,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmO);
-    if (RES) tma_prefetch_desc(&tmR);
+    if (RES != 0) tma_prefetch_desc(&tmR);
     for (int s = 0; s < 8; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
@@ -451,7 +454,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int total_units = my_tiles * NOB;
     // residual of unit q (tile q / NOB, channel block q % NOB) -> slot q & 1   (leader only)
     auto issue_res = [&](int q) {
-      if constexpr (RES) {
+      if constexpr (RES != 0) {
         const int ti = q / NOB, ob = q - ti * NOB;
         const int t = blockIdx.x + ti * gridDim.x;
         const int n = t / tiles_per_img;
@@ -459,7 +462,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
         uint8_t* dst = tslots + (q & 1) * C::SLOT + (SEP_RS ? C::OSLOT : 0u);
         if (tix * kT + mb * 8 < args.W) {
-          mbar_expect_tx(&rfull[q & 1], 128 * 128);
+          mbar_expect_tx(&rfull[q & 1], RES == 2 ? 128 * 64 : 128 * 128);
           tma_load_4d(dst, &tmR, &rfull[q & 1], ob * 32, tix * kT + mb * 8, tiy * kT, n);
         } else {
           mbar_arrive(&rfull[q & 1]);    // M block wholly outside the image: nothing to load (nothing is stored either)
@@ -485,7 +488,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         uint32_t acc[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * 2 * COUT + mb * COUT + ob * 32, acc);
         if (leader) {
-          if constexpr (RES) {
+          if constexpr (RES != 0) {
             tma_store_wait_read();                     // store of unit q-1 has drained the other slot
             if (q + 1 < total_units) issue_res(q + 1);   // next unit's residual: in flight during this unit
           } else {
@@ -498,19 +501,30 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tc_fence_before();
           mbar_arrive(&acc_empty[st]);
         }
-        if constexpr (RES) mbar_wait(&rfull[q & 1], (q >> 1) & 1);
+        if constexpr (RES != 0) mbar_wait(&rfull[q & 1], (q >> 1) & 1);
         else asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // slot free (leader saw store q-2 drained in unit q-1)
         {
           const uint8_t* rl = rslot + m * 128;
           uint8_t* ol = oslot + m * OLB;
+          uint4 r16[4] = {};
+          if constexpr (RES == 2) {   // 16-bit residual line: TMA put it where the result goes
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r16[j] = *reinterpret_cast<const uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4));
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = reinterpret_cast<const float4*>(sbias + ob * 32)[j];   // broadcast
             float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
             float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
-            if constexpr (RES) {
+            if constexpr (RES == 1) {
               const float4 rv = *reinterpret_cast<const float4*>(rl + ((j ^ (m & 7)) << 4));
               v0 += rv.x; v1 += rv.y; v2 += rv.z; v3 += rv.w;
+            }
+            if constexpr (RES == 2) {
+              float r0, r1, r2, r3;
+              unpack2<F16>((j & 1) ? r16[j >> 1].z : r16[j >> 1].x, r0, r1);
+              unpack2<F16>((j & 1) ? r16[j >> 1].w : r16[j >> 1].y, r2, r3);
+              v0 += r0; v1 += r1; v2 += r2; v3 += r3;
             }
             if constexpr (OUT32) {
               *reinterpret_cast<float4*>(ol + ((j ^ (m & 7)) << 4)) = make_float4(v0, v1, v2, v3);
@@ -605,7 +619,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int CIN, int COUT, bool IN32, bool RES, bool OUT32, int SC = 0>
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32, int SC = 0>
 static int launch(const FusedCall& c, cudaStream_t stream) {
   using C = Cfg<CIN, COUT, IN32, RES, OUT32, SC>;
   if constexpr (!C::FITS) {
@@ -648,11 +662,17 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
       int rc = encode_tmap(&tmO, c.out, OUT32 ? 2 : 1, 4, d, s, b, C::OLB);
       if (rc) return rc;
     }
-    if (RES) {
+    if (RES == 1) {
       uint64_t d[4] = {uint64_t(COUT), W, H, N};
       uint64_t s[3] = {uint64_t(COUT) * 4, W * COUT * 4, H * W * COUT * 4};
       uint32_t b[4] = {32, 8, kT, 1};
       int rc = encode_tmap(&tmR, c.residual, 2, 4, d, s, b, 128);
+      if (rc) return rc;
+    } else if (RES == 2) {   // 16-bit residual unit: the output unit's geometry
+      uint64_t d[4] = {uint64_t(COUT), W, H, N};
+      uint64_t s[3] = {uint64_t(COUT) * 2, W * COUT * 2, H * W * COUT * 2};
+      uint32_t b[4] = {32, 8, kT, 1};
+      int rc = encode_tmap(&tmR, c.residual, 1, 4, d, s, b, 64);
       if (rc) return rc;
     } else {
       tmR = tmO;
@@ -685,20 +705,25 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
 
 template <int CIN, int COUT>
 static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
-  const bool in32 = c.in_fmt == 2, res = c.residual != nullptr, out32 = c.out_f32 != 0;
+  const bool in32 = c.in_fmt == 2, out32 = c.out_f32 != 0;
+  const int res = c.residual == nullptr ? 0 : (c.res_f32 ? 1 : 2);
   if (c.sc_x != nullptr) {   // conv2 with the block's 1x1 shortcut fused in (no residual tensor at all)
-    if (in32 || res || !out32 || !c.sc_w) return PTIVAE_ERR_UNSUPPORTED;
+    if (in32 || res != 0 || !c.sc_w) return PTIVAE_ERR_UNSUPPORTED;
     if constexpr (CIN == 32 && COUT == 32) {
-      if (c.sc_cin == 64) return launch<32, 32, false, false, true, 64>(c, stream);
+      if (c.sc_cin == 64)
+        return out32 ? launch<32, 32, false, 0, true, 64>(c, stream) : launch<32, 32, false, 0, false, 64>(c, stream);
     }
     if constexpr (CIN == 64 && COUT == 64) {
-      if (c.sc_cin == 32) return launch<64, 64, false, false, true, 32>(c, stream);
+      if (c.sc_cin == 32)
+        return out32 ? launch<64, 64, false, 0, true, 32>(c, stream) : launch<64, 64, false, 0, false, 32>(c, stream);
     }
     return PTIVAE_ERR_UNSUPPORTED;
   }
-  if (in32 && !res && !out32) return launch<CIN, COUT, true, false, false>(c, stream);   // ResBlock conv1
-  if (!in32 && res && out32) return launch<CIN, COUT, false, true, true>(c, stream);     // ResBlock conv2 -> stream
-  if (!in32 && res && !out32) return launch<CIN, COUT, false, true, false>(c, stream);   // conv2 -> 16-bit operand
+  if (in32 && res == 0 && !out32) return launch<CIN, COUT, true, 0, false>(c, stream);    // ResBlock conv1
+  if (!in32 && res == 1 && out32) return launch<CIN, COUT, false, 1, true>(c, stream);    // ResBlock conv2 -> fp32 stream
+  if (!in32 && res == 1 && !out32) return launch<CIN, COUT, false, 1, false>(c, stream);  // conv2 -> 16-bit operand
+  if (!in32 && res == 0 && !out32) return launch<CIN, COUT, false, 0, false>(c, stream);  // conv1 on a 16-bit stream
+  if (!in32 && res == 2 && !out32) return launch<CIN, COUT, false, 2, false>(c, stream);  // conv2 on a 16-bit stream
   return PTIVAE_ERR_UNSUPPORTED;
 }
 
@@ -706,7 +731,6 @@ static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
 
 int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream) {
   if (!c.f16) return PTIVAE_ERR_UNSUPPORTED;                           // fp16 operands only
-  if (c.residual != nullptr && !c.res_f32) return PTIVAE_ERR_UNSUPPORTED;
   if (2 * c.gn_groups > tma4::NEW * 32) return PTIVAE_ERR_UNSUPPORTED;
 #define PTIVAE_T2_CASE(CI, CO) \
   if (c.Cin == CI && c.Cout == CO) return tma4::dispatch_mode<CI, CO>(c, stream)

@@ -32,7 +32,8 @@ constexpr uint32_t LB = 128;                                   // operand line: 
 constexpr uint32_t CHUNK = (kHalo * LB + 1023u) / 1024u * 1024u;
 constexpr uint32_t SLOT32 = 128 * 128, SLOT16 = 128 * 64;      // 128 pixels x 32 channels, fp32 | 16-bit
 
-template <int C, bool EMIT16>
+// EMIT16: 0 = fp32 output only, 1 = fp32 output + a 16-bit copy, 2 = 16-bit output only (16-bit residual stream)
+template <int C, int EMIT16>
 struct Cfg {
   static constexpr int NCH = C / 64;
   static constexpr uint32_t OPBUF = NCH * CHUNK;
@@ -58,7 +59,7 @@ struct Args {
   float* gn_part;       // [N][tiles][groups][2]
 };
 
-template <int C, bool EMIT16>
+template <int C, int EMIT16>
 __global__ void __launch_bounds__(kThreads, 1)
 up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ Maps maps, const Args args) {
@@ -238,15 +239,19 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 bb = reinterpret_cast<const float4*>(sbias + ob * 32)[q];   // broadcast
-              const float v0 = __uint_as_float(acc[4 * q + 0]) + bb.x, v1 = __uint_as_float(acc[4 * q + 1]) + bb.y;
-              const float v2 = __uint_as_float(acc[4 * q + 2]) + bb.z, v3 = __uint_as_float(acc[4 * q + 3]) + bb.w;
-              *reinterpret_cast<float4*>(l32 + ((q ^ (m & 7)) << 4)) = make_float4(v0, v1, v2, v3);
-              if constexpr (EMIT16) {
+              float v0 = __uint_as_float(acc[4 * q + 0]) + bb.x, v1 = __uint_as_float(acc[4 * q + 1]) + bb.y;
+              float v2 = __uint_as_float(acc[4 * q + 2]) + bb.z, v3 = __uint_as_float(acc[4 * q + 3]) + bb.w;
+              if constexpr (EMIT16 != 0) {
                 acc[4 * q + 0] = pack2<true>(v0, v1);
                 acc[4 * q + 1] = pack2<true>(v2, v3);
               }
+              if constexpr (EMIT16 == 2) {   // the fp32 slot only feeds the statistics: they describe the STORED values
+                unpack2<true>(acc[4 * q + 0], v0, v1);
+                unpack2<true>(acc[4 * q + 1], v2, v3);
+              }
+              *reinterpret_cast<float4*>(l32 + ((q ^ (m & 7)) << 4)) = make_float4(v0, v1, v2, v3);
             }
-            if constexpr (EMIT16) {
+            if constexpr (EMIT16 != 0) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<uint4*>(l16 + ((q ^ ((m >> 1) & 3)) << 4)) =
@@ -256,8 +261,8 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // unit written by all four warps
           if (leader && x0 + mb * 8 < args.W) {     // (a right-edge M block may lie wholly outside the image)
-            tma_store_4d(&maps.o32[phase], slot32, ob * 32, x0 + mb * 8, y0, n);
-            if constexpr (EMIT16) tma_store_4d(&maps.o16[phase], slot16, ob * 32, x0 + mb * 8, y0, n);
+            if constexpr (EMIT16 != 2) tma_store_4d(&maps.o32[phase], slot32, ob * 32, x0 + mb * 8, y0, n);
+            if constexpr (EMIT16 != 0) tma_store_4d(&maps.o16[phase], slot16, ob * 32, x0 + mb * 8, y0, n);
             tma_store_commit();
           }
           if (cpg > 0) {
@@ -325,7 +330,7 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == W_MMA) tmem_dealloc<512>(tmem_base);
 }
 
-template <int C, bool EMIT16>
+template <int C, int EMIT16>
 static int launch(const void* x, const void* w_packed, const float* bias, float* out, void* out16, float* gn_part,
                   int gn_groups, int N, int H, int W, cudaStream_t stream) {
   using Cf = Cfg<C, EMIT16>;
@@ -354,7 +359,7 @@ static int launch(const void* x, const void* w_packed, const float* bias, float*
   }
   for (int p = 0; p < 4; ++p) {
     const int py = p >> 1, px = p & 1;
-    {  // fp32 output, phase view: (c, x, y, n) -> out[n][2y+py][2x+px][c]
+    if (EMIT16 != 2) {  // fp32 output, phase view: (c, x, y, n) -> out[n][2y+py][2x+px][c]
       uint64_t d[4] = {uint64_t(C), uW, uH, uN};
       uint64_t s[3] = {2ull * C * 4, 4ull * uW * C * 4, 4ull * uH * uW * C * 4};
       uint32_t b[4] = {32, 8, kT, 1};
@@ -371,6 +376,7 @@ static int launch(const void* x, const void* w_packed, const float* bias, float*
     } else {
       maps.o16[p] = maps.o32[p];
     }
+    if (EMIT16 == 2) maps.o32[p] = maps.o16[p];
   }
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(up2x_conv3x3_kernel<C, EMIT16>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
@@ -394,13 +400,15 @@ extern "C" int ptivae_up2x_conv3x3_parts(int H, int W) {
 extern "C" int ptivae_up2x_conv3x3(const void* x, const void* w_packed, const float* bias, float* out, void* out16,
                                    float* gn_part, int gn_groups, int N, int H, int W, int C, int f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
+  if (!x || !w_packed || !bias || (!out && !out16) || N <= 0 || H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
   if (!f16 || !(C == 64 || C == 128)) return PTIVAE_ERR_UNSUPPORTED;   // callers use ptivae_conv_umma mode 2 instead
   if (gn_groups > 0 && (!gn_part || C % gn_groups != 0 || 32 % (C / gn_groups) != 0 || 2 * gn_groups > up2::NEW * 32))
     return PTIVAE_ERR_ARG;
-  if (C == 64)
-    return out16 ? up2::launch<64, true>(x, w_packed, bias, out, out16, gn_part, gn_groups, N, H, W, stream)
-                 : up2::launch<64, false>(x, w_packed, bias, out, out16, gn_part, gn_groups, N, H, W, stream);
-  return out16 ? up2::launch<128, true>(x, w_packed, bias, out, out16, gn_part, gn_groups, N, H, W, stream)
-               : up2::launch<128, false>(x, w_packed, bias, out, out16, gn_part, gn_groups, N, H, W, stream);
+  const int emit = !out ? 2 : (out16 ? 1 : 0);
+#define PTIVAE_UP_CASE(CC, E) \
+  if (C == CC && emit == E) return up2::launch<CC, E>(x, w_packed, bias, out, out16, gn_part, gn_groups, N, H, W, stream)
+  PTIVAE_UP_CASE(64, 0); PTIVAE_UP_CASE(64, 1); PTIVAE_UP_CASE(64, 2);
+  PTIVAE_UP_CASE(128, 0); PTIVAE_UP_CASE(128, 1); PTIVAE_UP_CASE(128, 2);
+#undef PTIVAE_UP_CASE
+  return PTIVAE_ERR_UNSUPPORTED;
 }

@@ -132,21 +132,28 @@ def up2x_supported(x: torch.Tensor) -> bool:
     return x.dtype == F16 and x.shape[-1] in (64, 128)
 
 
-def up2x_conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_groups: int = 0, emit16: bool = False):
+def up2x_conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_groups: int = 0, emit16: bool = False,
+                 out_f32: bool = True):
     """conv3x3(nearest_upsample_2x(x)) + bias.  x fp16 NHWC [N,H,W,C] -> fp32 NHWC [N,2H,2W,C]; returns out,
-    (out, partials [N,P,G,2]) with gn_groups > 0, and the fp16 copy of out appended when emit16."""
+    (out, partials [N,P,G,2]) with gn_groups > 0, and the fp16 copy of out appended when emit16.  out_f32=False
+    (16-bit residual stream): the output itself is fp16 (statistics of the stored values), no fp32 tensor is written."""
     _need_cuda(x, w_packed, bias)
     if w_packed.dtype != x.dtype:
         raise _lib.PtivaeError("activation and packed-weight operand dtypes differ")
     n, h, w, c = x.shape
-    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.float32)
-    out16 = torch.empty(out.shape, device=x.device, dtype=x.dtype) if emit16 else None
+    if not out_f32:
+        out, out16, emit16 = None, torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype), False
+    else:
+        out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.float32)
+        out16 = torch.empty(out.shape, device=x.device, dtype=x.dtype) if emit16 else None
     part = None
     if gn_groups > 0:
         part = torch.empty((n, _lib.lib().ptivae_up2x_conv3x3_parts(h, w), gn_groups, 2), device=x.device,
                            dtype=torch.float32)
-    _call("up2x_conv3x3", (n, h, w, c, int(emit16)), 1, _lib.lib().ptivae_up2x_conv3x3, _p(x), _p(w_packed), _p(bias),
-          _p(out), _p(out16), _p(part), gn_groups, n, h, w, c, _op16(x), _stream())
+    _call("up2x_conv3x3", (n, h, w, c, int(emit16) if out_f32 else 2), 1, _lib.lib().ptivae_up2x_conv3x3, _p(x), _p(w_packed),
+          _p(bias), _p(out), _p(out16), _p(part), gn_groups, n, h, w, c, _op16(x), _stream())
+    if not out_f32:
+        out = out16
     r = (out, part) if gn_groups > 0 else (out,)
     if emit16:
         r = r + (out16,)
@@ -174,6 +181,8 @@ def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tens
         if residual.shape != out.shape:
             raise _lib.PtivaeError("residual shape mismatch")
         res_f32 = int(residual.dtype == torch.float32)
+        if not res_f32 and residual.dtype != w_packed.dtype:
+            raise _lib.PtivaeError("a 16-bit residual must use the operand dtype")
     part = None
     if gn_groups > 0:
         part = torch.empty((n, _lib.lib().ptivae_conv3x3_fused_parts(h, w), gn_groups, 2), device=x.device,
@@ -192,7 +201,7 @@ def fused_sc_supported(dtype: torch.dtype, cin: int, cout: int, sc_cin: int) -> 
 
 
 def conv3x3_fused_sc(h: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tensor, bias: torch.Tensor,
-                     sc_x: torch.Tensor, sc_w_packed: torch.Tensor, gn_groups: int = 0):
+                     sc_x: torch.Tensor, sc_w_packed: torch.Tensor, gn_groups: int = 0, out_f32: bool = True):
     """out = conv3x3(act(h*scale+shift)) + conv1x1(sc_x) + bias as ONE kernel (bias = sum of both conv biases).
     h, sc_x fp16 NHWC; returns the fp32 stream tensor, or (out, statistics partials) with gn_groups > 0."""
     _need_cuda(h, w_packed, bias, sc_x, sc_w_packed)
@@ -200,13 +209,13 @@ def conv3x3_fused_sc(h: torch.Tensor, scale_shift, silu: bool, w_packed: torch.T
     cout = w_packed.shape[1]
     if sc_x.shape[:3] != h.shape[:3] or sc_x.dtype != h.dtype or sc_w_packed.shape != (1, cout, sc_x.shape[-1]):
         raise _lib.PtivaeError("shortcut operand / weight shape mismatch")
-    out = torch.empty((n, hh, w, cout), device=h.device, dtype=torch.float32)
+    out = torch.empty((n, hh, w, cout), device=h.device, dtype=torch.float32 if out_f32 else h.dtype)
     part = None
     if gn_groups > 0:
         part = torch.empty((n, _lib.lib().ptivae_conv3x3_fused_parts(hh, w), gn_groups, 2), device=h.device, dtype=torch.float32)
-    meta = (n, hh, w, cin, cout, h.element_size(), 4, 0, sc_x.shape[-1])
+    meta = (n, hh, w, cin, cout, h.element_size(), out.element_size(), 0, sc_x.shape[-1])
     _call("conv3x3_fused_sc", meta, 1, _lib.lib().ptivae_conv3x3_fused_sc, _p(h), _p(scale_shift), int(silu), _p(w_packed),
-          _p(bias), _p(sc_x), _p(sc_w_packed), sc_x.shape[-1], _p(out), 1, _p(part), gn_groups, n, hh, w, cin, cout, _op16(h),
+          _p(bias), _p(sc_x), _p(sc_w_packed), sc_x.shape[-1], _p(out), int(out_f32), _p(part), gn_groups, n, hh, w, cin, cout, _op16(h),
           _stream())
     return (out, part) if gn_groups > 0 else out
 

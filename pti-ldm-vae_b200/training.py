@@ -213,6 +213,14 @@ class TrainRun:
         return out
 
     def forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):
+        # the backward kernels read the fp32 residual stream: a 16-bit inference stream setting does not apply here
+        saved, self.ex.stream16 = self.ex.stream16, False
+        try:
+            return self._forward(x, eps)
+        finally:
+            self.ex.stream16 = saved
+
+    def _forward(self, x: torch.Tensor, eps: torch.Tensor | None = None):
         ae, ex = self.ae, self.ex
         x = ae._prep(x)
         self.tape.append(("mark", "encoder"))

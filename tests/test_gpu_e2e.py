@@ -112,9 +112,14 @@ def test_api_contract(b200, oracle):
     assert torch.allclose(m_all[2:3], m_one, rtol=1e-3, atol=1e-4)
     with pytest.raises(RuntimeError):
         vae(x.cpu())
+    # train mode: forward is differentiable (train_vae.py:385,444), the stand-alone encode()/decode() are inference-only
     vae.train()
+    rec_t, mu_t, _ = vae(x)
+    assert rec_t.requires_grad and mu_t.requires_grad
+    rec_t.float().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in vae.parameters())
     with pytest.raises(NotImplementedError):
-        vae(x)
+        vae.autoencoder.encode(x)
 
 
 def test_graph_replay_matches_eager(b200, oracle):

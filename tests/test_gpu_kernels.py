@@ -211,6 +211,14 @@ def test_up2x_conv3x3(b200, n, h, w, c, groups, emit16):
         assert torch.allclose(part.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
         r2 = b200.ops.up2x_conv3x3(x, wp, bias, gn_groups=groups, emit16=emit16)
         assert torch.equal(r2[0], out) and torch.equal(r2[1], part), "deterministic"
+    # 16-bit residual stream: only the fp16 tensor is written; statistics describe the stored (rounded) values
+    r16 = b200.ops.up2x_conv3x3(x, wp, bias, gn_groups=groups, out_f32=False)
+    o16 = r16[0] if groups else r16
+    assert o16.dtype == DT and torch.equal(o16, out.to(DT))
+    if groups:
+        o = o16.float().view(n, -1, groups, c // groups)
+        assert torch.allclose(r16[1].sum(1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(r16[1].sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("n,h,w,c,groups,silu,f32", [(2, 32, 32, 128, 16, True, True), (2, 64, 64, 32, 16, True, False),
@@ -276,6 +284,14 @@ TMA_CASES = [
     (2, 16, 16, 64, 32, False, True, True, 16),
     (1, 8, 8, 32, 64, False, True, False, 32),       # image smaller than a tile
     (9, 64, 64, 32, 32, False, True, True, 16),      # several tiles per CTA on any SM count >= 16
+    # 16-bit residual stream: conv1 (16-bit in, 16-bit out) and conv2 (16-bit residual added in place, 16-bit out)
+    (2, 32, 32, 32, 32, False, False, False, 16),
+    (2, 32, 32, 32, 32, False, "h16", False, 16),
+    (1, 48, 40, 32, 32, False, "h16", False, 16),
+    (3, 40, 24, 64, 64, False, "h16", False, 32),
+    (1, 24, 24, 64, 32, False, False, False, 16),
+    (1, 8, 8, 32, 64, False, "h16", False, 32),
+    (9, 64, 64, 32, 32, False, "h16", False, 16),
 ]
 
 
@@ -289,9 +305,11 @@ def test_conv3x3_fused_tma(b200, n, h, w, cin, cout, in_f32, res, out_f32, group
     ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
     xin = F.silu(x.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
     r = torch.randn(n, h, w, cout, device=DEV) if res else None
+    if res == "h16":
+        r = r.to(DT)
     ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
     if res:
-        ref = ref + r
+        ref = ref + r.float()
     wp = b200.ops.pack_conv_weight(wt, 0, DT)
     outs = {}
     try:
@@ -313,7 +331,8 @@ def test_conv3x3_fused_tma(b200, n, h, w, cin, cout, in_f32, res, out_f32, group
 
 
 TMA2_SHAPES = [(32, 32), (32, 64), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128)]
-TMA2_MODES = [(True, False, False), (False, True, True), (False, True, False)]    # (in_f32, res, out_f32): conv1 | conv2 | conv2 -> operand
+# (in_f32, res, out_f32): conv1 | conv2 | conv2 -> operand | conv1, conv2 on a 16-bit residual stream
+TMA2_MODES = [(True, False, False), (False, True, True), (False, True, False), (False, False, False), (False, "h16", False)]
 
 
 @pytest.mark.parametrize("cin,cout", TMA2_SHAPES)
@@ -330,9 +349,11 @@ def test_conv3x3_fused_tma2(b200, cin, cout, in_f32, res, out_f32, n, h, w, grou
     ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
     xin = F.silu(x.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
     r = torch.randn(n, h, w, cout, device=DEV) if res else None
+    if res == "h16":
+        r = r.to(DT)
     ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
     if res:
-        ref = ref + r
+        ref = ref + r.float()
     wp = b200.ops.pack_conv_weight(wt, 0, DT)
     outs = {}
     try:
@@ -379,6 +400,12 @@ def test_conv3x3_fused_shortcut(b200, c, sc, n, h, w, groups):
     scv = b200.ops.conv_umma(xr, wscp, bsc, 3, out_f32=True)
     two, _ = b200.ops.conv3x3_fused(hh, ss, True, wp, bias, residual=scv, gn_groups=groups, out_f32=True)
     assert float((out - two).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+    # 16-bit residual stream: the same sums rounded once on the way out, statistics of the stored values
+    o16, p16 = b200.ops.conv3x3_fused_sc(hh, ss, True, wp, bias + bsc, xr, wscp, gn_groups=groups, out_f32=False)
+    assert o16.dtype == DT and torch.equal(o16, out.to(DT))
+    o = o16.float().view(n, h * w, groups, c // groups)
+    assert torch.allclose(p16.sum(dim=1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(p16.sum(dim=1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,in_f32,norm,silu,res,out_f32,groups", FUSED_CASES)
