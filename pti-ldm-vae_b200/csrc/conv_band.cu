@@ -1,0 +1,584 @@
+// Row-band implementation of the fused GroupNorm(+SiLU) -> 3x3 conv -> (+bias, +residual, statistics) kernel for the
+// layers with 32 OUTPUT channels (the full-resolution stage: 32->32 and 64->32 ResBlock convs), 16-bit in / 16-bit out.
+//
+// Why another formulation: with N = Cout = 32 a 128x32x16 tcgen05 MMA still reads the whole 128-row A operand from shared
+// memory (4 KB per MMA against a 16-cycle tensor floor), so the 16x16-tile kernels (conv_tma*.cu) top out near 300 TFLOP/s on
+// these layers whatever the HBM traffic is (measured).  Here one A read feeds up to THREE output rows:
+//   * an M block is 128 consecutive pixels of ONE image row (rows of the K-major operand = pixels along x, a kx tap is a
+//     one-line shift of the descriptor, as before);
+//   * the accumulator holds R = 4 output rows side by side: TMEM column (dy, co) = output row y0+dy, channel co;
+//   * input row r of the band contributes to output rows dy = r - ky: ONE MMA per (r, kx, k-step) with
+//     B = [W(ky=2,kx); W(ky=1,kx); W(ky=0,kx)] sliced to the valid dy range (N = 32, 64 or 96) and the D column base moved
+//     to dy_min*32 -- no zero padding of the weights, no wasted MACs, average N = 64 instead of 32;
+//   * rows stream through a ring in shared memory: a CTA walks down a column of bands, every input row is TMA-loaded,
+//     normalised + SiLU'd in place and consumed by the (up to two) bands that need it exactly once -- no halo re-reads
+//     in y, one halo pixel per side in x.
+// Output / residual / statistics move exactly as in conv_tma2.cu: units of 128 pixels x 32 channels through swizzled slots,
+// TMA tensor stores, column sums in fixed order (deterministic).
+// Warp roles (736 threads): 0-7 epilogue (two teams, team t owns output rows dy = t, t+2), 8-19 transform, 20 MMA issuer
+// (+TMEM), 21 row loader, 22 weight loader.
+#include "common.cuh"
+#include "ptivae_internal.h"
+
+namespace ptivae {
+namespace band {
+
+constexpr int kR = 4;                 // output rows per band
+constexpr int kMW = 128;              // pixels per M block
+constexpr int kLW = kMW + 2;          // input row segment incl. one halo pixel per side
+constexpr int COUT = 32;
+constexpr int NTEAM = 2, NEW = NTEAM * 4, NTW = 12, NT = NTW * 32;
+constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
+constexpr int kThreads = (NEW + NTW + 3) * 32;
+constexpr uint32_t kSmemMax = 232448;
+constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
+
+template <int CIN, int RES>
+struct Cfg {
+  static_assert(CIN == 32 || CIN == 64, "input widths with a row-band instantiation");
+  static_assert(RES == 0 || RES == 2, "no residual, or a 16-bit residual added in place");
+  static constexpr uint32_t LB = CIN * 2;                      // operand line: one pixel's channels
+  static constexpr uint32_t ROWB = r1k(kLW * LB);              // one ring slot
+  static constexpr int NR = CIN == 32 ? 16 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
+  static constexpr uint32_t BLK = COUT * LB;                   // one tap's weights [32 co][CIN]
+  static constexpr uint32_t WBYTES = 12u * BLK;                // kx = 0: W2 W1 W0 0 0 0 | kx = 1: W2 W1 W0 | kx = 2: W2 W1 W0
+  static constexpr uint32_t OSLOT = 128 * 64;                  // 128 pixels x 32 channels, 16-bit
+  static constexpr uint32_t SMEM = 1024 + NR * ROWB + WBYTES + NTEAM * 2 * OSLOT + 2 * NEW * COUT * 2 * 4 + COUT * 4 + 80 * 8 + 64;
+  static_assert(SMEM <= kSmemMax, "shared memory budget");
+};
+
+struct Args {
+  int N, H, W;
+  int bands, colblocks, seg_len, segs_per_col, num_segs;   // bands = ceil(H/4); a segment = seg_len consecutive bands of one column block
+  int parts;                 // statistics partials per image in gn_part (>= bands*colblocks; the rest is zero-filled)
+  int silu, gn_groups;
+  const float* scale_shift;  // [N][CIN][2] or nullptr
+  const float* bias;
+  float* gn_part;            // [N][parts][groups][2]
+  unsigned long long* trace; // debug timeline of CTA 0: [64 bands][32] band events, then [256 rows][4] row events; or nullptr
+};
+
+#define BAND_TRACE(band, slot)                                                                                  \
+  do {                                                                                                          \
+    if (args.trace != nullptr && blockIdx.x == 0 && (band) < 64) args.trace[(band) * 32 + (slot)] = clock64(); \
+  } while (0)
+#define ROW_TRACE(row, slot)                                                                                        \
+  do {                                                                                                              \
+    if (args.trace != nullptr && blockIdx.x == 0 && (row) < 256) args.trace[2048 + (row) * 4 + (slot)] = clock64(); \
+  } while (0)
+
+// SiLU from HALF the pre-activation: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- one SFU op and one FMA per element (the
+// halving is folded into the GroupNorm scale/shift).  The kernel is bound by instruction issue, and the
+// __expf/__fdividef form costs 2 SFU ops + 9 other instructions per element (each carries a denormal-range rescale).
+// tanh.approx.f32 has a relative error of 2^-11: <= 2^-12 of the result for x >= 0, <= |x| * 2.4e-4 absolute for x < 0.
+__device__ __forceinline__ float silu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+__host__ __device__ constexpr uint32_t strip_off(int kx) { return kx == 0 ? 0u : (kx == 1 ? 6u : 9u); }   // in BLK units
+
+template <int CIN, int RES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
+  using C = Cfg<CIN, RES>;
+  constexpr bool F16 = true;
+  constexpr uint32_t LB = C::LB, ROWB = C::ROWB, BLK = C::BLK;
+  constexpr int NR = C::NR;
+  constexpr uint32_t kLayout = (CIN == 64) ? kLayoutSW128 : kLayoutSW64;
+  constexpr uint32_t kSBO = 8u * LB;
+  constexpr int KS = CIN / 16;                  // K steps per input row and kx
+  constexpr int UPC = CIN / 8;                  // 16-byte vectors per operand line
+  constexpr uint32_t TMEM_COLS = 256;           // two accumulator stages of kR * 32 columns
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* ring = smem;                                     // [NR][ROWB]
+  uint8_t* wts = ring + NR * ROWB;                          // [12][BLK]
+  uint8_t* slots = wts + C::WBYTES;                         // [NTEAM][2][OSLOT]
+  float* colsum = reinterpret_cast<float*>(slots + NTEAM * 2 * C::OSLOT);   // [2][NEW][COUT][2]
+  float* sbias = colsum + 2 * NEW * COUT * 2;               // [COUT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
+  uint64_t* row_full = bars;            // [NR] raw row landed (TMA) or known to be out of the image
+  uint64_t* row_ready = bars + 16;      // [NR] row normalised in place
+  uint64_t* row_free = bars + 32;       // [NR] every MMA that reads the row has retired
+  uint64_t* acc_full = bars + 48;       // [2]
+  uint64_t* acc_empty = bars + 50;      // [2]
+  uint64_t* res_full = bars + 52;       // [NTEAM][2]
+  uint64_t* w_full = bars + 56;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 58);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == W_IN && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO);
+    if (RES != 0) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < NR; ++s) {
+      mbar_init(&row_full[s], 1);
+      mbar_init(&row_ready[s], NT);
+      mbar_init(&row_free[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], NEW * 32);
+    }
+    for (int i = 0; i < NTEAM * 2; ++i) mbar_init(&res_full[i], 1);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sbias[i] = args.bias[i];
+  // the three zero blocks behind kx = 0's strip (the first MMA of a band clears all four output rows with them)
+  for (uint32_t i = threadIdx.x; i < 3u * BLK / 16u; i += blockDim.x)
+    reinterpret_cast<uint4*>(wts + 3u * BLK)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // statistics slots this kernel's tiling does not use (the caller sized gn_part for 16x16 tiles)
+  if (args.gn_groups > 0) {
+    const int used = args.bands * args.colblocks, extra = args.parts - used, per = args.gn_groups * 2;
+    const long long total = static_cast<long long>(args.N) * extra * per;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long n = i / (static_cast<long long>(extra) * per), rem = i - n * extra * per;
+      args.gn_part[(n * args.parts + used) * per + rem] = 0.f;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // segment s -> (image, column block, first band, end band)
+  auto seg_decode = [&](int s, int& n, int& cb, int& b0, int& b1) {
+    const int per_img = args.colblocks * args.segs_per_col;
+    n = s / per_img;
+    const int r = s - n * per_img;
+    cb = r / args.segs_per_col;
+    b0 = (r - cb * args.segs_per_col) * args.seg_len;
+    b1 = min(args.bands, b0 + args.seg_len);
+  };
+
+  if (warp == W_W) {
+    // ------------------------------------------------------------------ weights: resident, (kx, reversed ky) order
+    if (elect_one()) {
+      mbar_expect_tx(w_full, 9u * BLK);
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          tma_load_3d(wts + (strip_off(kx) + (2 - ky)) * BLK, &tmW, w_full, 0, 0, ky * 3 + kx);
+    }
+  } else if (warp == W_IN) {
+    // ------------------------------------------------------------------ input rows (TMA) into the ring
+    if (elect_one()) {
+      int g = 0;   // rows issued so far (ring position)
+      for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
+        int n, cb, b0, b1;
+        seg_decode(s, n, cb, b0, b1);
+        const int rows = kR * (b1 - b0) + 2;
+        for (int i = 0; i < rows; ++i, ++g) {
+          const int slot = g % NR;
+          const int y = kR * b0 - 1 + i;
+          mbar_wait(&row_free[slot], ((g / NR) & 1) ^ 1u);
+          ROW_TRACE(g, 0);
+          if (y >= 0 && y < args.H) {
+            mbar_expect_tx(&row_full[slot], kLW * LB);
+            tma_load_4d(ring + slot * ROWB, &tmX, &row_full[slot], 0, cb * kMW - 1, y, n);
+          } else {
+            mbar_arrive(&row_full[slot]);     // zero padding row: the transform writes it
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t hi = desc_hi(kSBO, kLayout);
+      const uint32_t w_lo = desc_lo(smem_u32(wts));
+      const uint32_t r_lo = desc_lo(smem_u32(ring));
+      constexpr uint32_t kI32 = make_idesc_16(128, 32, F16), kI64 = make_idesc_16(128, 64, F16);
+      constexpr uint32_t kI96 = make_idesc_16(128, 96, F16), kI128 = make_idesc_16(128, 128, F16);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      int g0 = 0, it = 0;
+      for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
+        int n, cb, b0, b1;
+        seg_decode(s, n, cb, b0, b1);
+        for (int b = b0; b < b1; ++b, ++it) {
+          const int st = it & 1;
+          mbar_wait(&acc_empty[st], ((it >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          BAND_TRACE(it, 0);
+          const uint32_t acc = tmem_base + st * (kR * COUT);
+#pragma unroll
+          for (int rl = 0; rl < kR + 2; ++rl) {
+            const int g = g0 + kR * (b - b0) + rl;
+            const int slot = g % NR;
+            mbar_wait(&row_ready[slot], (g / NR) & 1);
+            tc_fence_after();
+            BAND_TRACE(it, 1 + rl);
+            const int dy_min = rl > 2 ? rl - 2 : 0, dy_max = rl < kR - 1 ? rl : kR - 1;
+            const int nblk = dy_max - dy_min + 1;
+            const uint32_t idesc = nblk == 1 ? kI32 : (nblk == 2 ? kI64 : kI96);
+            const uint32_t blk0 = static_cast<uint32_t>(2 - rl + dy_min);      // first weight block of the slice
+            const uint32_t a_row = r_lo + ((slot * ROWB) >> 4);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t b_base = w_lo + (((strip_off(kx) + blk0) * BLK) >> 4);
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                const uint32_t a_lo = a_row + ((kx * LB + k * 32) >> 4);
+                const uint32_t b_lo = b_base + ((k * 32) >> 4);
+                if (rl == 0 && kx == 0 && k == 0)   // first MMA of the band: [W0 0 0 0] overwrites all four output rows
+                  umma_f16_lohi(acc, a_lo, hi, b_lo, hi, kI128, 0u);
+                else
+                  umma_f16_lohi(acc + dy_min * COUT, a_lo, hi, b_lo, hi, idesc, 1u);
+              }
+            }
+            if (rl < kR || b == b1 - 1) umma_commit(&row_free[slot]);   // rows kR, kR+1 are the next band's rows 0, 1
+          }
+          umma_commit(&acc_full[st]);
+          BAND_TRACE(it, 7);
+        }
+        g0 += kR * (b1 - b0) + 2;
+      }
+    }
+  } else if (warp >= W_TR0) {
+    // ------------------------------------------------------------------ transform: normalise + SiLU rows in place
+    // A batch = the rows one band adds to the ring (the first batch of a segment: the two rows above its first band).
+    // The whole batch is processed with ONE proxy fence (the fence, not the arithmetic, dominated a row-at-a-time
+    // version: ~1k cycles per fence, measured with the clock64 timeline below).
+    const int tt = threadIdx.x - W_TR0 * 32;
+    const bool has_norm = args.scale_shift != nullptr;
+    const bool do_silu = args.silu != 0;
+    constexpr int LS = NT / UPC;                 // stride between a thread's vectors, in pixels of the batch
+    constexpr int VB = 3;                        // vectors in flight per thread
+    const int u = tt % UPC, Lbase = tt / UPC;
+    int g = 0;
+    for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
+      int n, cb, b0, b1;
+      seg_decode(s, n, cb, b0, b1);
+      float4 sp[4];
+      if (has_norm) {
+        const float4* src = reinterpret_cast<const float4*>(args.scale_shift + (static_cast<size_t>(n) * CIN + u * 8) * 2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sp[e] = __ldg(src + e);
+          if (do_silu) { sp[e].x *= 0.5f; sp[e].y *= 0.5f; sp[e].z *= 0.5f; sp[e].w *= 0.5f; }   // see silu_half
+        }
+      }
+      const int xbase = cb * kMW - 1;
+      for (int bt = 0; bt <= b1 - b0; ++bt) {
+        const int nrows = bt == 0 ? 2 : kR;
+        const int ybase = kR * b0 - 1 + (bt == 0 ? 0 : 2 + kR * (bt - 1));   // image row of the batch's first row
+        for (int r = 0; r < nrows; ++r) mbar_wait(&row_full[(g + r) % NR], ((g + r) / NR) & 1);
+        if (tt == 0) ROW_TRACE(g, 1);
+        const int nq = nrows * kLW;
+#pragma unroll 1
+        for (int q0 = Lbase; q0 < nq; q0 += VB * LS) {
+          uint4 v[VB];
+          uint4* p[VB];
+#pragma unroll
+          for (int j = 0; j < VB; ++j) {
+            const int q = q0 + j * LS;
+            const int r = (q >= kLW) + (q >= 2 * kLW) + (q >= 3 * kLW);
+            const int L = q - r * kLW;
+            const uint32_t sw = (CIN == 64) ? ((u ^ (L & 7)) << 4) : ((u ^ ((L >> 1) & 3)) << 4);
+            p[j] = reinterpret_cast<uint4*>(ring + ((g + r) % NR) * ROWB + L * LB + sw);
+            const int x = xbase + L, y = ybase + r;
+            const bool inimg = y >= 0 && y < args.H && x >= 0 && x < args.W;
+            v[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (q >= nq) {
+              p[j] = nullptr;
+            } else if (!inimg) {          // zero padding is applied AFTER the normalisation: the pixel is just cleared
+              *p[j] = v[j];
+              p[j] = nullptr;
+            } else {
+              v[j] = *p[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < VB; ++j) {
+            if (p[j] == nullptr) continue;
+            uint4 o = v[j];
+            if (has_norm) {
+              float f[8];
+              unpack2<F16>(v[j].x, f[0], f[1]); unpack2<F16>(v[j].y, f[2], f[3]);
+              unpack2<F16>(v[j].z, f[4], f[5]); unpack2<F16>(v[j].w, f[6], f[7]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = fmaf(f[2 * e], sp[e].x, sp[e].y);
+                float c = fmaf(f[2 * e + 1], sp[e].z, sp[e].w);
+                if (do_silu) {
+                  a = silu_half(a);
+                  c = silu_half(c);
+                }
+                f[2 * e] = a;
+                f[2 * e + 1] = c;
+              }
+              o = make_uint4(pack2<F16>(f[0], f[1]), pack2<F16>(f[2], f[3]), pack2<F16>(f[4], f[5]), pack2<F16>(f[6], f[7]));
+            }
+            *p[j] = o;
+          }
+        }
+        fence_proxy_async_smem();
+        for (int r = 0; r < nrows; ++r) mbar_arrive(&row_ready[(g + r) % NR]);
+        if (tt == 0) ROW_TRACE(g, 2);
+        g += nrows;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue teams (team t: output rows dy = t, t + 2)
+    // Per band a team drains its two units into its two slots, then ONE proxy fence, two TMA stores, and the statistics of
+    // both units; the residuals of the team's next band are already in flight (they land in the slots, added in place).
+    const int team = warp >> 2, ew = warp & 3;      // ew == TMEM lane quarter
+    const int m = ew * 32 + lane;                   // accumulator row = pixel x0 + m of the output row
+    const bool leader = (ew == 0 && lane == 0);
+    const int cpg = args.gn_groups > 0 ? COUT / args.gn_groups : 0;
+    const int bar_id = 1 + team;
+    uint8_t* tslots = slots + team * 2 * C::OSLOT;
+    uint64_t* rfull = res_full + team * 2;
+    // residuals of the team's next band (leader only); the cursor walks the CTA's segments band by band
+    int rs_seg = blockIdx.x, rs_b = -1;
+    auto issue_res = [&]() {
+      if constexpr (RES != 0) {
+        if (rs_seg >= args.num_segs) return;
+        int n, cb, b0, b1;
+        seg_decode(rs_seg, n, cb, b0, b1);
+        if (rs_b < 0) rs_b = b0;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          const int y = kR * rs_b + team + 2 * uu;
+          if (y < args.H) {
+            mbar_expect_tx(&rfull[uu], 128 * 64);
+            tma_load_4d(tslots + uu * C::OSLOT, &tmR, &rfull[uu], 0, cb * kMW, y, n);
+          } else {
+            mbar_arrive(&rfull[uu]);    // row below the image: nothing to load (nothing is stored either)
+          }
+        }
+        if (++rs_b == b1) { rs_seg += gridDim.x; rs_b = -1; }
+      }
+    };
+    if (leader) issue_res();
+    int it = 0;
+    for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
+      int n, cb, b0, b1;
+      seg_decode(s, n, cb, b0, b1);
+      const int x0 = cb * kMW;
+      for (int b = b0; b < b1; ++b, ++it) {
+        const int st = it & 1;
+        if (threadIdx.x == 0) BAND_TRACE(it, 8);
+        mbar_wait(&acc_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0) BAND_TRACE(it, 9);
+#pragma unroll 1
+        for (int uu = 0; uu < 2; ++uu) {
+          const int dy = team + 2 * uu;
+          uint8_t* oslot = tslots + uu * C::OSLOT;
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * (kR * COUT) + dy * COUT, acc);
+          tmem_ld_wait();
+          if (uu == 1) {                                // all of this band's columns of the team are in registers
+            tc_fence_before();
+            mbar_arrive(&acc_empty[st]);
+          }
+          if (threadIdx.x == 0) BAND_TRACE(it, 10 + 3 * uu);
+          if constexpr (RES != 0) mbar_wait(&rfull[uu], it & 1);
+          else if (uu == 0) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // slots free: the leader saw the last band's stores drained
+          if (threadIdx.x == 0) BAND_TRACE(it, 11 + 3 * uu);
+          {
+            uint8_t* ol = oslot + m * 64;
+            uint4 r16[4] = {};
+            if constexpr (RES == 2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) r16[j] = *reinterpret_cast<const uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = reinterpret_cast<const float4*>(sbias)[j];   // broadcast
+              float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
+              float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
+              if constexpr (RES == 2) {
+                float r0, r1, r2, r3;
+                unpack2<F16>((j & 1) ? r16[j >> 1].z : r16[j >> 1].x, r0, r1);
+                unpack2<F16>((j & 1) ? r16[j >> 1].w : r16[j >> 1].y, r2, r3);
+                v0 += r0; v1 += r1; v2 += r2; v3 += r3;
+              }
+              acc[4 * j + 0] = pack2<F16>(v0, v1);
+              acc[4 * j + 1] = pack2<F16>(v2, v3);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4)) =
+                  make_uint4(acc[8 * j + 0], acc[8 * j + 1], acc[8 * j + 4], acc[8 * j + 5]);
+          }
+          if (threadIdx.x == 0) BAND_TRACE(it, 12 + 3 * uu);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // both units written by all four warps
+        if (leader) {
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            const int y = kR * b + team + 2 * uu;
+            if (y < args.H) tma_store_4d(&tmO, tslots + uu * C::OSLOT, 0, x0, y, n);
+          }
+          tma_store_commit();
+        }
+        if (threadIdx.x == 0) BAND_TRACE(it, 16);
+        // column sums of the stored values over this warp's own 32 rows of both units (lane = (row sub-index, 16-byte chunk))
+        const int rsub = lane >> 2, j4 = lane & 3;
+        uint4 w[8];
+        if (cpg > 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = ew * 32 + (i & 3) * 8 + rsub;
+            const bool ok = (x0 + r < args.W) && (kR * b + team + 2 * (i >> 2) < args.H);
+            w[i] = ok ? *reinterpret_cast<const uint4*>(tslots + (i >> 2) * C::OSLOT + r * 64 + ((j4 ^ ((r >> 1) & 3)) << 4))
+                      : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        if (threadIdx.x == 0) BAND_TRACE(it, 18);
+        if constexpr (RES != 0) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // every statistics read of the slots is done
+        if (leader) {
+          tma_store_wait_read();          // the stores have drained the slots ...
+          issue_res();                    // ... which now receive the next band's residuals
+        }
+        if (threadIdx.x == 0) BAND_TRACE(it, 19);
+        if (cpg > 0) {
+          float s1[8], s2[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x[8];
+            unpack2<F16>(w[i].x, x[0], x[1]); unpack2<F16>(w[i].y, x[2], x[3]);
+            unpack2<F16>(w[i].z, x[4], x[5]); unpack2<F16>(w[i].w, x[6], x[7]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              s1[k] += x[k];
+              s2[k] = fmaf(x[k], x[k], s2[k]);
+            }
+          }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {       // fold the row sub-lanes (fixed pattern)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+            }
+          }
+          float* cs = colsum + ((it & 1) * NEW + warp) * COUT * 2;      // double buffered: one CTA-wide barrier per band
+          if (rsub == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              cs[(j4 * 8 + k) * 2] = s1[k];
+              cs[(j4 * 8 + k) * 2 + 1] = s2[k];
+            }
+          }
+          if (threadIdx.x == 0) BAND_TRACE(it, 20);
+          asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
+          if (threadIdx.x == 0) BAND_TRACE(it, 21);
+          const int ei = threadIdx.x;                 // epilogue warps are warps 0 .. NEW-1
+          if (ei < 2 * args.gn_groups) {
+            const int gi = ei >> 1, k = ei & 1;
+            const float* cb2 = colsum + (it & 1) * NEW * COUT * 2;
+            float tsum = 0.f;
+            for (int c = gi * cpg; c < (gi + 1) * cpg; ++c)
+#pragma unroll
+              for (int w8 = 0; w8 < NEW; ++w8) tsum += cb2[(w8 * COUT + c) * 2 + k];
+            const int pidx = b * args.colblocks + cb;
+            args.gn_part[((static_cast<size_t>(n) * args.parts + pidx) * args.gn_groups + gi) * 2 + k] = tsum;
+          }
+        }
+        if (threadIdx.x == 0) BAND_TRACE(it, 17);
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int CIN, int RES>
+static int launch(const FusedCall& c, cudaStream_t stream) {
+  using C = Cfg<CIN, RES>;
+  Args a{};
+  a.N = c.N; a.H = c.H; a.W = c.W;
+  a.bands = (c.H + kR - 1) / kR;
+  a.colblocks = (c.W + kMW - 1) / kMW;
+  a.parts = ((c.H + 15) / 16) * ((c.W + 15) / 16);           // what ptivae_conv3x3_fused_parts promises the caller
+  if (c.gn_groups > 0 && a.bands * a.colblocks > a.parts) return PTIVAE_ERR_UNSUPPORTED;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // segment length: long enough to amortise the two halo rows, short enough that the last wave of segments is full
+  {
+    const long long cols = static_cast<long long>(c.N) * a.colblocks;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int sl = 1; sl <= a.bands && sl <= 64; ++sl) {
+      const long long segs = cols * ((a.bands + sl - 1) / sl);
+      const long long waves = (segs + sms - 1) / sms;
+      const double cost = static_cast<double>(waves) * (kR * sl + 2);   // rows the busiest CTA streams
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = sl; }
+    }
+    a.seg_len = best;
+  }
+  a.segs_per_col = (a.bands + a.seg_len - 1) / a.seg_len;
+  a.num_segs = c.N * a.colblocks * a.segs_per_col;
+  a.silu = c.silu; a.gn_groups = c.gn_groups; a.scale_shift = c.scale_shift; a.bias = c.bias; a.gn_part = c.gn_part;
+  a.trace = c.trace;
+
+  CUtensorMap tmX, tmW, tmR, tmO;
+  const uint64_t H = c.H, W = c.W, N = c.N;
+  {  // input row segment: dims (C, W, H, N), box (CIN, 130, 1, 1), swizzle = line bytes (the K-major UMMA operand layout)
+    uint64_t d[4] = {uint64_t(CIN), W, H, N};
+    uint64_t s[3] = {uint64_t(CIN) * 2, W * CIN * 2, H * W * CIN * 2};
+    uint32_t b[4] = {uint32_t(CIN), kLW, 1, 1};
+    int rc = encode_tmap(&tmX, c.x, 1, 4, d, s, b, C::LB);
+    if (rc) return rc;
+  }
+  {  // weights [9][32][Cin] fp16: one tap per box
+    uint64_t d[3] = {uint64_t(CIN), uint64_t(COUT), 9};
+    uint64_t s[2] = {uint64_t(CIN) * 2, uint64_t(COUT) * CIN * 2};
+    uint32_t b[3] = {uint32_t(CIN), uint32_t(COUT), 1};
+    int rc = encode_tmap(&tmW, c.w_packed, 1, 3, d, s, b, C::LB);
+    if (rc) return rc;
+  }
+  {  // output unit: box (32 channels, 128 pixels, 1 row, 1), 64B swizzle
+    uint64_t d[4] = {uint64_t(COUT), W, H, N};
+    uint64_t s[3] = {uint64_t(COUT) * 2, W * COUT * 2, H * W * COUT * 2};
+    uint32_t b[4] = {32, kMW, 1, 1};
+    int rc = encode_tmap(&tmO, c.out, 1, 4, d, s, b, 64);
+    if (rc) return rc;
+    if (RES != 0) {
+      rc = encode_tmap(&tmR, c.residual, 1, 4, d, s, b, 64);
+      if (rc) return rc;
+    } else {
+      tmR = tmO;
+    }
+  }
+  static bool attr_set[64] = {};
+  if (int rc_attr = ensure_dyn_smem(conv3x3_band_kernel<CIN, RES>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
+  const int grid = a.num_segs < sms ? a.num_segs : sms;
+  conv3x3_band_kernel<CIN, RES><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace band
+
+// Row-band kernel: 16-bit input, 32 output channels, 16-bit output, optional 16-bit residual; -2 otherwise.
+int conv3x3_band_launch(const FusedCall& c, cudaStream_t stream) {
+  if (!c.f16 || c.Cout != 32 || c.in_fmt == 2 || c.out_f32 || c.sc_x != nullptr) return PTIVAE_ERR_UNSUPPORTED;
+  if (c.residual != nullptr && c.res_f32) return PTIVAE_ERR_UNSUPPORTED;
+  if (2 * c.gn_groups > band::NEW * 32) return PTIVAE_ERR_UNSUPPORTED;
+  const bool res = c.residual != nullptr;
+  if (c.Cin == 32) return res ? band::launch<32, 2>(c, stream) : band::launch<32, 0>(c, stream);
+  if (c.Cin == 64) return res ? band::launch<64, 2>(c, stream) : band::launch<64, 0>(c, stream);
+  return PTIVAE_ERR_UNSUPPORTED;
+}
+
+}  // namespace ptivae

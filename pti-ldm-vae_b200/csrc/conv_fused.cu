@@ -465,9 +465,10 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                                     void* out, int out_f32, float* gn_part, int gn_groups, int N, int H, int W,
                                     int Cin, int Cout, int f16, int desc_base_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  // 0 = auto, 1 = register-staged kernel (this file), 2 = TMA-staged (conv_tma.cu), 3 = chunk-pipelined TMA (conv_tma2.cu)
+  // 0 = auto, 1 = register-staged kernel (this file), 2 = TMA-staged (conv_tma.cu), 3 = chunk-pipelined TMA (conv_tma2.cu),
+  // 4 = row-band kernel (conv_band.cu: 32 output channels, 16-bit in/out)
   const int impl = desc_base_offset;
-  if (impl < 0 || impl > 3) return PTIVAE_ERR_ARG;
+  if (impl < 0 || impl > 4) return PTIVAE_ERR_ARG;
   if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   if (in_fmt != 2 && in_fmt != (f16 ? 1 : 0)) return PTIVAE_ERR_ARG;  // 16-bit input must use the operand format
   if (!(Cin == 32 || Cin == 64 || Cin == 128) || !(Cout == 32 || Cout == 64 || Cout == 128)) return PTIVAE_ERR_UNSUPPORTED;
@@ -476,8 +477,15 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
   if (impl != 1) {
     FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
                 N, H, W, Cin, Cout, f16, g_fused_trace, impl == 2};
+    if (impl == 4) return conv3x3_band_launch(c, stream);
     if (impl == 3) return conv3x3_tma2_launch(c, stream);
     if (impl == 2) return conv3x3_tma_launch(c, stream);
+    // auto: the row-band kernel takes the 32-output-channel layers of a 16-bit stream when the rows are long enough to
+    // fill its 128-pixel M blocks
+    if (Cout == 32 && W >= 96) {
+      const int rcb = conv3x3_band_launch(c, stream);
+      if (rcb != PTIVAE_ERR_UNSUPPORTED) return rcb;
+    }
     // auto: measured winners (B200, batch 64) -- the chunk-pipelined kernel for every shape with >= 64 input
     // channels or 128 output channels; the whole-tile kernel for the 32-channel-input layers
     const bool wide = Cin >= 64 || Cout == 128;

@@ -27,6 +27,8 @@ struct FusedCall {   // arguments of ptivae_conv3x3_fused, shared by its two imp
 int conv3x3_tma_launch(const FusedCall& c, cudaStream_t stream);
 // chunk-pipelined TMA implementation (conv_tma2.cu): all widths in {32, 64, 128}; same contract
 int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream);
+// row-band implementation (conv_band.cu): Cout = 32, Cin in {32, 64}, 16-bit input / output / residual; same contract
+int conv3x3_band_launch(const FusedCall& c, cudaStream_t stream);
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a function: remember per device (a process
 // that drives several GPUs must opt in on each of them).  `flags` is a function-local static array of 64 bools.

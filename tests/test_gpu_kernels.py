@@ -373,6 +373,49 @@ def test_conv3x3_fused_tma2(b200, cin, cout, in_f32, res, out_f32, n, h, w, grou
     assert float((outs[1] - outs[3]).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("cin", [32, 64])
+@pytest.mark.parametrize("res", [False, "h16"])
+@pytest.mark.parametrize("n,h,w,groups", [(2, 16, 128, 16), (1, 40, 200, 16), (3, 64, 256, 8), (1, 7, 130, 16), (200, 16, 128, 16),
+                                          (1, 260, 256, 16)])
+def test_conv3x3_fused_band(b200, cin, res, n, h, w, groups):
+    """Row-band kernel (impl 4: 32 output channels, 16-bit in/out, rows streamed through a ring) vs the fp32 reference and
+    vs the register-staged kernel (impl 1): multi-segment CTAs, ring wrap-around, ragged right / bottom edges."""
+    if DT != torch.float16:
+        pytest.skip("the row-band kernel is instantiated for fp16 operands only")
+    cout = 32
+    x = (_rand_act(n, h, w, cin, 71).float() * 1.5 + 0.2).to(DT)
+    wt, bias = _rand_conv(cout, cin, 3, 72)
+    ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
+    xin = F.silu(x.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
+    r = torch.randn(n, h, w, cout, device=DEV).to(DT) if res else None
+    ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    wp = b200.ops.pack_conv_weight(wt, 0, DT)
+    outs = {}
+    try:
+        for impl in (4, 1):
+            b200.ops.FUSED_IMPL = impl
+            out, part = b200.ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=False)
+            out2, part2 = b200.ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=False)
+            assert torch.equal(out, out2) and torch.equal(part, part2), f"impl {impl} not deterministic"
+            # impl 4 evaluates SiLU as h + h*tanh(h) with tanh.approx.f32 (relative error 2^-11): twice the tolerances
+            _check_bf16(out, ref, f"fused conv impl={impl}", rel=6e-3 if impl == 4 else 3e-3, ulp=2.0 ** -6 if impl == 4 else 2.0 ** -7)
+            o = out.float().view(n, h * w, groups, cout // groups)
+            acc = part.sum(dim=1)
+            assert torch.allclose(acc[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2), impl
+            assert torch.allclose(acc[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2), impl
+            outs[impl] = out.float()
+        print(f"band vs fp32 reference rel-L2 {_rel_l2(outs[4], ref):.2e} (register-staged kernel: {_rel_l2(outs[1], ref):.2e})")
+        b200.ops.FUSED_IMPL = 4     # no statistics, identity prologue
+        o_plain = b200.ops.conv3x3_fused(x, None, False, wp, bias, residual=r, out_f32=False)
+        ref_plain = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1).permute(0, 2, 3, 1)
+        _check_bf16(o_plain, ref_plain + (r.float() if res else 0.0), "band, identity prologue")
+    finally:
+        b200.ops.FUSED_IMPL = 0
+    assert float((outs[1] - outs[4]).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("c,sc", [(32, 64), (64, 32)])
 @pytest.mark.parametrize("n,h,w,groups", [(2, 32, 32, 16), (1, 40, 24, 16), (5, 48, 48, 32)])
 def test_conv3x3_fused_shortcut(b200, c, sc, n, h, w, groups):
