@@ -132,8 +132,42 @@ def run_reference(args) -> None:
 
 
 # --------------------------------------------------------------------------------------------- roofline
+def survey_bytes(name, meta):
+    """SURVEY.md 8(d) bytes of one launch: 16-bit activations, every tensor read once + written once per fused op
+    (conv = (Cin*HW_in + Cout*HW_out) * 2 B; residuals / fp32 copies of this schedule are NOT counted)."""
+    if name == "conv_umma":
+        mode, n, h, w, cin, cout = meta
+        ho, wo = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+        return 2.0 * n * (h * w * cin + ho * wo * cout)
+    if name == "conv3x3_fused":
+        n, h, w, cin, cout = meta[:5]
+        return 2.0 * n * h * w * (cin + cout)
+    if name == "conv3x3_fused_sc":
+        n, h, w, cin, cout = meta[:5]
+        return 2.0 * n * h * w * (cin + cout + meta[8])
+    if name == "up2x_conv3x3":
+        n, h, w, c, _ = meta
+        return 2.0 * n * h * w * c * 5
+    if name == "conv3x3_small_cin":
+        n, h, w, cin, cout, _ = meta
+        return n * h * w * (4.0 * cin + 2.0 * cout)
+    if name == "conv3x3_small_cout":
+        n, h, w, cin, cout, _ = meta
+        return n * h * w * (2.0 * cin + 4.0 * cout)
+    if name == "gn_stats":
+        n, hw, c, _ = meta
+        return 2.0 * n * hw * c
+    if name == "gn_apply":
+        n, hw, c, _, raw = meta
+        return (4.0 + 2.0 * raw) * n * hw * c
+    if name == "attention_fwd":
+        b, l, d = meta
+        return 8.0 * b * l * d
+    return 0.0
+
+
 def classify(name, meta):
-    """-> (class key, algorithmic flops, algorithmic bytes) for one launch."""
+    """-> (class key, algorithmic flops, algorithmic bytes of THIS schedule) for one launch."""
     if name == "conv_umma":
         mode, n, h, w, cin, cout = meta
         taps = {0: 9, 1: 9, 2: 9, 3: 1}[mode]
@@ -159,8 +193,9 @@ def classify(name, meta):
         return (f"fused3x3+sc{sc}_{cin}->{cout}@{h}x{w}", flops, byt)
     if name == "up2x_conv3x3":
         n, h, w, c, e16 = meta
-        return (f"up2x_conv3x3_{c}@{h}x{w}", 2.0 * n * 4 * h * w * c * c * 9,      # nominal direct-form count
-                n * h * w * c * (2.0 + 4 * (4.0 + 2.0 * e16)) + 2.0 * 16 * c * c)
+        out_b = 2.0 if e16 == 2 else (4.0 + 2.0 * e16)     # e16 == 2: 16-bit output only (16-bit residual stream)
+        return (f"up2x_conv3x3_{c}@{h}x{w}_out{'2' if e16 == 2 else '4'}", 2.0 * n * 4 * h * w * c * c * 9,      # nominal direct-form count
+                n * h * w * c * (2.0 + 4 * out_b) + 2.0 * 16 * c * c)
     if name == "conv3x3_small_cin":
         n, h, w, cin, cout, oesz = meta
         return (f"small_cin_{cin}->{cout}@{h}x{w}", 2.0 * n * h * w * cin * cout * 9, n * h * w * (4.0 * cin + float(oesz) * cout))
@@ -185,11 +220,12 @@ def kernel_breakdown(model, x, passes: int):
         torch.cuda.synchronize()
         for name, meta, e0, e1 in ops.PROFILE:
             key, fl, by = classify(name, meta)
-            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})   # sums over launches
+            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0, "survey_bytes": 0.0})   # sums over launches
             a["ms"] += e0.elapsed_time(e1)
             a["launches"] += 1
             a["flops"] += fl
             a["bytes"] += by
+            a["survey_bytes"] += survey_bytes(name, meta)
         ops.PROFILE = None
     return agg
 
@@ -229,6 +265,10 @@ def run_b200(args) -> None:
     vae = b200.VAEModel.from_config(cfg)
     vae.load_state_dict(ref.state_dict(), strict=True)
     vae = vae.to(dev).eval()
+    if not args.fp32_stream:
+        # inference: the residual stream between blocks is kept in the 16-bit operand format too (SURVEY 8d counts 16-bit
+        # activations); the parity gate below runs with the same setting
+        vae.autoencoder.set_stream_dtype(torch.float16)
     # each rank owns its contiguous shard of the global batch (weak scaling: B images per GPU)
     x_global = aekl_ref.synthetic_images(B * world, S, S, seed=0)
     x_host = b200.parallel.shard_batch(x_global, rank, world).clone().pin_memory()
@@ -322,6 +362,10 @@ def run_b200(args) -> None:
             roof = {"bound": "hbm", "achieved": top["bytes"] / tot_s / 1e9, "peak": peak, "unit": "GB/s"}
             roof["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
         roof["frac"] = roof["achieved"] / roof["peak"]
+        # the same launches against SURVEY.md 8(d)'s per-kernel byte count (16-bit activations in and out, nothing else)
+        roof["survey_8d"] = {"bytes_per_launch": top["survey_bytes"] / top["launches"],
+                             "achieved_gbs": top["survey_bytes"] / tot_s / 1e9,
+                             "frac_of_hbm_peak": top["survey_bytes"] / tot_s / 1e9 / peaks.get("hbm_gbs", 6650.0)}
         # DRAM traffic per launch of that kernel class from the committed ncu --set full capture, if any
         traffic_file = ROOT / "profiles" / "traffic.json"
         roof["traffic"] = None
@@ -335,7 +379,8 @@ def run_b200(args) -> None:
         model_tflops = GFLOP_PER_IMG_A256 * (S / 256.0) ** 2 * 1e9 * value / world / 1e12 if S == 256 else None
         breakdown = {k: {"ms_per_step": v["ms"] / 2, "launches": v["launches"] // 2,
                          "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None,
-                         "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
+                         "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                         "survey_8d_gbs": v["survey_bytes"] / (v["ms"] * 1e-3) / 1e9}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
         # whole-step view: sum over launches of max(bytes / HBM peak, flops / tensor peak) against the measured step
         hbm_pk, tc_pk = peaks.get("hbm_gbs", 6650.0) * 1e9, peaks.get("bf16_tflops_sustained", 1400.0) * 1e12
@@ -344,7 +389,7 @@ def run_b200(args) -> None:
                          "algorithmic_gb_per_step": sum(a["bytes"] for a in agg.values()) / 2 / 1e9,
                          "algorithmic_tflop_per_step": sum(a["flops"] for a in agg.values()) / 2 / 1e12,
                          "note": "per-launch max(bytes/HBM peak, flops/tensor peak) summed over the step's launches "
-                                 "(this schedule's own traffic: fp32 residual stream, 16-bit operands) / measured step time"}
+                                 "(this schedule's own traffic) / measured step time"}
         out_dir = ROOT / "gpurun_out"
         out_dir.mkdir(exist_ok=True)
         (out_dir / "bench_breakdown.json").write_text(json.dumps({"eager_ms_per_step": tot_ms / 2, "classes": breakdown}, indent=1))
@@ -371,7 +416,8 @@ def run_b200(args) -> None:
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "vae_dente_no_adv.json AutoencoderKL forward (encode->sample->decode), 16-bit tensor-core "
                                    "kernels (fp16 operands: the bf16 operand format misses the 5e-3 z_mu tolerance, "
-                                   "measured 9e-3; fp32 accumulate + fp32 residual stream), "
+                                   "measured 9e-3; fp32 accumulate; residual stream "
+                                   + ("fp32" if args.fp32_stream else "fp16 = the operand format") + "), "
                                    f"batch {B} per GPU, 1x{S}x{S}",
                        "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "no flush needed: every layer's activations (>=268 MB at 256^2) exceed the 126 MB L2",
@@ -404,6 +450,8 @@ def main():
                          "KL + backward + gradient all-reduce + Adam, see tools/bench_train.py)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 64 infer / 8 train)")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--fp32-stream", action="store_true",
+                    help="keep the residual stream between blocks in fp32 (round-1 schedule) instead of fp16")
     ap.add_argument("--no-eager-baseline", action="store_true",
                     help="skip the stock-PyTorch-on-the-same-GPU arm (a subprocess after the timed runs, N = 1 only)")
     args = ap.parse_args()

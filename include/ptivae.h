@@ -188,6 +188,16 @@ int ptivae_spatial_mean(const float* x, float* out, int BC, int HW, void* stream
 int ptivae_ar_vae_loss(const float* zbar, const float* attrs, const int* channel, const float* delta, const int* pairs,
                        int P, int B, int C, int L, float* loss_per_attr, int* pair_count, float* total, void* stream);
 
+/* Gradient of compute_ar_vae_loss w.r.t. the latent vectors (the loss is a training regulariser: train_vae.py:407-415 adds
+ * ar_gamma * total to loss_g before loss_g.backward()).  pair_count: as written by ptivae_ar_vae_loss for the SAME inputs;
+ * g_total: device scalar dL/d(total) (NULL = 0);  g_attr: device [L] dL/d(loss_per_attr) (NULL = 0);
+ * dzbar: fp32 [B][C], overwritten (channels no attribute maps to get 0).  One thread per sample, fixed order. */
+int ptivae_ar_vae_loss_bwd(const float* zbar, const float* attrs, const int* channel, const float* delta, const int* pairs,
+                           int P, int B, int C, int L, const int* pair_count, const float* g_total, const float* g_attr,
+                           float* dzbar, void* stream);
+/* backward of ptivae_spatial_mean: dx [BC][HW] = dmean[BC] / HW */
+int ptivae_spatial_mean_bwd(const float* dmean, float* dx, int BC, int HW, void* stream);
+
 /* y [B][O] = act(x [B][I] * W[O][I]^T + b): nn.Linear (+activation) of LatentRegressor
  * (/root/reference/src/pti_ldm_vae/models/regression_head.py:30-78).  act: 0 none, 1 relu, 2 gelu, 3 leaky_relu, 4 elu. */
 int ptivae_linear_act(const float* x, const float* w, const float* bias, float* y, int B, int I, int O, int act,

@@ -49,6 +49,8 @@ SIGNATURES = {
     "ptivae_l1l2": [_c_void_p] * 4 + [_c_ll, _c_void_p],
     "ptivae_spatial_mean": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
     "ptivae_ar_vae_loss": [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p] * 4,
+    "ptivae_ar_vae_loss_bwd": [_c_void_p] * 5 + [_c_int] * 4 + [_c_void_p] * 5,
+    "ptivae_spatial_mean_bwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
     "ptivae_linear_act": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
     # backward pass
     "ptivae_wgrad": [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p],

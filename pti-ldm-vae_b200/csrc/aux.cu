@@ -79,6 +79,60 @@ __global__ void __launch_bounds__(256) ar_vae_loss_kernel(const float* __restric
   }
 }
 
+// Gradient of the AR-VAE loss w.r.t. the latent vectors: one thread per sample b, attributes and pairs walked in index
+// order (deterministic, no atomics).  For attribute l with cnt_l contributing pairs and upstream weight g_l
+//   d loss_l / d z[b][ch_l] = (2 * delta / cnt_l) * ( sum_{pairs (i, j=b)} (t-s)(1-t^2) - sum_{pairs (i=b, j)} (t-s)(1-t^2) ),
+//   t = tanh(delta * (z_j - z_i)), s = sign(a_j - a_i).
+__global__ void __launch_bounds__(128) ar_vae_loss_bwd_kernel(const float* __restrict__ zbar, const float* __restrict__ attrs,
+                                                              const int* __restrict__ channel, const float* __restrict__ delta,
+                                                              const int* __restrict__ pairs, int P, int B, int C, int L,
+                                                              const int* __restrict__ count, const float* __restrict__ g_total,
+                                                              const float* __restrict__ g_attr, float* __restrict__ dz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int c = 0; c < C; ++c) dz[static_cast<size_t>(b) * C + c] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const int cnt = count[l];
+    if (cnt == 0) continue;
+    const float gw = (g_total ? g_total[0] : 0.f) + (g_attr ? g_attr[l] : 0.f);
+    if (gw == 0.f) continue;
+    const int ch = channel[l];
+    const float d = delta[l];
+    const float* a = attrs + static_cast<size_t>(l) * B;
+    const float zb = zbar[static_cast<size_t>(b) * C + ch], ab = a[b];
+    float acc = 0.f;
+    auto term = [&](float zi, float zj, float ai, float aj) -> float {   // (t - s)(1 - t^2) of the ordered pair (i, j)
+      const float da = aj - ai;
+      if (da == 0.f) return 0.f;
+      const float t = tanhf(d * (zj - zi));
+      return (t - (da > 0.f ? 1.f : -1.f)) * (1.f - t * t);
+    };
+    if (pairs) {
+      for (int p = 0; p < P; ++p) {
+        const int i = pairs[2 * p], j = pairs[2 * p + 1];
+        if (j == b) acc += term(zbar[static_cast<size_t>(i) * C + ch], zb, a[i], ab);
+        if (i == b) acc -= term(zb, zbar[static_cast<size_t>(j) * C + ch], ab, a[j]);
+      }
+    } else {
+      for (int o = 0; o < B; ++o) {
+        if (o == b) continue;
+        const float zo = zbar[static_cast<size_t>(o) * C + ch], ao = a[o];
+        acc += term(zo, zb, ao, ab);      // pair (i = o, j = b)
+        acc -= term(zb, zo, ab, ao);      // pair (i = b, j = o)
+      }
+    }
+    dz[static_cast<size_t>(b) * C + ch] += gw * 2.f * d * acc / static_cast<float>(cnt);
+  }
+}
+
+// backward of spatial_mean: dx[bc][p] = dmean[bc] / HW
+__global__ void spatial_mean_bwd_kernel(const float* __restrict__ dmean, float* __restrict__ dx, long long total, int HW) {
+  const float inv = 1.f / static_cast<float>(HW);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dx[i] = dmean[i / HW] * inv;
+}
+
 __global__ void sum_small_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
   float s = 0.f;
   for (int i = 0; i < n; ++i) s += in[i];
@@ -135,6 +189,24 @@ extern "C" int ptivae_ar_vae_loss(const float* zbar, const float* attrs, const i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ar_vae_loss_kernel<<<L, 256, 0, stream>>>(zbar, attrs, channel, delta, pairs, P, B, C, loss_per_attr, pair_count);
   sum_small_kernel<<<1, 1, 0, stream>>>(loss_per_attr, total, L);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptivae_ar_vae_loss_bwd(const float* zbar, const float* attrs, const int* channel, const float* delta,
+                                      const int* pairs, int P, int B, int C, int L, const int* pair_count,
+                                      const float* g_total, const float* g_attr, float* dzbar, void* stream_) {
+  if (!zbar || !attrs || !channel || !delta || !pair_count || !dzbar || (!g_total && !g_attr) || B <= 0 || C <= 0 || L <= 0)
+    return PTIVAE_ERR_ARG;
+  if (pairs && P <= 0) return PTIVAE_ERR_ARG;
+  ar_vae_loss_bwd_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(zbar, attrs, channel, delta, pairs, P, B, C,
+                                                                                       L, pair_count, g_total, g_attr, dzbar);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptivae_spatial_mean_bwd(const float* dmean, float* dx, int BC, int HW, void* stream_) {
+  if (!dmean || !dx || BC <= 0 || HW <= 0) return PTIVAE_ERR_ARG;
+  const long long total = static_cast<long long>(BC) * HW;
+  spatial_mean_bwd_kernel<<<grid_for(static_cast<size_t>(total), 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(dmean, dx, total, HW);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -52,6 +52,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1   // (ptxas otherwise unrolls this loop ~60x at every call site: ~5 KB of instructions per wait)
   for (uint32_t it = 0; it < 4096u; ++it) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"

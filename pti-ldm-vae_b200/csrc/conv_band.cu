@@ -13,10 +13,17 @@
 //   * rows stream through a ring in shared memory: a CTA walks down a column of bands, every input row is TMA-loaded,
 //     normalised + SiLU'd in place and consumed by the (up to two) bands that need it exactly once -- no halo re-reads
 //     in y, one halo pixel per side in x.
-// Output / residual / statistics move exactly as in conv_tma2.cu: units of 128 pixels x 32 channels through swizzled slots,
-// TMA tensor stores, column sums in fixed order (deterministic).
-// Warp roles (736 threads): 0-7 epilogue (two teams, team t owns output rows dy = t, t+2), 8-19 transform, 20 MMA issuer
-// (+TMEM), 21 row loader, 22 weight loader.
+// Output: units of 128 pixels x 32 channels through swizzled slots and TMA tensor stores; the 16-bit residual line of a
+// pixel is read straight from global memory one band ahead; GroupNorm statistics are column sums of the stored values in
+// fixed order, finalised per band by an otherwise idle warp (deterministic, no atomics).
+// What bounds it (clock64 timelines of CTA 0, tools/prof_band.py): the MMAs of a band take ~1.8k cycles, but every warp of
+// the prologue / epilogue runs latency bound at ~0.12 IPC, and the SiLU of the 4 x 130 x Cin prologue elements costs two
+// SFU slots each (tanh is half rate: the tanh, the fp32 ex2+rcp and the packed half2 forms all measured the same) =
+// ~2.1k cycles per band at 16 SFU lanes per clock.  The prologue therefore runs in packed half2 (1.5 instructions per
+// element instead of 9) to leave the issue slots to the epilogue, and is still the longest stage.
+// Warp roles (864 threads): 0-15 epilogue (four teams of four warps, team = output row dy of the band), 16-23 transform,
+// 24 MMA issuer (+TMEM), 25 row loader, 26 weight loader, then the per-band statistics finalizer (so that no epilogue warp
+// waits on another team).
 #include "common.cuh"
 #include "ptivae_internal.h"
 
@@ -27,7 +34,7 @@ constexpr int kR = 4;                 // output rows per band
 constexpr int kMW = 128;              // pixels per M block
 constexpr int kLW = kMW + 2;          // input row segment incl. one halo pixel per side
 constexpr int COUT = 32;
-constexpr int NTEAM = 2, NEW = NTEAM * 4, NTW = 12, NT = NTW * 32;
+constexpr int NTEAM = 4, NEW = NTEAM * 4, NTW = 8, NT = NTW * 32;
 constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
 constexpr int kThreads = (NEW + NTW + 3) * 32;
 constexpr uint32_t kSmemMax = 232448;
@@ -39,11 +46,12 @@ struct Cfg {
   static_assert(RES == 0 || RES == 2, "no residual, or a 16-bit residual added in place");
   static constexpr uint32_t LB = CIN * 2;                      // operand line: one pixel's channels
   static constexpr uint32_t ROWB = r1k(kLW * LB);              // one ring slot
-  static constexpr int NR = CIN == 32 ? 16 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
+  static constexpr int NR = CIN == 32 ? 12 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
+  static constexpr int SLOTS = CIN == 32 ? 2 : 1;              // output slots per team (2: the store of band i drains under band i+1)
   static constexpr uint32_t BLK = COUT * LB;                   // one tap's weights [32 co][CIN]
   static constexpr uint32_t WBYTES = 12u * BLK;                // kx = 0: W2 W1 W0 0 0 0 | kx = 1: W2 W1 W0 | kx = 2: W2 W1 W0
   static constexpr uint32_t OSLOT = 128 * 64;                  // 128 pixels x 32 channels, 16-bit
-  static constexpr uint32_t SMEM = 1024 + NR * ROWB + WBYTES + NTEAM * 2 * OSLOT + 2 * NEW * COUT * 2 * 4 + COUT * 4 + 80 * 8 + 64;
+  static constexpr uint32_t SMEM = 1024 + NR * ROWB + WBYTES + NTEAM * SLOTS * OSLOT + 2 * NEW * COUT * 2 * 4 + COUT * 4 + 80 * 8 + 64;
   static_assert(SMEM <= kSmemMax, "shared memory budget");
 };
 
@@ -54,6 +62,7 @@ struct Args {
   int silu, gn_groups;
   const float* scale_shift;  // [N][CIN][2] or nullptr
   const float* bias;
+  const void* residual;      // 16-bit NHWC [N][H][W][32] or nullptr
   float* gn_part;            // [N][parts][groups][2]
   unsigned long long* trace; // debug timeline of CTA 0: [64 bands][32] band events, then [256 rows][4] row events; or nullptr
 };
@@ -67,22 +76,12 @@ struct Args {
     if (args.trace != nullptr && blockIdx.x == 0 && (row) < 256) args.trace[2048 + (row) * 4 + (slot)] = clock64(); \
   } while (0)
 
-// SiLU from HALF the pre-activation: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- one SFU op and one FMA per element (the
-// halving is folded into the GroupNorm scale/shift).  The kernel is bound by instruction issue, and the
-// __expf/__fdividef form costs 2 SFU ops + 9 other instructions per element (each carries a denormal-range rescale).
-// tanh.approx.f32 has a relative error of 2^-11: <= 2^-12 of the result for x >= 0, <= |x| * 2.4e-4 absolute for x < 0.
-__device__ __forceinline__ float silu_half(float h) {
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-
 __host__ __device__ constexpr uint32_t strip_off(int kx) { return kx == 0 ? 0u : (kx == 1 ? 6u : 9u); }   // in BLK units
 
 template <int CIN, int RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
+                    const __grid_constant__ CUtensorMap tmO, const Args args) {
   using C = Cfg<CIN, RES>;
   constexpr bool F16 = true;
   constexpr uint32_t LB = C::LB, ROWB = C::ROWB, BLK = C::BLK;
@@ -98,8 +97,8 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint8_t* smem = smem_raw + pad;
   uint8_t* ring = smem;                                     // [NR][ROWB]
   uint8_t* wts = ring + NR * ROWB;                          // [12][BLK]
-  uint8_t* slots = wts + C::WBYTES;                         // [NTEAM][2][OSLOT]
-  float* colsum = reinterpret_cast<float*>(slots + NTEAM * 2 * C::OSLOT);   // [2][NEW][COUT][2]
+  uint8_t* slots = wts + C::WBYTES;                         // [NTEAM][SLOTS][OSLOT]
+  float* colsum = reinterpret_cast<float*>(slots + NTEAM * C::SLOTS * C::OSLOT);   // [2][NEW][COUT][2]
   float* sbias = colsum + 2 * NEW * COUT * 2;               // [COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
   uint64_t* row_full = bars;            // [NR] raw row landed (TMA) or known to be out of the image
@@ -107,9 +106,10 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* row_free = bars + 32;       // [NR] every MMA that reads the row has retired
   uint64_t* acc_full = bars + 48;       // [2]
   uint64_t* acc_empty = bars + 50;      // [2]
-  uint64_t* res_full = bars + 52;       // [NTEAM][2]
-  uint64_t* w_full = bars + 56;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 58);
+  uint64_t* w_full = bars + 60;
+  uint64_t* st_full = bars + 61;        // [2] every epilogue warp has written its column sums of the band
+  uint64_t* st_free = bars + 63;        // [2] the finalizer has read them
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 66);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -117,7 +117,6 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmO);
-    if (RES != 0) tma_prefetch_desc(&tmR);
     for (int s = 0; s < NR; ++s) {
       mbar_init(&row_full[s], 1);
       mbar_init(&row_ready[s], NT);
@@ -127,8 +126,11 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], NEW * 32);
     }
-    for (int i = 0; i < NTEAM * 2; ++i) mbar_init(&res_full[i], 1);
     mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&st_full[i], NEW);
+      mbar_init(&st_free[i], 32);
+    }
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
@@ -169,6 +171,34 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx)
           tma_load_3d(wts + (strip_off(kx) + (2 - ky)) * BLK, &tmW, w_full, 0, 0, ky * 3 + kx);
+    }
+    __syncwarp();
+    // ---- statistics finalizer: per band, (sum, sum of squares) of every group over the 16 warps' column sums, in index
+    // order (deterministic), written as this tile's partial.  lane = (group, moment); groups beyond 16: second pass.
+    if (args.gn_groups > 0) {
+      const int cpg = COUT / args.gn_groups;
+      int it = 0;
+      for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
+        int n, cb, b0, b1;
+        seg_decode(s, n, cb, b0, b1);
+        for (int b = b0; b < b1; ++b, ++it) {
+          mbar_wait(&st_full[it & 1], (it >> 1) & 1);
+          const float* cb2 = colsum + (it & 1) * NEW * COUT * 2;
+          for (int e = lane; e < 2 * args.gn_groups; e += 32) {
+            const int gi = e >> 1, k = e & 1;
+            float tsum = 0.f;
+            for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+              float part = 0.f;
+#pragma unroll
+              for (int w8 = 0; w8 < NEW; ++w8) part += cb2[(w8 * COUT + c) * 2 + k];
+              tsum += part;
+            }
+            const int pidx = b * args.colblocks + cb;
+            args.gn_part[((static_cast<size_t>(n) * args.parts + pidx) * args.gn_groups + gi) * 2 + k] = tsum;
+          }
+          mbar_arrive(&st_free[it & 1]);
+        }
+      }
     }
   } else if (warp == W_IN) {
     // ------------------------------------------------------------------ input rows (TMA) into the ring
@@ -247,82 +277,82 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp >= W_TR0) {
     // ------------------------------------------------------------------ transform: normalise + SiLU rows in place
-    // A batch = the rows one band adds to the ring (the first batch of a segment: the two rows above its first band).
-    // The whole batch is processed with ONE proxy fence (the fence, not the arithmetic, dominated a row-at-a-time
-    // version: ~1k cycles per fence, measured with the clock64 timeline below).
+    // A batch = the rows one band adds to the ring (the first batch of a segment: the two rows above its first band), done
+    // with ONE proxy fence.  The kernel is bound by instruction issue, so the prologue runs in packed half2:
+    //   h = x * (scale/2) + shift/2 (HFMA2), t = tanh(h) (tanh.approx.f16x2), silu(2h) = h*t + h (HFMA2)
+    // = 1.5 instructions per element instead of 9 (fp32 unpack / affine / ex2 / rcp / pack); three fp16 roundings instead
+    // of one (measured against the fp32 reference in tests/test_gpu_kernels.py::test_conv3x3_fused_band).
+    // A thread owns fixed (pixel, 16-byte chunk) positions of a row: offsets and the x-range test are per segment.
     const int tt = threadIdx.x - W_TR0 * 32;
     const bool has_norm = args.scale_shift != nullptr;
     const bool do_silu = args.silu != 0;
-    constexpr int LS = NT / UPC;                 // stride between a thread's vectors, in pixels of the batch
-    constexpr int VB = 3;                        // vectors in flight per thread
+    constexpr int LS = NT / UPC;                      // pixel stride between a thread's vectors
+    constexpr int KV = (kLW + LS - 1) / LS;           // vectors per thread and row (the last one only for a few threads)
     const int u = tt % UPC, Lbase = tt / UPC;
     int g = 0;
     for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
       int n, cb, b0, b1;
       seg_decode(s, n, cb, b0, b1);
-      float4 sp[4];
+      uint32_t sc2[4], sh2[4];
       if (has_norm) {
         const float4* src = reinterpret_cast<const float4*>(args.scale_shift + (static_cast<size_t>(n) * CIN + u * 8) * 2);
+        const float f = do_silu ? 0.5f : 1.0f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          sp[e] = __ldg(src + e);
-          if (do_silu) { sp[e].x *= 0.5f; sp[e].y *= 0.5f; sp[e].z *= 0.5f; sp[e].w *= 0.5f; }   // see silu_half
+          const float4 v = __ldg(src + e);          // (scale, shift) of channels 2e, 2e+1
+          sc2[e] = pack2<F16>(v.x * f, v.z * f);
+          sh2[e] = pack2<F16>(v.y * f, v.w * f);
         }
       }
-      const int xbase = cb * kMW - 1;
+      uint32_t off[KV];
+      uint32_t st = 0;                              // per vector: bit k = exists, bit 8+k = inside the image in x
+#pragma unroll
+      for (int k = 0; k < KV; ++k) {
+        const int L = Lbase + k * LS;
+        const uint32_t sw = (CIN == 64) ? ((u ^ (L & 7)) << 4) : ((u ^ ((L >> 1) & 3)) << 4);
+        off[k] = L * LB + sw;
+        const int x = cb * kMW - 1 + L;
+        if (L < kLW) st |= 1u << k;
+        if (L < kLW && x >= 0 && x < args.W) st |= 256u << k;
+      }
       for (int bt = 0; bt <= b1 - b0; ++bt) {
         const int nrows = bt == 0 ? 2 : kR;
         const int ybase = kR * b0 - 1 + (bt == 0 ? 0 : 2 + kR * (bt - 1));   // image row of the batch's first row
         for (int r = 0; r < nrows; ++r) mbar_wait(&row_full[(g + r) % NR], ((g + r) / NR) & 1);
         if (tt == 0) ROW_TRACE(g, 1);
-        const int nq = nrows * kLW;
-#pragma unroll 1
-        for (int q0 = Lbase; q0 < nq; q0 += VB * LS) {
-          uint4 v[VB];
-          uint4* p[VB];
+#pragma unroll 2
+        for (int r = 0; r < nrows; ++r) {
+          uint8_t* rb = ring + ((g + r) % NR) * ROWB;
+          const int y = ybase + r;
+          const bool row_in = y >= 0 && y < args.H;
+          uint4 v[KV];
 #pragma unroll
-          for (int j = 0; j < VB; ++j) {
-            const int q = q0 + j * LS;
-            const int r = (q >= kLW) + (q >= 2 * kLW) + (q >= 3 * kLW);
-            const int L = q - r * kLW;
-            const uint32_t sw = (CIN == 64) ? ((u ^ (L & 7)) << 4) : ((u ^ ((L >> 1) & 3)) << 4);
-            p[j] = reinterpret_cast<uint4*>(ring + ((g + r) % NR) * ROWB + L * LB + sw);
-            const int x = xbase + L, y = ybase + r;
-            const bool inimg = y >= 0 && y < args.H && x >= 0 && x < args.W;
-            v[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (q >= nq) {
-              p[j] = nullptr;
-            } else if (!inimg) {          // zero padding is applied AFTER the normalisation: the pixel is just cleared
-              *p[j] = v[j];
-              p[j] = nullptr;
-            } else {
-              v[j] = *p[j];
-            }
+          for (int k = 0; k < KV; ++k) {
+            v[k] = make_uint4(0u, 0u, 0u, 0u);     // zero padding is applied AFTER the normalisation
+            if (row_in && (st & (256u << k))) v[k] = *reinterpret_cast<const uint4*>(rb + off[k]);
           }
 #pragma unroll
-          for (int j = 0; j < VB; ++j) {
-            if (p[j] == nullptr) continue;
-            uint4 o = v[j];
-            if (has_norm) {
-              float f[8];
-              unpack2<F16>(v[j].x, f[0], f[1]); unpack2<F16>(v[j].y, f[2], f[3]);
-              unpack2<F16>(v[j].z, f[4], f[5]); unpack2<F16>(v[j].w, f[6], f[7]);
+          for (int k = 0; k < KV; ++k) {
+            if (!(st & (1u << k))) continue;
+            if (has_norm && row_in && (st & (256u << k))) {
+              uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float a = fmaf(f[2 * e], sp[e].x, sp[e].y);
-                float c = fmaf(f[2 * e + 1], sp[e].z, sp[e].w);
+                uint32_t h;
+                asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(w[e]), "r"(sc2[e]), "r"(sh2[e]));
                 if (do_silu) {
-                  a = silu_half(a);
-                  c = silu_half(c);
+                  uint32_t t;
+                  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+                  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h) : "r"(h), "r"(t));
                 }
-                f[2 * e] = a;
-                f[2 * e + 1] = c;
+                w[e] = h;
               }
-              o = make_uint4(pack2<F16>(f[0], f[1]), pack2<F16>(f[2], f[3]), pack2<F16>(f[4], f[5]), pack2<F16>(f[6], f[7]));
+              v[k] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *p[j] = o;
+            *reinterpret_cast<uint4*>(rb + off[k]) = v[k];
           }
         }
+        if (tt == 0) ROW_TRACE(g, 3);
         fence_proxy_async_smem();
         for (int r = 0; r < nrows; ++r) mbar_arrive(&row_ready[(g + r) % NR]);
         if (tt == 0) ROW_TRACE(g, 2);
@@ -330,38 +360,38 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue teams (team t: output rows dy = t, t + 2)
-    // Per band a team drains its two units into its two slots, then ONE proxy fence, two TMA stores, and the statistics of
-    // both units; the residuals of the team's next band are already in flight (they land in the slots, added in place).
+    // ------------------------------------------------------------------ epilogue teams (team = output row dy of the band)
+    // Per band: TMEM -> +bias (+ the 16-bit residual that TMA put into the slot) -> 16-bit swizzled slot -> one proxy fence
+    // -> one TMA store; then the column sums of the stored values (this warp's own 32 rows) go to the finalizer warp.
     const int team = warp >> 2, ew = warp & 3;      // ew == TMEM lane quarter
     const int m = ew * 32 + lane;                   // accumulator row = pixel x0 + m of the output row
     const bool leader = (ew == 0 && lane == 0);
-    const int cpg = args.gn_groups > 0 ? COUT / args.gn_groups : 0;
+    const bool want_stats = args.gn_groups > 0;
     const int bar_id = 1 + team;
-    uint8_t* tslots = slots + team * 2 * C::OSLOT;
-    uint64_t* rfull = res_full + team * 2;
-    // residuals of the team's next band (leader only); the cursor walks the CTA's segments band by band
-    int rs_seg = blockIdx.x, rs_b = -1;
-    auto issue_res = [&]() {
+    constexpr int SLOTS = C::SLOTS;
+    uint8_t* tslots = slots + team * SLOTS * C::OSLOT;
+    // 16-bit residual line of this thread's pixel (32 channels = 64 B), read straight from global memory ONE BAND AHEAD
+    // (the loads are issued after the band's slot is written and land under its store / statistics / the next TMEM wait)
+    uint4 rnext[4] = {};
+    auto load_res = [&](int n, int cb, int b) {
       if constexpr (RES != 0) {
-        if (rs_seg >= args.num_segs) return;
-        int n, cb, b0, b1;
-        seg_decode(rs_seg, n, cb, b0, b1);
-        if (rs_b < 0) rs_b = b0;
+        const int y = kR * b + team, x = cb * kMW + m;
+        if (y < args.H && x < args.W) {
+          const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(args.residual) +
+                                                            ((static_cast<size_t>(n) * args.H + y) * args.W + x) * (COUT * 2));
 #pragma unroll
-        for (int uu = 0; uu < 2; ++uu) {
-          const int y = kR * rs_b + team + 2 * uu;
-          if (y < args.H) {
-            mbar_expect_tx(&rfull[uu], 128 * 64);
-            tma_load_4d(tslots + uu * C::OSLOT, &tmR, &rfull[uu], 0, cb * kMW, y, n);
-          } else {
-            mbar_arrive(&rfull[uu]);    // row below the image: nothing to load (nothing is stored either)
-          }
+          for (int j = 0; j < 4; ++j) rnext[j] = __ldg(src + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (++rs_b == b1) { rs_seg += gridDim.x; rs_b = -1; }
       }
     };
-    if (leader) issue_res();
+    if (static_cast<int>(blockIdx.x) < args.num_segs) {
+      int n, cb, b0, b1;
+      seg_decode(blockIdx.x, n, cb, b0, b1);
+      load_res(n, cb, b0);
+    }
     int it = 0;
     for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
       int n, cb, b0, b1;
@@ -369,89 +399,77 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int x0 = cb * kMW;
       for (int b = b0; b < b1; ++b, ++it) {
         const int st = it & 1;
+        const int sl = it & (SLOTS - 1);
+        const int y = kR * b + team;
+        uint8_t* oslot = tslots + sl * C::OSLOT;
         if (threadIdx.x == 0) BAND_TRACE(it, 8);
         mbar_wait(&acc_full[st], (it >> 1) & 1);
         tc_fence_after();
         if (threadIdx.x == 0) BAND_TRACE(it, 9);
-#pragma unroll 1
-        for (int uu = 0; uu < 2; ++uu) {
-          const int dy = team + 2 * uu;
-          uint8_t* oslot = tslots + uu * C::OSLOT;
-          uint32_t acc[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * (kR * COUT) + dy * COUT, acc);
-          tmem_ld_wait();
-          if (uu == 1) {                                // all of this band's columns of the team are in registers
-            tc_fence_before();
-            mbar_arrive(&acc_empty[st]);
-          }
-          if (threadIdx.x == 0) BAND_TRACE(it, 10 + 3 * uu);
-          if constexpr (RES != 0) mbar_wait(&rfull[uu], it & 1);
-          else if (uu == 0) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // slots free: the leader saw the last band's stores drained
-          if (threadIdx.x == 0) BAND_TRACE(it, 11 + 3 * uu);
-          {
-            uint8_t* ol = oslot + m * 64;
-            uint4 r16[4] = {};
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * (kR * COUT) + team * COUT, acc);
+        if (leader) {   // the slot's previous store has drained it
+          if constexpr (SLOTS == 2) tma_store_wait_read1(); else tma_store_wait_read();
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[st]);
+        if (threadIdx.x == 0) BAND_TRACE(it, 10);
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // slot free (and every reader of its last contents is past)
+        if (threadIdx.x == 0) BAND_TRACE(it, 11);
+        {
+          uint8_t* ol = oslot + m * 64;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = reinterpret_cast<const float4*>(sbias)[j];   // broadcast
+            float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
+            float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
             if constexpr (RES == 2) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) r16[j] = *reinterpret_cast<const uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4));
+              float r0, r1, r2, r3;
+              unpack2<F16>((j & 1) ? rnext[j >> 1].z : rnext[j >> 1].x, r0, r1);
+              unpack2<F16>((j & 1) ? rnext[j >> 1].w : rnext[j >> 1].y, r2, r3);
+              v0 += r0; v1 += r1; v2 += r2; v3 += r3;
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = reinterpret_cast<const float4*>(sbias)[j];   // broadcast
-              float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
-              float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
-              if constexpr (RES == 2) {
-                float r0, r1, r2, r3;
-                unpack2<F16>((j & 1) ? r16[j >> 1].z : r16[j >> 1].x, r0, r1);
-                unpack2<F16>((j & 1) ? r16[j >> 1].w : r16[j >> 1].y, r2, r3);
-                v0 += r0; v1 += r1; v2 += r2; v3 += r3;
-              }
-              acc[4 * j + 0] = pack2<F16>(v0, v1);
-              acc[4 * j + 1] = pack2<F16>(v2, v3);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4)) =
-                  make_uint4(acc[8 * j + 0], acc[8 * j + 1], acc[8 * j + 4], acc[8 * j + 5]);
+            acc[4 * j + 0] = pack2<F16>(v0, v1);
+            acc[4 * j + 1] = pack2<F16>(v2, v3);
           }
-          if (threadIdx.x == 0) BAND_TRACE(it, 12 + 3 * uu);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4)) =
+                make_uint4(acc[8 * j + 0], acc[8 * j + 1], acc[8 * j + 4], acc[8 * j + 5]);
+        }
+        if (threadIdx.x == 0) BAND_TRACE(it, 12);
+        {   // next band of this CTA: its residual line starts its trip now
+          if (b + 1 < b1) {
+            load_res(n, cb, b + 1);
+          } else if (s + static_cast<int>(gridDim.x) < args.num_segs) {
+            int n2, cb2, b02, b12;
+            seg_decode(s + gridDim.x, n2, cb2, b02, b12);
+            load_res(n2, cb2, b02);
+          }
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // both units written by all four warps
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // the unit is written by all four warps
         if (leader) {
-#pragma unroll
-          for (int uu = 0; uu < 2; ++uu) {
-            const int y = kR * b + team + 2 * uu;
-            if (y < args.H) tma_store_4d(&tmO, tslots + uu * C::OSLOT, 0, x0, y, n);
-          }
+          if (y < args.H) tma_store_4d(&tmO, oslot, 0, x0, y, n);
           tma_store_commit();
         }
         if (threadIdx.x == 0) BAND_TRACE(it, 16);
-        // column sums of the stored values over this warp's own 32 rows of both units (lane = (row sub-index, 16-byte chunk))
-        const int rsub = lane >> 2, j4 = lane & 3;
-        uint4 w[8];
-        if (cpg > 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = ew * 32 + (i & 3) * 8 + rsub;
-            const bool ok = (x0 + r < args.W) && (kR * b + team + 2 * (i >> 2) < args.H);
-            w[i] = ok ? *reinterpret_cast<const uint4*>(tslots + (i >> 2) * C::OSLOT + r * 64 + ((j4 ^ ((r >> 1) & 3)) << 4))
-                      : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        if (threadIdx.x == 0) BAND_TRACE(it, 18);
-        if constexpr (RES != 0) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // every statistics read of the slots is done
-        if (leader) {
-          tma_store_wait_read();          // the stores have drained the slots ...
-          issue_res();                    // ... which now receive the next band's residuals
-        }
-        if (threadIdx.x == 0) BAND_TRACE(it, 19);
-        if (cpg > 0) {
+        if (want_stats) {
+          // column sums of the stored values over this warp's own 32 rows (lane = (row sub-index, 16-byte chunk))
+          const int rsub = lane >> 2, j4 = lane & 3;
           float s1[8], s2[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+          uint4 w[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
+            const int r = ew * 32 + i * 8 + rsub;
+            const bool ok = (x0 + r < args.W) && (y < args.H);
+            w[i] = ok ? *reinterpret_cast<const uint4*>(oslot + r * 64 + ((j4 ^ ((r >> 1) & 3)) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
             float x[8];
             unpack2<F16>(w[i].x, x[0], x[1]); unpack2<F16>(w[i].y, x[2], x[3]);
             unpack2<F16>(w[i].z, x[4], x[5]); unpack2<F16>(w[i].w, x[6], x[7]);
@@ -469,7 +487,8 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
             }
           }
-          float* cs = colsum + ((it & 1) * NEW + warp) * COUT * 2;      // double buffered: one CTA-wide barrier per band
+          if (it >= 2) mbar_wait(&st_free[it & 1], ((it >> 1) - 1) & 1);    // the finalizer has read band it-2's sums
+          float* cs = colsum + ((it & 1) * NEW + warp) * COUT * 2;
           if (rsub == 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -477,20 +496,8 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               cs[(j4 * 8 + k) * 2 + 1] = s2[k];
             }
           }
-          if (threadIdx.x == 0) BAND_TRACE(it, 20);
-          asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
-          if (threadIdx.x == 0) BAND_TRACE(it, 21);
-          const int ei = threadIdx.x;                 // epilogue warps are warps 0 .. NEW-1
-          if (ei < 2 * args.gn_groups) {
-            const int gi = ei >> 1, k = ei & 1;
-            const float* cb2 = colsum + (it & 1) * NEW * COUT * 2;
-            float tsum = 0.f;
-            for (int c = gi * cpg; c < (gi + 1) * cpg; ++c)
-#pragma unroll
-              for (int w8 = 0; w8 < NEW; ++w8) tsum += cb2[(w8 * COUT + c) * 2 + k];
-            const int pidx = b * args.colblocks + cb;
-            args.gn_part[((static_cast<size_t>(n) * args.parts + pidx) * args.gn_groups + gi) * 2 + k] = tsum;
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_full[it & 1]);
         }
         if (threadIdx.x == 0) BAND_TRACE(it, 17);
       }
@@ -531,8 +538,9 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
   a.num_segs = c.N * a.colblocks * a.segs_per_col;
   a.silu = c.silu; a.gn_groups = c.gn_groups; a.scale_shift = c.scale_shift; a.bias = c.bias; a.gn_part = c.gn_part;
   a.trace = c.trace;
+  a.residual = c.residual;
 
-  CUtensorMap tmX, tmW, tmR, tmO;
+  CUtensorMap tmX, tmW, tmO;
   const uint64_t H = c.H, W = c.W, N = c.N;
   {  // input row segment: dims (C, W, H, N), box (CIN, 130, 1, 1), swizzle = line bytes (the K-major UMMA operand layout)
     uint64_t d[4] = {uint64_t(CIN), W, H, N};
@@ -554,17 +562,11 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     uint32_t b[4] = {32, kMW, 1, 1};
     int rc = encode_tmap(&tmO, c.out, 1, 4, d, s, b, 64);
     if (rc) return rc;
-    if (RES != 0) {
-      rc = encode_tmap(&tmR, c.residual, 1, 4, d, s, b, 64);
-      if (rc) return rc;
-    } else {
-      tmR = tmO;
-    }
   }
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(conv3x3_band_kernel<CIN, RES>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
   const int grid = a.num_segs < sms ? a.num_segs : sms;
-  conv3x3_band_kernel<CIN, RES><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, a);
+  conv3x3_band_kernel<CIN, RES><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmO, a);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -41,6 +41,42 @@ class _L1L2Fn(torch.autograd.Function):
         return (d if ctx.needs_input_grad[0] else None), (-d if ctx.needs_input_grad[1] else None)
 
 
+class _SpatialMeanFn(torch.autograd.Function):
+    """latent_vectors = z_mu.mean((2, 3)) with its (broadcast) gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return ops.spatial_mean(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.spatial_mean_bwd(g, ctx.shape)
+
+
+class _ARFn(torch.autograd.Function):
+    """All attributes of the AR-VAE loss in one kernel, differentiable w.r.t. the latent vectors [B, C].
+    Returns (total [scalar], per-attribute losses [L], pair counts int32 [L])."""
+
+    @staticmethod
+    def forward(ctx, zbar, attrs, ch, dl, pairs):
+        z = zbar.detach().contiguous().float()
+        loss, cnt, tot = ops.ar_vae_loss(z, attrs, ch, dl, pairs)
+        ctx.save_for_backward(z, attrs, ch, dl, cnt)
+        ctx.pairs = pairs
+        ctx.mark_non_differentiable(cnt)
+        return tot[0], loss, cnt
+
+    @staticmethod
+    def backward(ctx, g_total, g_attr, _g_cnt):
+        z, attrs, ch, dl, cnt = ctx.saved_tensors
+        gt = None if g_total is None else g_total.detach().reshape(1).float().contiguous()
+        ga = None if g_attr is None else g_attr.detach().float().contiguous()
+        if gt is None and ga is None:
+            return None, None, None, None, None
+        return ops.ar_vae_loss_bwd(z, attrs, ch, dl, ctx.pairs, cnt, gt, ga), None, None, None, None
+
+
 def _wants_grad(*ts) -> bool:
     return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
 
@@ -84,11 +120,12 @@ def compute_ar_vae_loss(latent_vectors: torch.Tensor, attributes: dict, attribut
     All attributes are evaluated by ONE kernel (no host pair lists in "all" mode, one device->host read for the
     pair counts instead of two syncs per attribute).  "subset" mode samples pairs on the host with
     ``random.sample`` exactly like the reference, so a seeded ``random`` gives the same pairs."""
+    grad = _wants_grad(latent_vectors)      # the loss is a training regulariser (train_vae.py:407-415): keep the graph
     if latent_vectors.dim() == 4:
-        latent_vectors = ops.spatial_mean(latent_vectors)
+        latent_vectors = _SpatialMeanFn.apply(latent_vectors.contiguous().float()) if grad else ops.spatial_mean(latent_vectors)
     elif latent_vectors.dim() != 2:
         raise ValueError(f"Expected latent shape [B, C] or [B, C, H, W], got {latent_vectors.shape}")
-    latent_vectors = latent_vectors.detach().contiguous().float()
+    latent_vectors = latent_vectors.contiguous().float() if grad else latent_vectors.detach().contiguous().float()
     batch_size, latent_dim = latent_vectors.shape
     if pairwise_mode not in {"all", "subset"}:
         raise ValueError(f"pairwise must be 'all' or 'subset', got {pairwise_mode}")
@@ -121,10 +158,8 @@ def compute_ar_vae_loss(latent_vectors: torch.Tensor, attributes: dict, attribut
     ch = torch.tensor(chans, device=dev, dtype=torch.int32)
     dl = torch.tensor(deltas, device=dev, dtype=torch.float32)
     if pairwise_mode == "all":
-        loss, cnt, tot = ops.ar_vae_loss(latent_vectors, attrs, ch, dl, None)
+        total, per, cnt = _ARFn.apply(latent_vectors, attrs, ch, dl, None)
         cnt_h = cnt.tolist()
-        total = tot[0]
-        per = loss
     else:
         import random
         all_pairs = [(i, j) for i in range(batch_size) for j in range(batch_size) if i != j]
@@ -132,8 +167,8 @@ def compute_ar_vae_loss(latent_vectors: torch.Tensor, attributes: dict, attribut
         for k in range(len(names)):           # the reference draws a fresh sample per attribute, in mapping order
             pairs = random.sample(all_pairs, min(len(all_pairs), int(subset_pairs)))
             pt = torch.tensor(pairs, device=dev, dtype=torch.int32).contiguous()
-            l1, c1, _ = ops.ar_vae_loss(latent_vectors, attrs[k:k + 1].contiguous(), ch[k:k + 1].contiguous(),
-                                        dl[k:k + 1].contiguous(), pt)
+            _, l1, c1 = _ARFn.apply(latent_vectors, attrs[k:k + 1].contiguous(), ch[k:k + 1].contiguous(),
+                                    dl[k:k + 1].contiguous(), pt)
             per_list.append(l1[0])
             cnt_h.append(int(c1[0]))
         per = torch.stack(per_list)

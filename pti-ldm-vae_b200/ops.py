@@ -402,6 +402,27 @@ def ar_vae_loss(zbar: torch.Tensor, attrs: torch.Tensor, channel: torch.Tensor, 
     return loss, cnt, tot
 
 
+def ar_vae_loss_bwd(zbar, attrs, channel, delta, pairs, count, g_total=None, g_attr=None) -> torch.Tensor:
+    """Gradient of ar_vae_loss w.r.t. zbar [B,C]; g_total: device scalar dL/d(total), g_attr: [L] dL/d(per-attribute loss)."""
+    _need_cuda(zbar, attrs, channel, delta, count)
+    b, c = zbar.shape
+    l = attrs.shape[0]
+    dz = torch.empty((b, c), device=zbar.device, dtype=torch.float32)
+    _call("ar_vae_loss_bwd", None, 1, _lib.lib().ptivae_ar_vae_loss_bwd, _p(zbar), _p(attrs), _p(channel), _p(delta), _p(pairs),
+          0 if pairs is None else pairs.shape[0], b, c, l, _p(count), _p(g_total), _p(g_attr), _p(dz), _stream())
+    return dz
+
+
+def spatial_mean_bwd(dmean: torch.Tensor, shape) -> torch.Tensor:
+    """[B,C] gradient of spatial_mean -> [B,C,H,W] (each pixel gets dmean / (H*W))."""
+    _need_cuda(dmean)
+    dmean = dmean.detach().contiguous().float()
+    dx = torch.empty(tuple(shape), device=dmean.device, dtype=torch.float32)
+    b, c = shape[0], shape[1]
+    _call("spatial_mean_bwd", None, 1, _lib.lib().ptivae_spatial_mean_bwd, _p(dmean), _p(dx), b * c, dx.numel() // (b * c), _stream())
+    return dx
+
+
 _ACTS = {None: 0, "none": 0, "relu": 1, "gelu": 2, "leaky_relu": 3, "elu": 4}
 
 

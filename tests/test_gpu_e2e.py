@@ -165,6 +165,35 @@ def test_ar_vae_loss_matches_reference_golden(b200, oracle):
     assert float(t0) == 0.0 and c0["a0"] == 0
 
 
+def test_ar_vae_loss_gradient_matches_oracle_autograd(b200, oracle):
+    """The AR-VAE loss is a training regulariser (train_vae.py:407-415 adds ar_gamma * total to loss_g): its gradient
+    w.r.t. the latents, through the device kernels, vs autograd through the oracle's restatement of losses.py:69-166
+    (fp32 CPU).  "all" and seeded "subset" pairs, [B, C] and [B, C, H, W] latents, total and a per-attribute loss."""
+    import random
+    gen = torch.Generator().manual_seed(3)
+    attrs = {"a0": torch.randint(20, 200, (12,), generator=gen).float(), "a1": torch.randint(20, 24, (12,), generator=gen).float(),
+             "a2": torch.randint(20, 200, (12,), generator=gen).float()}
+    for shape, mode, npairs in (((12, 10), "all", None), ((12, 10), "subset", 40), ((12, 10, 4, 4), "all", None)):
+        z_cpu = torch.randn(shape, generator=gen).requires_grad_(True)
+        z_gpu = z_cpu.detach().to(DEV).requires_grad_(True)
+        random.seed(11)
+        tot_r, per_r, _, _ = oracle.ar_vae_loss_ref(z_cpu, attrs, AR_MAPPING, mode, npairs, AR_DG)
+        (tot_r + 0.5 * per_r["a2"]).backward()
+        random.seed(11)
+        tot, per, cnt, _ = b200.compute_ar_vae_loss(z_gpu, attrs, AR_MAPPING, mode, npairs, AR_DG)
+        assert tot.requires_grad and per["a2"].requires_grad
+        (tot + 0.5 * per["a2"]).backward()
+        assert abs(float(tot) - float(tot_r)) <= TOL_LOSS * float(tot_r)
+        g, gr = z_gpu.grad.cpu(), z_cpu.grad
+        assert g.shape == gr.shape
+        assert float((g - gr).abs().max()) <= 1e-5 + 1e-4 * float(gr.abs().max()), (shape, mode)
+        untouched = [c for c in range(10) if c not in (0, 4, 9)]
+        assert float(g[:, untouched].abs().max()) == 0.0
+    # no gradient requested: plain tensors, no graph
+    tot, _, _, _ = b200.compute_ar_vae_loss(z_gpu.detach(), attrs, AR_MAPPING, "all", None, AR_DG)
+    assert not tot.requires_grad
+
+
 def test_regressor_matches_reference_golden(b200, oracle):
     """LatentRegressor (row a18) vs outputs of the reference's own class; encode -> flatten -> head end to end vs the oracle."""
     g = np.load(GOLD / "regressor_ref.npz")

@@ -34,4 +34,4 @@ if len(sys.argv) > 4:
         print(f"{i:3d} " + " ".join(f"{int(bt[i, k]) - t0:8d}" for k in range(22)))
     print("row: loader_issue  xf_start  xf_done")
     for g in range(0, 60):
-        print(f"{g:3d} " + " ".join(f"{(int(rt[g, k]) - t0) if int(rt[g, k]) else -1:8d}" for k in range(3)))
+        print(f"{g:3d} " + " ".join(f"{(int(rt[g, k]) - t0) if int(rt[g, k]) else -1:8d}" for k in range(4)))
