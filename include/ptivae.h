@@ -131,6 +131,16 @@ int ptivae_gn_finalize(const float* partial, const float* gamma, const float* be
                        float* mean_rstd, int N, int HW, int C, int G, int P, float eps, void* stream);
 int ptivae_gn_apply(const void* x, const float* scale_shift, void* y, void* raw16, int N, int HW, int C, int silu,
                     int in_fmt, int out_f16, void* stream);
+/* fp16 RANGE CHECK.  Everything stored in the fp16 operand format is clamped to +-65504 (cvt.rn.satfinite); the reference
+ * computes in fp32, so a clamped activation would be a silent parity error.  Every tensor that is stored in 16 bits carries
+ * statistics partials (sum, sum of squares per tile and group); a clamped element puts >= 65504^2 into its tile's sum of
+ * squares, so "no partial reaches 65504^2" PROVES that nothing was clamped (the converse flags magnitudes within a factor
+ * sqrt(tile elements) of the limit -- a warning worth having).  gn_finalize_checked = gn_finalize that also sets
+ * range_flag[0] = 1 (device int, never cleared by the library) when a partial trips; range_check does the same for the
+ * partials of a tensor that no GroupNorm consumes (pairs = N*P*G).  AutoencoderKL.check_range(x) drives both. */
+int ptivae_gn_finalize_checked(const float* partial, const float* gamma, const float* beta, float* scale_shift,
+                               float* mean_rstd, int N, int HW, int C, int G, int P, float eps, int* range_flag, void* stream);
+int ptivae_range_check(const float* partial, long long pairs, int* range_flag, void* stream);
 
 /* Thin-end 3x3 s1 p1 convolutions on CUDA cores.
  *   small_cin : x fp32 NCHW [N][Cin<=16][H][W], w fp32 [Cout][Cin][3][3] -> out NHWC (storage out_fmt)

@@ -38,6 +38,8 @@ SIGNATURES = {
     "ptivae_gn_stats_parts": [_c_int] * 3,
     "ptivae_gn_finalize": [_c_void_p] * 5 + [_c_int] * 5 + [_c_float, _c_void_p],
     "ptivae_gn_apply": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
+    "ptivae_gn_finalize_checked": [_c_void_p] * 5 + [_c_int] * 5 + [_c_float, _c_void_p, _c_void_p],
+    "ptivae_range_check": [_c_void_p, _c_ll, _c_void_p, _c_void_p],
     "ptivae_conv3x3_small_cin": [_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p],
     "ptivae_conv3x3_small_cin_parts": [_c_int] * 3,
     "ptivae_conv3x3_small_cout": [_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p],

@@ -154,6 +154,9 @@ class _Executor:
         # Every block output is then rounded once more (fp16: +0.9e-3 rel-L2 at z_mu, +1.8e-3 at recon over configs A/B,
         # measured with the oracle) and the stream traffic halves; training keeps the fp32 stream.
         self.stream16 = False
+        # fp16 range check (AutoencoderKL.check_range): int32 [1] device flag handed to every gn_finalize; while it is set,
+        # tensors that feed no GroupNorm get statistics too, and their partials are scanned (ops.range_check)
+        self.range_flag = None
         self._packed: dict = {}
         # how each cached pack is produced: key -> list of (src fp32 weight, dst 16-bit tensor, dst element offset,
         # st_r, pack mode); and derived fp32 tensors (bias sums, mirrored thin weights): key -> refresh closure.
@@ -250,7 +253,8 @@ class _Executor:
     def scale_shift(self, a: _Act, norm: nn.GroupNorm) -> torch.Tensor:
         part = a.part if a.part is not None else ops.gn_stats(a.t, norm.num_groups)
         n, c = a.t.shape[0], a.t.shape[-1]
-        return ops.gn_finalize(part, self.f32(norm.weight), self.f32(norm.bias), a.t.numel() // (n * c), norm.eps)
+        return ops.gn_finalize(part, self.f32(norm.weight), self.f32(norm.bias), a.t.numel() // (n * c), norm.eps,
+                               range_flag=self.range_flag)
 
     def resblock(self, blk: AEKLResBlock, a: _Act, out_f32: bool, stats: bool) -> _Act:
         sc = a.t
@@ -309,10 +313,11 @@ class _Executor:
             nxt_operand = operand_only(i + 1)
             # the last body tensor is read only by the final norm + conv: 16-bit storage (statistics still needed)
             to_stream = not (nxt_operand or i + 1 == len(body))
+            checking = self.range_flag is not None
             if isinstance(blk, AEKLResBlock):
-                a = self.resblock(blk, a, out_f32=to_stream, stats=not nxt_operand)
+                a = self.resblock(blk, a, out_f32=to_stream, stats=(not nxt_operand) or checking)
             elif isinstance(blk, SpatialAttentionBlock):
-                a = self.attention(blk, a, out_f32=to_stream, stats=not nxt_operand)
+                a = self.attention(blk, a, out_f32=to_stream, stats=(not nxt_operand) or checking)
             elif isinstance(blk, (AEKLDownsample, UpSample)):
                 xin = a.t
                 assert xin.dtype == self.op_dtype, "scheduler bug: down/up-sample operand must be 16-bit"
@@ -321,6 +326,8 @@ class _Executor:
                               stats=not nxt_operand, emit16=(not nxt_operand) and needs_raw16(i + 1))
             else:  # pragma: no cover
                 raise TypeError(f"unexpected block {type(blk)}")
+            if checking and nxt_operand:      # no GroupNorm will read this tensor's statistics: scan them here
+                ops.range_check(a.part if a.part is not None else ops.gn_stats(a.t, self.groups), self.range_flag)
         ss = self.scale_shift(a, last_norm)
         return ops.conv3x3_small_cout(a.t, self.f32(last.conv.weight), self.f32(last.conv.bias), ss)
 
@@ -436,8 +443,8 @@ class AutoencoderKL(nn.Module):
         """Storage format of the residual stream (block outputs) for INFERENCE: torch.float32 (default; reference
         precision between blocks) or the 16-bit operand format (torch.float16): half the stream traffic, one extra
         rounding per block -- measured against the fp32 oracle: z_mu rel-L2 1.3e-3 -> ~1.7e-3, recon 2.1e-3 -> ~2.8e-3
-        (gates 5e-3 / 1e-2).  fp16 clamps at +-65504: `stream_overflow()` reports whether any stored value reached the
-        clamp.  Training always runs the fp32 stream."""
+        (gates 5e-3 / 1e-2).  fp16 clamps at +-65504: `check_range(x)` proves for a given input that no stored value
+        reached the clamp.  Training always runs the fp32 stream."""
         if dtype == torch.float32:
             self._exec.stream16 = False
         elif dtype == torch.float16:
@@ -447,6 +454,26 @@ class AutoencoderKL(nn.Module):
             self._exec.stream16 = True
         else:
             raise ValueError("stream dtype must be torch.float32 or torch.float16")
+
+    @torch.no_grad()
+    def check_range(self, x: torch.Tensor) -> bool:
+        """fp16 range check of one (eager) deterministic encode -> decode pass over ``x``: True when no 16-bit tensor on
+        the path can have reached the fp16 clamp at +-65504 (the kernels store with ``cvt.rn.satfinite``; the fp32
+        reference would simply carry the larger value).  The proof rides on the GroupNorm statistics every stored
+        tensor has anyway: a clamped element contributes 65504^2 to its tile's sum of squares, so a pass in which no
+        partial reaches that value clamped nothing (include/ptivae.h, "fp16 RANGE CHECK").  On False, run the model with
+        ``set_stream_dtype(torch.float32)`` and ``set_operand_dtype(torch.bfloat16)`` (8-bit significand operands, fp32
+        range; looser tolerances) or rescale the checkpoint."""
+        ex = self._exec
+        with self._dev():
+            flag = torch.zeros(1, device=next(self.parameters()).device, dtype=torch.int32)
+            ex.range_flag = flag
+            try:
+                mu, _ = self._encode(x)
+                self._decode(mu)
+            finally:
+                ex.range_flag = None
+            return int(flag.item()) == 0
 
     def set_fused_conv(self, enabled: bool) -> None:
         """ResBlock convs as one fused kernel (default) vs. gn_apply + conv_umma."""

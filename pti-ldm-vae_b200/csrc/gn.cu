@@ -10,6 +10,7 @@
 // The same partial format [N][P][G][2] is produced by conv_umma's epilogue.
 #include "common.cuh"
 #include "ptivae_internal.h"
+#include "../../include/ptivae.h"
 
 namespace ptivae {
 
@@ -87,6 +88,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
   }
 }
 
+constexpr float kFp16MaxSq = 65504.0f * 65504.0f;
+
+// range check of tensors that feed no GroupNorm: scan the sum-of-squares entries of their statistics partials
+__global__ void range_check_kernel(const float2* __restrict__ partial, long long n, int* __restrict__ flag) {
+  bool over = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    over |= !(__ldg(partial + i).y < kFp16MaxSq);
+  if (over) *flag = 1;
+}
+
 // one warp per (n, g): lanes stride over the P partials, fixed-pattern shuffle reduction (deterministic),
 // then the first C/G lanes (looping if C/G > 32) write scale/shift of the group's channels.
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial,
@@ -94,13 +106,14 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
                                                           const float* __restrict__ beta,
                                                           float* __restrict__ scale_shift,
                                                           float* __restrict__ mean_rstd, int N, int C, int G, int P,
-                                                          float inv_count, float eps) {
+                                                          float inv_count, float eps, int* __restrict__ range_flag) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= N * G) return;
   const int n = wid / G, g = wid - n * G;
   const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * G + g;
   float s = 0.f, q = 0.f;
+  bool over = false;   // some tile's sum of squares reaches 65504^2: an element MAY have hit the fp16 clamp (see ptivae.h)
   // batches of 8 independent loads per lane, then the adds in the same order as a plain loop: the kernel is pure
   // load latency (44 launches per forward), the sums stay bit-identical
   for (int p0 = lane; p0 < P; p0 += 256) {
@@ -115,6 +128,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
       if (p0 + 32 * i < P) {
         s += t[i].x;
         q += t[i].y;
+        over |= !(t[i].y < kFp16MaxSq);
       }
     }
   }
@@ -123,6 +137,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  if (range_flag != nullptr && __any_sync(0xffffffffu, over) && lane == 0) *range_flag = 1;
   const float mean = s * inv_count;
   const float var = fmaxf(q * inv_count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
@@ -206,11 +221,24 @@ extern "C" int ptivae_gn_stats(const void* x, float* partial, int N, int HW, int
 
 extern "C" int ptivae_gn_finalize(const float* partial, const float* gamma, const float* beta, float* scale_shift,
                                   float* mean_rstd, int N, int HW, int C, int G, int P, float eps, void* stream_) {
+  return ptivae_gn_finalize_checked(partial, gamma, beta, scale_shift, mean_rstd, N, HW, C, G, P, eps, nullptr, stream_);
+}
+
+extern "C" int ptivae_range_check(const float* partial, long long pairs, int* range_flag, void* stream_) {
+  if (!partial || !range_flag || pairs <= 0) return PTIVAE_ERR_ARG;
+  range_check_kernel<<<grid_for(static_cast<size_t>(pairs), 256, 148), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const float2*>(partial), pairs, range_flag);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ptivae_gn_finalize_checked(const float* partial, const float* gamma, const float* beta, float* scale_shift,
+                                          float* mean_rstd, int N, int HW, int C, int G, int P, float eps, int* range_flag,
+                                          void* stream_) {
   if (!partial || !gamma || !beta || !scale_shift || N <= 0 || C % G != 0 || P <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
   gn_finalize_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(partial, gamma, beta, scale_shift, mean_rstd, N, C, G, P, inv,
-                                                                   eps);
+                                                                   eps, range_flag);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -238,15 +238,26 @@ def gn_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
 
 
 def gn_finalize(part: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, eps: float,
-                return_mean_rstd: bool = False):
-    """partials [N,P,G,2] -> scale/shift [N,C,2] (and, for the backward pass, (mean, rstd) [N,G,2])."""
+                return_mean_rstd: bool = False, range_flag: torch.Tensor | None = None):
+    """partials [N,P,G,2] -> scale/shift [N,C,2] (and, for the backward pass, (mean, rstd) [N,G,2]).  range_flag (int32 [1],
+    optional): set to 1 when a partial's sum of squares reaches 65504^2 (fp16 range check, see include/ptivae.h)."""
     n, parts, g, _ = part.shape
     c = gamma.numel()
     ss = torch.empty((n, c, 2), device=part.device, dtype=torch.float32)
     mr = torch.empty((n, g, 2), device=part.device, dtype=torch.float32) if return_mean_rstd else None
-    _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(part), _p(gamma), _p(beta), _p(ss), _p(mr), n, hw, c, g,
-          parts, float(eps), _stream())
+    if range_flag is None:
+        _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize, _p(part), _p(gamma), _p(beta), _p(ss), _p(mr), n, hw, c, g,
+              parts, float(eps), _stream())
+    else:
+        _call("gn_finalize", None, 1, _lib.lib().ptivae_gn_finalize_checked, _p(part), _p(gamma), _p(beta), _p(ss), _p(mr), n, hw,
+              c, g, parts, float(eps), _p(range_flag), _stream())
     return (ss, mr) if return_mean_rstd else ss
+
+
+def range_check(part: torch.Tensor, range_flag: torch.Tensor) -> None:
+    """fp16 range check on the statistics partials [N,P,G,2] of a tensor that no GroupNorm consumes."""
+    _need_cuda(part, range_flag)
+    _call("range_check", None, 1, _lib.lib().ptivae_range_check, _p(part), part.numel() // 2, _p(range_flag), _stream())
 
 
 def gn_apply(x: torch.Tensor, scale_shift: torch.Tensor, silu: bool, emit_raw: bool = False,
