@@ -85,7 +85,50 @@ def attn(l, d, b=64):
     return ms, 8 * b * l * d
 
 
+def band(cin, res):
+    """row-band kernel (impl 4): 16-bit in / out, optional 16-bit residual; bytes = SURVEY 8(d) count (+ residual)."""
+    ops.FUSED_IMPL = 4
+    x = torch.randn(N, 256, 256, cin, device="cuda").to(DT)
+    wp = ops.pack_conv_weight(torch.randn(32, cin, 3, 3, device="cuda") / math.sqrt(9 * cin), 0, DT)
+    bias = torch.randn(32, device="cuda"); ss = torch.randn(N, cin, 2, device="cuda")
+    r = torch.randn(N, 256, 256, 32, device="cuda").to(DT) if res else None
+    by = x.numel() * 2 + N * 65536 * 32 * 2 * (2 if res else 1)
+    ms = timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=16, out_f32=False))
+    ops.FUSED_IMPL = 0
+    print(f"   band {cin}->32: {2.0 * N * 65536 * cin * 32 * 9 / ms / 1e9:.0f} TFLOP/s")
+    return ms, by
+
+
+def gnstats(c, hw, dt):
+    x = torch.randn(N, hw, hw, c, device="cuda").to(dt)
+    return timeit(lambda: ops.gn_stats(x, 16)), x.numel() * x.element_size()
+
+
+def gnapply(c, hw, dt):
+    x = torch.randn(N, hw, hw, c, device="cuda").to(dt); ss = torch.randn(N, c, 2, device="cuda")
+    return timeit(lambda: ops.gn_apply(x, ss, silu=True, dtype=DT)), x.numel() * (x.element_size() + 2)
+
+
+def l1l2():
+    a, b = torch.randn(N, 1, 256, 256, device="cuda"), torch.randn(N, 1, 256, 256, device="cuda")
+    return timeit(lambda: ops.l1l2(a, b)), a.numel() * 8
+
+
+def kl():
+    mu, sg = torch.randn(N, 4, 32, 32, device="cuda"), torch.rand(N, 4, 32, 32, device="cuda") + 0.5
+    return timeit(lambda: ops.kl_loss(mu, sg, True)), mu.numel() * 8
+
+
+def sample():
+    mu, sg = torch.randn(N, 4, 32, 32, device="cuda"), torch.rand(N, 4, 32, 32, device="cuda") + 0.5
+    return timeit(lambda: ops.latent_sample(mu, sg, seed=1, offset=1)), mu.numel() * 12
+
+
 CASES = {
+    "band32c1": lambda: band(32, False), "band32c2": lambda: band(32, True), "band64c1": lambda: band(64, False),
+    "gnstats32": lambda: gnstats(32, 256, DT), "gnstats128": lambda: gnstats(128, 32, torch.float32),
+    "gnapply32": lambda: gnapply(32, 256, DT), "gnapply128": lambda: gnapply(128, 32, torch.float32),
+    "l1l2": l1l2, "kl": kl, "sample": sample,
     "attn1k": lambda: attn(1024, 128), "attn4k": lambda: attn(4096, 128, 16), "attn4k256": lambda: attn(4096, 256, 8),
     "f32c2sc": lambda: fused_sc(32, 64, 256), "f64c2sc": lambda: fused_sc(64, 32, 128),
     "cout1": cout1, "cout4": cout4, "cin1": cin1, "cin4": cin4,
