@@ -164,12 +164,36 @@ class _Executor:
         self._recipes: dict = {}
         self._derived: dict = {}
 
+    def _repack_in_place(self, key, hit, ver, same_storage: bool):
+        """A cached pack whose master only CHANGED VALUE (optimizer step, in-place load_state_dict) is recomputed into
+        the same tensors: captured CUDA graphs (GraphedVAE, the training edge) hold their addresses.  Returns the updated
+        cache entry, or None when the entry must be rebuilt (master re-allocated / moved, operand format changed)."""
+        if hit is None or not same_storage or key not in self._recipes and key not in self._derived:
+            return None
+        rs = self._recipes.get(key)
+        if rs:
+            tabs = self.__dict__.setdefault("_key_tables", {})
+            tab = tabs.get(key)
+            if tab is None or tab[0] != tuple(r[1].data_ptr() for r in rs):
+                tab = (tuple(r[1].data_ptr() for r in rs),) + ops.build_pack_table(rs)
+                tabs[key] = tab
+            ops.pack_many(*tab[1:])
+        fn = self._derived.get(key)
+        if fn is not None:
+            fn()
+        hit = (ver,) + tuple(hit[1:])
+        self._packed[key] = hit
+        return hit
+
     # -- weights: 16-bit UMMA operands cached until the fp32 master changes (optimizer step, load_state_dict, .to())
     def packed(self, w: torch.Tensor, mode: int = 0) -> torch.Tensor:
         key = (id(w), mode)
         ver = (w.data_ptr(), w._version, w.device, self.op_dtype)
         hit = self._packed.get(key)
-        if hit is None or hit[0] != ver:
+        if hit is not None and hit[0] != ver:
+            same = hit[0][0] == ver[0] and hit[0][2:] == ver[2:]
+            hit = self._repack_in_place(key, hit, ver, same)
+        if hit is None:
             hit = (ver, ops.pack_conv_weight(w, mode, self.op_dtype))
             self._packed[key] = hit
             self._recipes[key] = [(w, hit[1], 0, hit[1].shape[2], mode)]
@@ -188,7 +212,10 @@ class _Executor:
         key = (id(ws[0]), "qkv")
         ver = tuple((t.data_ptr(), t._version) for t in ws + bs) + (self.op_dtype, ws[0].device)
         hit = self._packed.get(key)
-        if hit is None or hit[0] != ver:
+        if hit is not None and hit[0] != ver:
+            same = tuple(v[0] for v in hit[0][:-2]) == tuple(v[0] for v in ver[:-2]) and hit[0][-2:] == ver[-2:]
+            hit = self._repack_in_place(key, hit, ver, same)
+        if hit is None:
             wcat = torch.cat([t.detach() for t in ws], dim=0)
             hit = (ver, ops.pack_conv_weight(wcat, 0, self.op_dtype), torch.cat([t.detach().float() for t in bs]).contiguous())
             self._packed[key] = hit
@@ -203,7 +230,10 @@ class _Executor:
         key = (id(a), id(b), "bias_sum")
         ver = (a.data_ptr(), a._version, b.data_ptr(), b._version, a.device)
         hit = self._packed.get(key)
-        if hit is None or hit[0] != ver:
+        if hit is not None and hit[0] != ver:
+            same = (hit[0][0], hit[0][2], hit[0][4]) == (ver[0], ver[2], ver[4])
+            hit = self._repack_in_place(key, hit, ver, same)
+        if hit is None:
             hit = (ver, (a.detach().float() + b.detach().float()).contiguous())
             self._packed[key] = hit
             out = hit[1]
@@ -386,6 +416,7 @@ class AutoencoderKL(nn.Module):
         self._exec = _Executor(norm_num_groups, norm_eps)
         self._rng_offset = 0
         self._rng_dev = None  # device-resident (seed, offset) when running under CUDA-graph capture
+        self._train_graphs = True   # training forward/backward: replay CUDA graphs from the second step of a shape on
 
     # -- helpers ------------------------------------------------------------------------------
     def _prep(self, x: torch.Tensor, channels: int | None = None) -> torch.Tensor:
@@ -414,6 +445,9 @@ class AutoencoderKL(nn.Module):
         self._exec._packed.clear()
         self._exec._recipes.clear()
         self._exec._derived.clear()
+        self._exec.__dict__.pop("_key_tables", None)
+        self.__dict__.pop("_edge", None)          # captured training graphs hold the old pack addresses
+        self.__dict__.pop("_edge_seen", None)
 
     def refresh_packed(self) -> None:
         """Recompute every cached weight pack IN PLACE from the current fp32 masters: one pack_many launch for all conv /
@@ -474,6 +508,15 @@ class AutoencoderKL(nn.Module):
             finally:
                 ex.range_flag = None
             return int(flag.item()) == 0
+
+    def set_train_graphs(self, enabled: bool) -> None:
+        """Training mode: from the second consecutive ``forward`` of a shape on, replay the forward (with its tape) and the
+        backward as two CUDA graphs instead of launching ~700 kernels eagerly (default on; the reference loop at batch 8 is
+        host bound otherwise).  Falls back to eager launches for injected ``eps``, inputs that require grad and under
+        ``torch.autograd.set_detect_anomaly``.  Switch off (or call again) after replacing parameter tensors."""
+        self._train_graphs = bool(enabled)
+        self.__dict__.pop("_edge", None)
+        self.__dict__.pop("_edge_seen", None)
 
     def set_fused_conv(self, enabled: bool) -> None:
         """ResBlock convs as one fused kernel (default) vs. gn_apply + conv_umma."""

@@ -450,3 +450,55 @@ def test_train_step_graph_replay(b200, oracle):
         out = ts.replay(x)
         losses.append(float(out["recon_loss"]))
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
+
+
+def test_autograd_edge_replays_graphs_like_eager(b200, oracle):
+    """The reference's own loop (`autoencoder(images)`, `loss_g.backward()`, torch.optim.Adam: train_vae.py:385-445):
+    from the second step of a shape on the autograd edge replays CUDA graphs.  With the sampling noise switched off
+    (sigma ~ 3e-7) the graphed model must take the same steps as a model that launches every kernel eagerly, keep
+    following parameter updates (weight packs refreshed in place), survive an eval-mode forward between steps, and
+    leave gradient accumulation intact (the returned gradients are private copies)."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    models = []
+    for graphs in (True, False):
+        _, vae = _models(b200, oracle, cfg)
+        ae = vae.autoencoder
+        with torch.no_grad():
+            ae.quant_conv_log_sigma.conv.weight.zero_()
+            ae.quant_conv_log_sigma.conv.bias.fill_(-30.0)
+        ae.set_train_graphs(graphs)
+        vae.train()
+        models.append((vae, torch.optim.Adam(ae.parameters(), lr=1e-4)))
+    x = oracle.synthetic_images(2, 64, 64, seed=0).to(DEV)
+    hist = [[], []]
+    for step in range(5):
+        for i, (vae, opt) in enumerate(models):
+            opt.zero_grad(set_to_none=True)
+            recon, mu, sigma = vae(x)
+            loss = b200.l1_loss(recon, x) + 1e-3 * b200.compute_kl_loss(mu, sigma)
+            loss.backward()
+            opt.step()
+            hist[i].append(float(loss.detach()))
+            if step == 2:            # an eval-mode forward between training steps must not detach the graphs from the weights
+                vae.eval()
+                with torch.no_grad():
+                    vae.reconstruct_deterministic(x)
+                vae.train()
+    assert "_edge" in models[0][0].autoencoder.__dict__ and "_edge" not in models[1][0].autoencoder.__dict__
+    assert hist[0][-1] < hist[0][0], hist
+    assert max(abs(a - b) for a, b in zip(*hist)) <= 2e-5 * max(hist[1]), hist
+    pa = torch.cat([p.detach().reshape(-1) for p in models[0][0].parameters()])
+    pb = torch.cat([p.detach().reshape(-1) for p in models[1][0].parameters()])
+    assert float((pa - pb).abs().max()) <= 2e-5, float((pa - pb).abs().max())
+    # gradient accumulation: two backward passes without zero_grad give twice the gradient
+    vae, opt = models[0]
+    opt.zero_grad(set_to_none=True)
+    for _ in range(2):
+        recon, mu, sigma = vae(x)
+        (b200.l1_loss(recon, x) + 1e-3 * b200.compute_kl_loss(mu, sigma)).backward()
+    g2 = torch.cat([p.grad.reshape(-1) for p in vae.parameters()]).clone()
+    opt.zero_grad(set_to_none=True)
+    recon, mu, sigma = vae(x)
+    (b200.l1_loss(recon, x) + 1e-3 * b200.compute_kl_loss(mu, sigma)).backward()
+    g1 = torch.cat([p.grad.reshape(-1) for p in vae.parameters()])
+    assert _rel(g2, 2 * g1) <= 1e-3, _rel(g2, 2 * g1)     # (the ~3e-7 noise flips a few 16-bit operand roundings; a lost pass would give 0.5)
