@@ -230,6 +230,11 @@ int ptivae_eval_metrics_workspace(int B, int C, int H, int W);
  *   ptivae_local_normalize_workspace(B) bytes (fp64 partial sums, fixed order) */
 int ptivae_local_normalize(const float* x, float* out, float* stats, void* workspace, int B, int per_img, void* stream);
 int ptivae_local_normalize_workspace(int B);
+/* Resize(patch_size) of the reference's preprocessing (data/dataloaders.py:263-272, :323-327: MONAI Resize, default mode
+ * "area" = torch.nn.functional.interpolate(mode="area") = adaptive average pooling) for a batch of equally sized raw images:
+ *   in  [B][H][W], in_fmt 0 = uint8, 1 = uint16, 2 = float32 (as decoded from the TIFF);  out fp32 [B][Ho][Wo]
+ *   out[oy][ox] = mean of in[floor(oy*H/Ho) : ceil((oy+1)*H/Ho)][floor(ox*W/Wo) : ceil((ox+1)*W/Wo)] */
+int ptivae_resize_area(const void* in, int in_fmt, float* out, int B, int H, int W, int Ho, int Wo, void* stream);
 
 /* ---- backward pass (`loss_g.backward()`, vae_scripts/train_vae.py:444) -----------------
  * Gradient tensors are NHWC; every 16-bit operand of a backward GEMM is bf16 (the gradients' range; both operands of

@@ -33,6 +33,7 @@ SIGNATURES = {
     "ptivae_eval_metrics_workspace": [_c_int] * 4,
     "ptivae_local_normalize": [_c_void_p] * 4 + [_c_int] * 2 + [_c_void_p],
     "ptivae_local_normalize_workspace": [_c_int],
+    "ptivae_resize_area": [_c_void_p, _c_int, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_pack_conv_weight": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
     "ptivae_gn_stats_parts": [_c_int] * 3,

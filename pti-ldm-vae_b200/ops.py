@@ -474,6 +474,22 @@ def eval_metrics(pred: torch.Tensor, target: torch.Tensor, window: torch.Tensor,
     return out
 
 
+def resize_area(x: torch.Tensor, size) -> torch.Tensor:
+    """[B,H,W] uint8 | uint16 (stored as int16 / uint16) | float32 -> fp32 [B,Ho,Wo], area interpolation (MONAI Resize default)."""
+    _need_cuda(x)
+    fmt = {torch.uint8: 0, torch.int16: 1, torch.float32: 2}.get(x.dtype)
+    if fmt is None and hasattr(torch, "uint16") and x.dtype == torch.uint16:
+        fmt = 1
+    if fmt is None or x.dim() != 3:
+        raise _lib.PtivaeError("resize_area takes a [B, H, W] uint8 / uint16 / float32 tensor")
+    x = x.contiguous()
+    b, h, w = x.shape
+    ho, wo = int(size[0]), int(size[1])
+    out = torch.empty((b, ho, wo), device=x.device, dtype=torch.float32)
+    _call("resize_area", None, 1, _lib.lib().ptivae_resize_area, _p(x), fmt, _p(out), b, h, w, ho, wo, _stream())
+    return out
+
+
 def local_normalize(x: torch.Tensor, return_stats: bool = False):
     """Batch of fp32 images [B, ...] -> z-score over each image's non-zero pixels, zeros stay zero."""
     _need_cuda(x)

@@ -13,6 +13,7 @@ import pathlib
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 GOLD = pathlib.Path(__file__).resolve().parent / "golden"
@@ -416,3 +417,39 @@ def test_eval_metrics_multichannel_and_ragged_vs_oracle(b200, oracle):
         assert np.allclose(got["psnr"].cpu().numpy(), want["psnr"].numpy(), atol=1e-3), shape
         assert np.allclose(got["mse"].cpu().numpy(), want["mse"].numpy(), rtol=1e-4)
         assert np.allclose(got["mae"].cpu().numpy(), want["mae"].numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("dt,h,w,size", [(torch.uint8, 300, 517, (256, 256)), (torch.int16, 1024, 2048, (256, 256)),
+                                         (torch.float32, 100, 90, (256, 256)), (torch.float32, 512, 512, (384, 384)),
+                                         (torch.uint8, 77, 33, (20, 64))])
+def test_resize_area_and_preprocess_batch(b200, oracle, dt, h, w, size):
+    """the device Resize (MONAI Resize's default "area" mode delegates to
+    torch.nn.functional.interpolate(mode="area"), which is the oracle here) for raw uint8 / uint16 / float32 batches,
+    down- and up-scaling at non-integer ratios; and preprocess_batch = resize -> LocalNormalizeByMask (pinned to the
+    reference transform by the golden test above) -> [B, 1, h, w]."""
+    gen = torch.Generator().manual_seed(5)
+    if dt == torch.float32:
+        raw = torch.rand(3, h, w, generator=gen) * 1000.0
+        as_float = raw
+    elif dt == torch.uint8:
+        raw = torch.randint(0, 256, (3, h, w), generator=gen).to(torch.uint8)
+        as_float = raw.float()
+    else:   # uint16 bits in an int16 tensor (values above 32767 included)
+        vals = torch.randint(0, 65536, (3, h, w), generator=gen)
+        raw = vals.to(torch.int32).numpy().astype("uint16").view("int16")
+        raw = torch.from_numpy(raw)
+        as_float = vals.float()
+    as_float[:, :, : w // 4] = 0.0           # background band, as in the reference's data
+    if dt != torch.float32:
+        raw[:, :, : w // 4] = 0
+    ref = F.interpolate(as_float[:, None], size=size, mode="area")[:, 0]
+    out = b200.ops.resize_area(raw.to(DEV), size)
+    assert out.shape == ref.shape and float((out.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    host = [r.numpy() for r in raw] if dt == torch.float32 else (raw.numpy().view("uint16") if dt == torch.int16 else raw.numpy())
+    x = b200.transforms.preprocess_batch(host, size)
+    assert x.shape == (3, 1) + tuple(size) and x.is_cuda and x.dtype == torch.float32
+    expect = b200.transforms.LocalNormalizeByMask()(ref.to(DEV))
+    assert float((x[:, 0] - expect).abs().max()) <= 1e-3
+    vae = b200.VAEModel.from_config(b200.config.AUTOENCODER_DEF_A).to(DEV).eval()
+    if size[0] % 8 == 0 and size[1] % 8 == 0:
+        assert torch.isfinite(vae.encode_deterministic(x)).all()

@@ -87,7 +87,9 @@ def main():
     for src, dst in (("r2_bench.json", "r2_bench.json"), ("r2_bench_ref.json", "r2_bench_ref.json"), ("r2_train_b8.json", "r2_train_b8.json"),
                      ("r2_train_b32.json", "r2_train_b32.json"), ("r2_train_launch_summary_b8.txt", "r2_train_launch_summary_b8.txt"),
                      ("r2_ops.log", "r2_ops.txt"), ("bench_breakdown.json", "r2_bench_breakdown.json"),
-                     ("r2_train_full.json", "r2_train_full.json"), ("r2_configs.json", "r2_configs.json")):
+                     ("r2_train_full.json", "r2_train_full.json"), ("r2_configs.json", "r2_configs.json"),
+                     ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_train_b8_n2.json", "r2_train_b8_n2.json"),
+                     ("r2_train_full_n2.json", "r2_train_full_n2.json")):
         if (G / src).exists():
             shutil.copy(G / src, P / dst)
 
