@@ -318,7 +318,11 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int bt = 0; bt <= b1 - b0; ++bt) {
         const int nrows = bt == 0 ? 2 : kR;
         const int ybase = kR * b0 - 1 + (bt == 0 ? 0 : 2 + kR * (bt - 1));   // image row of the batch's first row
-        for (int r = 0; r < nrows; ++r) mbar_wait(&row_full[(g + r) % NR], ((g + r) / NR) & 1);
+        // one warp polls the TMA barriers, the other seven sleep in a hardware barrier (a polling warp burns issue slots:
+        // 27 polling warps accounted for a third of all executed instructions)
+        if (tt < 32)
+          for (int r = 0; r < nrows; ++r) mbar_wait(&row_full[(g + r) % NR], ((g + r) / NR) & 1);
+        asm volatile("bar.sync 5, %0;" ::"n"(NT) : "memory");
         if (tt == 0) ROW_TRACE(g, 1);
 #pragma unroll 2
         for (int r = 0; r < nrows; ++r) {
@@ -403,19 +407,22 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int y = kR * b + team;
         uint8_t* oslot = tslots + sl * C::OSLOT;
         if (threadIdx.x == 0) BAND_TRACE(it, 8);
-        mbar_wait(&acc_full[st], (it >> 1) & 1);
+        // the team's first warp polls for the accumulator (and its leader for the drained slot); the other three warps
+        // wait in the team's hardware barrier instead of polling
+        if (ew == 0) {
+          mbar_wait(&acc_full[st], (it >> 1) & 1);
+          if (leader) {   // the slot's previous store has drained it
+            if constexpr (SLOTS == 2) tma_store_wait_read1(); else tma_store_wait_read();
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // accumulator ready, slot free, every reader of its last contents past
         tc_fence_after();
         if (threadIdx.x == 0) BAND_TRACE(it, 9);
         uint32_t acc[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * (kR * COUT) + team * COUT, acc);
-        if (leader) {   // the slot's previous store has drained it
-          if constexpr (SLOTS == 2) tma_store_wait_read1(); else tma_store_wait_read();
-        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc_empty[st]);
-        if (threadIdx.x == 0) BAND_TRACE(it, 10);
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // slot free (and every reader of its last contents is past)
         if (threadIdx.x == 0) BAND_TRACE(it, 11);
         {
           uint8_t* ol = oslot + m * 64;
