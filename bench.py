@@ -120,7 +120,8 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "vae_dente_no_adv AutoencoderKL forward (encode->sample->decode), 1x%dx%d" % (args.size, args.size),
+        "config": {"workload": "vae_dente_no_adv AutoencoderKL forward (encode->sample->decode), 1x%dx%d; CPU arm: bounded sample of "
+                               "%d images per step of the same per-image workload (the b200 arm steps 64)" % (args.size, args.size, sample_b),
                    "batch_per_step": sample_b},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{len(times)} steps x {sample_b} images of the B=64 workload, torch {torch.__version__} CPU fp32, "
@@ -425,7 +426,8 @@ def run_b200(args) -> None:
             "clocks": clocks,
             "step_roofline": step_roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4,
-                    "ms_per_step": ms_e2e / args.steps, "api": "PipelinedVAE(GraphedVAE(VAEModel)).submit(pinned host batch, pinned host recon): H2D(i+1) || kernels(i) || D2H(i-1)"},
+                    "ms_per_step": ms_e2e / args.steps, "api": "PipelinedVAE(GraphedVAE(VAEModel)).submit(pinned host batch, pinned host recon): H2D(i+1) || kernels(i) || D2H(i-1); "
+                           "the reconstruction is copied back every step, z_mu / z_sigma (2 x 1 MB per step) stay on the device"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
