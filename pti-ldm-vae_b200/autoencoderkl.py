@@ -6,7 +6,8 @@ checkpoints load with ``strict=True``.
 
 The ``nn.Module`` tree below only HOLDS parameters (fp32 masters).  No torch operator computes
 anything on the hot path: ``_Executor`` walks the tree and launches the sm_100a kernels of
-libptivae.so (bf16 NHWC activations, fp32 accumulation, fp32 latents / outputs).
+libptivae.so (16-bit NHWC tensor-core operands -- fp16 by default, bf16 on request --, fp32 or fp16 residual stream, fp32
+accumulation, fp32 latents / outputs).
 """
 from __future__ import annotations
 

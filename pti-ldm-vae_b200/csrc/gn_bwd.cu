@@ -309,6 +309,195 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------- small images: one pass
+// For the layers whose (image, group) slice fits in shared memory (HW * C/G * 6 bytes: everything at 32^2 and 64^2, the
+// 64-wide layers at 128^2) the three stages above collapse into ONE kernel: CTA = (group, image) loads its slice of x
+// (kept as fp32) and of dA (kept as bf16) once, reduces S1/S2 over the slice, derives the group coefficients and writes dx
+// straight from shared memory -- 2 launches per norm instead of 5 (the training step at batch 8 is launch-latency bound:
+// 43 norms x 5 launches were a third of it).  Fixed summation order; an image's result does not depend on the batch.
+template <int CPG>
+__device__ __forceinline__ void ld_group(const void* base, size_t elem, int fmt, float (&v)[CPG]) {
+  if (fmt == 2) {
+    const float* p = reinterpret_cast<const float*>(base) + elem;
+    if constexpr (CPG == 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if constexpr (CPG == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+      v[0] = a.x; v[1] = a.y;
+    }
+  } else {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + elem);
+    uint32_t w[CPG / 2];
+    if constexpr (CPG == 8) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else if constexpr (CPG == 4) {
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+      w[0] = a.x; w[1] = a.y;
+    } else {
+      w[0] = __ldg(p);
+    }
+#pragma unroll
+    for (int e = 0; e < CPG / 2; ++e) {
+      if (fmt == 1) unpack2<true>(w[e], v[2 * e], v[2 * e + 1]);
+      else unpack2<false>(w[e], v[2 * e], v[2 * e + 1]);
+    }
+  }
+}
+
+// fixed-order block sum of NV per-thread values: xor-shuffle tree inside the warp, then the 8 warps in index order
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red /* [8][NV] */, float* out /* [NV] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int e = 0; e < NV; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int e = 0; e < NV; ++e) red[warp * NV + e] = v[e];
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w * NV + threadIdx.x];
+    out[threadIdx.x] = a;
+  }
+  __syncthreads();
+}
+
+// grid (G, N); block 256; dynamic smem: HW*CPG fp32 (x) + HW*CPG bf16 (dA)
+template <bool kSilu, int CPG>
+__global__ void __launch_bounds__(256) gn_bwd_small_kernel(const void* __restrict__ x, const void* __restrict__ da,
+                                                           const float* __restrict__ ss, const float* __restrict__ mr,
+                                                           const float* __restrict__ gamma, const void* __restrict__ residual,
+                                                           float* __restrict__ out32, uint16_t* __restrict__ out16,
+                                                           uint16_t* __restrict__ act_out, float* __restrict__ totals,
+                                                           float* __restrict__ colpart, int HW, int C, int G, int x_fmt,
+                                                           int da_fmt, int res_fmt, float inv_count) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ float red[8 * 2 * CPG];
+  __shared__ float tot[2 * CPG];
+  float* xs = reinterpret_cast<float*>(gsm);                                   // [HW][CPG]
+  uint32_t* ds = reinterpret_cast<uint32_t*>(gsm + static_cast<size_t>(HW) * CPG * 4);   // [HW][CPG/2] bf16 pairs
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int c0 = g * CPG;
+  float sc[CPG], sh[CPG];
+#pragma unroll
+  for (int e = 0; e < CPG; ++e) {
+    sc[e] = __ldg(ss + (static_cast<size_t>(n) * C + c0 + e) * 2);
+    sh[e] = __ldg(ss + (static_cast<size_t>(n) * C + c0 + e) * 2 + 1);
+  }
+  const float mean = __ldg(mr + (static_cast<size_t>(n) * G + g) * 2), rstd = __ldg(mr + (static_cast<size_t>(n) * G + g) * 2 + 1);
+  float acc[2 * CPG];
+#pragma unroll
+  for (int e = 0; e < 2 * CPG; ++e) acc[e] = 0.f;
+  const size_t img = static_cast<size_t>(n) * HW * C + c0;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    float f[CPG], d[CPG];
+    ld_group<CPG>(x, img + static_cast<size_t>(p) * C, x_fmt, f);
+    ld_group<CPG>(da, img + static_cast<size_t>(p) * C, da_fmt, d);
+#pragma unroll
+    for (int e = 0; e < CPG; ++e) {
+      xs[p * CPG + e] = f[e];
+      const float du = act_grad<kSilu>(f[e], sc[e], sh[e], d[e]);
+      acc[e] += du;
+      acc[CPG + e] = fmaf(du, (f[e] - mean) * rstd, acc[CPG + e]);
+    }
+#pragma unroll
+    for (int e = 0; e < CPG / 2; ++e) ds[p * (CPG / 2) + e] = pack2<false>(d[2 * e], d[2 * e + 1]);
+    if (act_out != nullptr) {
+      uint32_t a2[CPG / 2];
+#pragma unroll
+      for (int e = 0; e < CPG / 2; ++e) {
+        const float u0 = fmaf(f[2 * e], sc[2 * e], sh[2 * e]), u1 = fmaf(f[2 * e + 1], sc[2 * e + 1], sh[2 * e + 1]);
+        a2[e] = pack2<false>(kSilu ? silu_f(u0) : u0, kSilu ? silu_f(u1) : u1);
+      }
+      uint32_t* dst = reinterpret_cast<uint32_t*>(act_out + img + static_cast<size_t>(p) * C);
+#pragma unroll
+      for (int e = 0; e < CPG / 2; ++e) dst[e] = a2[e];
+    }
+  }
+  block_sum<2 * CPG>(acc, red, tot);         // tot[e] = S1 of channel e, tot[CPG + e] = S2
+  if (threadIdx.x < CPG) {
+    totals[(static_cast<size_t>(n) * C + c0 + threadIdx.x) * 2] = tot[threadIdx.x];
+    totals[(static_cast<size_t>(n) * C + c0 + threadIdx.x) * 2 + 1] = tot[CPG + threadIdx.x];
+  }
+  float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < CPG; ++e) {
+    const float gm = __ldg(gamma + c0 + e);
+    p1 = fmaf(gm, tot[e], p1);
+    p2 = fmaf(gm, tot[CPG + e], p2);
+  }
+  const float k1 = rstd * p1 * inv_count, k2 = rstd * p2 * inv_count;
+  const float ce = k1 - mean * rstd * k2, cf = rstd * k2;
+  float cs[CPG];
+#pragma unroll
+  for (int e = 0; e < CPG; ++e) cs[e] = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    float r[CPG], o[CPG];
+    if (residual != nullptr) {
+      ld_group<CPG>(residual, img + static_cast<size_t>(p) * C, res_fmt, r);
+    } else {
+#pragma unroll
+      for (int e = 0; e < CPG; ++e) r[e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < CPG / 2; ++e) {
+      float d0, d1;
+      unpack2<false>(ds[p * (CPG / 2) + e], d0, d1);
+      const float f0 = xs[p * CPG + 2 * e], f1 = xs[p * CPG + 2 * e + 1];
+      const float du0 = act_grad<kSilu>(f0, sc[2 * e], sh[2 * e], d0);
+      const float du1 = act_grad<kSilu>(f1, sc[2 * e + 1], sh[2 * e + 1], d1);
+      o[2 * e] = fmaf(sc[2 * e], du0, -ce) - f0 * cf + r[2 * e];
+      o[2 * e + 1] = fmaf(sc[2 * e + 1], du1, -ce) - f1 * cf + r[2 * e + 1];
+    }
+#pragma unroll
+    for (int e = 0; e < CPG; ++e) cs[e] += o[e];
+    if (out32 != nullptr) {
+      float* dst = out32 + img + static_cast<size_t>(p) * C;
+      if constexpr (CPG == 8) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+      } else if constexpr (CPG == 4) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        reinterpret_cast<float2*>(dst)[0] = make_float2(o[0], o[1]);
+      }
+    }
+    if (out16 != nullptr) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out16 + img + static_cast<size_t>(p) * C);
+#pragma unroll
+      for (int e = 0; e < CPG / 2; ++e) dst[e] = pack2<false>(o[2 * e], o[2 * e + 1]);
+    }
+  }
+  if (colpart != nullptr) {
+    block_sum<CPG>(cs, red, tot);            // tot[e] = column sum of dx over this image, channel e
+    if (threadIdx.x < CPG) colpart[static_cast<size_t>(n) * C + c0 + threadIdx.x] = tot[threadIdx.x];
+  }
+}
+
+// dgamma / dbeta (and the fused bias gradient) = index-order sums over the batch of the per-image values
+__global__ void gn_bwd_small_final_kernel(const float* __restrict__ totals, const float* __restrict__ colpart,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum,
+                                          int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f, s = 0.f;
+  for (int n = 0; n < N; ++n) {
+    a += totals[(static_cast<size_t>(n) * C + c) * 2];
+    b += totals[(static_cast<size_t>(n) * C + c) * 2 + 1];
+    if (colpart != nullptr) s += colpart[static_cast<size_t>(n) * C + c];
+  }
+  dbeta[c] = a;
+  dgamma[c] = b;
+  if (colsum != nullptr) colsum[c] = s;
+}
+
 // ---------------------------------------------------------------------------------------------- column sums
 // stage 1: grid (blocks); block 256 = (vecs x prows); block b walks rows [b*rpb, (b+1)*rpb) -> partial[b][C]
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ x, float* __restrict__ partial,
@@ -387,6 +576,37 @@ extern "C" int ptivae_gn_bwd(const void* x, int x_fmt, const void* da, int da_fm
   const int P = (HW + gb_pix(HW) - 1) / gb_pix(HW);
   float* partial = workspace;
   float* totals = workspace + static_cast<size_t>(N) * P * C * 2;
+  {  // small images: one pass per (group, image) slice held in shared memory
+    const int cpg = C / G;
+    const size_t smem = static_cast<size_t>(HW) * cpg * 6;
+    // (only where the tensor is small enough to be launch-latency bound: the slice loads are 32-byte pieces at a stride
+    // of C elements, which loses to the streaming kernels above once there is enough work -- measured at batch 32)
+    if ((cpg == 2 || cpg == 4 || cpg == 8) && da_fmt != 2 && smem <= 200 * 1024 && N <= 65535 &&
+        static_cast<long long>(N) * HW * C <= (2ll << 20)) {
+      const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(cpg));
+      float* colpart = colsum_out ? partial : nullptr;          // [N][C]: the chunk partials are not used on this path
+      dim3 grid(G, N);
+      int rc = 0;
+#define PTIVAE_GNB_SMALL(SILU, CPG_)                                                                                         \
+  do {                                                                                                                      \
+    static bool attr[64] = {};                                                                                              \
+    rc = ensure_dyn_smem(gn_bwd_small_kernel<SILU, CPG_>, 200 * 1024, attr);                                                \
+    if (rc == 0)                                                                                                            \
+      gn_bwd_small_kernel<SILU, CPG_><<<grid, 256, smem, stream>>>(x, da, scale_shift, mean_rstd, gamma, residual, dx32,    \
+          static_cast<uint16_t*>(dx16), static_cast<uint16_t*>(act_out), totals, colpart, HW, C, G, x_fmt, da_fmt, res_fmt, \
+          inv);                                                                                                             \
+  } while (0)
+      if (silu) {
+        if (cpg == 8) PTIVAE_GNB_SMALL(true, 8); else if (cpg == 4) PTIVAE_GNB_SMALL(true, 4); else PTIVAE_GNB_SMALL(true, 2);
+      } else {
+        if (cpg == 8) PTIVAE_GNB_SMALL(false, 8); else if (cpg == 4) PTIVAE_GNB_SMALL(false, 4); else PTIVAE_GNB_SMALL(false, 2);
+      }
+#undef PTIVAE_GNB_SMALL
+      if (rc) return rc;
+      gn_bwd_small_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(totals, colpart, dgamma, dbeta, colsum_out, N, C);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   float* colpart = colsum_out ? totals + static_cast<size_t>(N) * C * 2 : nullptr;
   uint4* act = static_cast<uint4*>(act_out);
   dim3 grid(P, N);

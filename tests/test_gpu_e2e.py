@@ -453,3 +453,19 @@ def test_resize_area_and_preprocess_batch(b200, oracle, dt, h, w, size):
     vae = b200.VAEModel.from_config(b200.config.AUTOENCODER_DEF_A).to(DEV).eval()
     if size[0] % 8 == 0 and size[1] % 8 == 0:
         assert torch.isfinite(vae.encode_deterministic(x)).all()
+
+
+def test_wide_levels_256_and_512(b200, oracle):
+    """The constructor accepts channel widths up to 512; 256- and 512-wide levels take the unfused route
+    (gn_apply -> conv_umma).  A small model with both widths against the oracle, forward and deterministic paths."""
+    cfg = dict(spatial_dims=2, in_channels=1, out_channels=1, latent_channels=4, channels=[64, 256, 512],
+               num_res_blocks=[1, 1, 1], norm_num_groups=32, norm_eps=1e-6, attention_levels=[False, False, False],
+               with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False)
+    ref, vae = _models(b200, oracle, cfg)
+    x = oracle.synthetic_images(2, 32, 48, seed=9)
+    with torch.no_grad():
+        mu_r, sg_r = ref.encode(x)
+        eps = torch.randn(mu_r.shape, generator=torch.Generator().manual_seed(7))
+        rec_r, _, _ = ref(x, eps)
+    rec, mu, sg = vae.autoencoder(x.to(DEV), eps.to(DEV))
+    assert _rel_l2(rec, rec_r) <= 1e-2 and _rel_l2(mu, mu_r) <= 5e-3 and _rel_l2(sg, sg_r) <= 5e-3
