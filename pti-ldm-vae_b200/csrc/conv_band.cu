@@ -27,6 +27,10 @@
 #include "common.cuh"
 #include "ptivae_internal.h"
 
+#ifndef BAND_NR32
+#define BAND_NR32 16     // ring slots for 32 input channels (measured: 16 slots + single output slots beat 12 + double by 2-4 %)
+#define BAND_SLOTS32 1
+#endif
 namespace ptivae {
 namespace band {
 
@@ -46,8 +50,8 @@ struct Cfg {
   static_assert(RES == 0 || RES == 2, "no residual, or a 16-bit residual added in place");
   static constexpr uint32_t LB = CIN * 2;                      // operand line: one pixel's channels
   static constexpr uint32_t ROWB = r1k(kLW * LB);              // one ring slot
-  static constexpr int NR = CIN == 32 ? 12 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
-  static constexpr int SLOTS = CIN == 32 ? 2 : 1;              // output slots per team (2: the store of band i drains under band i+1)
+  static constexpr int NR = CIN == 32 ? BAND_NR32 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
+  static constexpr int SLOTS = CIN == 32 ? BAND_SLOTS32 : 1;              // output slots per team (2: the store of band i drains under band i+1)
   static constexpr uint32_t BLK = COUT * LB;                   // one tap's weights [32 co][CIN]
   static constexpr uint32_t WBYTES = 12u * BLK;                // kx = 0: W2 W1 W0 0 0 0 | kx = 1: W2 W1 W0 | kx = 2: W2 W1 W0
   static constexpr uint32_t OSLOT = 128 * 64;                  // 128 pixels x 32 channels, 16-bit
