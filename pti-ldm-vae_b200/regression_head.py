@@ -8,7 +8,8 @@ mirrored here.  This module supplies only the piece that runs on the device:
 
 * ``LatentRegressor`` -- holds the ``mlp.<i>.weight / bias`` parameters in the reference's ``nn.Sequential`` positions (so
   ``head_best.pth`` checkpoints load) and evaluates every ``Linear (+ activation)`` pair as ONE ``ptivae_linear_act``
-  launch; eval-mode dropout is the identity.  Inference only.
+  launch under ``torch.no_grad()`` (eval-mode dropout is the identity); with grad enabled (training the head over the
+  frozen encoder) the same ``nn.Sequential`` runs as ordinary autograd ops.
 * ``regress_from_images(vae, head, images)`` -- the three-step composition as a function, for callers without the
   reference package on their path.
 """
@@ -46,9 +47,12 @@ class LatentRegressor(nn.Module):
     def forward(self, latent_flat: torch.Tensor) -> torch.Tensor:
         if not latent_flat.is_cuda:
             raise RuntimeError("LatentRegressor runs on CUDA only (no CPU fallback; the CPU restatement is in oracle/)")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("the MLP head is an inference kernel (ptivae_linear_act): call it under "
-                                      "torch.no_grad() / .eval(); train the 1.1 M-parameter head with stock PyTorch")
+        if torch.is_grad_enabled() and (self.training or latent_flat.requires_grad):
+            # TRAINING the head (reg_scripts: frozen encoder -> trainable 1.1 M-parameter MLP with dropout): the 2 MFLOP
+            # stack and its backward are ordinary autograd ops on the GPU -- the hot path of that loop is the frozen
+            # encoder (17.5 GFLOP per image), which runs on the kernels under no_grad.  Same parameters, same
+            # nn.Sequential, so checkpoints and optimizers are shared with the kernel-backed inference path below.
+            return self.mlp(latent_flat)
         linears = [m for m in self.mlp if isinstance(m, nn.Linear)]
         y = latent_flat
         with torch.cuda.device(latent_flat.device):

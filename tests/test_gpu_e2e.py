@@ -469,3 +469,33 @@ def test_wide_levels_256_and_512(b200, oracle):
         rec_r, _, _ = ref(x, eps)
     rec, mu, sg = vae.autoencoder(x.to(DEV), eps.to(DEV))
     assert _rel_l2(rec, rec_r) <= 1e-2 and _rel_l2(mu, mu_r) <= 5e-3 and _rel_l2(sg, sg_r) <= 5e-3
+
+
+def test_regression_head_trains_over_the_frozen_encoder(b200, oracle):
+    """reg_scripts' loop (regression_head.py:119-138 + an optimizer over the head): frozen kernel-backed encoder under
+    no_grad, trainable MLP head with dropout.  In train mode the head is differentiable (ordinary autograd ops over the
+    same nn.Sequential the inference kernel reads), the loss goes down, and eval-mode inference afterwards runs the kernel
+    on the UPDATED parameters and agrees with the autograd evaluation."""
+    cfg = b200.config.AUTOENCODER_DEF_A
+    _, vae = _models(b200, oracle, cfg)
+    for p in vae.parameters():
+        p.requires_grad = False
+    torch.manual_seed(5)
+    head = b200.LatentRegressor(4 * 8 * 8, [64, 16], 6, dropout=0.1).to(DEV).train()
+    opt = torch.optim.Adam(head.parameters(), lr=1e-2)
+    x = oracle.synthetic_images(8, 64, 64, seed=8).to(DEV)
+    target = torch.randn(8, 6, generator=torch.Generator().manual_seed(1)).to(DEV)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad(set_to_none=True)
+        pred = b200.regress_from_images(vae, head, x)
+        loss = torch.nn.functional.mse_loss(pred, target)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.5 * losses[0], losses
+    head.eval()
+    with torch.no_grad():
+        out_kernel = b200.regress_from_images(vae, head, x)
+        out_torch = head.mlp(torch.flatten(vae.encode_deterministic(x), start_dim=1))
+    assert float((out_kernel - out_torch).abs().max()) <= 1e-4 * max(1.0, float(out_torch.abs().max()))
