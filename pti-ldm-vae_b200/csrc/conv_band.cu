@@ -13,9 +13,11 @@
 //   * rows stream through a ring in shared memory: a CTA walks down a column of bands, every input row is TMA-loaded,
 //     normalised + SiLU'd in place and consumed by the (up to two) bands that need it exactly once -- no halo re-reads
 //     in y, one halo pixel per side in x.
-// Output: units of 128 pixels x 32 channels through swizzled slots and TMA tensor stores; the 16-bit residual line of a
-// pixel is read straight from global memory one band ahead; GroupNorm statistics are column sums of the stored values in
-// fixed order, finalised per band by an otherwise idle warp (deterministic, no atomics).
+// Output: each epilogue warp parks its 32 pixel lines (64 B each) in a private 2 KB scratch and reads them back transposed
+// -- four fully coalesced 512-byte global stores, and at the same time the operands of the column sums (no proxy fence, no
+// TMA store, no team barrier); the 16-bit residual line of a pixel is read straight from global memory one band ahead;
+// GroupNorm statistics are column sums of the stored values in fixed order, finalised per band by an otherwise idle warp
+// (deterministic, no atomics).
 // What bounds it (clock64 timelines of CTA 0, tools/prof_band.py): the MMAs of a band take ~1.8k cycles, but every warp of
 // the prologue / epilogue runs latency bound at ~0.12 IPC, and the SiLU of the 4 x 130 x Cin prologue elements costs two
 // SFU slots each (tanh is half rate: the tanh, the fp32 ex2+rcp and the packed half2 forms all measured the same) =
@@ -28,8 +30,7 @@
 #include "ptivae_internal.h"
 
 #ifndef BAND_NR32
-#define BAND_NR32 16     // ring slots for 32 input channels (measured: 16 slots + single output slots beat 12 + double by 2-4 %)
-#define BAND_SLOTS32 1
+#define BAND_NR32 16     // ring slots for 32 input channels (measured: 16 slots beat 12 by 2-4 %)
 #endif
 namespace ptivae {
 namespace band {
@@ -51,7 +52,7 @@ struct Cfg {
   static constexpr uint32_t LB = CIN * 2;                      // operand line: one pixel's channels
   static constexpr uint32_t ROWB = r1k(kLW * LB);              // one ring slot
   static constexpr int NR = CIN == 32 ? BAND_NR32 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
-  static constexpr int SLOTS = CIN == 32 ? BAND_SLOTS32 : 1;              // output slots per team (2: the store of band i drains under band i+1)
+  static constexpr int SLOTS = 1;                              // one 8 KB scratch per epilogue team = 2 KB per warp
   static constexpr uint32_t BLK = COUT * LB;                   // one tap's weights [32 co][CIN]
   static constexpr uint32_t WBYTES = 12u * BLK;                // kx = 0: W2 W1 W0 0 0 0 | kx = 1: W2 W1 W0 | kx = 2: W2 W1 W0
   static constexpr uint32_t OSLOT = 128 * 64;                  // 128 pixels x 32 channels, 16-bit
@@ -67,6 +68,7 @@ struct Args {
   const float* scale_shift;  // [N][CIN][2] or nullptr
   const float* bias;
   const void* residual;      // 16-bit NHWC [N][H][W][32] or nullptr
+  void* out;                 // 16-bit NHWC [N][H][W][32]
   float* gn_part;            // [N][parts][groups][2]
   unsigned long long* trace; // debug timeline of CTA 0: [64 bands][32] band events, then [256 rows][4] row events; or nullptr
 };
@@ -84,8 +86,7 @@ __host__ __device__ constexpr uint32_t strip_off(int kx) { return kx == 0 ? 0u :
 
 template <int CIN, int RES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmO, const Args args) {
+conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Args args) {
   using C = Cfg<CIN, RES>;
   constexpr bool F16 = true;
   constexpr uint32_t LB = C::LB, ROWB = C::ROWB, BLK = C::BLK;
@@ -120,7 +121,6 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == W_IN && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmO);
     for (int s = 0; s < NR; ++s) {
       mbar_init(&row_full[s], 1);
       mbar_init(&row_ready[s], NT);
@@ -373,11 +373,9 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // -> one TMA store; then the column sums of the stored values (this warp's own 32 rows) go to the finalizer warp.
     const int team = warp >> 2, ew = warp & 3;      // ew == TMEM lane quarter
     const int m = ew * 32 + lane;                   // accumulator row = pixel x0 + m of the output row
-    const bool leader = (ew == 0 && lane == 0);
     const bool want_stats = args.gn_groups > 0;
     const int bar_id = 1 + team;
-    constexpr int SLOTS = C::SLOTS;
-    uint8_t* tslots = slots + team * SLOTS * C::OSLOT;
+    uint8_t* tslots = slots + team * C::OSLOT;
     // 16-bit residual line of this thread's pixel (32 channels = 64 B), read straight from global memory ONE BAND AHEAD
     // (the loads are issued after the band's slot is written and land under its store / statistics / the next TMEM wait)
     uint4 rnext[4] = {};
@@ -407,19 +405,11 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int x0 = cb * kMW;
       for (int b = b0; b < b1; ++b, ++it) {
         const int st = it & 1;
-        const int sl = it & (SLOTS - 1);
         const int y = kR * b + team;
-        uint8_t* oslot = tslots + sl * C::OSLOT;
         if (threadIdx.x == 0) BAND_TRACE(it, 8);
-        // the team's first warp polls for the accumulator (and its leader for the drained slot); the other three warps
-        // wait in the team's hardware barrier instead of polling
-        if (ew == 0) {
-          mbar_wait(&acc_full[st], (it >> 1) & 1);
-          if (leader) {   // the slot's previous store has drained it
-            if constexpr (SLOTS == 2) tma_store_wait_read1(); else tma_store_wait_read();
-          }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // accumulator ready, slot free, every reader of its last contents past
+        // the team's first warp polls for the accumulator; the other three wait in the team's hardware barrier
+        if (ew == 0) mbar_wait(&acc_full[st], (it >> 1) & 1);
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         tc_fence_after();
         if (threadIdx.x == 0) BAND_TRACE(it, 9);
         uint32_t acc[32];
@@ -428,8 +418,13 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc_fence_before();
         mbar_arrive(&acc_empty[st]);
         if (threadIdx.x == 0) BAND_TRACE(it, 11);
+        // +bias (+residual), round to the stored format, and park the pixel's 64-byte line in this WARP's scratch
+        // (2 KB, swizzled): the transposed read below turns 32 lines into four fully coalesced 512-byte global stores
+        // and is at the same time the access pattern of the column sums.  No proxy fence, no TMA store, no team barrier:
+        // the scratch is private to the warp (the TMA-store version paid ~700 cycles per band for the fence alone).
+        uint8_t* scratch = tslots + ew * 2048;
         {
-          uint8_t* ol = oslot + m * 64;
+          uint8_t* ol = scratch + lane * 64;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = reinterpret_cast<const float4*>(sbias)[j];   // broadcast
@@ -444,10 +439,12 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             acc[4 * j + 0] = pack2<F16>(v0, v1);
             acc[4 * j + 1] = pack2<F16>(v2, v3);
           }
+          __syncwarp();                                   // the previous band's reads of the scratch are done
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(ol + ((j ^ ((m >> 1) & 3)) << 4)) =
+            *reinterpret_cast<uint4*>(ol + ((j ^ ((lane >> 1) & 3)) << 4)) =
                 make_uint4(acc[8 * j + 0], acc[8 * j + 1], acc[8 * j + 4], acc[8 * j + 5]);
+          __syncwarp();
         }
         if (threadIdx.x == 0) BAND_TRACE(it, 12);
         {   // next band of this CTA: its residual line starts its trip now
@@ -459,61 +456,60 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             load_res(n2, cb2, b02);
           }
         }
-        fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // the unit is written by all four warps
-        if (leader) {
-          if (y < args.H) tma_store_4d(&tmO, oslot, 0, x0, y, n);
-          tma_store_commit();
-        }
-        if (threadIdx.x == 0) BAND_TRACE(it, 16);
-        if (want_stats) {
-          // column sums of the stored values over this warp's own 32 rows (lane = (row sub-index, 16-byte chunk))
+        {
+          // lane = (row sub-index, 16-byte chunk): instruction i covers pixels i*8 .. i*8+7 of the warp's 32 = 512 contiguous bytes
           const int rsub = lane >> 2, j4 = lane & 3;
-          float s1[8], s2[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
           uint4 w[4];
+          uint4* gout = reinterpret_cast<uint4*>(static_cast<uint8_t*>(args.out) +
+                                                 ((static_cast<size_t>(n) * args.H + y) * args.W + x0 + ew * 32) * (COUT * 2));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int r = ew * 32 + i * 8 + rsub;
-            const bool ok = (x0 + r < args.W) && (y < args.H);
-            w[i] = ok ? *reinterpret_cast<const uint4*>(oslot + r * 64 + ((j4 ^ ((r >> 1) & 3)) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+            const int r = i * 8 + rsub;
+            w[i] = *reinterpret_cast<const uint4*>(scratch + r * 64 + ((j4 ^ ((r >> 1) & 3)) << 4));
+            const bool ok = (x0 + ew * 32 + r < args.W) && (y < args.H);
+            if (ok) gout[i * 32 + lane] = w[i];
+            else w[i] = make_uint4(0u, 0u, 0u, 0u);       // pixels outside the image add nothing to the statistics
           }
+          if (threadIdx.x == 0) BAND_TRACE(it, 16);
+          if (want_stats) {
+            float s1[8], s2[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float x[8];
-            unpack2<F16>(w[i].x, x[0], x[1]); unpack2<F16>(w[i].y, x[2], x[3]);
-            unpack2<F16>(w[i].z, x[4], x[5]); unpack2<F16>(w[i].w, x[6], x[7]);
+            for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              s1[k] += x[k];
-              s2[k] = fmaf(x[k], x[k], s2[k]);
+            for (int i = 0; i < 4; ++i) {
+              float x[8];
+              unpack2<F16>(w[i].x, x[0], x[1]); unpack2<F16>(w[i].y, x[2], x[3]);
+              unpack2<F16>(w[i].z, x[4], x[5]); unpack2<F16>(w[i].w, x[6], x[7]);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                s1[k] += x[k];
+                s2[k] = fmaf(x[k], x[k], s2[k]);
+              }
             }
-          }
 #pragma unroll
-          for (int o = 4; o < 32; o <<= 1) {       // fold the row sub-lanes (fixed pattern)
+            for (int o = 4; o < 32; o <<= 1) {       // fold the row sub-lanes (fixed pattern)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
-              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+              for (int k = 0; k < 8; ++k) {
+                s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+                s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+              }
             }
-          }
-          if (it >= 2) mbar_wait(&st_free[it & 1], ((it >> 1) - 1) & 1);    // the finalizer has read band it-2's sums
-          float* cs = colsum + ((it & 1) * NEW + warp) * COUT * 2;
-          if (rsub == 0) {
+            if (it >= 2) mbar_wait(&st_free[it & 1], ((it >> 1) - 1) & 1);    // the finalizer has read band it-2's sums
+            float* cs = colsum + ((it & 1) * NEW + warp) * COUT * 2;
+            if (rsub == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              cs[(j4 * 8 + k) * 2] = s1[k];
-              cs[(j4 * 8 + k) * 2 + 1] = s2[k];
+              for (int k = 0; k < 8; ++k) {
+                cs[(j4 * 8 + k) * 2] = s1[k];
+                cs[(j4 * 8 + k) * 2 + 1] = s2[k];
+              }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_full[it & 1]);
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&st_full[it & 1]);
         }
         if (threadIdx.x == 0) BAND_TRACE(it, 17);
       }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
 
   tc_fence_before();
@@ -550,8 +546,9 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
   a.silu = c.silu; a.gn_groups = c.gn_groups; a.scale_shift = c.scale_shift; a.bias = c.bias; a.gn_part = c.gn_part;
   a.trace = c.trace;
   a.residual = c.residual;
+  a.out = c.out;
 
-  CUtensorMap tmX, tmW, tmO;
+  CUtensorMap tmX, tmW;
   const uint64_t H = c.H, W = c.W, N = c.N;
   {  // input row segment: dims (C, W, H, N), box (CIN, 130, 1, 1), swizzle = line bytes (the K-major UMMA operand layout)
     uint64_t d[4] = {uint64_t(CIN), W, H, N};
@@ -567,17 +564,10 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     int rc = encode_tmap(&tmW, c.w_packed, 1, 3, d, s, b, C::LB);
     if (rc) return rc;
   }
-  {  // output unit: box (32 channels, 128 pixels, 1 row, 1), 64B swizzle
-    uint64_t d[4] = {uint64_t(COUT), W, H, N};
-    uint64_t s[3] = {uint64_t(COUT) * 2, W * COUT * 2, H * W * COUT * 2};
-    uint32_t b[4] = {32, kMW, 1, 1};
-    int rc = encode_tmap(&tmO, c.out, 1, 4, d, s, b, 64);
-    if (rc) return rc;
-  }
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(conv3x3_band_kernel<CIN, RES>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
   const int grid = a.num_segs < sms ? a.num_segs : sms;
-  conv3x3_band_kernel<CIN, RES><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmO, a);
+  conv3x3_band_kernel<CIN, RES><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, a);
   return static_cast<int>(cudaGetLastError());
 }
 
