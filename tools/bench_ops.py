@@ -69,6 +69,20 @@ def fused(cin, cout, hw, conv2, out32=True, impl=0):
     return timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=min(32, cout // 2), out_f32=o32)), by
 
 
+def fused16(cin, cout, hw, res, impl=0):
+    """ResBlock conv on the fp16 stream: 16-bit in, 16-bit out, optional 16-bit residual."""
+    ops.FUSED_IMPL = impl
+    x = torch.randn(N, hw, hw, cin, device="cuda").to(DT)
+    wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda") / math.sqrt(9 * cin), 0, DT)
+    bias = torch.randn(cout, device="cuda"); ss = torch.randn(N, cin, 2, device="cuda")
+    r = torch.randn(N, hw, hw, cout, device="cuda").to(DT) if res else None
+    by = x.numel() * 2 + N * hw * hw * cout * 2 * (2 if res else 1)
+    ms = timeit(lambda: ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=min(32, cout // 2), out_f32=False))
+    ops.FUSED_IMPL = 0
+    print(f"   {cin}->{cout}@{hw} res={int(res)}: {2.0 * N * hw * hw * cin * cout * 9 / ms / 1e9:.0f} TFLOP/s")
+    return ms, by
+
+
 def fused_sc(c, sc, hw):
     h = torch.randn(N, hw, hw, c, device="cuda").to(DT); xr = torch.randn(N, hw, hw, sc, device="cuda").to(DT)
     wp = ops.pack_conv_weight(torch.randn(c, c, 3, 3, device="cuda") / math.sqrt(9 * c), 0, DT)
@@ -125,6 +139,9 @@ def sample():
 
 
 CASES = {
+    "s64c1": lambda: fused16(64, 64, 128, False), "s64c2": lambda: fused16(64, 64, 128, True), "s12864": lambda: fused16(128, 64, 128, False),
+    "s128c1": lambda: fused16(128, 128, 64, False), "s128c2": lambda: fused16(128, 128, 64, True),
+    "s128c1s": lambda: fused16(128, 128, 32, False), "s128c2s": lambda: fused16(128, 128, 32, True), "s3264": lambda: fused16(32, 64, 128, False),
     "band32c1": lambda: band(32, False), "band32c2": lambda: band(32, True), "band64c1": lambda: band(64, False),
     "gnstats32": lambda: gnstats(32, 256, DT), "gnstats128": lambda: gnstats(128, 32, torch.float32),
     "gnapply32": lambda: gnapply(32, 256, DT), "gnapply128": lambda: gnapply(128, 32, torch.float32),
