@@ -89,7 +89,8 @@ def main():
                      ("r2_ops.log", "r2_ops.txt"), ("bench_breakdown.json", "r2_bench_breakdown.json"),
                      ("r2_train_full.json", "r2_train_full.json"), ("r2_configs.json", "r2_configs.json"),
                      ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_train_b8_n2.json", "r2_train_b8_n2.json"),
-                     ("r2_train_full_n2.json", "r2_train_full_n2.json")):
+                     ("r2_train_full_n2.json", "r2_train_full_n2.json"), ("r2_bench_n4.json", "r2_bench_n4.json"),
+                     ("r2_train_b8_n4.json", "r2_train_b8_n4.json"), ("r2_train_full_n4.json", "r2_train_full_n4.json")):
         if (G / src).exists():
             shutil.copy(G / src, P / dst)
 
