@@ -364,7 +364,6 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             sp[e] = __ldg(src + e);
-            if (do_silu) { sp[e].x *= 0.5f; sp[e].y *= 0.5f; sp[e].z *= 0.5f; sp[e].w *= 0.5f; }
           }
         }
         const int cb = cq % NBUF;
@@ -419,14 +418,18 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 float a = fmaf(f[2 * e], sp[e].x, sp[e].y);
                 float c = fmaf(f[2 * e + 1], sp[e].z, sp[e].w);
                 if (do_silu) {
-                  // sp holds HALF the scale/shift: silu(2h) = h + h*tanh(h) -- one SFU op + one FMA per element instead of
-                  // ex2 + rcp + ~9 (the __expf / __fdividef forms carry a denormal rescale each); measured -2..-14 % on
-                  // the 64- and 128-wide layers.  tanh.approx.f32: relative error 2^-11 (conv error unchanged, 2.1e-4)
-                  float ta, tc;
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(tc) : "f"(c));
-                  a = fmaf(a, ta, a);
-                  c = fmaf(c, tc, c);
+                  // x * sigmoid(x) with the flush-to-zero SFU approximations (ex2 + rcp + three FP32 instructions; the
+                  // __expf / __fdividef forms carry a denormal rescale and a division sequence: ~15 instructions).
+                  // The cheaper h + h*tanh(h) form (h = x/2) measured another -2..-14 % here, but its error for x < 0
+                  // (cancellation in 1 + tanh) is systematic: through the depth of config B it moved a few parameter
+                  // gradients from 4e-2 to 5e-2 against the oracle (tests/test_gpu_backward.py), so it is not used.
+                  float ea, ec, ra, rc;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(a * -1.4426950408889634f));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ec) : "f"(c * -1.4426950408889634f));
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f + ea));
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ec));
+                  a *= ra;
+                  c *= rc;
                 }
                 f[2 * e] = a;
                 f[2 * e + 1] = c;

@@ -83,6 +83,19 @@ def fused16(cin, cout, hw, res, impl=0):
     return ms, by
 
 
+def gnbwd(n, hw, c, res=True):
+    """GroupNorm+SiLU backward as the training step calls it: fp32 x, bf16 dA, fp32 residual gradient -> dx fp32 + bf16,
+    re-materialised activation, fused bias gradient.  bytes = reads (x twice, dA twice, residual) + writes."""
+    x = torch.randn(n, hw, hw, c, device="cuda"); da = torch.randn(n, hw, hw, c, device="cuda").to(torch.bfloat16)
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    r = torch.randn(n, hw, hw, c, device="cuda") if res else None
+    ss, mr = ops.gn_finalize(ops.gn_stats(x, 16), gamma, beta, hw * hw, 1e-6, return_mean_rstd=True)
+    dg, db, cs = torch.empty(c, device="cuda"), torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    e = n * hw * hw * c
+    by = e * (2 * 4 + 2 * 2 + (4 if res else 0) + 4 + 2 + 2)
+    return timeit(lambda: ops.gn_bwd(x, da, ss, mr, gamma, True, dg, db, residual=r, want_act=True, colsum_out=cs)), by
+
+
 def fused_sc(c, sc, hw):
     h = torch.randn(N, hw, hw, c, device="cuda").to(DT); xr = torch.randn(N, hw, hw, sc, device="cuda").to(DT)
     wp = ops.pack_conv_weight(torch.randn(c, c, 3, 3, device="cuda") / math.sqrt(9 * c), 0, DT)
@@ -142,6 +155,8 @@ CASES = {
     "s64c1": lambda: fused16(64, 64, 128, False), "s64c2": lambda: fused16(64, 64, 128, True), "s12864": lambda: fused16(128, 64, 128, False),
     "s128c1": lambda: fused16(128, 128, 64, False), "s128c2": lambda: fused16(128, 128, 64, True),
     "s128c1s": lambda: fused16(128, 128, 32, False), "s128c2s": lambda: fused16(128, 128, 32, True), "s3264": lambda: fused16(32, 64, 128, False),
+    "gnb256": lambda: gnbwd(8, 256, 32), "gnb128": lambda: gnbwd(8, 128, 64), "gnb64": lambda: gnbwd(8, 64, 128), "gnb32": lambda: gnbwd(8, 32, 128),
+    "gnb256b32": lambda: gnbwd(32, 256, 32),
     "band32c1": lambda: band(32, False), "band32c2": lambda: band(32, True), "band64c1": lambda: band(64, False),
     "gnstats32": lambda: gnstats(32, 256, DT), "gnstats128": lambda: gnstats(128, 32, torch.float32),
     "gnapply32": lambda: gnapply(32, 256, DT), "gnapply128": lambda: gnapply(128, 32, torch.float32),
