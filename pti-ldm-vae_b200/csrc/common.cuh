@@ -282,5 +282,13 @@ __device__ __forceinline__ float round16(float x) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the flush-to-zero SFU approximations: ex2 + rcp + three FP32 instructions.  (__expf / __fdividef carry
+// a denormal-range rescale and a division sequence, ~15 instructions per element; the conv prologues are issue / SFU bound.)
+__device__ __forceinline__ float silu_ftz(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 }  // namespace ptivae

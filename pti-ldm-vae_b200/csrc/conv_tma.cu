@@ -532,8 +532,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               float a = fmaf(f[2 * e], sp[e].x, sp[e].y);
               float c = fmaf(f[2 * e + 1], sp[e].z, sp[e].w);
               if (do_silu) {
-                a = __fdividef(a, 1.0f + __expf(-a));
-                c = __fdividef(c, 1.0f + __expf(-c));
+                a = silu_ftz(a);
+                c = silu_ftz(c);
               }
               f[2 * e] = a;
               f[2 * e + 1] = c;
