@@ -18,11 +18,11 @@
 // TMA store, no team barrier); the 16-bit residual line of a pixel is read straight from global memory one band ahead;
 // GroupNorm statistics are column sums of the stored values in fixed order, finalised per band by an otherwise idle warp
 // (deterministic, no atomics).
-// What bounds it (clock64 timelines of CTA 0, tools/prof_band.py): the MMAs of a band take ~1.8k cycles, but every warp of
-// the prologue / epilogue runs latency bound at ~0.12 IPC, and the SiLU of the 4 x 130 x Cin prologue elements costs two
-// SFU slots each (tanh is half rate: the tanh, the fp32 ex2+rcp and the packed half2 forms all measured the same) =
-// ~2.1k cycles per band at 16 SFU lanes per clock.  The prologue therefore runs in packed half2 (1.5 instructions per
-// element instead of 9) to leave the issue slots to the epilogue, and is still the longest stage.
+// What bounds it (clock64 timelines of CTA 0, tools/prof_band.py): the MMAs of a band take ~1.8k cycles and
+// the epilogue ~1k, but the prologue needs ~5k cycles per 4-row batch -- 3.3 SiLU elements per clock and SM, close to what
+// the SFU delivers for MUFU.TANH (the fp32 tanh, fp32 ex2+rcp and packed-half2 forms all measured the same or worse;
+// without the SiLU the kernel runs at 0.156 ms instead of 0.200).  The prologue runs in packed half2 (1.5 instructions per
+// element instead of 9), which leaves the issue slots to the other roles, and is the pipeline's period.
 // Warp roles (864 threads): 0-15 epilogue (four teams of four warps, team = output row dy of the band), 16-23 transform,
 // 24 MMA issuer (+TMEM), 25 row loader, 26 weight loader, then the per-band statistics finalizer (so that no epilogue warp
 // waits on another team).
@@ -51,7 +51,7 @@ struct Cfg {
   static_assert(RES == 0 || RES == 2, "no residual, or a 16-bit residual added in place");
   static constexpr uint32_t LB = CIN * 2;                      // operand line: one pixel's channels
   static constexpr uint32_t ROWB = r1k(kLW * LB);              // one ring slot
-  static constexpr int NR = CIN == 32 ? BAND_NR32 : 8;                // ring slots (a band uses 6, the next batch of 4 is being transformed, the rest in flight)
+  static constexpr int NR = CIN == 32 ? BAND_NR32 : 8;         // ring slots (a band uses 6, the next batch of 4 is in the prologue, the rest in flight)
   static constexpr int SLOTS = 1;                              // one 8 KB scratch per epilogue team = 2 KB per warp
   static constexpr uint32_t BLK = COUT * LB;                   // one tap's weights [32 co][CIN]
   static constexpr uint32_t WBYTES = 12u * BLK;                // kx = 0: W2 W1 W0 0 0 0 | kx = 1: W2 W1 W0 | kx = 2: W2 W1 W0
