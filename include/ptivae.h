@@ -66,7 +66,7 @@ int ptivae_conv_parts(int H, int W, int mode);
  *   x           NHWC [N][H][W][Cin], storage in_fmt (fp32 stream or the h16 operand format)
  *   scale_shift fp32 [N][Cin][2] from ptivae_gn_finalize, or NULL (identity prologue); silu != 0 -> SiLU.
  *               Zero padding is applied AFTER the normalisation, as nn.Conv2d(padding=1) does.
- *   w_packed    h16 [9][Cout][Cin]; Cin, Cout in {32, 64, 128}
+ *   w_packed    h16 [9][Cout][Cin]; Cin, Cout in {32, 64, 128} (and 256 on the h16 stream, see ptivae_conv3x3_fused_query)
  *   residual/out/gn_part: as ptivae_conv_umma, with P = ptivae_conv3x3_fused_parts(H, W) (16x16 tiles).
  *   impl: 0 = auto; 1 = register-staged kernel (all shapes, both operand formats); 2 = TMA-staged kernel
  *         (Cin,Cout <= 64); 3 = chunk-pipelined TMA kernel (all widths).  2 and 3 need fp16 operands and an fp32
@@ -76,6 +76,9 @@ int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, in
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,
                          int impl, void* stream);
 int ptivae_conv3x3_fused_parts(int H, int W);
+/* 0 when ptivae_conv3x3_fused has a kernel for (in_fmt, residual kind 0 none | 1 fp32 | 2 h16, out_f32, Cin, Cout, f16), -2
+ * otherwise (nothing is launched).  Widths 32/64/128: always; 256 (config B): h16 in, h16 or no residual, h16 out. */
+int ptivae_conv3x3_fused_query(int in_fmt, int res_kind, int out_f32, int Cin, int Cout, int f16);
 /* conv2 of an AEKLResBlock whose nin_shortcut is a 1x1 conv, with that shortcut fused into the same accumulators:
  *   out = conv3x3_s1_p1( act(h*scale + shift) ) + W_sc * x + bias      (fp32 stream out, no residual tensor)
  *   replaces: `return self.nin_shortcut(x) + h` of AEKLResBlock.forward together with its conv2.

@@ -24,6 +24,7 @@ SIGNATURES = {
     "ptivae_conv3x3_fused": [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
                              _c_int, _c_void_p] + [_c_int] * 8 + [_c_void_p],
     "ptivae_conv3x3_fused_parts": [_c_int] * 2,
+    "ptivae_conv3x3_fused_query": [_c_int] * 6,
     "ptivae_conv3x3_fused_sc": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
                                 _c_int, _c_void_p] + [_c_int] * 7 + [_c_void_p],
     "ptivae_up2x_conv3x3": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],

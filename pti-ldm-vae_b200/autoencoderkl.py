@@ -272,7 +272,8 @@ class _Executor:
         cout, cin = w.shape[0], w.shape[1]
         g = self._want_stats(cout, stats)
         out_f32 = out_f32 and not self.stream16
-        if self.fused_conv and cin in _FUSED_WIDTHS and cout in _FUSED_WIDTHS:
+        if self.fused_conv and ops.conv3x3_fused_supported(a.t.dtype, None if residual is None else residual.dtype, out_f32,
+                                                           cin, cout, self.op_dtype):
             r = ops.conv3x3_fused(a.t, ss, True, self.packed(w), self.f32(conv.bias), residual=residual, gn_groups=g,
                                   out_f32=out_f32)
         else:

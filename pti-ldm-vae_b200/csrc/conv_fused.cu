@@ -455,6 +455,19 @@ extern "C" int ptivae_debug_set_trace(void* buf) {
   return PTIVAE_OK;
 }
 
+// 0 if ptivae_conv3x3_fused has a kernel for this combination of widths and storage formats (res_kind: 0 none, 1 fp32,
+// 2 16-bit), -2 otherwise; nothing is launched.  (The 256-wide instantiations exist for the 16-bit stream only.)
+extern "C" int ptivae_conv3x3_fused_query(int in_fmt, int res_kind, int out_f32, int Cin, int Cout, int f16) {
+  if (!(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256) || !(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256))
+    return PTIVAE_ERR_UNSUPPORTED;
+  if (Cin <= 128 && Cout <= 128) return PTIVAE_OK;       // the register-staged kernel takes whatever the TMA kernels do not
+  static const int dummy = 0;
+  FusedCall c{&dummy, in_fmt, nullptr, 1, &dummy, nullptr, res_kind ? &dummy : nullptr, res_kind == 1, nullptr, out_f32, nullptr, 0,
+              1, 16, 16, Cin, Cout, f16, nullptr, false};
+  c.dry = true;
+  return conv3x3_tma2_launch(c, nullptr);
+}
+
 extern "C" int ptivae_conv3x3_fused_parts(int H, int W) {
   if (H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
   return ((H + kFT - 1) / kFT) * ((W + kFT - 1) / kFT);
@@ -471,9 +484,16 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
   if (impl < 0 || impl > 4) return PTIVAE_ERR_ARG;
   if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   if (in_fmt != 2 && in_fmt != (f16 ? 1 : 0)) return PTIVAE_ERR_ARG;  // 16-bit input must use the operand format
-  if (!(Cin == 32 || Cin == 64 || Cin == 128) || !(Cout == 32 || Cout == 64 || Cout == 128)) return PTIVAE_ERR_UNSUPPORTED;
+  if (!(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256) || !(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256))
+    return PTIVAE_ERR_UNSUPPORTED;
   if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
     return PTIVAE_ERR_ARG;
+  if (Cin == 256 || Cout == 256) {   // 256-wide layers (config B): the chunk-pipelined kernel only, 16-bit stream only
+    if (impl != 0 && impl != 3) return PTIVAE_ERR_UNSUPPORTED;
+    FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
+                N, H, W, Cin, Cout, f16, g_fused_trace, false};
+    return conv3x3_tma2_launch(c, stream);
+  }
   if (impl != 1) {
     FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
                 N, H, W, Cin, Cout, f16, g_fused_trace, impl == 2};

@@ -74,10 +74,11 @@ struct Cfg {
   static constexpr Pick pick() {
     // preference: double-buffered chunks > (fp32 input) a tile's worth of raw blocks in flight > weight-ring depth
     // (16-bit input: the chunk buffer is also the TMA landing zone, so more than two keep a load in flight)
-    const int nbufs[4] = {IN32 ? 0 : 4 * NCH, IN32 ? 0 : 3 * NCH, 2 * NCH, NCH};
+    // (256 input channels = 4 chunks per tile: the chunks flow through a ring of 3 or 2 buffers)
+    const int nbufs[6] = {IN32 ? 0 : 4 * NCH, IN32 ? 0 : 3 * NCH, 2 * NCH, NCH, NCH > 3 ? 3 : 0, NCH > 2 ? 2 : 0};
     for (int pass = 0; pass < 2; ++pass) {          // pass 0 insists on a ring of >= 3 stages
       const int min_nst = pass == 0 ? 3 : 2;
-      for (int bi = 0; bi < 4; ++bi) {
+      for (int bi = 0; bi < 6; ++bi) {
         const int nbuf = nbufs[bi];
         if (nbuf < 2 || nbuf > 4) continue;
         if (!IN32) {
@@ -140,7 +141,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   constexpr uint32_t kLayout = (KCH == 64) ? kLayoutSW128 : kLayoutSW64;
   constexpr uint32_t kSBO_A = kHP * LB, kSBO_B = 8u * LB;
   constexpr uint32_t kIdesc = make_idesc_16(128, COUT, F16);
-  constexpr uint32_t TMEM_COLS = 4 * COUT;
+  // two accumulator stages of 2 M blocks x COUT columns; 256 output channels fill TMEM with ONE stage (the MMAs of tile
+  // t+1 then wait for the drain of tile t)
+  constexpr int NSTG = COUT > 128 ? 1 : 2;
+  constexpr uint32_t TMEM_COLS = NSTG * 2 * COUT;
   constexpr int UPC = KCH / 8;                  // 16-byte vectors per operand line
   constexpr int NPIECE = IN32 ? CIN / XC : NCH; // input pieces per tile
   constexpr int PPC = IN32 ? KCH / XC : 1;      // pieces per chunk
@@ -275,8 +279,8 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc_fence_after();
       }
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
-        const int st = it & 1;
-        mbar_wait(&acc_empty[st], ((it >> 1) & 1) ^ 1u);
+        const int st = it % NSTG;
+        mbar_wait(&acc_empty[st], ((it / NSTG) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + st * 2 * COUT;
         uint32_t accum = 0;
@@ -484,13 +488,13 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (leader && total_units > 0) issue_res(0);
     int q = 0, it = 0;
     for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
-      const int st = it & 1;
+      const int st = it % NSTG;
       const int n = t / tiles_per_img;
       const int trem = t - n * tiles_per_img;
       const int tiy = trem / args.tiles_x, tix = trem - tiy * args.tiles_x;
       const int x0 = tix * kT + mb * 8, y0 = tiy * kT;
       if (threadIdx.x == 0) TMA4_TRACE(it, 4);
-      mbar_wait(&acc_full[st], (it >> 1) & 1);
+      mbar_wait(&acc_full[st], (it / NSTG) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) TMA4_TRACE(it, 6);
 #pragma unroll 1
@@ -637,6 +641,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
   if constexpr (!C::FITS) {
     return PTIVAE_ERR_UNSUPPORTED;
   } else {
+    if (c.dry) return PTIVAE_OK;
     Args a{};
     a.N = c.N; a.H = c.H; a.W = c.W;
     a.tiles_x = (c.W + kT - 1) / kT;
@@ -753,6 +758,9 @@ int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream) {
   PTIVAE_T2_CASE(64, 128);
   PTIVAE_T2_CASE(128, 64);
   PTIVAE_T2_CASE(128, 128);
+  PTIVAE_T2_CASE(128, 256);
+  PTIVAE_T2_CASE(256, 128);
+  PTIVAE_T2_CASE(256, 256);
 #undef PTIVAE_T2_CASE
   return PTIVAE_ERR_UNSUPPORTED;
 }

@@ -21,6 +21,7 @@ struct FusedCall {   // arguments of ptivae_conv3x3_fused, shared by its two imp
   const void* sc_x = nullptr;   // fused 1x1 shortcut: raw 16-bit block input [N][H][W][sc_cin] ...
   const void* sc_w = nullptr;   // ... its packed weights [1][Cout][sc_cin] (conv_tma2.cu only)
   int sc_cin = 0;
+  bool dry = false;             // query only: return 0 if a kernel is instantiated for this call, without launching
 };
 // TMA-staged implementation (conv_tma.cu): returns PTIVAE_ERR_UNSUPPORTED (-2) if the shape/mode has no
 // instantiation, so the caller can fall back to the register-staged kernel.

@@ -195,6 +195,13 @@ def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tens
     return (out, part) if gn_groups > 0 else out
 
 
+def conv3x3_fused_supported(x_dtype, res_dtype, out_f32: bool, cin: int, cout: int, op_dtype) -> bool:
+    """Whether conv3x3_fused has a kernel for this combination (widths 32/64/128 always; 256 on the 16-bit stream)."""
+    in_fmt = _FMT.get(x_dtype, -1)
+    res_kind = 0 if res_dtype is None else (1 if res_dtype == torch.float32 else 2)
+    return _lib.lib().ptivae_conv3x3_fused_query(in_fmt, res_kind, int(out_f32), cin, cout, int(op_dtype == F16)) == 0
+
+
 def fused_sc_supported(dtype: torch.dtype, cin: int, cout: int, sc_cin: int) -> bool:
     """(conv2 Cin, Cout, shortcut Cin) combinations for which conv2 + 1x1 shortcut run as one kernel."""
     return dtype == F16 and (cin, cout, sc_cin) in ((32, 32, 64), (64, 64, 32))

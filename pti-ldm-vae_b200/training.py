@@ -120,7 +120,8 @@ class TrainRun:
         w = conv.weight
         cout, cin = w.shape[0], w.shape[1]
         g = ex._want_stats(cout, stats)
-        if ex.fused_conv and cin in (32, 64, 128) and cout in (32, 64, 128):
+        if ex.fused_conv and ops.conv3x3_fused_supported(x.dtype, None if residual is None else residual.dtype, out_f32, cin, cout,
+                                                         ex.op_dtype):
             r = ops.conv3x3_fused(x, ss, True, ex.packed(w), ex.f32(conv.bias), residual=residual, gn_groups=g,
                                   out_f32=out_f32)
         else:

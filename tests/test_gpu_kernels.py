@@ -373,6 +373,49 @@ def test_conv3x3_fused_tma2(b200, cin, cout, in_f32, res, out_f32, n, h, w, grou
     assert float((outs[1] - outs[3]).abs().max()) <= 2.0 ** -9 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("cin,cout", [(128, 256), (256, 128), (256, 256)])
+@pytest.mark.parametrize("in_f32,res,out_f32", TMA2_MODES)
+@pytest.mark.parametrize("n,h,w,groups", [(2, 32, 32, 32), (1, 40, 24, 16), (5, 48, 48, 32), (3, 8, 8, 32)])
+def test_conv3x3_fused_tma2_wide(b200, cin, cout, in_f32, res, out_f32, n, h, w, groups):
+    """256-wide layers (config B) on the chunk-pipelined kernel (one accumulator stage for 256 outputs, 2-chunk ring) vs the
+    fp32 reference and vs the unfused route (gn_apply + conv_umma).  The 16-bit stream forms always exist; the fp32-stream
+    forms only where their staging fits in shared memory (ptivae_conv3x3_fused_query), and the rest raise."""
+    if DT != torch.float16:
+        pytest.skip("the TMA-staged kernels are instantiated for fp16 operands only")
+    ops = b200.ops
+    rdt = None if not res else (DT if res == "h16" else torch.float32)
+    ok = ops.conv3x3_fused_supported(torch.float32 if in_f32 else DT, rdt, out_f32, cin, cout, DT)
+    if not in_f32 and not out_f32 and rdt != torch.float32:
+        assert ok, "the 16-bit stream forms must be instantiated"
+    x = _rand_act(n, h, w, cin, 61).float() * 1.5 + 0.2
+    x = x + 1e-3 * torch.randn_like(x) if in_f32 else x.to(DT)
+    wt, bias = _rand_conv(cout, cin, 3, 62)
+    ss = (torch.randn(n, cin, 2, device=DEV) * 0.5 + torch.tensor([1.0, 0.0], device=DEV)).contiguous()
+    r = torch.randn(n, h, w, cout, device=DEV) if res else None
+    if res == "h16":
+        r = r.to(DT)
+    wp = ops.pack_conv_weight(wt, 0, DT)
+    if not ok:
+        with pytest.raises(b200._lib.PtivaeError):
+            ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+        return
+    xin = F.silu(x.float().permute(0, 3, 1, 2) * ss[:, :, 0, None, None] + ss[:, :, 1, None, None]).to(DT).float()
+    ref = F.conv2d(xin, wt, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    out, part = ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+    out2, part2 = ops.conv3x3_fused(x, ss, True, wp, bias, residual=r, gn_groups=groups, out_f32=out_f32)
+    assert torch.equal(out, out2) and torch.equal(part, part2), "not deterministic"
+    _check_bf16(out.to(DT), ref, "fused conv 256")
+    o = out.float().view(n, h * w, groups, cout // groups)
+    acc = part.sum(dim=1)
+    assert torch.allclose(acc[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(acc[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    y = ops.gn_apply(x, ss, silu=True, dtype=DT)
+    un = ops.conv_umma(y, wp, bias, 0, residual=r, out_f32=out_f32)
+    assert float((un.float() - out.float()).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("cin", [32, 64])
 @pytest.mark.parametrize("res", [False, "h16"])
 @pytest.mark.parametrize("n,h,w,groups", [(2, 16, 128, 16), (1, 40, 200, 16), (3, 64, 256, 8), (1, 7, 130, 16), (200, 16, 128, 16),
