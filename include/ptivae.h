@@ -75,6 +75,13 @@ int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, in
                          const float* bias, const void* residual, int res_f32, void* out, int out_f32,
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,
                          int impl, void* stream);
+/* Chained launches: the kernels of the forward chain can be launched with programmatic stream serialization, so their
+ * set-up (barrier init, TMEM allocation, loads of the static weights) overlaps the drain of the previous kernel on the
+ * stream; they then wait (griddepcontrol.wait) before reading or writing anything else.  mask bit 0: the tensor-core
+ * kernels (default on), bit 1: the small statistics / direct-conv / latent kernels (default off: measured slower).
+ * PTIVAE_CHAIN=<mask> in the environment sets the initial value; returns the previous mask.  Results are bit-identical
+ * for every mask. */
+int ptivae_set_chained_launch(int mask);
 int ptivae_conv3x3_fused_parts(int H, int W);
 /* 0 when ptivae_conv3x3_fused has a kernel for (in_fmt, residual kind 0 none | 1 fp32 | 2 h16, out_f32, Cin, Cout, f16), -2
  * otherwise (nothing is launched).  Widths 32/64/128: always; 256 (config B): h16 in, h16 or no residual, h16 out. */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "ptivae_conv_parts": [_c_int] * 3,
     "ptivae_conv3x3_fused": [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
                              _c_int, _c_void_p] + [_c_int] * 8 + [_c_void_p],
+    "ptivae_set_chained_launch": [_c_int],
     "ptivae_conv3x3_fused_parts": [_c_int] * 2,
     "ptivae_conv3x3_fused_query": [_c_int] * 6,
     "ptivae_conv3x3_fused_sc": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,

@@ -97,6 +97,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  chain_release();   // chained launch (common.cuh): set-up above overlaps the previous kernel's drain
+  chain_wait();
   const uint32_t tmem_S = tmem_base;             // S(j) lives at columns (j & 1) * BKV
   const uint32_t tmem_O = tmem_base + 2 * BKV;
 
@@ -302,7 +304,7 @@ static int launch_attn(const void* q, const void* k, const void* v, void* out, f
   a.out = static_cast<uint16_t*>(out);
   a.lse = lse;
   dim3 grid((L + 127) / 128, B);
-  attn_fwd_kernel<D, BKV, F16><<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, a);
+  launch_chain(attn_fwd_kernel<D, BKV, F16>, grid, dim3(320), smem, stream, tmQ, tmK, tmV, a);
   return static_cast<int>(cudaGetLastError());
 }
 

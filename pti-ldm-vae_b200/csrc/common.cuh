@@ -71,6 +71,39 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the forward chain is launched with the programmatic-stream-serialization attribute (launch_chain below):
+// its CTAs may become resident while the previous kernel of the stream is still draining, run their set-up (barrier init,
+// TMEM allocation, descriptor prefetch, loads of the static weights / bias) and block in chain_wait() until the previous
+// kernel has completed and its writes are visible.  Rules every such kernel follows:
+//   * chain_wait() before the first read of anything an earlier kernel of the stream wrote AND before the first global
+//     write (the output buffer may be memory an earlier kernel is still reading); every CTA executes it, so completion of
+//     this kernel implies completion of all earlier ones (the chain stays transitive);
+//   * chain_release() only after this CTA holds everything it will ever allocate (TMEM in particular): the next kernel's
+//     CTAs can only start once every CTA here has released, so they can never starve a CTA of this kernel.
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Persistent kernels release when their CTA starts its LAST tile (chain_release_late, issued by the MMA thread): CTAs of the
+// next kernels that are resident early poll in chain_wait() and measurably slow the running kernel down (a release at
+// kernel start cost +3 % on the forward step), so they should only arrive for the tail.
+#ifndef PTIVAE_CHAIN_RELEASE
+#define PTIVAE_CHAIN_RELEASE 2   // 0: never (implicit at kernel end) | 1: at kernel start | 2: persistent kernels at their last tile
+#endif
+__device__ __forceinline__ void chain_release() {        // one-tile-per-CTA and small kernels: after set-up
+#if PTIVAE_CHAIN_RELEASE
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void chain_release_early() {  // persistent kernels, after set-up (mode 1 only)
+#if PTIVAE_CHAIN_RELEASE == 1
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void chain_release_late(bool last_tile) {
+#if PTIVAE_CHAIN_RELEASE == 2
+  if (last_tile) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -289,6 +322,29 @@ __device__ __forceinline__ float silu_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
+}
+
+// Host side of the chain: a launch that lets the kernel start while its predecessor on the stream drains.  Only kernels
+// that call chain_wait() may be launched this way.  ptivae_set_chained_launch(0) (or PTIVAE_CHAIN=0) falls back to plain
+// stream order (chain_wait() then returns at once).
+int chained_launch_mask();   // bit 0: the tensor-core kernels, bit 1: the small (statistics / direct / latent) kernels
+template <int BIT = 1, typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (chained_launch_mask() & BIT) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return launch_chain<2>(kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 }  // namespace ptivae

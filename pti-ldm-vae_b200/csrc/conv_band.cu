@@ -142,6 +142,24 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   // the three zero blocks behind kx = 0's strip (the first MMA of a band clears all four output rows with them)
   for (uint32_t i = threadIdx.x; i < 3u * BLK / 16u; i += blockDim.x)
     reinterpret_cast<uint4*>(wts + 3u * BLK)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // chained launch (common.cuh): TMEM is held, the next kernel may start arriving; the (static) weights are fetched while
+  // the previous kernel of the stream drains, everything else waits for it
+  chain_release_early();
+  if (warp == W_W) {   // weights: resident, (kx, reversed ky) order
+    if (elect_one()) {
+      mbar_expect_tx(w_full, 9u * BLK);
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          tma_load_3d(wts + (strip_off(kx) + (2 - ky)) * BLK, &tmW, w_full, 0, 0, ky * 3 + kx);
+    }
+    __syncwarp();
+  }
+  chain_wait();
   // statistics slots this kernel's tiling does not use (the caller sized gn_part for 16x16 tiles)
   if (args.gn_groups > 0) {
     const int used = args.bands * args.colblocks, extra = args.parts - used, per = args.gn_groups * 2;
@@ -152,11 +170,6 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       args.gn_part[(n * args.parts + used) * per + rem] = 0.f;
     }
   }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
 
   // segment s -> (image, column block, first band, end band)
   auto seg_decode = [&](int s, int& n, int& cb, int& b0, int& b1) {
@@ -169,14 +182,6 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   };
 
   if (warp == W_W) {
-    // ------------------------------------------------------------------ weights: resident, (kx, reversed ky) order
-    if (elect_one()) {
-      mbar_expect_tx(w_full, 9u * BLK);
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx)
-          tma_load_3d(wts + (strip_off(kx) + (2 - ky)) * BLK, &tmW, w_full, 0, 0, ky * 3 + kx);
-    }
-    __syncwarp();
     // ---- statistics finalizer: per band, (sum, sum of squares) of every group over the 16 warps' column sums, in index
     // order (deterministic), written as this tile's partial.  lane = (group, moment); groups beyond 16: second pass.
     if (args.gn_groups > 0) {
@@ -241,6 +246,7 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         int n, cb, b0, b1;
         seg_decode(s, n, cb, b0, b1);
         for (int b = b0; b < b1; ++b, ++it) {
+          chain_release_late(b + 1 == b1 && s + static_cast<int>(gridDim.x) >= args.num_segs);
           const int st = it & 1;
           mbar_wait(&acc_empty[st], ((it >> 1) & 1) ^ 1u);
           tc_fence_after();
@@ -567,7 +573,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(conv3x3_band_kernel<CIN, RES>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
   const int grid = a.num_segs < sms ? a.num_segs : sms;
-  conv3x3_band_kernel<CIN, RES><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, a);
+  launch_chain(conv3x3_band_kernel<CIN, RES>, dim3(grid), dim3(kThreads), C::SMEM, stream, tmX, tmW, a);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
                                                                 const float* __restrict__ bias,
                                                                 void* __restrict__ out, int H, int W, int Cin,
                                                                 int Cout, int out_fmt, int rows) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   extern __shared__ float sw[];  // [9*Cin][Cout] then bias [Cout]
   float* sb = sw + 9 * Cin * Cout;
   for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
                                                                  const float* __restrict__ ss,  // [N][Cin][2] or null
                                                                  float* __restrict__ out, int H, int W, int Cin,
                                                                  int in_fmt, int lp) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   extern __shared__ float sw[];  // [9*Cin][COUT]
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) {
     const int co = i % COUT;
@@ -185,6 +189,8 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const void* __r
 __global__ void __launch_bounds__(256) conv3x3_small_cin_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                     const float* __restrict__ bias, void* __restrict__ out,
                                                                     int H, int W, int Cin, int Cout, int out_fmt) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   extern __shared__ float sw[];  // [9*Cin][Cout] then bias [Cout]
   float* sb = sw + 9 * Cin * Cout;
   for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
@@ -263,6 +269,8 @@ __global__ void __launch_bounds__(256, 2) conv3x3_cin1_kernel(const float* __res
                                                            const float* __restrict__ bias, void* __restrict__ out,
                                                            int H, int W, int Cout, int out_fmt,
                                                            float* __restrict__ gn_part, int gn_groups) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   __shared__ float red[8][32][16];     // [warp][lane-of-octet][sum x8, sumsq x8]
   const int vecs = Cout / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +391,8 @@ __global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void*
                                                                      const float* __restrict__ bias,
                                                                      const float* __restrict__ ss, float* __restrict__ out,
                                                                      int H, int W, int Cin, int Cout, int nvt) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   constexpr int kFcHW = FcTile<kFcTW>::HW, kFcHalo = FcTile<kFcTW>::Halo, kFcQ = FcTile<kFcTW>::Q;
   extern __shared__ float fsm[];
   float* sp = fsm;                        // [9][kFcHalo] tap partials
@@ -488,6 +498,8 @@ __global__ void __launch_bounds__(kFcThreads) conv3x3_fewcout_kernel(const void*
 __global__ void conv1x1_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                      const float* __restrict__ bias, float* __restrict__ out, int N, int HW, int Cin,
                                      int Cout, int act) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   const size_t total = static_cast<size_t>(N) * HW;
   for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
        pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -534,7 +546,7 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
   if (H > 65535 || N > 65535) return PTIVAE_ERR_UNSUPPORTED;
   dim3 grid((W * (Cout / 8) + 255) / 256, (H + kSmallRows - 1) / kSmallRows, N);
   if (Cin == 1) {
-    conv3x3_cin1_kernel<<<grid, 256, 0, stream>>>(x, w, bias, out, H, W, Cout, out_fmt, gn_part, gn_groups);
+    launch_chain_small(conv3x3_cin1_kernel, grid, dim3(256), 0, stream, x, w, bias, out, H, W, Cout, out_fmt, gn_part, gn_groups);
     return static_cast<int>(cudaGetLastError());
   }
   if (Cin > 1) {   // register-blocked over 4 pixels: one thread per (row, pixel quad, channel octet)
@@ -546,13 +558,13 @@ extern "C" int ptivae_conv3x3_small_cin(const float* x, const float* w, const fl
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
       }
-      conv3x3_small_cin_px4_kernel<<<g4, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt);
+      launch_chain_small(conv3x3_small_cin_px4_kernel, g4, dim3(256), smem, stream, x, w, bias, out, H, W, Cin, Cout, out_fmt);
       return static_cast<int>(cudaGetLastError());
     }
   }
   const int rows = H <= 64 ? 4 : kSmallRows;     // small images: more, shorter blocks (the layer is latency bound)
   grid.y = (H + rows - 1) / rows;
-  conv3x3_small_cin_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, H, W, Cin, Cout, out_fmt, rows);
+  launch_chain_small(conv3x3_small_cin_kernel, grid, dim3(256), smem, stream, x, w, bias, out, H, W, Cin, Cout, out_fmt, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -571,7 +583,7 @@ static int launch_small_cout(const void* x, const float* w, const float* bias, c
   if ((lp & (lp - 1)) || (Cin / 4) % lp != 0 || H > 65535 || N > 65535) return PTIVAE_ERR_UNSUPPORTED;
   const int ppb = 256 / lp;
   dim3 grid((W + ppb - 1) / ppb, (H + kSmallRows - 1) / kSmallRows, N);
-  conv3x3_small_cout_kernel<COUT><<<grid, 256, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, in_fmt, lp);
+  launch_chain_small(conv3x3_small_cout_kernel<COUT>, grid, dim3(256), smem, stream, x, w, bias, ss, out, H, W, Cin, in_fmt, lp);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -580,7 +592,7 @@ static int launch_fewcout(dim3 grid, size_t smem, const void* x, const float* w,
                           float* out, int H, int W, int Cin, int Cout, int nvt, cudaStream_t stream) {
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(conv3x3_fewcout_kernel<FMT, TW>, 64 * 1024, attr_set)) return rc_attr;
-  conv3x3_fewcout_kernel<FMT, TW><<<grid, kFcThreads, smem, stream>>>(x, w, bias, ss, out, H, W, Cin, Cout, nvt);
+  launch_chain_small(conv3x3_fewcout_kernel<FMT, TW>, grid, dim3(kFcThreads), smem, stream, x, w, bias, ss, out, H, W, Cin, Cout, nvt);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -625,6 +637,6 @@ extern "C" int ptivae_conv1x1_small(const float* x, const float* w, const float*
     return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t total = static_cast<size_t>(N) * HW;
-  conv1x1_small_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, w, bias, out, N, HW, Cin, Cout, act);
+  launch_chain_small(conv1x1_small_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x, w, bias, out, N, HW, Cin, Cout, act);
   return static_cast<int>(cudaGetLastError());
 }

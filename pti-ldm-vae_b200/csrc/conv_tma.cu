@@ -153,6 +153,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tiles_per_img = args.tiles_x * args.tiles_y;
+  chain_release_early();                // chained launch (common.cuh): TMEM is held; only the weight loader runs ahead
+  if (warp != W_PRODB) chain_wait();
 
   if (warp == W_PRODB) {
     // ------------------------------------------------------------------ weights
@@ -250,6 +252,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_after();
       }
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        chain_release_late(t + static_cast<int>(gridDim.x) >= args.num_tiles);
         const int b = it & 1;
         const uint32_t ph2 = (it >> 1) & 1;
         mbar_wait(&op_full[b], ph2);
@@ -617,7 +620,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  conv3x3_tma_kernel<CIN, COUT, IN32, RES, OUT32><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, a);
+  launch_chain(conv3x3_tma_kernel<CIN, COUT, IN32, RES, OUT32>, dim3(grid), dim3(kThreads), C::SMEM, stream, tmX, tmW, tmR, tmO, a);
   return static_cast<int>(cudaGetLastError());
   }
 }

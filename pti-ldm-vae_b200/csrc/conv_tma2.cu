@@ -209,6 +209,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tiles_per_img = args.tiles_x * args.tiles_y;
+  // chained launch (common.cuh): this CTA holds its TMEM, so the next kernel may start arriving; everything but the loader
+  // of the (static) weights waits for the previous kernel of the stream before touching activations / statistics / outputs
+  chain_release_early();
+  if (warp != W_W) chain_wait();
 
   if (warp == W_W) {
     // ------------------------------------------------------------------ weights (order: chunk outer, tap inner)
@@ -279,6 +283,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc_fence_after();
       }
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        chain_release_late(t + static_cast<int>(gridDim.x) >= args.num_tiles);
         const int st = it % NSTG;
         mbar_wait(&acc_empty[st], ((it / NSTG) & 1) ^ 1u);
         tc_fence_after();
@@ -715,7 +720,8 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
     constexpr int kThreads = (NEW + ntw<CIN, COUT, IN32>() + 3) * 32;
-    conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC><<<grid, kThreads, C::SMEM, stream>>>(tmX, tmW, tmR, tmO, tmXs, tmWs, a);
+    launch_chain(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC>, dim3(grid), dim3(kThreads), C::SMEM, stream, tmX, tmW, tmR,
+                 tmO, tmXs, tmWs, a);
     return static_cast<int>(cudaGetLastError());
   }
 }

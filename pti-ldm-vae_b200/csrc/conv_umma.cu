@@ -108,6 +108,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  chain_release();   // chained launch (common.cuh): set-up above overlaps the previous kernel's drain
+  chain_wait();
 
   if (warp == 0) {
     if (elect_one()) {   // single elected thread (lets ptxas issue UTCHMMA / UTMALDG without an ELECT loop)
@@ -270,7 +272,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs&
   static bool attr_set[64] = {};
   if (int rc_attr = ensure_dyn_smem(conv_umma_kernel<KCH, BN, F16>, 200 * 1024, attr_set)) return rc_attr;
   dim3 grid(a.tiles_x * a.tiles_y * N, a.Cout / BN, nphase);
-  conv_umma_kernel<KCH, BN, F16><<<grid, 192, smem, stream>>>(tmA, tmB, a);
+  launch_chain(conv_umma_kernel<KCH, BN, F16>, grid, dim3(192), smem, stream, tmA, tmB, a);
   return static_cast<int>(cudaGetLastError());
 }
 

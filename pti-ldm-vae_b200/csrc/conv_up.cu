@@ -110,6 +110,8 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int tiles_per_img = args.tiles_x * args.tiles_y;
+  chain_release_early();            // chained launch (common.cuh): TMEM is held; only the weight loader runs ahead
+  if (warp != W_W) chain_wait();
 
   if (warp == W_W) {
     // ------------------------------------------------------------------ weight ring: 16 (phase, tap) x NCH slabs per tile
@@ -149,6 +151,7 @@ up2x_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       int s = 0, it = 0, gc = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        chain_release_late(t + static_cast<int>(gridDim.x) >= args.num_tiles);
         const int b = it % NOP;
         mbar_wait(&in_full[b], (it / NOP) & 1);
         tc_fence_after();
@@ -383,7 +386,7 @@ static int launch(const void* x, const void* w_packed, const float* bias, float*
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  up2x_conv3x3_kernel<C, EMIT16><<<grid, kThreads, Cf::SMEM, stream>>>(tmX, tmW, maps, a);
+  launch_chain(up2x_conv3x3_kernel<C, EMIT16>, dim3(grid), dim3(kThreads), Cf::SMEM, stream, tmX, tmW, maps, a);
   return static_cast<int>(cudaGetLastError());
 }
 

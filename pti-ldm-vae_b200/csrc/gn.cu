@@ -8,6 +8,8 @@
 //   gn_apply    : y = act(x*scale + shift) as a bf16 GEMM operand, act in {identity, SiLU};
 //                 optionally also emits the raw input rounded to bf16 (operand of nin_shortcut).
 // The same partial format [N][P][G][2] is produced by conv_umma's epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptivae_internal.h"
 #include "../../include/ptivae.h"
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
                                                        int HW, int C, int G, int pix_per_block, int in_fmt) {
   __shared__ float sm[256][8];     // per-thread (4 channel pairs) x (sum, sumsq)
   __shared__ float pairs[256][2];  // per channel pair of the image chunk
+  chain_release();
+  chain_wait();
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int v = threadIdx.x % vecs;
@@ -109,6 +113,8 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
                                                           float inv_count, float eps, int* __restrict__ range_flag) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  chain_release();
+  chain_wait();
   if (wid >= N * G) return;
   const int n = wid / G, g = wid - n * G;
   const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(n) * P * G + g;
@@ -160,6 +166,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
                                                        size_t total_vecs, int HW, int C, int in_fmt) {
   const int vecs = C / 8;
   const size_t per_img = static_cast<size_t>(HW) * vecs;
+  chain_release();
+  chain_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vecs;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / per_img);
@@ -200,6 +208,24 @@ static int stats_chunks(int /*N*/, int HW, int C, int* ppb_out) {
   return (HW + ppb - 1) / ppb;
 }
 
+// ---- chained (programmatic dependent) launches, see common.cuh ---------------------------------------------------------
+// Default: the tensor-core kernels only (mask 1).  Chaining the small kernels as well (mask 3) is correct but slower: a CTA
+// that sits in griddepcontrol.wait while the previous kernel finishes resumes later than a fresh launch would start, and
+// with ~64 small launches per forward that cost +0.19 ms per 5.47 ms step (measured, profiles/r2_chained_launch.txt).
+static int g_chain = -1;   // -1: not decided yet; PTIVAE_CHAIN=<mask> in the environment (0 turns it off)
+int ptivae::chained_launch_mask() {
+  if (g_chain < 0) {
+    const char* e = getenv("PTIVAE_CHAIN");
+    g_chain = e ? (atoi(e) & 3) : 1;
+  }
+  return g_chain;
+}
+extern "C" int ptivae_set_chained_launch(int mask) {
+  const int was = ptivae::chained_launch_mask();
+  g_chain = mask & 3;
+  return was;
+}
+
 extern "C" int ptivae_gn_stats_parts(int N, int HW, int C) {
   if (N <= 0 || HW <= 0 || C % 8 != 0 || C / 8 > 64 || 256 % (C / 8) != 0) return PTIVAE_ERR_ARG;
   int ppb;
@@ -215,7 +241,7 @@ extern "C" int ptivae_gn_stats(const void* x, float* partial, int N, int HW, int
   int ppb;
   const int chunks = stats_chunks(N, HW, C, &ppb);
   dim3 grid(chunks, N);
-  gn_stats_kernel<<<grid, 256, 0, stream>>>(x, partial, HW, C, G, ppb, in_fmt);
+  launch_chain_small(gn_stats_kernel, grid, dim3(256), 0, stream, x, partial, HW, C, G, ppb, in_fmt);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -237,8 +263,8 @@ extern "C" int ptivae_gn_finalize_checked(const float* partial, const float* gam
   if (!partial || !gamma || !beta || !scale_shift || N <= 0 || C % G != 0 || P <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float inv = 1.0f / (static_cast<float>(HW) * static_cast<float>(C / G));
-  gn_finalize_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(partial, gamma, beta, scale_shift, mean_rstd, N, C, G, P, inv,
-                                                                   eps, range_flag);
+  launch_chain_small(gn_finalize_kernel, dim3((N * G * 32 + 255) / 256), dim3(256), 0, stream, partial, gamma, beta, scale_shift,
+               mean_rstd, N, C, G, P, inv, eps, range_flag);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -251,11 +277,11 @@ extern "C" int ptivae_gn_apply(const void* x, const float* scale_shift, void* y,
   uint4* yy = static_cast<uint4*>(y);
   uint4* rr = static_cast<uint4*>(raw16);
   if (silu) {
-    if (out_f16) gn_apply_kernel<true, true><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
-    else gn_apply_kernel<true, false><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
+    if (out_f16) launch_chain_small(gn_apply_kernel<true, true>, dim3(grid), dim3(256), 0, stream, x, scale_shift, yy, rr, total, HW, C, in_fmt);
+    else launch_chain_small(gn_apply_kernel<true, false>, dim3(grid), dim3(256), 0, stream, x, scale_shift, yy, rr, total, HW, C, in_fmt);
   } else {
-    if (out_f16) gn_apply_kernel<false, true><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
-    else gn_apply_kernel<false, false><<<grid, 256, 0, stream>>>(x, scale_shift, yy, rr, total, HW, C, in_fmt);
+    if (out_f16) launch_chain_small(gn_apply_kernel<false, true>, dim3(grid), dim3(256), 0, stream, x, scale_shift, yy, rr, total, HW, C, in_fmt);
+    else launch_chain_small(gn_apply_kernel<false, false>, dim3(grid), dim3(256), 0, stream, x, scale_shift, yy, rr, total, HW, C, in_fmt);
   }
   return static_cast<int>(cudaGetLastError());
 }

@@ -32,6 +32,8 @@ __global__ void latent_sample_kernel(const float* __restrict__ mu, const float* 
                                      const float* __restrict__ eps_in, float* __restrict__ z,
                                      float* __restrict__ eps_out, const unsigned long long* __restrict__ rng_dev,
                                      size_t n, uint64_t seed, uint64_t offset) {
+  chain_release();   // chained launch (common.cuh)
+  chain_wait();
   if (rng_dev) {  // graph-replay friendly: (seed, offset) live in device memory
     seed = rng_dev[0];
     offset = rng_dev[1];
@@ -261,8 +263,8 @@ extern "C" int ptivae_latent_sample(const float* mu, const float* sigma, const f
                                     unsigned long long offset, void* stream_) {
   if (!mu || !sigma || !z || n <= 0) return PTIVAE_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  latent_sample_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, stream>>>(mu, sigma, eps_in, z, eps_out, rng_dev,
-                                                                      static_cast<size_t>(n), seed, offset);
+  launch_chain_small(latent_sample_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, stream, mu, sigma, eps_in, z, eps_out, rng_dev,
+               static_cast<size_t>(n), seed, offset);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -195,6 +195,12 @@ def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tens
     return (out, part) if gn_groups > 0 else out
 
 
+def set_chained_launch(mask: int) -> int:
+    """Programmatic dependent launches for the forward chain (ptivae.h): bit 0 the tensor-core kernels (default), bit 1 the
+    small kernels; returns the previous mask."""
+    return int(_lib.lib().ptivae_set_chained_launch(int(mask)))
+
+
 def conv3x3_fused_supported(x_dtype, res_dtype, out_f32: bool, cin: int, cout: int, op_dtype) -> bool:
     """Whether conv3x3_fused has a kernel for this combination (widths 32/64/128 always; 256 on the 16-bit stream)."""
     in_fmt = _FMT.get(x_dtype, -1)

@@ -94,6 +94,35 @@ def test_forward_matches_oracle_live(b200, oracle, b, h, w):
         assert _rel_l2(dec, ref.decode(mu_r)) <= TOL_RECON
 
 
+@pytest.mark.parametrize("cfg_name", ["A", "B"])
+def test_chained_launch_masks_are_bit_identical(b200, cfg_name):
+    """Programmatic dependent launches (ptivae_set_chained_launch) only move WHEN a kernel's set-up runs: the forward of
+    both configurations, eager and as a replayed CUDA graph, is bit-identical for every mask, on both residual streams."""
+    cfg = b200.config.AUTOENCODER_DEF_A if cfg_name == "A" else b200.config.AUTOENCODER_DEF_B
+    torch.manual_seed(5)
+    vae = b200.VAEModel.from_config(cfg).to(DEV).eval()
+    x = torch.randn(3, 1, 128, 144, device=DEV)
+    was = b200.ops.set_chained_launch(0)
+    try:
+        for stream in (torch.float16, torch.float32):
+            vae.autoencoder.set_stream_dtype(stream)
+            b200.ops.set_chained_launch(0)
+            ref = (vae.reconstruct_deterministic(x).clone(), vae.encode_deterministic(x).clone())
+            for mask in (1, 2, 3):
+                b200.ops.set_chained_launch(mask)
+                for _ in range(3):
+                    assert torch.equal(vae.reconstruct_deterministic(x), ref[0]), (stream, mask)
+                    assert torch.equal(vae.encode_deterministic(x), ref[1]), (stream, mask)
+                g = b200.GraphedVAE(vae, 3, 128, 144, mode="reconstruct")
+                g.x.copy_(x)
+                for _ in range(3):
+                    out = g()
+                    out = out[0] if isinstance(out, (tuple, list)) else out
+                    assert torch.equal(out, ref[0]), (stream, mask, "graph")
+    finally:
+        b200.ops.set_chained_launch(was)
+
+
 @pytest.mark.parametrize("h,w", [(64, 64), (128, 144)])
 def test_fp16_stream_matches_oracle(b200, oracle, h, w):
     """Inference with the residual stream in the fp16 operand format (AutoencoderKL.set_stream_dtype; the row-band conv
