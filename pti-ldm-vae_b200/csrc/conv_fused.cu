@@ -479,15 +479,21 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                                     int Cin, int Cout, int f16, int desc_base_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // 0 = auto, 1 = register-staged kernel (this file), 2 = TMA-staged (conv_tma.cu), 3 = chunk-pipelined TMA (conv_tma2.cu),
-  // 4 = row-band kernel (conv_band.cu: 32 output channels, 16-bit in/out)
+  // 4 = row-band kernel (conv_band.cu: 32 output channels, 16-bit in/out), 5 = two-SM kernel (conv_pair.cu: 128 / 256
+  // channels, 16-bit in/out)
   const int impl = desc_base_offset;
-  if (impl < 0 || impl > 4) return PTIVAE_ERR_ARG;
+  if (impl < 0 || impl > 5) return PTIVAE_ERR_ARG;
   if (!x || !w_packed || !bias || !out || N <= 0 || H <= 0 || W <= 0 || in_fmt < 0 || in_fmt > 2) return PTIVAE_ERR_ARG;
   if (in_fmt != 2 && in_fmt != (f16 ? 1 : 0)) return PTIVAE_ERR_ARG;  // 16-bit input must use the operand format
   if (!(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256) || !(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256))
     return PTIVAE_ERR_UNSUPPORTED;
   if (gn_groups > 0 && (!gn_part || Cout % gn_groups != 0 || 32 % (Cout / gn_groups) != 0 || Cout / gn_groups < 2))
     return PTIVAE_ERR_ARG;
+  if (impl == 5) {
+    FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
+                N, H, W, Cin, Cout, f16, nullptr, false};
+    return conv3x3_pair_launch(c, stream);
+  }
   if (Cin == 256 || Cout == 256) {   // 256-wide layers (config B): the chunk-pipelined kernel only, 16-bit stream only
     if (impl != 0 && impl != 3) return PTIVAE_ERR_UNSUPPORTED;
     FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,

@@ -30,6 +30,7 @@ int conv3x3_tma_launch(const FusedCall& c, cudaStream_t stream);
 int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream);
 // row-band implementation (conv_band.cu): Cout = 32, Cin in {32, 64}, 16-bit input / output / residual; same contract
 int conv3x3_band_launch(const FusedCall& c, cudaStream_t stream);
+int conv3x3_pair_launch(const FusedCall& c, cudaStream_t stream);   // conv_pair.cu: two-SM MMAs, 128/256 channels, 16-bit stream
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a function: remember per device (a process
 // that drives several GPUs must opt in on each of them).  `flags` is a function-local static array of 64 bools.

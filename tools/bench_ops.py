@@ -157,6 +157,10 @@ CASES = {
     "s128c1s": lambda: fused16(128, 128, 32, False), "s128c2s": lambda: fused16(128, 128, 32, True), "s3264": lambda: fused16(32, 64, 128, False),
     "s256c1": lambda: fused16(256, 256, 64, False), "s256c2": lambda: fused16(256, 256, 64, True),
     "s128256": lambda: fused16(128, 256, 64, False), "s256128": lambda: fused16(256, 128, 128, False),
+    "p128c1": lambda: fused16(128, 128, 64, False, impl=5), "p128c2": lambda: fused16(128, 128, 64, True, impl=5),
+    "p128c1s": lambda: fused16(128, 128, 32, False, impl=5), "p128c2s": lambda: fused16(128, 128, 32, True, impl=5),
+    "p256c1": lambda: fused16(256, 256, 64, False, impl=5), "p256c2": lambda: fused16(256, 256, 64, True, impl=5),
+    "p128256": lambda: fused16(128, 256, 64, False, impl=5), "p256128": lambda: fused16(256, 128, 128, False, impl=5),
     "gnb256": lambda: gnbwd(8, 256, 32), "gnb128": lambda: gnbwd(8, 128, 64), "gnb64": lambda: gnbwd(8, 64, 128), "gnb32": lambda: gnbwd(8, 32, 128),
     "gnb256b32": lambda: gnbwd(32, 256, 32),
     "band32c1": lambda: band(32, False), "band32c2": lambda: band(32, True), "band64c1": lambda: band(64, False),

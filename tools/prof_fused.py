@@ -8,20 +8,23 @@ trace = len(sys.argv) > 1 and sys.argv[1] == "trace"
 if len(sys.argv) > 2: ops.FUSED_IMPL = int(sys.argv[2])
 print("FUSED_IMPL", ops.FUSED_IMPL)
 only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
+H16 = len(sys.argv) > 4 and sys.argv[4] == "h16"    # 16-bit residual stream: 16-bit in / residual / out
 cases = [(64, 256, 256, 32, 32, True), (64, 256, 256, 32, 32, False), (64, 64, 64, 128, 128, True), (64, 128, 128, 64, 64, True), (64, 128, 128, 64, 64, False), (64, 256, 256, 64, 32, False), (64, 128, 128, 32, 64, False)]
 cases += [(64, 64, 64, 128, 128, False), (64, 128, 128, 128, 64, False), (64, 32, 32, 128, 128, True)]
 for (n, h, w, cin, cout, conv2) in cases:
     if only and f"{cin}-{cout}-{h}-{int(conv2)}" not in only:
         continue
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(n, h, w, cin, device="cuda", dtype=torch.float32 if not conv2 else torch.float16)
+    x = torch.randn(n, h, w, cin, device="cuda", dtype=torch.float32 if not (conv2 or H16) else torch.float16)
     wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).cuda()
     wp = ops.pack_conv_weight(wt, 0, torch.float16)
     bias = torch.randn(cout, generator=g).cuda()
     ss = torch.randn(n, cin, 2, device="cuda")
     res = torch.randn(n, h, w, cout, device="cuda") if conv2 else None
+    if H16 and conv2:
+        res = res.half()
     def run():
-        return ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=16, out_f32=conv2)
+        return ops.conv3x3_fused(x, ss, True, wp, bias, residual=res, gn_groups=16, out_f32=conv2 and not H16)
     for _ in range(2): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
