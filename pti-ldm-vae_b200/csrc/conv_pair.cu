@@ -510,6 +510,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       if (cpg > 0) {
         asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
         const int ei = threadIdx.x;                 // epilogue warps are warps 0 .. NEW-1
+        // (one thread per (group, moment): its loads are 2*cpg words apart -- bank conflicts that ncu shows as 60 % of the
+        // kernel's LDS wavefronts; a conflict-free thread-per-channel fold + shuffles measured no faster, the epilogue is not
+        // the stage that sets the tile period, and it changes the summation order of the statistics, so this stays)
         if (real && ei < 2 * args.gn_groups) {
           const int g = ei >> 1, k = ei & 1;
           float tsum = 0.f;

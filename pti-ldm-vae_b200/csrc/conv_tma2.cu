@@ -23,13 +23,21 @@
 
 namespace ptivae {
 namespace tma4 {
+#ifndef PTIVAE_NTW4
+#define PTIVAE_NTW4 8
+#endif
 
 constexpr int kT = 16, kHP = kT + 2, kHalo = kHP * kHP;
-constexpr int NTEAM = 2, NEW = NTEAM * 4;
-constexpr int W_TR0 = NEW;   // transform warps [NEW, NEW + NTW), then the MMA issuer and the two TMA producers
-// transform warps: 12 where the transform is the widest stage (64-channel fp32 input into a narrow output), else 8
-template <int CIN, int COUT, bool IN32>
-constexpr int ntw() { return (IN32 && CIN >= 64) ? 12 : 8; }
+// Epilogue teams (4 warps = the four TMEM lane quarters): 2 (team = M block), or 4 (team = M block x parity of the
+// 32-channel unit; 864 threads at 72 registers).  Four teams were measured on every 16-bit-stream shape with 64 or 128
+// output channels: -7 % on 64 -> 64 with a residual, +-1 % or worse elsewhere (the wide layers are bound by shared-memory
+// bandwidth), so only that shape uses them.
+template <int COUT, bool IN32, int RES, bool OUT32, int SC>
+constexpr int nteam() { return (!IN32 && !OUT32 && RES == 2 && SC == 0 && COUT == 64) ? 4 : 2; }
+// transform warps: 12 where the transform is the widest stage (64-channel fp32 input into a narrow output), else 8;
+// 8 beside four epilogue teams as well (4 were measured: the transform became the longest stage)
+template <int CIN, int COUT, bool IN32, int RES, bool OUT32, int SC>
+constexpr int ntw() { return nteam<COUT, IN32, RES, OUT32, SC>() == 4 ? PTIVAE_NTW4 : ((IN32 && CIN >= 64) ? 12 : 8); }
 constexpr uint32_t kSmemMax = 232448;
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 
@@ -38,6 +46,10 @@ constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 template <int CIN, int COUT, bool IN32, int RES, bool OUT32, int SC = 0>
 struct Cfg {
   static_assert(RES != 2 || !OUT32, "a 16-bit residual is added in place in a 16-bit output unit");
+  static constexpr int NTEAM = nteam<COUT, IN32, RES, OUT32, SC>(), NEW = NTEAM * 4;
+  // operand chunks of 64 channels.  (32-channel chunks for the 128-channel layers -- four buffers per tile instead of two,
+  // so that a buffer's MMA -> reload -> transform cycle overlaps three others -- measured 4 % SLOWER: the tile period is
+  // set by shared-memory bandwidth, not by that cycle)
   static constexpr int KCH = CIN >= 64 ? 64 : 32;
   static constexpr int NCH = CIN / KCH;
   static constexpr uint32_t LB = KCH * 2;
@@ -50,7 +62,7 @@ struct Cfg {
   static constexpr uint32_t RSLOT = SEP_RS ? 128 * 128 : 0;
   static constexpr uint32_t SLOT = OSLOT + RSLOT;
   static constexpr int NOB = COUT / 32;                       // units per M block
-  static constexpr uint32_t MISC = 1024 + NEW * COUT * 2 * 4 + COUT * 4 + 64 * 8 + 64;
+  static constexpr uint32_t MISC = 1024 + 8 * COUT * 2 * 4 + COUT * 4 + 64 * 8 + 64;
   // fused 1x1 shortcut (SC = its input channels, 32 or 64): two raw halo chunks of the block input + its weights
   static constexpr uint32_t LBS = SC * 2;
   static constexpr uint32_t SCHUNK = SC ? r1k(kHalo * LBS) : 0u;
@@ -126,14 +138,16 @@ struct Args {
   } while (0)
 
 template <int CIN, int COUT, bool IN32, int RES, bool OUT32, int SC>
-__global__ void __launch_bounds__((NEW + ntw<CIN, COUT, IN32>() + 3) * 32, 1)
+__global__ void __launch_bounds__((nteam<COUT, IN32, RES, OUT32, SC>() * 4 + ntw<CIN, COUT, IN32, RES, OUT32, SC>() + 3) * 32, 1)
 conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmXs, const __grid_constant__ CUtensorMap tmWs, const Args args) {
   using C = Cfg<CIN, COUT, IN32, RES, OUT32, SC>;
   static_assert(SC == 0 || (RES == 0 && !IN32), "the fused shortcut replaces the residual of a 16-bit-input conv2");
   constexpr bool F16 = true;
-  constexpr int NTW = ntw<CIN, COUT, IN32>(), NT = NTW * 32;
+  constexpr int NTEAM = C::NTEAM, NEW = C::NEW;
+  constexpr int NTW = ntw<CIN, COUT, IN32, RES, OUT32, SC>(), NT = NTW * 32;
+  constexpr int W_TR0 = NEW;   // transform warps [NEW, NEW + NTW), then the MMA issuer and the two TMA producers
   constexpr int W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
   constexpr int KCH = C::KCH, NCH = C::NCH, NBUF = C::NBUF, XC = C::XC, NXS = C::NXS, NST = C::NST, NOB = C::NOB;
   constexpr uint32_t LB = C::LB, CHUNK = C::CHUNK, SLAB = C::SLAB, OLB = C::OLB;
@@ -160,7 +174,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint8_t* scw = scbuf + 2 * C::SCHUNK;                     // [COUT][SC] shortcut weights (resident)
   uint8_t* wts = scw + C::SWBYTES;                          // resident [9*NCH][SLAB] | ring [NST][SLAB]
   float* colsum = reinterpret_cast<float*>(wts + (RESB ? C::WBYTES : NST * SLAB));   // [NEW][COUT][2]
-  float* sbias = colsum + NEW * COUT * 2;                   // [COUT]
+  float* sbias = colsum + 8 * COUT * 2;                     // [COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
   uint64_t* b_full = bars;             // [8]
   uint64_t* b_empty = bars + 8;        // [8]
@@ -171,10 +185,10 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* acc_full = bars + 32;      // [2]
   uint64_t* acc_empty = bars + 34;     // [2]
   uint64_t* res_full = bars + 36;      // [NTEAM][2]
-  uint64_t* sc_full = bars + 40;       // [2] shortcut chunk landed
-  uint64_t* sc_empty = bars + 42;      // [2] shortcut chunk consumed
-  uint64_t* scw_full = bars + 44;      // shortcut weights landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 46);
+  uint64_t* sc_full = bars + 44;       // [2] shortcut chunk landed
+  uint64_t* sc_empty = bars + 46;      // [2] shortcut chunk consumed
+  uint64_t* scw_full = bars + 48;      // shortcut weights landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 50);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -192,8 +206,8 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_init(&in_empty[s], NT);
       mbar_init(&op_full[s], NT);
       mbar_init(&op_empty[s], 1);
-      mbar_init(&res_full[s], 1);
     }
+    for (int s = 0; s < NTEAM * 2; ++s) mbar_init(&res_full[s], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], NEW * 32);
@@ -402,6 +416,62 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         uint8_t* ob = opbuf + cb * CHUNK;
         const uint32_t uu = IN32 ? static_cast<uint32_t>((p % PPC) * VPL + u) : static_cast<uint32_t>(u);   // 16-byte column in the line
+        if constexpr (H2) {
+          // 16-bit stream (inference only): the prologue in packed half2, as in conv_band.cu --
+          //   h = x * (scale/2) + shift/2 (HFMA2), t = tanh(h) (MUFU.TANH.F16 x2), silu(2h) = h*t + h (HFMA2)
+          // one SFU operation per element instead of two (SFU rate, measured: 16 results/clk/SM for ex2, rcp and tanh alike)
+          // and a fifth of the issue slots.  Vectors go through in batches of four with predicated loads / stores and no
+          // branch inside a batch: the straight-line form (load, compute, store, branch per vector) ran at one instruction
+          // per ~13 cycles -- nothing to overlap the LDS and SFU latencies with (5k cycles per chunk, SFU floor 1.4k).
+          constexpr int BT = 4;
+          const int mode = has_norm ? (do_silu ? 2 : 1) : 0;   // kernel-uniform
+#pragma unroll 1
+          for (int k0 = 0; k0 < VPT; k0 += BT) {
+            uint4 v[BT];
+            uint4* dst[BT];
+            bool live[BT], inb[BT];
+#pragma unroll
+            for (int j = 0; j < BT; ++j) {
+              const int L = Lbase + (k0 + j) * LS;
+              live[j] = (k0 + j < VPT) && L < kHalo;
+              inb[j] = live[j];
+              if (!interior) {
+                const int hy = (L * 3641) >> 16, hx = L - hy * kHP;
+                inb[j] = live[j] && static_cast<unsigned>(y0 + hy) < static_cast<unsigned>(args.H) &&
+                         static_cast<unsigned>(x0 + hx) < static_cast<unsigned>(args.W);
+              }
+              const uint32_t sw = (KCH == 64) ? ((uu ^ (L & 7)) << 4) : ((uu ^ ((L >> 1) & 3)) << 4);
+              dst[j] = reinterpret_cast<uint4*>(ob + L * LB + sw);
+              v[j] = make_uint4(0u, 0u, 0u, 0u);     // out-of-image halo stays exactly zero (padding AFTER the norm)
+              if (inb[j]) v[j] = *dst[j];
+            }
+            if (mode == 2) {
+#pragma unroll
+              for (int j = 0; j < BT; ++j) {
+                uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  uint32_t h, t;
+                  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(w[e]), "r"(sc2[e]), "r"(sh2[e]));
+                  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+                  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(w[e]) : "r"(h), "r"(t));
+                }
+                v[j] = inb[j] ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+              }
+            } else if (mode == 1) {
+#pragma unroll
+              for (int j = 0; j < BT; ++j) {
+                uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(w[e]) : "r"(w[e]), "r"(sc2[e]), "r"(sh2[e]));
+                v[j] = inb[j] ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < BT; ++j)
+              if (live[j]) *dst[j] = v[j];
+          }
+        } else {
 #pragma unroll 2
         for (int k = 0; k < VPT; ++k) {
           const int L = Lbase + k * LS;
@@ -415,30 +485,6 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t sw = (KCH == 64) ? ((uu ^ (L & 7)) << 4) : ((uu ^ ((L >> 1) & 3)) << 4);
           uint4* dst = reinterpret_cast<uint4*>(ob + L * LB + sw);
           uint4 o = make_uint4(0u, 0u, 0u, 0u);   // out-of-image halo stays exactly zero (padding AFTER the norm)
-          if constexpr (H2) {
-            if (inb) {
-              // 16-bit stream (inference only): the prologue in packed half2, as in conv_band.cu --
-              //   h = x * (scale/2) + shift/2 (HFMA2), t = tanh(h) (tanh.approx.f16x2), silu(2h) = h*t + h (HFMA2)
-              // 1.5 instructions and a quarter of an SFU operation per element instead of 9 and 2: the transform of a
-              // 64-channel chunk took 7.2k cycles (timeline, CTA 0) against 4.6k for its MMAs
-              const uint4 lo = *dst;
-              uint32_t w[4] = {lo.x, lo.y, lo.z, lo.w};
-              if (has_norm) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  uint32_t h;
-                  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(w[e]), "r"(sc2[e]), "r"(sh2[e]));
-                  if (do_silu) {
-                    uint32_t t;
-                    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
-                    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h) : "r"(h), "r"(t));
-                  }
-                  w[e] = h;
-                }
-              }
-              o = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          } else
           if (inb) {
             float f[8];
             if constexpr (IN32) {
@@ -482,6 +528,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
           *dst = o;
         }
+        }
         if constexpr (IN32) mbar_arrive(&in_empty[pq % NXS]);
         if (tt == 0) {
           TMA4_TRACE(it, 18 + (p & 3));
@@ -496,21 +543,23 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue teams (team = M block)
+    constexpr int TPB = NTEAM / 2;                  // teams per M block: the 32-channel units alternate between them
+    constexpr int NOBT = NOB / TPB;                 // units per team and tile
     const int team = warp >> 2, ew = warp & 3;      // ew == TMEM lane quarter
-    const int m = ew * 32 + lane;                   // accumulator row = pixel (m >> 3, team*8 + (m & 7)) of the tile
-    const int mb = team;
+    const int m = ew * 32 + lane;                   // accumulator row = pixel (m >> 3, mb*8 + (m & 7)) of the tile
+    const int mb = team / TPB, obpar = team % TPB;
     const bool leader = (ew == 0 && lane == 0);
     const int cpg = args.gn_groups > 0 ? COUT / args.gn_groups : 0;
     const int bar_id = 1 + team;
     uint8_t* tslots = slots + team * 2 * C::SLOT;
     uint64_t* rfull = res_full + team * 2;
-    float* cs = colsum + warp * COUT * 2;
+    float* cs = colsum + (mb * 4 + ew) * COUT * 2;  // teams of one M block write disjoint channels of the same row
     const int my_tiles = (args.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int total_units = my_tiles * NOB;
-    // residual of unit q (tile q / NOB, channel block q % NOB) -> slot q & 1   (leader only)
+    const int total_units = my_tiles * NOBT;
+    // residual of this team's unit q (tile q / NOBT, its channel block number q % NOBT) -> slot q & 1   (leader only)
     auto issue_res = [&](int q) {
       if constexpr (RES != 0) {
-        const int ti = q / NOB, ob = q - ti * NOB;
+        const int ti = q / NOBT, ob = obpar + TPB * (q - ti * NOBT);
         const int t = blockIdx.x + ti * gridDim.x;
         const int n = t / tiles_per_img;
         const int trem = t - n * tiles_per_img;
@@ -537,7 +586,8 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       tc_fence_after();
       if (threadIdx.x == 0) TMA4_TRACE(it, 6);
 #pragma unroll 1
-      for (int ob = 0; ob < NOB; ++ob, ++q) {
+      for (int ku = 0; ku < NOBT; ++ku, ++q) {
+        const int ob = obpar + TPB * ku;
         uint8_t* oslot = tslots + (q & 1) * C::SLOT;
         uint8_t* rslot = oslot + (SEP_RS ? C::OSLOT : 0u);
         uint32_t acc[32];
@@ -552,7 +602,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         __syncwarp();
         tmem_ld_wait();
-        if (ob == NOB - 1) {                          // all of this tile's accumulator columns are in registers
+        if (ku == NOBT - 1) {                         // all of this team's accumulator columns of the tile are in registers
           tc_fence_before();
           mbar_arrive(&acc_empty[st]);
         }
@@ -601,7 +651,7 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tma_store_4d(&tmO, oslot, ob * 32, x0, y0, n);
           tma_store_commit();
         }
-        if (threadIdx.x == 0 && ob == 0) TMA4_TRACE(it, 7);
+        if (threadIdx.x == 0 && ku == 0) TMA4_TRACE(it, 7);
         if (cpg > 0) {
           // column sums of the stored values over this warp's own 32 rows (lane = (row sub-index, 16-byte chunk))
           constexpr int LPR = OLB / 16, RPI = 32 / LPR, CPC = OUT32 ? 4 : 8;
@@ -654,12 +704,15 @@ conv3x3_tma2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       if (cpg > 0) {
         asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
         const int ei = threadIdx.x;                 // epilogue warps are warps 0 .. NEW-1
+        // (one thread per (group, moment): its loads are 2*cpg words apart -- bank conflicts that ncu shows as 60 % of the
+        // kernel's LDS wavefronts; a conflict-free thread-per-channel fold + shuffles measured no faster, the epilogue is not
+        // the stage that sets the tile period, and it changes the summation order of the statistics, so this stays)
         if (ei < 2 * args.gn_groups) {
           const int g = ei >> 1, k = ei & 1;
           float tsum = 0.f;
           for (int c = g * cpg; c < (g + 1) * cpg; ++c)
 #pragma unroll
-            for (int w8 = 0; w8 < NEW; ++w8) tsum += colsum[(w8 * COUT + c) * 2 + k];
+            for (int w8 = 0; w8 < 8; ++w8) tsum += colsum[(w8 * COUT + c) * 2 + k];
           args.gn_part[((static_cast<size_t>(n) * tiles_per_img + trem) * args.gn_groups + g) * 2 + k] = tsum;
         }
         asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
@@ -753,7 +806,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    constexpr int kThreads = (NEW + ntw<CIN, COUT, IN32>() + 3) * 32;
+    constexpr int kThreads = (C::NEW + ntw<CIN, COUT, IN32, RES, OUT32, SC>() + 3) * 32;
     launch_chain(conv3x3_tma2_kernel<CIN, COUT, IN32, RES, OUT32, SC>, dim3(grid), dim3(kThreads), C::SMEM, stream, tmX, tmW, tmR,
                  tmO, tmXs, tmWs, a);
     return static_cast<int>(cudaGetLastError());
@@ -788,7 +841,7 @@ static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
 
 int conv3x3_tma2_launch(const FusedCall& c, cudaStream_t stream) {
   if (!c.f16) return PTIVAE_ERR_UNSUPPORTED;                           // fp16 operands only
-  if (2 * c.gn_groups > tma4::NEW * 32) return PTIVAE_ERR_UNSUPPORTED;
+  if (2 * c.gn_groups > 256) return PTIVAE_ERR_UNSUPPORTED;   // the tile's statistics are folded by the first 256 epilogue threads
 #define PTIVAE_T2_CASE(CI, CO) \
   if (c.Cin == CI && c.Cout == CO) return tma4::dispatch_mode<CI, CO>(c, stream)
   PTIVAE_T2_CASE(32, 32);
