@@ -16,6 +16,8 @@
 //   * operand buffer and TMEM accumulators are double buffered: transform(t+1) | MMA(t) | epilogue(t-1).
 // Warp roles: [0,NTW) transform, [NTW,NTW+NEW) epilogue, then the MMA issuer (+TMEM alloc), then the
 // weight TMA producer.  Cin = 32 runs two CTAs per SM (4+4 warps each); wider layers one CTA with 8+8.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptivae_internal.h"
@@ -468,6 +470,15 @@ extern "C" int ptivae_conv3x3_fused_query(int in_fmt, int res_kind, int out_f32,
   return conv3x3_tma2_launch(c, nullptr);
 }
 
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PTIVAE_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 extern "C" int ptivae_conv3x3_fused_parts(int H, int W) {
   if (H <= 0 || W <= 0) return PTIVAE_ERR_ARG;
   return ((H + kFT - 1) / kFT) * ((W + kFT - 1) / kFT);
@@ -494,7 +505,15 @@ extern "C" int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scal
                 N, H, W, Cin, Cout, f16, nullptr, false};
     return conv3x3_pair_launch(c, stream);
   }
-  if (Cin == 256 || Cout == 256) {   // 256-wide layers (config B): the chunk-pipelined kernel only, 16-bit stream only
+  // auto: the two-SM kernel takes the 128 / 256-channel layers of a 16-bit stream (3-9 % faster than the one-SM kernel on
+  // every such shape, profiles/r2_ops.txt); PTIVAE_PAIR=0 in the environment keeps them on the one-SM kernel
+  if (impl == 0 && Cin >= 128 && Cout >= 128 && pair_enabled()) {
+    FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
+                N, H, W, Cin, Cout, f16, nullptr, false};
+    const int rcp = conv3x3_pair_launch(c, stream);
+    if (rcp != PTIVAE_ERR_UNSUPPORTED) return rcp;
+  }
+  if (Cin == 256 || Cout == 256) {   // 256-wide layers (config B): the chunk-pipelined kernels only
     if (impl != 0 && impl != 3) return PTIVAE_ERR_UNSUPPORTED;
     FusedCall c{x, in_fmt, scale_shift, silu, w_packed, bias, residual, res_f32, out, out_f32, gn_part, gn_groups,
                 N, H, W, Cin, Cout, f16, g_fused_trace, false};

@@ -18,6 +18,8 @@
 //   * tcgen05.commit is multicast to the same barrier in both CTAs (buffers free, accumulator full);
 //   * tile 2i goes to the even CTA, 2i + 1 to the odd one; with an odd tile count the last pair runs a ghost tile
 //     (image index N: TMA zero-fills its loads and drops its stores, its statistics are not written).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptivae_internal.h"
 
@@ -25,9 +27,9 @@ namespace ptivae {
 namespace pair {
 
 constexpr int kT = 16, kHP = kT + 2, kHalo = kHP * kHP;
-constexpr int NTEAM = 2, NEW = NTEAM * 4, NTW = 8, NT = NTW * 32;
-constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
-constexpr int kThreads = (W_W + 1) * 32;
+// epilogue teams (4 warps = the four TMEM lane quarters): 2 (team = M block) or 4 (team = M block x parity of the
+// 32-channel unit); 8 transform warps, the MMA issuer (+TMEM), the halo loader, the weight loader
+constexpr int NTW = 8, NT = NTW * 32;
 constexpr uint32_t kSmemMax = 232448;
 constexpr uint32_t r1k(uint32_t v) { return (v + 1023u) / 1024u * 1024u; }
 
@@ -45,8 +47,11 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// (default semantics, as CUTLASS's ClusterBarrier::arrive: the data the arrival publishes is this CTA's OWN shared memory,
+// read by this SM's tensor core through the async proxy after the fence.proxy.async that precedes the arrive; an explicit
+// .release.cluster compiles to MEMBAR + ERRBAR per arrive -- 7.6 % of the kernel's stall samples)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // bounded like mbar_wait (a protocol bug traps instead of hanging the box); acquire at cluster scope: the barrier is
 // arrived on by threads of the other CTA
@@ -105,15 +110,18 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m,
 }
 
 // RES: 0 = no residual, 2 = 16-bit residual (lands in the output slot, added in place) -- conv_tma2.cu's numbering
-template <int CIN, int COUT, int RES>
+template <int CIN, int COUT, int RES, int NTEAM>
 struct Cfg {
+  static constexpr int NEW = NTEAM * 4;
+  static constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
+  static constexpr int kThreads = (W_W + 1) * 32;
   static constexpr int KCH = 64, NCH = CIN / KCH;
   static constexpr uint32_t LB = KCH * 2;
   static constexpr uint32_t CHUNK = r1k(kHalo * LB);
   static constexpr uint32_t HSLAB = uint32_t(COUT / 2) * LB;    // this CTA's half of a (chunk, tap) weight slab
   static constexpr uint32_t OLB = 64, SLOT = 128 * OLB;
   static constexpr int NOB = COUT / 32;
-  static constexpr uint32_t MISC = 1024 + NEW * COUT * 2 * 4 + COUT * 4 + 64 * 8 + 64;
+  static constexpr uint32_t MISC = 1024 + 8 * COUT * 2 * 4 + COUT * 4 + 64 * 8 + 64;
   static constexpr uint32_t FIXED = MISC + NTEAM * 2 * SLOT;
   static constexpr int nst_for(int nbuf) {
     const uint32_t used = FIXED + nbuf * CHUNK;
@@ -140,12 +148,13 @@ struct Args {
   float* gn_part;            // [N][tiles][groups][2]
 };
 
-template <int CIN, int COUT, int RES>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CIN, int COUT, int RES, int NTEAM>
+__global__ void __launch_bounds__(Cfg<CIN, COUT, RES, NTEAM>::kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const Args args) {
-  using C = Cfg<CIN, COUT, RES>;
+  using C = Cfg<CIN, COUT, RES, NTEAM>;
   constexpr bool F16 = true;
+  constexpr int NEW = C::NEW, W_TR0 = C::W_TR0, W_MMA = C::W_MMA, W_IN = C::W_IN, W_W = C::W_W;
   constexpr int KCH = C::KCH, NCH = C::NCH, NBUF = C::NBUF, NST = C::NST, NOB = C::NOB;
   constexpr uint32_t LB = C::LB, CHUNK = C::CHUNK, HSLAB = C::HSLAB, OLB = C::OLB;
   constexpr uint32_t kSBO_A = kHP * LB, kSBO_B = 8u * LB;
@@ -161,7 +170,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint8_t* slots = opbuf + NBUF * CHUNK;                    // [NTEAM][2][SLOT]
   uint8_t* wts = slots + NTEAM * 2 * C::SLOT;               // ring [NST][HSLAB]
   float* colsum = reinterpret_cast<float*>(wts + NST * HSLAB);   // [NEW][COUT][2]
-  float* sbias = colsum + NEW * COUT * 2;                   // [COUT]
+  float* sbias = colsum + 8 * COUT * 2;                     // [COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
   uint64_t* b_full = bars;             // [8]  leader: both halves of a slab landed
   uint64_t* b_empty = bars + 8;        // [8]  slab consumed (multicast commit)
@@ -171,7 +180,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* acc_full = bars + 28;      // [2]  accumulator stage complete (multicast commit)
   uint64_t* acc_empty = bars + 30;     // [2]  leader: stage drained by BOTH CTAs' epilogues
   uint64_t* res_full = bars + 32;      // [NTEAM][2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 36);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 40);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -190,8 +199,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_init(&in_full[s], 1);
       mbar_init(&op_full[s], 2 * NT);
       mbar_init(&op_empty[s], 1);
-      mbar_init(&res_full[s], 1);
     }
+    for (int s = 0; s < NTEAM * 2; ++s) mbar_init(&res_full[s], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 2 * NEW * 32);
@@ -371,23 +380,25 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue teams (team = M block of the own tile)
+    constexpr int TPB = NTEAM / 2;                  // teams per M block: the 32-channel units alternate between them
+    constexpr int NOBT = NOB / TPB;                 // units per team and tile
     const int team = warp >> 2, ew = warp & 3;      // ew == TMEM lane quarter
-    const int m = ew * 32 + lane;                   // accumulator row = pixel (m >> 3, team*8 + (m & 7)) of the tile
-    const int mb = team;
+    const int m = ew * 32 + lane;                   // accumulator row = pixel (m >> 3, mb*8 + (m & 7)) of the tile
+    const int mb = team / TPB, obpar = team % TPB;
     const bool leader = (ew == 0 && lane == 0);
     const int cpg = args.gn_groups > 0 ? COUT / args.gn_groups : 0;
     const int bar_id = 1 + team;
     uint8_t* tslots = slots + team * 2 * C::SLOT;
     uint64_t* rfull = res_full + team * 2;
-    float* cs = colsum + warp * COUT * 2;
+    float* cs = colsum + (mb * 4 + ew) * COUT * 2;  // teams of one M block write disjoint channels of the same row
     const uint32_t leader_acc_empty = map_to_rank(smem_u32(acc_empty), 0);
     int my_iters = 0;
     while (has_iter(my_iters)) ++my_iters;
-    const int total_units = my_iters * NOB;
-    // residual of unit q (iteration q / NOB, channel block q % NOB) -> slot q & 1   (team leader only)
+    const int total_units = my_iters * NOBT;
+    // residual of this team's unit q (iteration q / NOBT, its channel block number q % NOBT) -> slot q & 1   (team leader only)
     auto issue_res = [&](int q) {
       if constexpr (RES != 0) {
-        const int ti = q / NOB, ob = q - ti * NOB;
+        const int ti = q / NOBT, ob = obpar + TPB * (q - ti * NOBT);
         int n, trem, tiy, tix;
         decode(tile_of(ti), n, trem, tiy, tix);
         uint8_t* dst = tslots + (q & 1) * C::SLOT;
@@ -411,7 +422,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_wait(&acc_full[st], (it / NSTG) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int ob = 0; ob < NOB; ++ob, ++q) {
+      for (int ku = 0; ku < NOBT; ++ku, ++q) {
+        const int ob = obpar + TPB * ku;
         uint8_t* oslot = tslots + (q & 1) * C::SLOT;
         uint32_t acc[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * 2 * COUT + mb * COUT + ob * 32, acc);
@@ -425,7 +437,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         __syncwarp();
         tmem_ld_wait();
-        if (ob == NOB - 1) {                          // all of this tile's accumulator columns are in registers
+        if (ku == NOBT - 1) {                         // all of this team's accumulator columns of the tile are in registers
           tc_fence_before();
           mbar_arrive_cluster(leader_acc_empty + st * 8);
         }
@@ -518,7 +530,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           float tsum = 0.f;
           for (int c = g * cpg; c < (g + 1) * cpg; ++c)
 #pragma unroll
-            for (int w8 = 0; w8 < NEW; ++w8) tsum += colsum[(w8 * COUT + c) * 2 + k];
+            for (int w8 = 0; w8 < 8; ++w8) tsum += colsum[(w8 * COUT + c) * 2 + k];
           args.gn_part[((static_cast<size_t>(n) * tiles_per_img + trem) * args.gn_groups + g) * 2 + k] = tsum;
         }
         asm volatile("bar.sync 9, %0;" ::"n"(NEW * 32) : "memory");
@@ -533,9 +545,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == W_MMA) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
 }
 
-template <int CIN, int COUT, int RES>
+template <int CIN, int COUT, int RES, int NTEAM>
 static int launch(const FusedCall& c, cudaStream_t stream) {
-  using C = Cfg<CIN, COUT, RES>;
+  using C = Cfg<CIN, COUT, RES, NTEAM>;
   if constexpr (!C::FITS) {
     return PTIVAE_ERR_UNSUPPORTED;
   } else {
@@ -575,14 +587,14 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
       }
     }
     static bool attr_set[64] = {};
-    if (int rc_attr = ensure_dyn_smem(conv3x3_pair_kernel<CIN, COUT, RES>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
+    if (int rc_attr = ensure_dyn_smem(conv3x3_pair_kernel<CIN, COUT, RES, NTEAM>, static_cast<int>(kSmemMax), attr_set)) return rc_attr;
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int need = (a.num_tiles + 1) / 2;
     const int pairs = need < sms / 2 ? need : sms / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(C::kThreads);
     cfg.dynamicSmemBytes = C::SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -594,14 +606,26 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (chained_launch_mask() & 1) ? 2 : 1;
-    return static_cast<int>(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<CIN, COUT, RES>, tmX, tmW, tmR, tmO, a));
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<CIN, COUT, RES, NTEAM>, tmX, tmW, tmR, tmO, a));
   }
 }
 
+static int pair_teams() {   // PTIVAE_PAIR_TEAMS=2|4 (A/B switch; default below)
+  static int t = 0;
+  if (t == 0) {
+    const char* e = getenv("PTIVAE_PAIR_TEAMS");
+    t = (e && e[0] == '2') ? 2 : ((e && e[0] == '4') ? 4 : 2);
+  }
+  return t;
+}
 template <int CIN, int COUT>
 static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
-  if (c.residual == nullptr) return launch<CIN, COUT, 0>(c, stream);
-  return launch<CIN, COUT, 2>(c, stream);
+  if (pair_teams() == 4) {
+    if (c.residual == nullptr) return launch<CIN, COUT, 0, 4>(c, stream);
+    return launch<CIN, COUT, 2, 4>(c, stream);
+  }
+  if (c.residual == nullptr) return launch<CIN, COUT, 0, 2>(c, stream);
+  return launch<CIN, COUT, 2, 2>(c, stream);
 }
 
 }  // namespace pair
@@ -610,7 +634,7 @@ static int dispatch_mode(const FusedCall& c, cudaStream_t stream) {
 int conv3x3_pair_launch(const FusedCall& c, cudaStream_t stream) {
   if (!c.f16 || c.in_fmt == 2 || c.out_f32 || c.sc_x != nullptr || (c.residual != nullptr && c.res_f32))
     return PTIVAE_ERR_UNSUPPORTED;
-  if (2 * c.gn_groups > pair::NEW * 32) return PTIVAE_ERR_UNSUPPORTED;
+  if (2 * c.gn_groups > 256) return PTIVAE_ERR_UNSUPPORTED;   // folded by the first 256 epilogue threads
 #define PTIVAE_PAIR_CASE(CI, CO) \
   if (c.Cin == CI && c.Cout == CO) return pair::dispatch_mode<CI, CO>(c, stream)
   PTIVAE_PAIR_CASE(128, 128);
