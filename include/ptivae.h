@@ -68,9 +68,13 @@ int ptivae_conv_parts(int H, int W, int mode);
  *               Zero padding is applied AFTER the normalisation, as nn.Conv2d(padding=1) does.
  *   w_packed    h16 [9][Cout][Cin]; Cin, Cout in {32, 64, 128} (and 256 on the h16 stream, see ptivae_conv3x3_fused_query)
  *   residual/out/gn_part: as ptivae_conv_umma, with P = ptivae_conv3x3_fused_parts(H, W) (16x16 tiles).
- *   impl: 0 = auto; 1 = register-staged kernel (all shapes, both operand formats); 2 = TMA-staged kernel
- *         (Cin,Cout <= 64); 3 = chunk-pipelined TMA kernel (all widths).  2 and 3 need fp16 operands and an fp32
- *         residual and return -2 otherwise.  All implementations produce the same results. */
+ *   impl: 0 = auto; 1 = register-staged kernel (widths <= 128, both operand formats); 2 = TMA-staged kernel
+ *         (Cin,Cout <= 64); 3 = chunk-pipelined TMA kernel (all widths); 4 = row-band kernel (Cout = 32, h16 in / out,
+ *         none or h16 residual); 5 = two-SM kernel (tcgen05 cta_group::2; Cin, Cout in {128, 256}, h16 in / out, none or
+ *         h16 residual).  2-5 need fp16 operands and return -2 for a combination they do not instantiate.  On the fp32
+ *         stream all implementations produce the same results up to accumulation order; the h16-stream modes of 3, 4
+ *         and 5 evaluate the prologue in packed half2 (h + h*tanh(h), three fp16 roundings): within twice the per-layer
+ *         tolerance of the fp32 form (tests/test_gpu_kernels.py), end to end within the stated gates. */
 int ptivae_conv3x3_fused(const void* x, int in_fmt, const float* scale_shift, int silu, const void* w_packed,
                          const float* bias, const void* residual, int res_f32, void* out, int out_f32,
                          float* gn_part, int gn_groups, int N, int H, int W, int Cin, int Cout, int f16,

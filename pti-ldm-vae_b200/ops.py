@@ -160,7 +160,7 @@ def up2x_conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn
     return r if len(r) > 1 else r[0]
 
 
-FUSED_IMPL = 0   # 0 auto | 1 register-staged conv_fused.cu | 2 conv_tma.cu | 3 conv_tma2.cu | 4 conv_band.cu (tests force each)
+FUSED_IMPL = 0   # 0 auto | 1 register-staged conv_fused.cu | 2 conv_tma.cu | 3 conv_tma2.cu | 4 conv_band.cu | 5 conv_pair.cu (tests force each)
 
 
 def conv3x3_fused(x: torch.Tensor, scale_shift, silu: bool, w_packed: torch.Tensor, bias: torch.Tensor,

@@ -9,7 +9,13 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
-        "launch__shared_mem_per_block_dynamic"]
+        "launch__shared_mem_per_block_dynamic",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "sm__cycles_elapsed.max"]
 for w in want:
     if w in hdr:
         i = hdr.index(w)

@@ -23,6 +23,13 @@ CAPS = [
     ("l1l2", "l1l2_partial, 2 x [64,1,256,256] fp32 (latent_loss.cu): 33.6 MB read"),
     ("cin1", "conv3x3_cin1 1->32 @256x256 + first-norm statistics, fp32 out (conv_direct.cu): 16.8 MB in -> 537 MB out"),
     ("cout1", "conv3x3_fewcout 32->1 @256x256 with the final GroupNorm affine folded in (conv_direct.cu): 268 MB fp16 in -> 16.8 MB out"),
+    ("s128c2", "ResBlock conv2 128->128 @64x64, B = 64, fp16 stream, ONE-SM kernel (conv_tma2.cu <128,128,0,2,0,0>, PTIVAE_PAIR=0): 77.3 GFLOP; in 67 MB + residual 67 MB -> out 67 MB.  Shared-memory data pipe: tensor-core reads (tc) + LSU (LDS / STS / TMA) wavefronts"),
+    ("p128c2", "the same layer on the TWO-SM kernel (conv_pair.cu <128,128,2,2>, cta_group::2): each SM stages half of the weight rows"),
+    ("p128c1", "ResBlock conv1 128->128 @64x64 on the two-SM kernel (no residual)"),
+    ("p256c1", "config B: conv1 256->256 @64x64, B = 64, two-SM kernel (conv_pair.cu <256,256,0,2>): 309 GFLOP"),
+    ("s256c1", "config B: conv1 256->256 @64x64, B = 64, one-SM kernel (conv_tma2.cu <256,256,0,0,0,0>, captured before the packed-half2 prologue)"),
+    ("s64c2", "ResBlock conv2 64->64 @128x128, B = 64, fp16 stream (conv_tma2.cu <64,64,0,2,0,0>, four epilogue teams): 77.3 GFLOP; in 134 MB + residual 134 MB -> out 134 MB"),
+    ("s128c2s", "ResBlock conv2 128->128 @32x32, B = 64, fp16 stream, one-SM kernel (captured before the packed-half2 prologue): 256 tiles on 148 CTAs"),
     ("wgrad_col", "wgrad3x3_col_kernel (wgrad.cu), one launch of an eager B = 8 training step"),
     ("gn_bwd_reduce", "gn_bwd_reduce_kernel (gn_bwd.cu), one launch of an eager B = 8 training step"),
     ("dgrad_umma", "conv_umma_kernel as a data-gradient conv (conv_umma.cu mode 4), one launch of an eager B = 8 training step"),
@@ -86,7 +93,8 @@ def main():
 
     for src, dst in (("r2_bench.json", "r2_bench.json"), ("r2_bench_ref.json", "r2_bench_ref.json"), ("r2_train_b8.json", "r2_train_b8.json"),
                      ("r2_train_b32.json", "r2_train_b32.json"), ("r2_train_launch_summary_b8.txt", "r2_train_launch_summary_b8.txt"),
-                     ("r2_ops.log", "r2_ops.txt"), ("bench_breakdown.json", "r2_bench_breakdown.json"),
+                     ("r2_ops.log", "r2_ops.txt"), ("r2_ops_wide.log", "r2_ops_wide.txt"), ("r2_timeline_wide.log", "r2_timeline_wide.txt"),
+                     ("r2_sfu_rates.log", "r2_sfu_rates.txt"), ("r2_train_b8_after.json", "r2_train_b8_after.json"), ("bench_breakdown.json", "r2_bench_breakdown.json"),
                      ("r2_train_full.json", "r2_train_full.json"), ("r2_configs.json", "r2_configs.json"),
                      ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_train_b8_n2.json", "r2_train_b8_n2.json"),
                      ("r2_train_full_n2.json", "r2_train_full_n2.json"), ("r2_bench_n4.json", "r2_bench_n4.json"),
