@@ -39,7 +39,15 @@ constexpr int kR = 4;                 // output rows per band
 constexpr int kMW = 128;              // pixels per M block
 constexpr int kLW = kMW + 2;          // input row segment incl. one halo pixel per side
 constexpr int COUT = 32;
-constexpr int NTEAM = 4, NEW = NTEAM * 4, NTW = 8, NT = NTW * 32;
+// 24 worker warps: NTEAM epilogue teams of 4 warps (a team drains kR / NTEAM output rows of a band, one after the other)
+// and the rest transform warps.  The prologue is a dependent chain per vector (LDS -> HFMA2 -> MUFU -> HFMA2 -> STS) and was
+// the longest stage with 8 warps (4.4-4.9k cycles per batch; the epilogue needs ~1k per row), so it gets 16 and the epilogue 8.
+#ifndef BAND_NTEAM
+#define BAND_NTEAM 2
+#endif
+constexpr int NTEAM = BAND_NTEAM, NEW = NTEAM * 4, NTW = 24 - NEW, NT = NTW * 32;
+constexpr int RPT = kR / NTEAM;       // output rows per team
+constexpr int NCS = kR * 4;           // column-sum rows per band: (output row, TMEM lane quarter)
 constexpr int W_TR0 = NEW, W_MMA = NEW + NTW, W_IN = W_MMA + 1, W_W = W_MMA + 2;
 constexpr int kThreads = (NEW + NTW + 3) * 32;
 constexpr uint32_t kSmemMax = 232448;
@@ -56,7 +64,7 @@ struct Cfg {
   static constexpr uint32_t BLK = COUT * LB;                   // one tap's weights [32 co][CIN]
   static constexpr uint32_t WBYTES = 12u * BLK;                // kx = 0: W2 W1 W0 0 0 0 | kx = 1: W2 W1 W0 | kx = 2: W2 W1 W0
   static constexpr uint32_t OSLOT = 128 * 64;                  // 128 pixels x 32 channels, 16-bit
-  static constexpr uint32_t SMEM = 1024 + NR * ROWB + WBYTES + NTEAM * SLOTS * OSLOT + 2 * NEW * COUT * 2 * 4 + COUT * 4 + 80 * 8 + 64;
+  static constexpr uint32_t SMEM = 1024 + NR * ROWB + WBYTES + NTEAM * SLOTS * OSLOT + 2 * NCS * COUT * 2 * 4 + COUT * 4 + 80 * 8 + 64;
   static_assert(SMEM <= kSmemMax, "shared memory budget");
 };
 
@@ -103,8 +111,8 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint8_t* ring = smem;                                     // [NR][ROWB]
   uint8_t* wts = ring + NR * ROWB;                          // [12][BLK]
   uint8_t* slots = wts + C::WBYTES;                         // [NTEAM][SLOTS][OSLOT]
-  float* colsum = reinterpret_cast<float*>(slots + NTEAM * C::SLOTS * C::OSLOT);   // [2][NEW][COUT][2]
-  float* sbias = colsum + 2 * NEW * COUT * 2;               // [COUT]
+  float* colsum = reinterpret_cast<float*>(slots + NTEAM * C::SLOTS * C::OSLOT);   // [2][NCS][COUT][2]
+  float* sbias = colsum + 2 * NCS * COUT * 2;               // [COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + COUT);
   uint64_t* row_full = bars;            // [NR] raw row landed (TMA) or known to be out of the image
   uint64_t* row_ready = bars + 16;      // [NR] row normalised in place
@@ -192,14 +200,14 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         seg_decode(s, n, cb, b0, b1);
         for (int b = b0; b < b1; ++b, ++it) {
           mbar_wait(&st_full[it & 1], (it >> 1) & 1);
-          const float* cb2 = colsum + (it & 1) * NEW * COUT * 2;
+          const float* cb2 = colsum + (it & 1) * NCS * COUT * 2;
           for (int e = lane; e < 2 * args.gn_groups; e += 32) {
             const int gi = e >> 1, k = e & 1;
             float tsum = 0.f;
             for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
               float part = 0.f;
 #pragma unroll
-              for (int w8 = 0; w8 < NEW; ++w8) part += cb2[(w8 * COUT + c) * 2 + k];
+              for (int w8 = 0; w8 < NCS; ++w8) part += cb2[(w8 * COUT + c) * 2 + k];
               tsum += part;
             }
             const int pidx = b * args.colblocks + cb;
@@ -293,77 +301,124 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // = 1.5 instructions per element instead of 9 (fp32 unpack / affine / ex2 / rcp / pack); three fp16 roundings instead
     // of one (measured against the fp32 reference in tests/test_gpu_kernels.py::test_conv3x3_fused_band).
     // A thread owns fixed (pixel, 16-byte chunk) positions of a row: offsets and the x-range test are per segment.
+    // (The SFU is not the limit -- tanh issues at 16 results/clk/SM like ex2, profiles/r2_sfu_rates.txt, i.e. 1.0k cycles per
+    // 4-row batch; the stage is a dependent chain per vector, so it gets 16 warps and processes four rows' vectors at once.)
     const int tt = threadIdx.x - W_TR0 * 32;
     const bool has_norm = args.scale_shift != nullptr;
     const bool do_silu = args.silu != 0;
+    // main pixels (L = 1 .. 128 of the 130-pixel row segment): KV vectors per thread and row, no ragged tail; the two halo
+    // pixels of every row of a batch (2 * UPC vectors per row) are done by the first transform warp afterwards
     constexpr int LS = NT / UPC;                      // pixel stride between a thread's vectors
-    constexpr int KV = (kLW + LS - 1) / LS;           // vectors per thread and row (the last one only for a few threads)
+    constexpr int KV = kMW / LS;
+    static_assert(KV * LS == kMW && KV >= 1, "main pixels divide evenly among the transform threads");
     const int u = tt % UPC, Lbase = tt / UPC;
+    auto swz = [](int L, int uu) -> uint32_t {
+      return (CIN == 64) ? ((static_cast<uint32_t>(uu) ^ (L & 7)) << 4) : ((static_cast<uint32_t>(uu) ^ ((L >> 1) & 3)) << 4);
+    };
     int g = 0;
     for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
       int n, cb, b0, b1;
       seg_decode(s, n, cb, b0, b1);
+      const float4* ssrc = reinterpret_cast<const float4*>(args.scale_shift + static_cast<size_t>(n) * CIN * 2);
+      const float hf = do_silu ? 0.5f : 1.0f;
       uint32_t sc2[4], sh2[4];
       if (has_norm) {
-        const float4* src = reinterpret_cast<const float4*>(args.scale_shift + (static_cast<size_t>(n) * CIN + u * 8) * 2);
-        const float f = do_silu ? 0.5f : 1.0f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float4 v = __ldg(src + e);          // (scale, shift) of channels 2e, 2e+1
-          sc2[e] = pack2<F16>(v.x * f, v.z * f);
-          sh2[e] = pack2<F16>(v.y * f, v.w * f);
+          const float4 v = __ldg(ssrc + u * 4 + e);          // (scale, shift) of channels 8u + 2e, 8u + 2e + 1
+          sc2[e] = pack2<F16>(v.x * hf, v.z * hf);
+          sh2[e] = pack2<F16>(v.y * hf, v.w * hf);
         }
       }
       uint32_t off[KV];
-      uint32_t st = 0;                              // per vector: bit k = exists, bit 8+k = inside the image in x
+      uint32_t st = 0;                              // per vector: bit 8+k = inside the image in x
 #pragma unroll
       for (int k = 0; k < KV; ++k) {
-        const int L = Lbase + k * LS;
-        const uint32_t sw = (CIN == 64) ? ((u ^ (L & 7)) << 4) : ((u ^ ((L >> 1) & 3)) << 4);
-        off[k] = L * LB + sw;
+        const int L = 1 + Lbase + k * LS;
+        off[k] = L * LB + swz(L, u);
         const int x = cb * kMW - 1 + L;
-        if (L < kLW) st |= 1u << k;
-        if (L < kLW && x >= 0 && x < args.W) st |= 256u << k;
+        if (x >= 0 && x < args.W) st |= 256u << k;
       }
+      const int mode = has_norm ? (do_silu ? 2 : 1) : 0;      // kernel-uniform
+      // one vector through the prologue (h = x*scale/2 + shift/2; silu(2h) = h*tanh(h) + h), or zero outside the image
+      auto xform = [&](uint4 v, bool ok, const uint32_t (&a2)[4], const uint32_t (&b2)[4]) -> uint4 {
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if (mode == 2) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t h, t;
+            asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(w[e]), "r"(a2[e]), "r"(b2[e]));
+            asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+            asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(w[e]) : "r"(h), "r"(t));
+          }
+        } else if (mode == 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(w[e]) : "r"(w[e]), "r"(a2[e]), "r"(b2[e]));
+        }
+        return ok ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+      };
       for (int bt = 0; bt <= b1 - b0; ++bt) {
         const int nrows = bt == 0 ? 2 : kR;
         const int ybase = kR * b0 - 1 + (bt == 0 ? 0 : 2 + kR * (bt - 1));   // image row of the batch's first row
         // one warp polls the TMA barriers, the other seven sleep in a hardware barrier (a polling warp burns issue slots:
         // 27 polling warps accounted for a third of all executed instructions)
-        if (tt < 32)
-          for (int r = 0; r < nrows; ++r) mbar_wait(&row_full[(g + r) % NR], ((g + r) / NR) & 1);
+        // (one warp per row of the batch does the polling, in parallel)
+        if (tt < 32 * nrows) {
+          const int r = tt >> 5;
+          mbar_wait(&row_full[(g + r) % NR], ((g + r) / NR) & 1);
+        }
         asm volatile("bar.sync 5, %0;" ::"n"(NT) : "memory");
         if (tt == 0) ROW_TRACE(g, 1);
-#pragma unroll 2
-        for (int r = 0; r < nrows; ++r) {
-          uint8_t* rb = ring + ((g + r) % NR) * ROWB;
-          const int y = ybase + r;
-          const bool row_in = y >= 0 && y < args.H;
-          uint4 v[KV];
+        // RB rows go through at once (a batch has 2 or 4): all their vectors are loaded first, the arithmetic has no branch
+        // inside (predicated selects), then all are stored -- the per-vector form (load, branch, compute, store) left nothing
+        // to overlap the LDS and SFU latencies with: one instruction per ~24 cycles and warp, 4.9k cycles per batch (timeline)
+        constexpr int RB = KV == 1 ? 4 : 2;
+#pragma unroll 1
+        for (int r = 0; r < nrows; r += RB) {
+          uint8_t* rb[RB];
+          uint4 v[RB][KV];
+          bool ok[RB][KV];
 #pragma unroll
-          for (int k = 0; k < KV; ++k) {
-            v[k] = make_uint4(0u, 0u, 0u, 0u);     // zero padding is applied AFTER the normalisation
-            if (row_in && (st & (256u << k))) v[k] = *reinterpret_cast<const uint4*>(rb + off[k]);
+          for (int j = 0; j < RB; ++j) {
+            rb[j] = ring + ((g + r + j) % NR) * ROWB;
+            const int y = ybase + r + j;
+            const bool row_in = (r + j < nrows) && y >= 0 && y < args.H;
+#pragma unroll
+            for (int k = 0; k < KV; ++k) {
+              ok[j][k] = row_in && (st & (256u << k));
+              v[j][k] = make_uint4(0u, 0u, 0u, 0u);     // zero padding is applied AFTER the normalisation
+              if (ok[j][k]) v[j][k] = *reinterpret_cast<const uint4*>(rb[j] + off[k]);
+            }
           }
 #pragma unroll
-          for (int k = 0; k < KV; ++k) {
-            if (!(st & (1u << k))) continue;
-            if (has_norm && row_in && (st & (256u << k))) {
-              uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+          for (int j = 0; j < RB; ++j)
+#pragma unroll
+            for (int k = 0; k < KV; ++k) v[j][k] = xform(v[j][k], ok[j][k], sc2, sh2);
+#pragma unroll
+          for (int j = 0; j < RB; ++j)
+#pragma unroll
+            for (int k = 0; k < KV; ++k)
+              if (r + j < nrows) *reinterpret_cast<uint4*>(rb[j] + off[k]) = v[j][k];
+        }
+        if (tt >= NT - 32) {   // the halo pixels (L = 0 and L = 129) of the batch's rows, by the last warp (the first ones poll):
+          for (int idx = tt - (NT - 32); idx < nrows * 2 * UPC; idx += 32) {   // lane -> (row, side, 16-byte chunk)
+            const int j = idx / (2 * UPC), side = (idx / UPC) & 1, uh = idx % UPC;
+            const int L = side ? kLW - 1 : 0;
+            const int y = ybase + j, x = cb * kMW - 1 + L;
+            const bool ok = y >= 0 && y < args.H && x >= 0 && x < args.W;
+            uint4* q = reinterpret_cast<uint4*>(ring + ((g + j) % NR) * ROWB + L * LB + swz(L, uh));
+            uint32_t a2[4] = {}, b2[4] = {};
+            if (has_norm) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                uint32_t h;
-                asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(w[e]), "r"(sc2[e]), "r"(sh2[e]));
-                if (do_silu) {
-                  uint32_t t;
-                  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
-                  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h) : "r"(h), "r"(t));
-                }
-                w[e] = h;
+                const float4 sv = __ldg(ssrc + uh * 4 + e);
+                a2[e] = pack2<F16>(sv.x * hf, sv.z * hf);
+                b2[e] = pack2<F16>(sv.y * hf, sv.w * hf);
               }
-              v[k] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4*>(rb + off[k]) = v[k];
+            uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) hv = *q;
+            *q = xform(hv, ok, a2, b2);
           }
         }
         if (tt == 0) ROW_TRACE(g, 3);
@@ -385,9 +440,9 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // 16-bit residual line of this thread's pixel (32 channels = 64 B), read straight from global memory ONE BAND AHEAD
     // (the loads are issued after the band's slot is written and land under its store / statistics / the next TMEM wait)
     uint4 rnext[4] = {};
-    auto load_res = [&](int n, int cb, int b) {
+    auto load_res = [&](int n, int cb, int b, int dy) {
       if constexpr (RES != 0) {
-        const int y = kR * b + team, x = cb * kMW + m;
+        const int y = kR * b + dy, x = cb * kMW + m;
         if (y < args.H && x < args.W) {
           const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(args.residual) +
                                                             ((static_cast<size_t>(n) * args.H + y) * args.W + x) * (COUT * 2));
@@ -402,7 +457,7 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (static_cast<int>(blockIdx.x) < args.num_segs) {
       int n, cb, b0, b1;
       seg_decode(blockIdx.x, n, cb, b0, b1);
-      load_res(n, cb, b0);
+      load_res(n, cb, b0, team);
     }
     int it = 0;
     for (int s = blockIdx.x; s < args.num_segs; s += gridDim.x) {
@@ -411,18 +466,24 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int x0 = cb * kMW;
       for (int b = b0; b < b1; ++b, ++it) {
         const int st = it & 1;
-        const int y = kR * b + team;
         if (threadIdx.x == 0) BAND_TRACE(it, 8);
         // the team's first warp polls for the accumulator; the other three wait in the team's hardware barrier
         if (ew == 0) mbar_wait(&acc_full[st], (it >> 1) & 1);
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         tc_fence_after();
         if (threadIdx.x == 0) BAND_TRACE(it, 9);
+        if (want_stats && it >= 2) mbar_wait(&st_free[it & 1], ((it >> 1) - 1) & 1);    // the finalizer has read band it-2's sums
+#pragma unroll 1
+        for (int ri = 0; ri < RPT; ++ri) {   // this team's output rows of the band
+        const int dy = team + NTEAM * ri;
+        const int y = kR * b + dy;
         uint32_t acc[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * (kR * COUT) + team * COUT, acc);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + st * (kR * COUT) + dy * COUT, acc);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&acc_empty[st]);
+        if (ri == RPT - 1) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[st]);
+        }
         if (threadIdx.x == 0) BAND_TRACE(it, 11);
         // +bias (+residual), round to the stored format, and park the pixel's 64-byte line in this WARP's scratch
         // (2 KB, swizzled): the transposed read below turns 32 lines into four fully coalesced 512-byte global stores
@@ -453,13 +514,15 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           __syncwarp();
         }
         if (threadIdx.x == 0) BAND_TRACE(it, 12);
-        {   // next band of this CTA: its residual line starts its trip now
-          if (b + 1 < b1) {
-            load_res(n, cb, b + 1);
+        {   // this team's next output row (of this band, or the first of the CTA's next band): its residual line starts its trip now
+          if (ri + 1 < RPT) {
+            load_res(n, cb, b, dy + NTEAM);
+          } else if (b + 1 < b1) {
+            load_res(n, cb, b + 1, team);
           } else if (s + static_cast<int>(gridDim.x) < args.num_segs) {
             int n2, cb2, b02, b12;
             seg_decode(s + gridDim.x, n2, cb2, b02, b12);
-            load_res(n2, cb2, b02);
+            load_res(n2, cb2, b02, team);
           }
         }
         {
@@ -500,8 +563,7 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
               }
             }
-            if (it >= 2) mbar_wait(&st_free[it & 1], ((it >> 1) - 1) & 1);    // the finalizer has read band it-2's sums
-            float* cs = colsum + ((it & 1) * NEW + warp) * COUT * 2;
+            float* cs = colsum + ((it & 1) * NCS + dy * 4 + ew) * COUT * 2;
             if (rsub == 0) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
@@ -510,9 +572,10 @@ conv3x3_band_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&st_full[it & 1]);
+            if (ri == RPT - 1 && lane == 0) mbar_arrive(&st_full[it & 1]);
           }
         }
+        }   // ri
         if (threadIdx.x == 0) BAND_TRACE(it, 17);
       }
     }
@@ -583,7 +646,7 @@ static int launch(const FusedCall& c, cudaStream_t stream) {
 int conv3x3_band_launch(const FusedCall& c, cudaStream_t stream) {
   if (!c.f16 || c.Cout != 32 || c.in_fmt == 2 || c.out_f32 || c.sc_x != nullptr) return PTIVAE_ERR_UNSUPPORTED;
   if (c.residual != nullptr && c.res_f32) return PTIVAE_ERR_UNSUPPORTED;
-  if (2 * c.gn_groups > band::NEW * 32) return PTIVAE_ERR_UNSUPPORTED;
+  if (2 * c.gn_groups > 64) return PTIVAE_ERR_UNSUPPORTED;   // COUT = 32: at most 16 groups of >= 2 channels
   const bool res = c.residual != nullptr;
   if (c.Cin == 32) return res ? band::launch<32, 2>(c, stream) : band::launch<32, 0>(c, stream);
   if (c.Cin == 64) return res ? band::launch<64, 2>(c, stream) : band::launch<64, 0>(c, stream);
