@@ -93,7 +93,7 @@ def main():
 
     for src, dst in (("r2_bench.json", "r2_bench.json"), ("r2_bench_ref.json", "r2_bench_ref.json"), ("r2_train_b8.json", "r2_train_b8.json"),
                      ("r2_train_b32.json", "r2_train_b32.json"), ("r2_train_launch_summary_b8.txt", "r2_train_launch_summary_b8.txt"),
-                     ("r2_ops.log", "r2_ops.txt"), ("r2_ops_wide.log", "r2_ops_wide.txt"), ("r2_timeline_wide.log", "r2_timeline_wide.txt"),
+                     ("r2_ops.log", "r2_ops.txt"), ("r2_ops_wide.log", "r2_ops_wide.txt"), ("r2_timeline_wide.log", "r2_timeline_wide.txt"), ("r2_timeline_band.log", "r2_timeline_band.txt"),
                      ("r2_sfu_rates.log", "r2_sfu_rates.txt"), ("r2_train_b8_after.json", "r2_train_b8_after.json"), ("bench_breakdown.json", "r2_bench_breakdown.json"),
                      ("r2_train_full.json", "r2_train_full.json"), ("r2_configs.json", "r2_configs.json"),
                      ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_train_b8_n2.json", "r2_train_b8_n2.json"),
