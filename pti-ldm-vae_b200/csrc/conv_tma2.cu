@@ -15,8 +15,10 @@
 //     store (image edges clipped by the TMA unit);
 //   * GroupNorm statistics of the stored values: column sums over the warp's own 32 rows of the slot
 //     (conflict-free 16-byte loads), folded in fixed order -- deterministic, no atomics.
-// Warp roles: 0-7 epilogue teams, then 8 (or 12) transform warps, the MMA issuer (+TMEM), the halo TMA producer
-// and the weight TMA producer (608 or 736 threads).
+// Warp roles: 0-7 epilogue teams (0-15 where four teams are used, see nteam()), then 8 (or 12) transform warps, the MMA
+// issuer (+TMEM), the halo TMA producer and the weight TMA producer (608, 736 or 864 threads).
+// The 16-bit-stream modes (16-bit in and out, no fp32 residual: inference only) run the prologue in packed half2.
+// 128 / 256-channel layers of that stream normally go to the two-SM form of this kernel, conv_pair.cu.
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptivae_internal.h"
