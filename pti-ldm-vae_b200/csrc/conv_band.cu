@@ -30,7 +30,7 @@
 #include "ptivae_internal.h"
 
 #ifndef BAND_NR32
-#define BAND_NR32 16     // ring slots for 32 input channels (measured: 16 slots beat 12 by 2-4 %)
+#define BAND_NR32 16     // ring slots for 32 input channels (measured: 16 slots beat 12 by 2-4 %; the barrier arrays hold 16)
 #endif
 namespace ptivae {
 namespace band {
