@@ -18,14 +18,15 @@
 // TMA store, no team barrier); the 16-bit residual line of a pixel is read straight from global memory one band ahead;
 // GroupNorm statistics are column sums of the stored values in fixed order, finalised per band by an otherwise idle warp
 // (deterministic, no atomics).
-// What bounds it (clock64 timelines of CTA 0, tools/prof_band.py): the MMAs of a band take ~1.8k cycles and
-// the epilogue ~1k, but the prologue needs ~5k cycles per 4-row batch -- 3.3 SiLU elements per clock and SM, close to what
-// the SFU delivers for MUFU.TANH (the fp32 tanh, fp32 ex2+rcp and packed-half2 forms all measured the same or worse;
-// without the SiLU the kernel runs at 0.156 ms instead of 0.200).  The prologue runs in packed half2 (1.5 instructions per
-// element instead of 9), which leaves the issue slots to the other roles, and is the pipeline's period.
-// Warp roles (864 threads): 0-15 epilogue (four teams of four warps, team = output row dy of the band), 16-23 transform,
-// 24 MMA issuer (+TMEM), 25 row loader, 26 weight loader, then the per-band statistics finalizer (so that no epilogue warp
-// waits on another team).
+// What bounds it (clock64 timelines of CTA 0, tools/prof_band.py; ncu): the MMAs of a band take ~1.8k cycles,
+// the epilogue ~1k per output row.  The prologue was the pipeline's period at ~5k cycles per 4-row batch and first read as
+// SFU bound; the SFU issues 16 tanh results per clock and SM (profiles/r2_sfu_rates.txt: ~1k cycles per batch) -- it was a
+// dependent chain per vector with nothing to overlap.  It now runs on 16 warps, four rows per branch-free pass, in packed
+// half2 (1.5 instructions per element instead of 9): 2.3k cycles per batch, 32 -> 32 at 0.159 ms per launch (B = 64, 256^2),
+// and ncu puts the shared-memory data pipe at 90 % (tensor-core operand reads 33 % + LDS / STS / TMA 56 %).
+// Warp roles (864 threads): 0-7 epilogue (two teams of four warps; a team drains the band's output rows dy = team and
+// team + 2, one after the other), 8-23 transform, 24 MMA issuer (+TMEM), 25 row loader, 26 weight loader, then the per-band
+// statistics finalizer (so that no epilogue warp waits on another team).
 #include "common.cuh"
 #include "ptivae_internal.h"
 
