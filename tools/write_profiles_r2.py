@@ -63,9 +63,15 @@ def main():
         if rd is not None and wr is not None:
             key = {"band32c2": "fused3x3_32->32@256x256_in2_res2_out2", "band32c1": "fused3x3_32->32@256x256_in2_res0_out2"}.get(name)
             if key:
+                def pct(k):
+                    return float(vals[hdr.index(k)].replace(",", "")) if k in hdr else None
+                tc = pct("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")
+                lsu = pct("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")
                 traffic[key] = {"dram_bytes_per_launch": rd + wr,
                                 "note": f"ncu --set full: {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB write",
                                 "source": f"profiles/r2_ncu_kernels.txt ({name})"}
+                if tc is not None and lsu is not None:   # what actually limits the kernel: the shared-memory data pipe
+                    traffic[key]["shared_memory_pipe_pct_of_peak"] = {"tensor_core_operand_reads": tc, "lsu_lds_sts_tma": lsu}
     (P / "r2_ncu_kernels.txt").write_text("\n".join(out) + "\n")
     (P / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
 
@@ -100,7 +106,16 @@ def main():
                      ("r2_train_full_n2.json", "r2_train_full_n2.json"), ("r2_bench_n4.json", "r2_bench_n4.json"),
                      ("r2_train_b8_n4.json", "r2_train_b8_n4.json"), ("r2_train_full_n4.json", "r2_train_full_n4.json")):
         if (G / src).exists():
-            shutil.copy(G / src, P / dst)
+            # keep the explanatory header ('#' lines) of an already committed record when its raw log is copied again
+            head = ""
+            if dst.endswith(".txt") and (P / dst).exists():
+                old = (P / dst).read_text().splitlines(keepends=True)
+                head = "".join(l for l in old[:12] if l.startswith("#"))
+            new = (G / src).read_text() if dst.endswith(".txt") else None
+            if new is not None and head and not new.startswith("#"):
+                (P / dst).write_text(head + new)
+            else:
+                shutil.copy(G / src, P / dst)
 
     # SASS census of the shipped library
     so = ROOT / "pti-ldm-vae_b200" / "libptivae.so"
